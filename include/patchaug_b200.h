@@ -1,0 +1,168 @@
+/*
+ * patchaug_b200.h — C ABI of libpatchaug_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the descriptor-extraction-and-retrieval hot path of WHU-USI3DV/PatchAugNet.
+ * Every entry point takes plain device pointers + sizes + a CUDA stream (as void*) and returns an int:
+ *   0            success
+ *   > 0          a cudaError_t from the launch
+ *   PAB_EINVAL   argument outside the supported range (the reference would overflow / exit)
+ * Nothing is retained between calls; the caller owns every buffer.  Citations are relative to the
+ * reference tree (/root/reference).
+ *
+ * The "pab_<name>" pointops functions replace, one for one, the extern "C" launchers the reference's
+ * pybind module `pointops_cuda` calls (libs/pointops/src/pointops_api.cpp:15-40), with two deliberate
+ * differences: every launch goes to the caller's stream (most reference launchers use the legacy default
+ * stream), and failures are returned instead of exit(-1) (e.g. knnquery_cuda_kernel.cu:66-70).
+ */
+#ifndef PATCHAUG_B200_H
+#define PATCHAUG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PAB_EINVAL (-22)
+
+typedef void *pab_stream_t; /* cudaStream_t */
+
+/* ---- library info -------------------------------------------------------------------------------- */
+int pab_version(void);                 /* ABI version, bumped on any signature change */
+int pab_num_launches(void);            /* kernels launched by this library since load (bench.py gpu_launches) */
+void pab_reset_launch_counter(void);
+
+/* ---- libs/pointops ------------------------------------------------------------------------------- */
+
+/* furthestsampling_cuda_launcher  sampling/sampling_cuda_kernel.h:17, kernel .cu:58-168.
+ * xyz (b,n,3) f32; temp (b,n) f32 caller-initialised (1e10, pointops.py:21), updated in place;
+ * idx (b,m) i32 out.  Bit-exact with the reference including its tie-break order. */
+int pab_furthestsampling(int b, int n, int m, const float *xyz, float *temp, int *idx, pab_stream_t s);
+
+/* gathering_forward/backward_cuda_launcher  sampling_cuda_kernel.h:15-16.  points (b,c,n), idx (b,m),
+ * out (b,c,m); backward accumulates into grad_points (b,c,n) (caller-zeroed, pointops.py:52). */
+int pab_gathering_forward(int b, int c, int n, int m, const float *points, const int *idx, float *out, pab_stream_t s);
+int pab_gathering_backward(int b, int c, int n, int m, const float *grad_out, const int *idx, float *grad_points, pab_stream_t s);
+
+/* knnquery_cuda_launcher  knnquery/knnquery_cuda_kernel.h:14, kernel .cu:6-50.  xyz (b,n,3), new_xyz (b,m,3);
+ * idx (b,m,nsample) i32 ascending by distance, ties to the lower index; dist2 (b,m,nsample) f32 or NULL
+ * (the reference's dist2 write is an un-offset race, .cu:44-47; here it is the true squared distance).
+ * nsample <= 200 like the reference's fixed arrays (.cu:21-22), else PAB_EINVAL. */
+int pab_knnquery(int b, int n, int m, int nsample, const float *xyz, const float *new_xyz, int *idx, float *dist2, pab_stream_t s);
+
+/* ballquery_cuda_launcher_fast  ballquery/ballquery_cuda_kernel.h, kernel .cu:47-80.  idx caller-zeroed. */
+int pab_ballquery(int b, int n, int m, float radius, int nsample, const float *new_xyz, const float *xyz, int *idx, pab_stream_t s);
+
+/* grouping_forward_cuda_launcher_fast / grouping_backward_cuda_launcher  grouping/grouping_cuda_kernel.cu:60-92, 28-46 */
+int pab_grouping_forward(int b, int c, int n, int m, int nsample, const float *points, const int *idx, float *out, pab_stream_t s);
+int pab_grouping_backward(int b, int c, int n, int m, int nsample, const float *grad_out, const int *idx, float *grad_points, pab_stream_t s);
+/* grouping_int_forward_cuda_launcher_fast  grouping_int/grouping_int_cuda_kernel.cu:33-64 (int64 payload) */
+int pab_grouping_int_forward(int b, int c, int n, int m, int nsample, const int64_t *points, const int *idx, int64_t *out, pab_stream_t s);
+
+/* nearestneighbor_cuda_launcher_fast  interpolation/interpolation_cuda_kernel.cu:134-176, 200-214.
+ * unknown (b,n,3), known (b,m,3) -> dist2 (b,n,3) SQUARED f32, idx (b,n,3) i32. */
+int pab_nearestneighbor(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx, pab_stream_t s);
+/* interpolation_forward_cuda_launcher_fast .cu:181-195, 216-228; interpolation_backward_cuda_launcher .cu:90-129 */
+int pab_interpolation_forward(int b, int c, int m, int n, const float *points, const int *idx, const float *weight, float *out, pab_stream_t s);
+int pab_interpolation_backward(int b, int c, int n, int m, const float *grad_out, const int *idx, const float *weight, float *grad_points, pab_stream_t s);
+
+/* featuredistribute/featuredistribute_cuda_kernel.cu:4-30, 53-65, 89-101 */
+int pab_featuredistribute(int b, int n, int m, const float *max_xyz, const float *xyz, int *distribute_idx, pab_stream_t s);
+int pab_featuregather_forward(int b, int n, int m, int c, const float *max_feature, const int *distribute_idx, float *distribute_feature, pab_stream_t s);
+int pab_featuregather_backward(int b, int n, int m, int c, const float *grad_distribute_feature, const int *distribute_idx, float *grad_max_feature, pab_stream_t s);
+
+/* labelstat/labelstat_cuda_kernel.cu:131-151, 74-105, 6-49 */
+int pab_labelstat_idx(int b, int n, int m, int nsample, int nclass, const int *label_stat, const int *idx, int *new_label_stat, pab_stream_t s);
+int pab_labelstat_ballrange(int b, int n, int m, float radius, int nclass, const float *new_xyz, const float *xyz, const int *label_stat, int *new_label_stat, pab_stream_t s);
+int pab_labelstat_and_ballquery(int b, int n, int m, float radius, int nsample, int nclass, const float *new_xyz, const float *xyz,
+                                const int *label_stat, int *idx, int *new_label_stat, pab_stream_t s);
+
+/* ---- libs/chamfer_dist --------------------------------------------------------------------------- */
+/* chamfer_cuda_forward  chamfer_cuda.cpp:22-29, chamfer.cu:147-171: both directions in one call.
+ * xyz1 (B,n,3), xyz2 (B,m,3) -> dist1 (B,n), dist2 (B,m) squared f32; idx1, idx2 i32 (first minimum wins). */
+int pab_chamfer_forward(int B, int n, const float *xyz1, int m, const float *xyz2, float *dist1, float *dist2, int *idx1, int *idx2, pab_stream_t s);
+/* chamfer_cuda_backward  chamfer.cu:203-229: grad_xyz1 (B,n,3), grad_xyz2 (B,m,3) are overwritten
+ * (deterministic segmented sums, not atomics). */
+int pab_chamfer_backward(int B, int n, const float *xyz1, int m, const float *xyz2, const int *idx1, const int *idx2,
+                         const float *grad_dist1, const float *grad_dist2, float *grad_xyz1, float *grad_xyz2, pab_stream_t s);
+
+/* ---- libs/KNN_CUDA ------------------------------------------------------------------------------- */
+/* knn_device  knn_cuda/csrc/cuda/knn.cu:232-269 via knn.cpp:23-56.  ref (dim,nr), query (dim,nq) row-major f32
+ * -> dist (k,nq) f32 = sqrt(squared L2), ind (k,nq) int64 1-BASED (knn_cuda/__init__.py:41-44 subtracts 1).
+ * No nr x nq matrix is materialised.  k <= 1024. */
+int pab_knn(const float *ref, int nr, const float *query, int nq, int dim, int k, float *dist, int64_t *ind, pab_stream_t s);
+
+/* Retrieval kNN over row-major descriptors (replaces sklearn KDTree.query at
+ * datasets/place_recognition_dataset.py:60, scene_dataset.py:1052): db (ndb,dim), q (nq,dim) ->
+ * dist (nq,k) f32 Euclidean ascending, ind (nq,k) i32 0-based, ties to the lower index. k <= 1024. */
+int pab_retrieval_topk(const float *db, int ndb, const float *q, int nq, int dim, int k, float *dist, int *ind, pab_stream_t s);
+
+/* ---- libs/emd_module ----------------------------------------------------------------------------- */
+/* emd_cuda_forward  emd.cpp:14-22, emd_cuda.cu:228-282.  Same buffers, same return convention
+ * (1 ok, 0 CUDA error, -1 bad shape: n % 1024 != 0 or b > 512). */
+int pab_emd_forward(int b, int n, const float *xyz1, const float *xyz2, float *dist, int *assignment, float *price,
+                    int *assignment_inv, int *bid, float *bid_increments, float *max_increments, int *unass_idx,
+                    int *unass_cnt, int *unass_cnt_sum, int *cnt_tmp, int *max_idx, float eps, int iters, pab_stream_t s);
+/* emd_cuda_backward  emd_cuda.cu:284-316 */
+int pab_emd_backward(int b, int n, const float *xyz1, const float *xyz2, float *gradxyz, const float *graddist, const int *idx, pab_stream_t s);
+
+/* ---- fused descriptor-extraction path (no reference counterpart: replaces chains of reference ops) -- */
+
+/* Point-major row gather out[b,j,:] = feat[b,idx[b,j],:] (feat (b,n,c), idx (b,m), out (b,m,c)); used for
+ * new_xyz = xyz[center_idx] (patch_aug_net.py:222-225 does it with a transpose + gathering + transpose). */
+int pab_gather_rows(int b, int n, int m, int c, const float *feat, const int *idx, float *out, pab_stream_t s);
+
+/* Fused 3-NN + inverse-distance weights: pointops.nearestneighbor + patch_aug_net.py:350-353.
+ * unknown (b,n,3), known (b,m,3) -> idx (b,n,3) i32, weight (b,n,3) f32. */
+int pab_three_nn_weights(int b, int n, int m, const float *unknown, const float *known, int *idx, float *weight, pab_stream_t s);
+
+/* One folded SharedMLP layer: y = relu?(Wt^T x + shift).  Wt is (c_in_pad, c_out) row-major with the
+ * BatchNorm scale folded in and rows >= c_in zero; c_in_pad = c_in rounded up to a multiple of 4. */
+typedef struct {
+    const float *wt;    /* (c_in_pad, c_out) */
+    const float *shift; /* (c_out) */
+    int c_in, c_in_pad, c_out, relu;
+} pab_layer_t;
+
+/* Fused set-abstraction module (patch_aug_net.py:203-243 + pointops.py:533-582, eval mode):
+ * gather centres, gather k neighbours, subtract centre, concat [xyz_rel ; feat_rel], SharedMLP, max over k.
+ * xyz (b,n,3); feat (b,n,c) POINT-MAJOR (may alias xyz with c=3); center_idx (b,m); nbr_idx (b,m,nbr_stride),
+ * the first k entries of each row are used; out (b,m,c_out_last) point-major; new_xyz (b,m,3) out (or NULL). */
+int pab_sa_module_forward(int b, int n, int m, int k, int nbr_stride, int c, const float *xyz, const float *feat,
+                          const int *center_idx, const int *nbr_idx, const pab_layer_t *layers, int n_layers,
+                          float *out, float *new_xyz, pab_stream_t s);
+
+/* Fused feature-propagation module (patch_aug_net.py:331-363): 3-NN interpolation of known_feat
+ * (b,m,c_known) with idx/weight (b,n,3), concat skip (b,n,c_skip) (may be NULL with c_skip 0), SharedMLP.
+ * out (b,n,c_out_last) point-major. */
+int pab_fp_module_forward(int b, int n, int m, int c_known, int c_skip, const float *known_feat, const float *skip_feat,
+                          const int *idx, const float *weight, const pab_layer_t *layers, int n_layers,
+                          float *out, pab_stream_t s);
+
+/* Plain point-wise SharedMLP over rows: x (rows, c_in) -> out (rows, c_out_last). */
+int pab_pointwise_mlp_forward(int rows, const float *x, const pab_layer_t *layers, int n_layers, float *out, pab_stream_t s);
+
+/* NetVLADBase.forward (patch_aug_net/models/loupe.py:191-222), eval: x (b,n,c) point-major, wc (c,K) with the
+ * bn1 scale folded in, shift (K), w2 (c,K) = cluster_weights2; out written at out[b*out_bstride + ch*out_cstride + k]
+ * (lets the caller place levels side by side in the (B,C,sumK) concat of loupe.py:302).  c in {128,256}, K % 4 == 0,
+ * K <= 64.  workspace: >= pab_netvlad_workspace_bytes(b,n,c,K) bytes. */
+size_t pab_netvlad_workspace_bytes(int b, int n, int c, int K);
+int pab_netvlad_forward(int b, int n, int c, int K, const float *x, const float *wc, const float *shift, const float *w2,
+                        float *out, long out_bstride, long out_cstride, void *workspace, pab_stream_t s);
+
+/* AdaptiveFeatureAggregator.forward (loupe.py:57-66, 24-41), eval: v (b,c,K) -> desc (b,c_out), L2-normalised.
+ * w_att_t (c_in,c_out) = mlpa.mlps.0.weight[:, :, 0] TRANSPOSED; fc_wt (c*K, c_out) = fc.weight TRANSPOSED (so the
+ * 22 MB matrix streams coalesced); desc = normalize((fc_wt^T y) * fc_scale + fc_shift) with fc.bias and the
+ * BatchNorm1d folded into fc_scale/fc_shift.  workspace >= pab_afa_workspace_bytes(b,c,K,c_out). */
+size_t pab_afa_workspace_bytes(int b, int c, int K, int c_out);
+int pab_afa_forward(int b, int c, int K, int c_out, const float *v, const float *w_att_t, const float *fc_wt,
+                    const float *fc_scale, const float *fc_shift, int l2_norm, float *desc, void *workspace, pab_stream_t s);
+
+/* Tuning hook: force the FPS CTA size (power of two, 32..1024; 0 = automatic). */
+void pab_tune_fps_threads(int threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PATCHAUG_B200_H */

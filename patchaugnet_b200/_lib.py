@@ -1,0 +1,110 @@
+"""ctypes binding of libpatchaug_b200.so — the thin C-ABI doorway (include/patchaug_b200.h).
+
+There is deliberately NO fallback: if the library is missing or a call fails, an exception is raised.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpatchaug_b200.so")
+PAB_EINVAL = -22
+
+_lib = None
+
+_P = C.c_void_p
+_I = C.c_int
+_F = C.c_float
+_L = C.c_long
+_SZ = C.c_size_t
+
+
+class PabLayer(C.Structure):
+    """pab_layer_t"""
+    _fields_ = [("wt", _P), ("shift", _P), ("c_in", _I), ("c_in_pad", _I), ("c_out", _I), ("relu", _I)]
+
+
+# name -> (restype, argtypes); every symbol include/patchaug_b200.h declares
+SIGNATURES = {
+    "pab_version": (_I, []),
+    "pab_num_launches": (_I, []),
+    "pab_reset_launch_counter": (None, []),
+    "pab_tune_fps_threads": (None, [_I]),
+    "pab_furthestsampling": (_I, [_I, _I, _I, _P, _P, _P, _P]),
+    "pab_gathering_forward": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),
+    "pab_gathering_backward": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),
+    "pab_knnquery": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "pab_ballquery": (_I, [_I, _I, _I, _F, _I, _P, _P, _P, _P]),
+    "pab_grouping_forward": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "pab_grouping_backward": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "pab_grouping_int_forward": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "pab_nearestneighbor": (_I, [_I, _I, _I, _P, _P, _P, _P, _P]),
+    "pab_interpolation_forward": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "pab_interpolation_backward": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "pab_featuredistribute": (_I, [_I, _I, _I, _P, _P, _P, _P]),
+    "pab_featuregather_forward": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),
+    "pab_featuregather_backward": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),
+    "pab_labelstat_idx": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "pab_labelstat_ballrange": (_I, [_I, _I, _I, _F, _I, _P, _P, _P, _P, _P]),
+    "pab_labelstat_and_ballquery": (_I, [_I, _I, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "pab_chamfer_forward": (_I, [_I, _I, _P, _I, _P, _P, _P, _P, _P, _P]),
+    "pab_chamfer_backward": (_I, [_I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "pab_knn": (_I, [_P, _I, _P, _I, _I, _I, _P, _P, _P]),
+    "pab_retrieval_topk": (_I, [_P, _I, _P, _I, _I, _I, _P, _P, _P]),
+    "pab_emd_forward": (_I, [_I, _I] + [_P] * 14 + [_F, _I, _P]),
+    "pab_emd_backward": (_I, [_I, _I, _P, _P, _P, _P, _P, _P]),
+    "pab_gather_rows": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),
+    "pab_three_nn_weights": (_I, [_I, _I, _I, _P, _P, _P, _P, _P]),
+    "pab_sa_module_forward": (_I, [_I, _I, _I, _I, _I, _I, _P, _P, _P, _P, C.POINTER(PabLayer), _I, _P, _P, _P]),
+    "pab_fp_module_forward": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, C.POINTER(PabLayer), _I, _P, _P]),
+    "pab_pointwise_mlp_forward": (_I, [_I, _P, C.POINTER(PabLayer), _I, _P, _P]),
+    "pab_netvlad_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
+    "pab_netvlad_forward": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P, _L, _L, _P, _P]),
+    "pab_afa_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
+    "pab_afa_forward": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P]),
+}
+
+
+class PabError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the shared library (once).  Raises if it has not been built — never falls back."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PabError(
+                f"{LIB_PATH} is missing: build it with `python -m patchaugnet_b200.build` "
+                "(or __graft_entry__.build()); patchaugnet_b200 has no CPU or PyTorch fallback")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def stream_ptr():
+    """The caller's (PyTorch current) CUDA stream as a void*."""
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def check(rc, what):
+    if rc == 0:
+        return
+    if rc == PAB_EINVAL:
+        raise ValueError(f"{what}: argument outside the supported range (PAB_EINVAL)")
+    raise PabError(f"{what}: CUDA error {rc}")
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise PabError("patchaugnet_b200 ops run on CUDA tensors only (there is no CPU fallback)")

@@ -1,0 +1,350 @@
+// vlad.cu — NetVLAD soft-assignment + residual aggregation and the AdaptiveFeatureAggregator head (sm_100a).
+//
+// NetVLADBase.forward (place_recognition/patch_aug_net/models/loupe.py:191-222) is ~10 PyTorch kernels per level:
+// transpose+contiguous, matmul, BN1d, softmax, sum, mul, transpose, matmul, sub, normalize.  Here one kernel reads
+// each (128-point x C) tile of the point-major feature map ONCE into shared memory and runs both contractions on
+// it:  logits = x Wc + shift  ->  softmax over K (one thread per point)  ->  vlad[K,C] += act^T x, accumulated in
+// registers across the CTA's tiles; per-CTA partials are combined in a fixed order by a small finalize kernel that
+// also subtracts a_sum * cluster_weights2 and applies the intra-cluster L2 normalisation (deterministic, no atomics).
+//
+// AdaptiveFeatureAggregator (loupe.py:57-66) + MLPAttentionLayer (loupe.py:24-41):  attention logits = max over
+// output channels of conv1d(v); softmax over the K clusters; y = relu(v + v*w); fc over the flattened (C*K) vector
+// split along the 21504-long reduction so the 22 MB weight is streamed exactly once; bias + BN1d + L2 in finalize.
+#include <math.h>
+#include "tile_gemm.cuh"
+
+namespace {
+
+constexpr int VR = 128;          // rows (points) per tile
+constexpr int VROWS_PER_CTA = 512;
+constexpr int VKMAX = 64;
+
+struct VladArgs {
+    int n, c, K, sx;
+    const float *x, *wc, *shift;
+    float *part, *asum;   // part (b, nchunk, K, c); asum (b, nchunk, K)
+    int nchunk;
+};
+
+__global__ void __launch_bounds__(tg::THREADS, 1) vlad_partial_kernel(const VladArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int sx = a.sx;                       // stride_for(c)
+    constexpr int SL = 68;                     // logits row stride (>= VKMAX, = 4 mod 32)
+    constexpr int ST = VR + 4;                 // act^T row stride
+    float *xs = smem;                          // [VR][sx]
+    float *lg = xs + (size_t)VR * sx;          // [VR][SL]
+    float *actT = lg + VR * SL;                // [VKMAX][ST]
+    float *wstage = actT + VKMAX * ST;         // 2*KC*64
+
+    const int t = threadIdx.x, cloud = blockIdx.y, chunk = blockIdx.x;
+    const int row_begin = chunk * VROWS_PER_CTA;
+    const int row_end = min(a.n, row_begin + VROWS_PER_CTA);
+    const float *xg = a.x + (size_t)cloud * a.n * a.c;
+
+    pab_layer_t L;
+    L.wt = a.wc; L.shift = a.shift; L.c_in = a.c; L.c_in_pad = a.c; L.c_out = a.K; L.relu = 0;
+
+    using G2 = tg::Geo<64>;                    // second contraction: 64 "rows" (clusters) x 128-column passes
+    const int cg2 = G2::cg(), rg2 = G2::rg();
+    float acc[2][8][4];
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[p][i][j] = 0.f;
+    float asum = 0.f;
+
+    for (int e = t; e < VKMAX * ST; e += tg::THREADS) actT[e] = 0.f;
+
+    for (int r0 = row_begin; r0 < row_end; r0 += VR) {
+        __syncthreads();  // previous tile fully consumed
+        const int c4 = a.c / 4;
+        for (int e = t; e < VR * c4; e += tg::THREADS) {
+            const int r = e / c4, q = e - r * c4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r0 + r < row_end) v = __ldg(reinterpret_cast<const float4 *>(xg + (size_t)(r0 + r) * a.c) + q);
+            *reinterpret_cast<float4 *>(xs + (size_t)r * sx + 4 * q) = v;
+        }
+        tg::layer<VR>(xs, sx, lg, SL, L, wstage);   // logits (bn1 folded), first sync inside orders the xs writes
+        __syncthreads();
+        if (t < VR) {
+            const bool valid = r0 + t < row_end;
+            const float *row = lg + t * SL;
+            float mx = -INFINITY;
+            for (int k = 0; k < a.K; ++k) mx = fmaxf(mx, row[k]);
+            float sum = 0.f;
+            for (int k = 0; k < a.K; ++k) sum += expf(row[k] - mx);
+            const float inv = 1.f / sum;
+            for (int k = 0; k < a.K; ++k) actT[k * ST + t] = valid ? expf(row[k] - mx) * inv : 0.f;
+        }
+        __syncthreads();
+        if (t < a.K) {
+            const float *row = actT + t * ST;
+            float s = 0.f;
+            for (int r = 0; r < VR; ++r) s += row[r];
+            asum += s;
+        }
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+            if (p * 128 < a.c) tg::fma_block<G2::RG>(acc[p], actT, ST, rg2, xs + p * 128, sx, cg2, VR);
+    }
+    float *part = a.part + ((size_t)cloud * a.nchunk + chunk) * a.K * a.c;
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const int col = p * 128 + 4 * cg2;
+        if (col < a.c) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int k = rg2 + G2::RG * i;
+                if (k < a.K)
+                    *reinterpret_cast<float4 *>(part + (size_t)k * a.c + col) =
+                        make_float4(acc[p][i][0], acc[p][i][1], acc[p][i][2], acc[p][i][3]);
+            }
+        }
+    }
+    if (t < a.K) a.asum[((size_t)cloud * a.nchunk + chunk) * a.K + t] = asum;
+}
+
+// one CTA per cloud, one thread per channel
+__global__ void __launch_bounds__(256) vlad_finalize_kernel(int c, int K, int nchunk, const float *__restrict__ part,
+                                                           const float *__restrict__ asum, const float *__restrict__ w2,
+                                                           float *__restrict__ out, long out_bstride, long out_cstride) {
+    __shared__ float red[VKMAX][8];
+    __shared__ float as[VKMAX];
+    __shared__ float inv[VKMAX];
+    const int t = threadIdx.x, cloud = blockIdx.x, lane = t & 31, warp = t >> 5;
+    if (t < K) {
+        float s = 0.f;
+        for (int ch = 0; ch < nchunk; ++ch) s += asum[((size_t)cloud * nchunk + ch) * K + t];
+        as[t] = s;
+    }
+    __syncthreads();
+    float v[VKMAX];
+#pragma unroll
+    for (int k = 0; k < VKMAX; ++k) {
+        v[k] = 0.f;
+        if (k < K && t < c) {
+            float s = 0.f;
+            for (int ch = 0; ch < nchunk; ++ch) s += part[(((size_t)cloud * nchunk + ch) * K + k) * c + t];
+            v[k] = s - as[k] * __ldg(w2 + (size_t)t * K + k);   // vlad - a,  a = a_sum * cluster_weights2
+        }
+        float sq = v[k] * v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if (lane == 0) red[k][warp] = sq;
+    }
+    __syncthreads();
+    if (t < K) {
+        float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += red[t][w];
+        inv[t] = 1.f / fmaxf(sqrtf(s), 1e-12f);                   // F.normalize(dim=1, p=2, eps=1e-12)
+    }
+    __syncthreads();
+    if (t < c) {
+#pragma unroll
+        for (int k = 0; k < VKMAX; ++k)
+            if (k < K) out[(size_t)cloud * out_bstride + (size_t)t * out_cstride + k] = v[k] * inv[k];
+    }
+}
+
+// ---- AdaptiveFeatureAggregator ---------------------------------------------------------------------------
+
+constexpr int AKC = 28;  // clusters per CTA in the attention kernel
+
+// mx[b][k] = max_c' sum_c w_att_t[c][c'] * v[b][c][k]      (conv1d without bias, then max over channels)
+__global__ void __launch_bounds__(256) afa_att_kernel(int c, int K, const float *__restrict__ v, const float *__restrict__ w_att_t,
+                                                     float *__restrict__ mx) {
+    extern __shared__ __align__(16) float vs[];  // [c][AKC]
+    __shared__ float red[AKC][8];
+    const int t = threadIdx.x, cloud = blockIdx.y, k0 = blockIdx.x * AKC;
+    const int kn = min(AKC, K - k0);
+    for (int e = t; e < c * AKC; e += 256) {
+        const int ci = e / AKC, kk = e - ci * AKC;
+        vs[e] = kk < kn ? __ldg(v + ((size_t)cloud * c + ci) * K + k0 + kk) : 0.f;
+    }
+    __syncthreads();
+    float best[AKC];
+#pragma unroll
+    for (int kk = 0; kk < AKC; ++kk) best[kk] = -INFINITY;
+    for (int co = t; co < c; co += 256) {
+        float acc[AKC];
+#pragma unroll
+        for (int kk = 0; kk < AKC; ++kk) acc[kk] = 0.f;
+        for (int ci = 0; ci < c; ++ci) {
+            const float w = __ldg(w_att_t + (size_t)ci * c + co);
+            const float4 *vr = reinterpret_cast<const float4 *>(vs + ci * AKC);
+#pragma unroll
+            for (int q = 0; q < AKC / 4; ++q) {
+                const float4 x = vr[q];
+                acc[4 * q + 0] = fmaf(w, x.x, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(w, x.y, acc[4 * q + 1]);
+                acc[4 * q + 2] = fmaf(w, x.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(w, x.w, acc[4 * q + 3]);
+            }
+        }
+#pragma unroll
+        for (int kk = 0; kk < AKC; ++kk) best[kk] = fmaxf(best[kk], acc[kk]);
+    }
+    const int lane = t & 31, warp = t >> 5;
+#pragma unroll
+    for (int kk = 0; kk < AKC; ++kk) {
+        float m = best[kk];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0) red[kk][warp] = m;
+    }
+    __syncthreads();
+    if (t < kn) {
+        float m = red[t][0];
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, red[t][w]);
+        mx[(size_t)cloud * K + k0 + t] = m;
+    }
+}
+
+constexpr int FCH = 128;   // reduction slice per CTA in the fc kernel
+constexpr int FB = 32;     // clouds per register pass
+
+// wsm[b][k] = softmax_k(mx[b][:])      (MLPAttentionLayer softmax over the K clusters, loupe.py:31)
+__global__ void __launch_bounds__(128) afa_softmax_kernel(int K, const float *__restrict__ mx, float *__restrict__ wsm) {
+    __shared__ float red[4];
+    const int t = threadIdx.x, cloud = blockIdx.x, lane = t & 31, warp = t >> 5;
+    const float *m = mx + (size_t)cloud * K;
+    float mm = -INFINITY;
+    for (int k = t; k < K; k += 128) mm = fmaxf(mm, m[k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mm = fmaxf(mm, __shfl_xor_sync(0xffffffffu, mm, o));
+    if (lane == 0) red[warp] = mm;
+    __syncthreads();
+    mm = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    __syncthreads();
+    float sum = 0.f;
+    for (int k = t; k < K; k += 128) sum += expf(m[k] - mm);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    sum = (red[0] + red[1]) + (red[2] + red[3]);
+    for (int k = t; k < K; k += 128) wsm[(size_t)cloud * K + k] = expf(m[k] - mm) / sum;
+}
+
+// part[slice][b][o] = sum_{f in slice} y[b][f] * fc_wt[f][o],  y = relu(v + v * wsm[b][k]),  f = c*K + k
+__global__ void __launch_bounds__(256) afa_fc_kernel(int b, int c, int K, int c_out, const float *__restrict__ v,
+                                                    const float *__restrict__ wsm, const float *__restrict__ fc_wt,
+                                                    float *__restrict__ part) {
+    __shared__ __align__(16) float ys[FCH][FB];
+    const int t = threadIdx.x, slice = blockIdx.x;
+    const int F = c * K, f0 = slice * FCH, fn = min(FCH, F - f0);
+    for (int b0 = 0; b0 < b; b0 += FB) {
+        const int bn = min(FB, b - b0);
+        __syncthreads();
+        for (int e = t; e < FB * FCH; e += 256) {
+            const int bb = e / FCH, ff = e - bb * FCH;
+            float y = 0.f;
+            if (bb < bn && ff < fn) {
+                const int cloud = b0 + bb, k = (f0 + ff) % K;
+                const float w = __ldg(wsm + (size_t)cloud * K + k);
+                const float x = __ldg(v + (size_t)cloud * F + f0 + ff);
+                y = fmaxf(x + x * w, 0.f);
+            }
+            ys[ff][bb] = y;
+        }
+        __syncthreads();
+        for (int o = t; o < c_out; o += 256) {
+            float acc[FB];
+#pragma unroll
+            for (int bb = 0; bb < FB; ++bb) acc[bb] = 0.f;
+            for (int ff = 0; ff < fn; ++ff) {
+                const float w = __ldg(fc_wt + (size_t)(f0 + ff) * c_out + o);
+                const float4 *yr = reinterpret_cast<const float4 *>(&ys[ff][0]);
+#pragma unroll
+                for (int q = 0; q < FB / 4; ++q) {
+                    const float4 y = yr[q];
+                    acc[4 * q + 0] = fmaf(y.x, w, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(y.y, w, acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(y.z, w, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(y.w, w, acc[4 * q + 3]);
+                }
+            }
+#pragma unroll
+            for (int bb = 0; bb < FB; ++bb)
+                if (bb < bn) part[((size_t)slice * b + b0 + bb) * c_out + o] = acc[bb];
+        }
+    }
+}
+
+// desc[b][o] = normalize( (sum_slices part + ...) * scale[o] + shift[o] )     (fc bias and BN1d folded by the host)
+__global__ void __launch_bounds__(256) afa_finalize_kernel(int b, int c_out, int nslice, const float *__restrict__ part,
+                                                          const float *__restrict__ scale, const float *__restrict__ shift,
+                                                          int l2_norm, float *__restrict__ desc) {
+    __shared__ float red[8];
+    const int t = threadIdx.x, cloud = blockIdx.x, lane = t & 31, warp = t >> 5;
+    float sq = 0.f;
+    for (int o = t; o < c_out; o += 256) {
+        float s = 0.f;
+        for (int sl = 0; sl < nslice; ++sl) s += part[((size_t)sl * b + cloud) * c_out + o];
+        s = fmaf(s, __ldg(scale + o), __ldg(shift + o));
+        desc[(size_t)cloud * c_out + o] = s;
+        sq += s * s;
+    }
+    if (!l2_norm) return;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if (lane == 0) red[warp] = sq;
+    __syncthreads();
+    float tot = 0.f;
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    const float inv = 1.f / fmaxf(sqrtf(tot), 1e-12f);
+    for (int o = t; o < c_out; o += 256) desc[(size_t)cloud * c_out + o] *= inv;
+}
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
+
+PAB_API size_t pab_netvlad_workspace_bytes(int b, int n, int c, int K) {
+    const size_t nchunk = (n + VROWS_PER_CTA - 1) / VROWS_PER_CTA;
+    return align256(sizeof(float) * (size_t)b * nchunk * K * c) + align256(sizeof(float) * (size_t)b * nchunk * K);
+}
+
+PAB_API int pab_netvlad_forward(int b, int n, int c, int K, const float *x, const float *wc, const float *shift, const float *w2,
+                                float *out, long out_bstride, long out_cstride, void *workspace, pab_stream_t s) {
+    if (b < 0 || n <= 0 || (c != 128 && c != 256) || K <= 0 || K > VKMAX || K % 4 || !workspace) return PAB_EINVAL;
+    if (b == 0) return 0;
+    cudaStream_t st = (cudaStream_t)s;
+    const int nchunk = (n + VROWS_PER_CTA - 1) / VROWS_PER_CTA;
+    VladArgs a;
+    a.n = n; a.c = c; a.K = K; a.sx = tg::stride_for(c); a.x = x; a.wc = wc; a.shift = shift; a.nchunk = nchunk;
+    a.part = (float *)workspace;
+    a.asum = (float *)((char *)workspace + align256(sizeof(float) * (size_t)b * nchunk * K * c));
+    const size_t smem = sizeof(float) * ((size_t)VR * a.sx + VR * 68 + VKMAX * (VR + 4) + 2 * tg::KC * 64);
+    PAB_CUDA(cudaFuncSetAttribute(vlad_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    vlad_partial_kernel<<<dim3(nchunk, b), tg::THREADS, smem, st>>>(a);
+    PAB_LAUNCH_CHECK();
+    vlad_finalize_kernel<<<b, 256, 0, st>>>(c, K, nchunk, a.part, a.asum, w2, out, out_bstride, out_cstride);
+    PAB_LAUNCH_CHECK();
+    return 0;
+}
+
+PAB_API size_t pab_afa_workspace_bytes(int b, int c, int K, int c_out) {
+    const size_t nslice = ((size_t)c * K + FCH - 1) / FCH;
+    return 2 * align256(sizeof(float) * (size_t)b * K) + align256(sizeof(float) * nslice * b * c_out);
+}
+
+PAB_API int pab_afa_forward(int b, int c, int K, int c_out, const float *v, const float *w_att_t, const float *fc_wt,
+                            const float *fc_scale, const float *fc_shift, int l2_norm, float *desc, void *workspace, pab_stream_t s) {
+    if (b < 0 || c <= 0 || K <= 0 || c_out <= 0 || !workspace) return PAB_EINVAL;
+    if (b == 0) return 0;
+    cudaStream_t st = (cudaStream_t)s;
+    float *mx = (float *)workspace;
+    float *wsm = (float *)((char *)workspace + align256(sizeof(float) * (size_t)b * K));
+    float *part = (float *)((char *)workspace + 2 * align256(sizeof(float) * (size_t)b * K));
+    const int nslice = (c * K + FCH - 1) / FCH;
+    const size_t smem = sizeof(float) * (size_t)c * AKC;
+    if (smem > 48 * 1024) PAB_CUDA(cudaFuncSetAttribute(afa_att_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    afa_att_kernel<<<dim3(pab_divup(K, AKC), b), 256, smem, st>>>(c, K, v, w_att_t, mx);
+    PAB_LAUNCH_CHECK();
+    afa_softmax_kernel<<<b, 128, 0, st>>>(K, mx, wsm);
+    PAB_LAUNCH_CHECK();
+    afa_fc_kernel<<<nslice, 256, 0, st>>>(b, c, K, c_out, v, wsm, fc_wt, part);
+    PAB_LAUNCH_CHECK();
+    afa_finalize_kernel<<<b, 256, 0, st>>>(b, c_out, nslice, part, fc_scale, fc_shift, l2_norm, desc);
+    PAB_LAUNCH_CHECK();
+    return 0;
+}

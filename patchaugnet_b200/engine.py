@@ -1,0 +1,231 @@
+"""Fused eval-mode engine for PatchAugNet descriptor extraction (the north-star hot path).
+
+Takes the parameters of a ``patchaugnet_b200.patch_aug_net.Network`` (same ``state_dict`` as the reference),
+folds every eval-mode BatchNorm into its preceding weight once, and runs the whole forward
+(``patch_aug_net.py:48-107`` in the reference) as ~25 launches of hand-written kernels through the C ABI:
+
+    per SA level : FPS -> row gather (new_xyz) -> kNN(k) -> fused [group + centre-subtract + concat + SharedMLP + max_K]
+    per FP level : fused [3-NN + inverse-distance weights] -> fused [interpolate + skip concat + SharedMLP]
+    head         : NetVLAD level kernels (soft-assign + residual aggregation + intra-norm) -> AFA (attention, fc, BN, L2)
+
+Activations are POINT-MAJOR (B, n, C) between kernels, so neighbour gathers read contiguous rows and NetVLAD consumes
+the FP output without the reference's transpose+contiguous (loupe.py:192).  ``fp_features`` are returned as
+(B, C, n, 1) *views* of those buffers — same shape and values as the reference, different strides.
+
+Everything is launched on PyTorch's current stream, so the forward can be captured in a CUDA graph
+(``capture_graph``) to remove per-launch host overhead.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+def _fold_bn(bn):
+    """eval-mode BatchNorm -> (scale, shift):  y = x*scale + shift"""
+    scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    shift = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+    return scale, shift
+
+
+class _Layers:
+    """A folded SharedMLP as a ctypes array of pab_layer_t (keeps the device tensors alive)."""
+
+    def __init__(self, shared_mlp, device):
+        self.tensors = []
+        blocks = list(shared_mlp.children())
+        self.arr = (L.PabLayer * len(blocks))()
+        self.spec = []
+        for i, blk in enumerate(blocks):
+            w = blk.conv.weight.detach().float().reshape(blk.conv.weight.shape[0], -1)   # (c_out, c_in)
+            c_out, c_in = w.shape
+            if hasattr(blk, "bn"):
+                scale, shift = _fold_bn(blk.bn.bn)
+            else:
+                scale = torch.ones(c_out, device=w.device)
+                shift = blk.conv.bias.detach().float() if blk.conv.bias is not None else torch.zeros(c_out, device=w.device)
+            c_in_pad = (c_in + 3) // 4 * 4
+            wt = torch.zeros(c_in_pad, c_out, dtype=torch.float32, device=device)
+            wt[:c_in] = (w * scale[:, None]).t().to(device)
+            sh = shift.to(device).contiguous()
+            self.tensors += [wt, sh]
+            self.arr[i] = L.PabLayer(wt.data_ptr(), sh.data_ptr(), c_in, c_in_pad, c_out, 1 if hasattr(blk, "activation") else 0)
+            self.spec.append((c_in, c_out))
+        self.n = len(blocks)
+        self.c_out = self.spec[-1][1]
+
+
+class FusedPatchAugNet:
+    """Eval-mode fused forward.  ``net`` is a patch_aug_net.Network on a CUDA device."""
+
+    def __init__(self, net):
+        self.net = net
+        self.device = next(net.parameters()).device
+        if self.device.type != "cuda":
+            raise L.PabError("FusedPatchAugNet needs the network on a CUDA device (there is no CPU fallback)")
+        self._ws = {}
+        self._graphs = {}
+        self.refold()
+
+    # ---- weights -------------------------------------------------------------------------------------------------
+    def refold(self):
+        """(Re)build the folded inference weights from the module's current parameters."""
+        net, dev = self.net, self.device
+        bb = net.backbone
+        self.sa = []
+        for mod in bb.SA_modules:
+            g = mod.groupers[0]
+            self.sa.append(dict(npoint=mod.npoint, k=g.nsample, dilation=g.knn_dilation, layers=_Layers(mod.mlps[0], dev)))
+        self.fp = [_Layers(mod.mlp, dev) for mod in bb.FP_modules]
+        self.use_origin = bb.use_origin_pc_in_fp
+        agg = net.aggregation
+        self.vlad = []
+        for v in agg.vlads:
+            scale, shift = _fold_bn(v.bn1)
+            wc = (v.cluster_weights.detach().float() * scale[None, :]).contiguous().to(dev)      # (C, K), bn1 folded
+            w2 = v.cluster_weights2.detach().float()[0].contiguous().to(dev)                    # (C, K)
+            self.vlad.append(dict(K=v.cluster_size, C=v.feature_size, wc=wc, shift=shift.contiguous().to(dev), w2=w2))
+        afa = agg.afa
+        self.w_att_t = afa.mlpa.mlps[0].weight.detach().float()[:, :, 0].t().contiguous().to(dev)   # (c_in, c_out)
+        self.fc_wt = afa.fc.weight.detach().float().t().contiguous().to(dev)                        # (C*K, c_out)
+        scale, shift = _fold_bn(afa.bn)
+        self.fc_scale = scale.contiguous().to(dev)
+        self.fc_shift = (afa.fc.bias.detach().float() * scale + shift).contiguous().to(dev)
+        self.l2_norm = 1 if afa.l2_norm else 0
+        self.c_out = afa.fc.weight.shape[0]
+        self.sumK = sum(v["K"] for v in self.vlad)
+        self._ws.clear()
+        self._graphs.clear()
+
+    # ---- workspace -----------------------------------------------------------------------------------------------
+    def _workspace(self, B, N):
+        key = (B, N)
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        dev = self.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        lib = L.lib()
+        ws = dict(levels=[], fp=[])
+        n = N
+        for sa in self.sa:
+            m = sa["npoint"]
+            ws["levels"].append(dict(
+                n=n, m=m,
+                temp=torch.empty(B, n if n > 8192 else 1, **f32), cidx=torch.empty(B, m, **i32), new_xyz=torch.empty(B, m, 3, **f32),
+                nbr=torch.empty(B, m, sa["k"], **i32), feat=torch.empty(B, m, sa["layers"].c_out, **f32)))
+            n = m
+        ns = [N] + [sa["npoint"] for sa in self.sa]              # points per level 0..3
+        for li in range(len(self.fp)):                           # FP_modules[li] lifts level li+1 -> li
+            ws["fp"].append(dict(idx=torch.empty(B, ns[li], 3, **i32), w=torch.empty(B, ns[li], 3, **f32),
+                                 out=torch.empty(B, ns[li], self.fp[li].c_out, **f32)))
+        ws["v"] = torch.empty(B, self.vlad[0]["C"], self.sumK, **f32)
+        nbytes = max(lib.pab_netvlad_workspace_bytes(B, n_l, v["C"], v["K"])
+                     for n_l, v in zip([ns[2], ns[1], ns[0]], self.vlad))
+        nbytes = max(nbytes, lib.pab_afa_workspace_bytes(B, self.vlad[0]["C"], self.sumK, self.c_out))
+        ws["scratch"] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        ws["desc"] = torch.empty(B, self.c_out, **f32)
+        self._ws[key] = ws
+        return ws
+
+    # ---- forward -------------------------------------------------------------------------------------------------
+    def _launch(self, xyz0, ws):
+        lib, st, p, chk = L.lib(), L.stream_ptr(), L.ptr, L.check
+        B, N, _ = xyz0.shape
+        xyz, feat, c = xyz0, xyz0, 3
+        for sa, lv in zip(self.sa, ws["levels"]):
+            n, m, k = lv["n"], lv["m"], sa["k"]
+            temp = None                      # register-resident FPS initialises its own 1e10 distances
+            if n > 8192:                     # large-cloud fallback keeps them in global memory like the reference
+                temp = lv["temp"]
+                temp.fill_(1e10)
+            chk(lib.pab_furthestsampling(B, n, m, p(xyz), p(temp), p(lv["cidx"]), st), "furthestsampling")
+            chk(lib.pab_gather_rows(B, n, m, 3, p(xyz), p(lv["cidx"]), p(lv["new_xyz"]), st), "gather_rows")
+            chk(lib.pab_knnquery(B, n, m, k, p(xyz), p(lv["new_xyz"]), p(lv["nbr"]), p(None), st), "knnquery")
+            chk(lib.pab_sa_module_forward(B, n, m, k, k, c, p(xyz), p(feat), p(lv["cidx"]), p(lv["nbr"]),
+                                          sa["layers"].arr, sa["layers"].n, p(lv["feat"]), p(None), st), "sa_module")
+            xyz, feat, c = lv["new_xyz"], lv["feat"], sa["layers"].c_out
+        xyzs = [xyz0] + [lv["new_xyz"] for lv in ws["levels"]]
+        feats = [xyz0] + [lv["feat"] for lv in ws["levels"]]      # skip features per level (level 0 = raw xyz)
+        known_feat = feats[-1]
+        for li in range(len(self.fp) - 1, -1, -1):                # FP_modules[-1] first (patch_aug_net.py:183-187)
+            f = ws["fp"][li]
+            unknown, known = xyzs[li], xyzs[li + 1]
+            n, m = unknown.shape[1], known.shape[1]
+            chk(lib.pab_three_nn_weights(B, n, m, p(unknown), p(known), p(f["idx"]), p(f["w"]), st), "three_nn")
+            skip = feats[li]
+            c_skip = skip.shape[2]
+            if li == 0 and not self.use_origin:
+                skip, c_skip = None, 0
+            chk(lib.pab_fp_module_forward(B, n, m, known_feat.shape[2], c_skip, p(known_feat), p(skip), p(f["idx"]), p(f["w"]),
+                                          self.fp[li].arr, self.fp[li].n, p(f["out"]), st), "fp_module")
+            known_feat = f["out"]
+        # fp_features order of the reference: [l2 (128), l1 (1024), l0 (4096)] <-> vlads[0..2]
+        fp_out = [ws["fp"][2]["out"], ws["fp"][1]["out"], ws["fp"][0]["out"]] if len(self.fp) == 3 else \
+            [ws["fp"][i]["out"] for i in range(len(self.fp) - 1, -1, -1)]
+        v, koff = ws["v"], 0
+        for x, lvl in zip(fp_out, self.vlad):
+            chk(lib.pab_netvlad_forward(B, x.shape[1], lvl["C"], lvl["K"], p(x), p(lvl["wc"]), p(lvl["shift"]), p(lvl["w2"]),
+                                        C.c_void_p(v.data_ptr() + 4 * koff), v.stride(0), v.stride(1), p(ws["scratch"]), st),
+                "netvlad")
+            koff += lvl["K"]
+        chk(lib.pab_afa_forward(B, self.vlad[0]["C"], self.sumK, self.c_out, p(v), p(self.w_att_t), p(self.fc_wt),
+                                p(self.fc_scale), p(self.fc_shift), self.l2_norm, p(ws["desc"]), p(ws["scratch"]), st), "afa")
+        return fp_out
+
+    @torch.no_grad()
+    def forward(self, x, consume_rng=True, clone=True):
+        """x: (B,1,N,3) or (B,N,3) float32 CUDA -> (desc (B,256), fp_features [3 x (B,256,n,1)], center_idx_origin [3])."""
+        L.require_cuda(x)
+        xyz0 = x.squeeze(1) if x.dim() == 4 else x
+        xyz0 = xyz0.contiguous().float()
+        B, N, _ = xyz0.shape
+        if consume_rng:
+            # QueryAndGroup_Edge draws torch.randperm(nsample) on the CPU generator once per SA module when
+            # knn_dilation > 1 (pointops.py:555).  The draw only permutes neighbour order (max-pool invariant);
+            # it is repeated here so the global RNG stream stays in lock-step with the reference.
+            for sa in self.sa:
+                if sa["dilation"] > 1:
+                    torch.randperm(sa["k"])
+        ws = self._workspace(B, N)
+        g = self._graphs.get((B, N))
+        if g is not None:
+            g["x"].copy_(xyz0)
+            g["graph"].replay()
+            fp_out = g["fp_out"]
+        else:
+            fp_out = self._launch(xyz0, ws)
+        cidx = [lv["cidx"] for lv in ws["levels"]]
+        origin = [cidx[0]]
+        for ci in cidx[1:]:
+            origin.append(torch.gather(origin[-1], -1, ci.long()))       # patch_aug_net.py:169-177
+        desc = ws["desc"]
+        feats = [f.transpose(1, 2).unsqueeze(-1) for f in fp_out]
+        if clone:   # detach results from the reusable workspace
+            desc = desc.clone()
+            feats = [f.clone(memory_format=torch.preserve_format) for f in feats]
+            origin = [o.clone() for o in origin]
+        return desc, feats, origin
+
+    __call__ = forward
+
+    def capture_graph(self, B, N):
+        """Capture the (B,N) forward into a CUDA graph; later forwards of that shape replay it."""
+        ws = self._workspace(B, N)
+        x = torch.zeros(B, N, 3, dtype=torch.float32, device=self.device)
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._launch(x, ws)          # warm-up (sets func attributes outside capture)
+        torch.cuda.current_stream().wait_stream(s)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            fp_out = self._launch(x, ws)
+        self._graphs[(B, N)] = dict(graph=graph, x=x, fp_out=fp_out)
+        return graph
+
+    def launches_per_forward(self):
+        """Kernels this library launches per forward (for bench.py's gpu_launches)."""
+        return 4 * len(self.sa) + 2 * len(self.fp) + 2 * len(self.vlad) + 4
