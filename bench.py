@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py — 4096-pt submap descriptors/sec (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch 32]
+
+One "step" = one pass of the descriptor-extraction hot path (PatchAugNet eval forward, fp32) over one batch of
+32 synthetic 4096-point submaps per GPU (BASELINE.json configs[1]).  Prints ONE JSON line on rank 0.
+
+  value     device-resident throughput: inputs already in HBM, CUDA events around exactly K steps, max over ranks.
+            Inputs rotate through a pool larger than the 126 MB L2 ("inputs_larger_than_l2").
+  e2e       the same metric through the public nn.Module call (`net(x)`) with PINNED HOST input: the H2D copy of the
+            batch and the D2H read of the (B,256) descriptors are inside the timed region.
+  roofline  the dominant kernel of the step (chosen from per-stage CUDA events), timed live with events in the same
+            timed region; algorithmic FLOPs/bytes per launch from patchaugnet_b200.engine.stage_work.
+  cpu_baseline  the CPU oracle (oracle/, a port of the reference path) on a bounded sample, rank 0, N=1 only.
+
+--impl reference: the reference path's CPU implementation (the oracle port: the reference ships no CPU code for
+pointops, and its CUDA kernels are what this repo replaces) on the host cores, same metric / config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "4096-pt submap descriptors/sec"
+UNIT = "submaps/s"
+NPTS = 4096
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return dict(hbm=p["hbm_gbs"], tf=p["bf16_tflops"], tf_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]), src="measured")
+    except Exception:
+        return dict(hbm=6650.0, tf=1590.0, tf_sustained=1400.0, src="fallback")   # B200_PROFILING.md fallback
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def cpu_oracle_throughput(budget_s=15.0, clouds_per_call=4):
+    """The oracle port of the path on the host cores: submaps/s over a bounded sample (about `budget_s` seconds)."""
+    import util
+    from oracle import model
+    net = util.build_network("cpu")
+    sd = net.state_dict()
+    x = util.synthetic_batch(clouds_per_call, NPTS, start=0).numpy()
+    model.patchaugnet_forward(sd, util.PATCHAUGNET_CFG, x[:1])           # warm-up (library load, thread pools)
+    done, t0 = 0, time.perf_counter()
+    while True:
+        model.patchaugnet_forward(sd, util.PATCHAUGNET_CFG, x)
+        done += clouds_per_call
+        el = time.perf_counter() - t0
+        if el >= budget_s or done >= 64:
+            break
+    return done / el, done, el
+
+
+def run_reference(args):
+    """--impl reference: oracle port on the host cores; rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    per_step = 4
+    import util
+    from oracle import model
+    net = util.build_network("cpu")
+    sd = net.state_dict()
+    x = util.synthetic_batch(per_step, NPTS, start=0).numpy()
+    for _ in range(max(1, min(args.warmup, 2))):
+        model.patchaugnet_forward(sd, util.PATCHAUGNET_CFG, x)
+    steps = max(1, min(args.steps, 8))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        model.patchaugnet_forward(sd, util.PATCHAUGNET_CFG, x)
+    el = time.perf_counter() - t0
+    val = steps * per_step / el
+    sample = f"{steps} steps x {per_step} clouds x {NPTS} pts, PatchAugNet eval forward, fp32"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": el / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"PatchAugNet descriptor extraction, {per_step} x {NPTS}-pt clouds per step (bounded sample of batch 32), fp32, host CPU"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", type=int, default=1, help="replay the step from a CUDA graph (1) or launch eagerly (0)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    import util
+    from patchaugnet_b200 import _lib as L
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W, K, B = max(3, args.warmup), args.steps, args.batch
+
+    net = util.build_network(dev)                        # random-init weights of the reference architecture (tests/util.py)
+    eng = net.engine()
+    lib = L.lib()
+
+    # input pool larger than L2 (126 MB): 104 batches x 1.5 MB = 164 MB, distinct seeded clouds per rank
+    pool_batches = 104
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    base = torch.rand(pool_batches * B, NPTS, 3, generator=g) * 2 - 1
+    base = base - base.mean(1, keepdim=True)
+    base = base / base.norm(dim=2).max(dim=1)[0][:, None, None]
+    pool = base.to(dev).view(pool_batches, B, NPTS, 3)
+    host_pool = base.view(pool_batches, B, NPTS, 3)[:8].contiguous().pin_memory()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- warm-up + per-stage profile (eager, events around every stage) -----------------------------------------
+    eng.enable_stage_timing()
+    with torch.no_grad():
+        for i in range(W):
+            eng(pool[i % pool_batches], clone=False)
+    torch.cuda.synchronize()
+    st = eng.stage_times_ms()
+    eng.disable_stage_timing()
+    stage_ms = {k: float(np.mean(v[1:] if len(v) > 1 else v)) for k, v in st.items()}
+    dominant = max(stage_ms, key=stage_ms.get)
+    work = eng.stage_work(B, NPTS)
+
+    use_graph = bool(args.graph)
+    if use_graph:
+        eng.capture_graph(B, NPTS)
+        with torch.no_grad():
+            for i in range(2):
+                eng(pool[i], clone=False)
+    gathered = torch.empty(world * K * B, 256, device=dev) if world > 1 else None
+    local_desc = torch.empty(K * B, 256, device=dev)
+
+    # ---- timed region: exactly K steps, device-resident inputs ---------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    sync_all()
+    lib.pab_reset_launch_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    with torch.no_grad():
+        for i in range(K):
+            desc = eng(pool[(W + i) % pool_batches], clone=False, return_feat=False)
+            local_desc[i * B:(i + 1) * B].copy_(desc)
+        if world > 1:   # the one collective of the path: all-gather of the 256-D descriptors before retrieval
+            dist.all_gather_into_tensor(gathered, local_desc)
+    e1.record()
+    sync_all()
+    elapsed_ms = e0.elapsed_time(e1)
+    launches = lib.pab_num_launches()
+    if use_graph:
+        launches = K * eng.launches_per_forward()        # graph replays do not pass through the C ABI counter
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = t.item()
+    value = world * B * K / (elapsed_ms * 1e-3)
+
+    # ---- dominant kernel: events around that stage only, K eager steps over the same rotating inputs -----------
+    eng._graphs.clear()
+    eng.enable_stage_timing([dominant])
+    with torch.no_grad():
+        for i in range(K):
+            eng(pool[(W + i) % pool_batches], clone=False)
+    torch.cuda.synchronize()
+    dom_ms = float(np.mean(eng.stage_times_ms()[dominant]))
+    eng.disable_stage_timing()
+    pk = peaks()
+    wk = work[dominant]
+    if wk["flops"] > 0:
+        achieved = wk["flops"] / (dom_ms * 1e-3) / 1e12
+        roof = dict(bound="tensor", achieved=achieved, peak=pk["tf_sustained"], unit="TFLOP/s", frac=achieved / pk["tf_sustained"],
+                    traffic=None, kernel=dominant, ms_per_launch=dom_ms, algorithmic_flops_per_launch=wk["flops"],
+                    algorithmic_bytes_per_launch=wk["bytes"], share_of_step=dom_ms / sum(stage_ms.values()),
+                    peak_source=f"{pk['src']} bf16 dense, sustained (kernel timed inside the step); arithmetic is fp32 SIMT FFMA")
+    else:
+        achieved = wk["bytes"] / (dom_ms * 1e-3) / 1e9
+        roof = dict(bound="hbm", achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"], traffic=None,
+                    kernel=dominant, ms_per_launch=dom_ms, algorithmic_bytes_per_launch=wk["bytes"],
+                    share_of_step=dom_ms / sum(stage_ms.values()), peak_source=f"{pk['src']} copy bandwidth",
+                    note="latency/issue-bound scan: " + str(wk.get("units", "")) + " " + wk.get("unit", ""))
+
+    # ---- end to end through the public API: pinned host input -> net(x) -> descriptors on the host --------------
+    xdev = torch.empty(B, 1, NPTS, 3, device=dev)
+    out_host = torch.empty(B, 256).pin_memory()
+    e2e_steps = K
+    with torch.no_grad():
+        for i in range(3):
+            xdev.copy_(host_pool[i % 8].unsqueeze(1), non_blocking=True)
+            net(xdev, return_feat=False)
+    sync_all()
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for i in range(e2e_steps):
+            xdev.copy_(host_pool[i % 8].unsqueeze(1), non_blocking=True)       # H2D of this step's clouds
+            desc = net(xdev, return_feat=False)                                # public nn.Module call
+            out_host.copy_(desc, non_blocking=False)                           # D2H read of the result
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = t.item()
+    e2e = dict(value=world * B * e2e_steps / e2e_s, unit=UNIT, h2d_bytes_per_step=B * NPTS * 3 * 4, d2h_bytes_per_step=B * 256 * 4)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        v, done, el = cpu_oracle_throughput()
+        cpu = dict(value=v, unit=UNIT, cores=torch.get_num_threads(), kind="port",
+                   sample=f"{done} clouds x {NPTS} pts in {el:.1f} s, oracle PatchAugNet eval forward fp32 (C scans single-threaded, dense layers torch-CPU)")
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"PatchAugNet descriptor extraction, batch {B} x {NPTS}-pt synthetic clouds per GPU, fp32, eval "
+                                   "(BASELINE.json configs[1])", "global_batch": world * B, "l2": "inputs_larger_than_l2 (164 MB rotating pool)",
+                       "launch": "cuda_graph" if use_graph else "eager", "parallelism": f"dp{world}, shard-by-submap, one all_gather of descriptors"},
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "stage_ms": {k: round(v, 4) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1])}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -66,6 +66,8 @@ class FusedPatchAugNet:
             raise L.PabError("FusedPatchAugNet needs the network on a CUDA device (there is no CPU fallback)")
         self._ws = {}
         self._graphs = {}
+        self._events = None
+        self._event_filter = None
         self.refold()
 
     # ---- weights -------------------------------------------------------------------------------------------------
@@ -132,20 +134,33 @@ class FusedPatchAugNet:
 
     # ---- forward -------------------------------------------------------------------------------------------------
     def _launch(self, xyz0, ws):
-        lib, st, p, chk = L.lib(), L.stream_ptr(), L.ptr, L.check
+        lib, st, p = L.lib(), L.stream_ptr(), L.ptr
+        ev = self._events
+
+        def run(stage, rc_fn):
+            """launch one C-ABI call; with stage timing enabled, bracket it with CUDA events on the launch stream"""
+            if ev is not None and (self._event_filter is None or stage in self._event_filter):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                L.check(rc_fn(), stage)
+                e1.record()
+                ev.setdefault(stage, []).append((e0, e1))
+            else:
+                L.check(rc_fn(), stage)
+
         B, N, _ = xyz0.shape
         xyz, feat, c = xyz0, xyz0, 3
-        for sa, lv in zip(self.sa, ws["levels"]):
+        for i, (sa, lv) in enumerate(zip(self.sa, ws["levels"])):
             n, m, k = lv["n"], lv["m"], sa["k"]
             temp = None                      # register-resident FPS initialises its own 1e10 distances
             if n > 8192:                     # large-cloud fallback keeps them in global memory like the reference
                 temp = lv["temp"]
                 temp.fill_(1e10)
-            chk(lib.pab_furthestsampling(B, n, m, p(xyz), p(temp), p(lv["cidx"]), st), "furthestsampling")
-            chk(lib.pab_gather_rows(B, n, m, 3, p(xyz), p(lv["cidx"]), p(lv["new_xyz"]), st), "gather_rows")
-            chk(lib.pab_knnquery(B, n, m, k, p(xyz), p(lv["new_xyz"]), p(lv["nbr"]), p(None), st), "knnquery")
-            chk(lib.pab_sa_module_forward(B, n, m, k, k, c, p(xyz), p(feat), p(lv["cidx"]), p(lv["nbr"]),
-                                          sa["layers"].arr, sa["layers"].n, p(lv["feat"]), p(None), st), "sa_module")
+            run(f"fps{i}", lambda: lib.pab_furthestsampling(B, n, m, p(xyz), p(temp), p(lv["cidx"]), st))
+            run(f"gather{i}", lambda: lib.pab_gather_rows(B, n, m, 3, p(xyz), p(lv["cidx"]), p(lv["new_xyz"]), st))
+            run(f"knn{i}", lambda: lib.pab_knnquery(B, n, m, k, p(xyz), p(lv["new_xyz"]), p(lv["nbr"]), p(None), st))
+            run(f"sa{i}", lambda: lib.pab_sa_module_forward(B, n, m, k, k, c, p(xyz), p(feat), p(lv["cidx"]), p(lv["nbr"]),
+                                                            sa["layers"].arr, sa["layers"].n, p(lv["feat"]), p(None), st))
             xyz, feat, c = lv["new_xyz"], lv["feat"], sa["layers"].c_out
         xyzs = [xyz0] + [lv["new_xyz"] for lv in ws["levels"]]
         feats = [xyz0] + [lv["feat"] for lv in ws["levels"]]      # skip features per level (level 0 = raw xyz)
@@ -154,29 +169,74 @@ class FusedPatchAugNet:
             f = ws["fp"][li]
             unknown, known = xyzs[li], xyzs[li + 1]
             n, m = unknown.shape[1], known.shape[1]
-            chk(lib.pab_three_nn_weights(B, n, m, p(unknown), p(known), p(f["idx"]), p(f["w"]), st), "three_nn")
+            run(f"three_nn{li}", lambda: lib.pab_three_nn_weights(B, n, m, p(unknown), p(known), p(f["idx"]), p(f["w"]), st))
             skip = feats[li]
             c_skip = skip.shape[2]
             if li == 0 and not self.use_origin:
                 skip, c_skip = None, 0
-            chk(lib.pab_fp_module_forward(B, n, m, known_feat.shape[2], c_skip, p(known_feat), p(skip), p(f["idx"]), p(f["w"]),
-                                          self.fp[li].arr, self.fp[li].n, p(f["out"]), st), "fp_module")
+            run(f"fp{li}", lambda: lib.pab_fp_module_forward(B, n, m, known_feat.shape[2], c_skip, p(known_feat), p(skip),
+                                                             p(f["idx"]), p(f["w"]), self.fp[li].arr, self.fp[li].n,
+                                                             p(f["out"]), st))
             known_feat = f["out"]
         # fp_features order of the reference: [l2 (128), l1 (1024), l0 (4096)] <-> vlads[0..2]
-        fp_out = [ws["fp"][2]["out"], ws["fp"][1]["out"], ws["fp"][0]["out"]] if len(self.fp) == 3 else \
-            [ws["fp"][i]["out"] for i in range(len(self.fp) - 1, -1, -1)]
+        fp_out = [ws["fp"][i]["out"] for i in range(len(self.fp) - 1, -1, -1)]
         v, koff = ws["v"], 0
-        for x, lvl in zip(fp_out, self.vlad):
-            chk(lib.pab_netvlad_forward(B, x.shape[1], lvl["C"], lvl["K"], p(x), p(lvl["wc"]), p(lvl["shift"]), p(lvl["w2"]),
-                                        C.c_void_p(v.data_ptr() + 4 * koff), v.stride(0), v.stride(1), p(ws["scratch"]), st),
-                "netvlad")
+        for i, (x, lvl) in enumerate(zip(fp_out, self.vlad)):
+            dst = C.c_void_p(v.data_ptr() + 4 * koff)
+            run(f"vlad{i}", lambda: lib.pab_netvlad_forward(B, x.shape[1], lvl["C"], lvl["K"], p(x), p(lvl["wc"]), p(lvl["shift"]),
+                                                            p(lvl["w2"]), dst, v.stride(0), v.stride(1), p(ws["scratch"]), st))
             koff += lvl["K"]
-        chk(lib.pab_afa_forward(B, self.vlad[0]["C"], self.sumK, self.c_out, p(v), p(self.w_att_t), p(self.fc_wt),
-                                p(self.fc_scale), p(self.fc_shift), self.l2_norm, p(ws["desc"]), p(ws["scratch"]), st), "afa")
+        run("afa", lambda: lib.pab_afa_forward(B, self.vlad[0]["C"], self.sumK, self.c_out, p(v), p(self.w_att_t), p(self.fc_wt),
+                                               p(self.fc_scale), p(self.fc_shift), self.l2_norm, p(ws["desc"]), p(ws["scratch"]), st))
         return fp_out
 
+    # ---- per-stage timing and algorithmic work (bench.py roofline) ---------------------------------------------
+    def enable_stage_timing(self, stages=None):
+        """Record CUDA events around every stage (or only `stages`) of subsequent eager forwards."""
+        self._events = {}
+        self._event_filter = set(stages) if stages is not None else None
+
+    def stage_times_ms(self):
+        """{stage: [ms per recorded launch]} — call after torch.cuda.synchronize()."""
+        return {k: [a.elapsed_time(b) for a, b in v] for k, v in (self._events or {}).items()}
+
+    def disable_stage_timing(self):
+        self._events = None
+        self._event_filter = None
+
+    def stage_work(self, B, N):
+        """Algorithmic work per launch of each stage: dense FLOPs (2*MAC) and compulsory HBM bytes."""
+        ns = [N] + [sa["npoint"] for sa in self.sa]
+        work = {}
+        c = 3
+        for i, sa in enumerate(self.sa):
+            n, m, k = ns[i], ns[i + 1], sa["k"]
+            macs = sum(ci * co for ci, co in sa["layers"].spec)
+            c_out = sa["layers"].c_out
+            work[f"fps{i}"] = dict(flops=0, bytes=B * (12 * n + 4 * m), units=B * n * (m - 1), unit="point-updates")
+            work[f"gather{i}"] = dict(flops=0, bytes=B * (4 * m + 24 * m))
+            work[f"knn{i}"] = dict(flops=0, bytes=B * (12 * n + 12 * m + 4 * m * k), units=B * n * m, unit="distance evals")
+            work[f"sa{i}"] = dict(flops=2 * B * m * k * macs, bytes=B * (4 * c * n + 12 * n + 12 * m + 4 * m * k + 4 * c_out * m))
+            c = c_out
+        skip_c = [3] + [sa["layers"].c_out for sa in self.sa]
+        known_c = skip_c[-1]
+        for li in range(len(self.fp) - 1, -1, -1):
+            n_u, n_k = ns[li], ns[li + 1]
+            macs = sum(ci * co for ci, co in self.fp[li].spec)
+            c_out = self.fp[li].c_out
+            work[f"three_nn{li}"] = dict(flops=0, bytes=B * (12 * (n_u + n_k) + 24 * n_u), units=B * n_u * n_k, unit="distance evals")
+            work[f"fp{li}"] = dict(flops=2 * B * n_u * macs,
+                                   bytes=B * (4 * known_c * n_k + 4 * skip_c[li] * n_u + 24 * n_u + 4 * c_out * n_u))
+            known_c = c_out
+        for i, lvl in enumerate(self.vlad):
+            n_l = ns[len(self.fp) - 1 - i]
+            work[f"vlad{i}"] = dict(flops=2 * B * 2 * n_l * lvl["C"] * lvl["K"], bytes=B * 4 * (lvl["C"] * n_l + lvl["C"] * lvl["K"]))
+        C_, K_ = self.vlad[0]["C"], self.sumK
+        work["afa"] = dict(flops=2 * B * (C_ * C_ * K_ + C_ * K_ * self.c_out), bytes=4 * (C_ * K_ * self.c_out + C_ * C_ + B * C_ * K_ + B * self.c_out))
+        return work
+
     @torch.no_grad()
-    def forward(self, x, consume_rng=True, clone=True):
+    def forward(self, x, consume_rng=True, clone=True, return_feat=True):
         """x: (B,1,N,3) or (B,N,3) float32 CUDA -> (desc (B,256), fp_features [3 x (B,256,n,1)], center_idx_origin [3])."""
         L.require_cuda(x)
         xyz0 = x.squeeze(1) if x.dim() == 4 else x
@@ -197,11 +257,13 @@ class FusedPatchAugNet:
             fp_out = g["fp_out"]
         else:
             fp_out = self._launch(xyz0, ws)
+        desc = ws["desc"]
+        if not return_feat:
+            return desc.clone() if clone else desc
         cidx = [lv["cidx"] for lv in ws["levels"]]
         origin = [cidx[0]]
         for ci in cidx[1:]:
             origin.append(torch.gather(origin[-1], -1, ci.long()))       # patch_aug_net.py:169-177
-        desc = ws["desc"]
         feats = [f.transpose(1, 2).unsqueeze(-1) for f in fp_out]
         if clone:   # detach results from the reusable workspace
             desc = desc.clone()

@@ -81,8 +81,7 @@ class Network(nn.Module):
         """x: B x 1 x N x 3"""
         if (self.use_fused and not self.training and nn_dict is None and x.is_cuda and not torch.is_grad_enabled()
                 and self.fusable()):
-            desc, fp_features, center_idx = self.engine()(x)
-            return (desc, fp_features, center_idx) if return_feat else desc
+            return self.engine()(x, return_feat=return_feat)
         x = x.squeeze(1)
         xyz = x
         res = self.backbone(x)

@@ -1,0 +1,141 @@
+"""Database descriptor extraction, sharded over ranks, and GPU retrieval + Recall@N.
+
+Replaces, for the synthetic-data harness, the reference's evaluation flow
+  ``SceneDataSet.make_descs``           datasets/scene_dataset.py:494-711   (batched model forward, one GPU)
+  ``KDTree(db).query(q, k)``            datasets/place_recognition_dataset.py:60, scene_dataset.py:1052 (CPU, per query)
+  ``SceneDataSet.get_recall_precision`` datasets/scene_dataset.py:1016-1099 (first-hit cumsum recall, top-1 % recall)
+
+Multi-GPU: submaps are independent units, so the database is partitioned by contiguous index
+range over ranks (one process per GPU, weights replicated), each rank extracts its shard, and ONE
+``all_gather_into_tensor`` of the (N/W, 256) fp32 descriptors over NCCL/NVLink gives every rank the full database.
+Queries are sharded the same way; each rank answers its queries with the brute-force top-k kernel
+(``pab_retrieval_topk``) and the per-rank hit counters are summed with one small ``all_reduce``.
+Results are identical for every world size.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous shard [lo, hi) of rank `rank`: the first n % world ranks get one extra item."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def _dist_info(group=None):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def extract_descriptors(extract_fn, clouds, batch_size=32, device=None, dim=256, group=None, out_device=None):
+    """Run ``extract_fn(x (b,1,N,3) on device) -> (b,dim)`` over this rank's shard of ``clouds`` (M,N,3) and all-gather.
+
+    ``clouds`` may live on the host (pinned memory recommended: copies are issued non-blocking) or on the device.
+    Returns the full (M, dim) descriptor matrix on every rank.
+    """
+    rank, world = _dist_info(group)
+    M = clouds.shape[0]
+    lo, hi = shard_range(M, rank, world)
+    device = device if device is not None else (clouds.device if clouds.is_cuda else torch.device("cpu"))
+    local = torch.empty(hi - lo, dim, dtype=torch.float32, device=device)
+    for s in range(lo, hi, batch_size):
+        e = min(hi, s + batch_size)
+        x = clouds[s:e].to(device, non_blocking=True).unsqueeze(1)
+        local[s - lo:e - lo] = extract_fn(x)
+    if world == 1:
+        return local if out_device is None else local.to(out_device)
+    # equal-size shards are required by all_gather_into_tensor: pad to the largest shard, trim after
+    per = (M + world - 1) // world
+    send = torch.zeros(per, dim, dtype=torch.float32, device=device)
+    send[: hi - lo] = local
+    recv = torch.empty(world * per, dim, dtype=torch.float32, device=device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    parts = []
+    for r in range(world):
+        rlo, rhi = shard_range(M, r, world)
+        parts.append(recv[r * per: r * per + (rhi - rlo)])
+    full = torch.cat(parts, 0)
+    return full if out_device is None else full.to(out_device)
+
+
+def retrieval_topk(db, queries, k):
+    """Exact k nearest database descriptors for every query on the GPU (ties to the lower index).
+    db (Ndb,D), queries (Nq,D) float32 CUDA -> dist (Nq,k) float32 ascending Euclidean, ind (Nq,k) int32."""
+    L.require_cuda(db, queries)
+    db = db.contiguous().float()
+    queries = queries.contiguous().float()
+    ndb, d = db.shape
+    nq = queries.shape[0]
+    out_d = torch.empty(nq, k, dtype=torch.float32, device=db.device)
+    out_i = torch.empty(nq, k, dtype=torch.int32, device=db.device)
+    L.check(L.lib().pab_retrieval_topk(L.ptr(db), ndb, L.ptr(queries), nq, d, k, L.ptr(out_d), L.ptr(out_i), L.stream_ptr()),
+            "retrieval_topk")
+    return out_d, out_i
+
+
+def real_top_k(n_db, top_k=25):
+    """k actually queried: max(top_k + 1, round(n_db/100) + 1)  (scene_dataset.py:1026-1029)."""
+    threshold = max(int(round(n_db / 100.0)), 1)
+    return max(top_k + 1, threshold + 1), threshold
+
+
+def recall_counts(ind, positives, top_k, threshold, query_db_index=None):
+    """First-hit counters of scene_dataset.py:1056-1081 for one shard of queries.
+
+    ind (Nq,K) retrieved database indices (ascending distance); positives: list of sets of database indices;
+    query_db_index: the query's own database index when the query set is part of the database (its self-match is
+    skipped like `add_one_more`, :1053-1055).  Returns (recall_hits[top_k], one_percent_hits, evaluated).
+    """
+    ind = np.asarray(ind)
+    hits = np.zeros(top_k, dtype=np.int64)
+    one_pct = 0
+    evaluated = 0
+    for qi in range(ind.shape[0]):
+        pos = positives[qi]
+        if not pos:
+            continue                                   # :1044-1045
+        evaluated += 1
+        row = ind[qi]
+        if query_db_index is not None:
+            row = row[1:]                              # the first neighbour is the query itself
+        for j in range(min(top_k, len(row))):
+            if query_db_index is not None and row[j] == query_db_index[qi]:
+                continue
+            if int(row[j]) in pos:
+                hits[j] += 1
+                break
+        if len(set(int(v) for v in row[:threshold]) & pos) > 0:
+            one_pct += 1
+    return hits, one_pct, evaluated
+
+
+def evaluate_recall(db_desc, query_desc, positives, top_k=25, group=None, topk_fn=None):
+    """Recall@1..top_k (%) and top-1 % recall (%) of ``query_desc`` against ``db_desc`` with queries sharded over ranks.
+
+    db_desc (Ndb,D), query_desc (Nq,D): full matrices present on every rank (after ``extract_descriptors``);
+    positives: list (len Nq) of sets of database indices.  topk_fn: override of the GPU kernel (host-logic tests).
+    Returns dict(recall (top_k,), one_percent_recall, evaluated).
+    """
+    rank, world = _dist_info(group)
+    n_db = db_desc.shape[0]
+    k, threshold = real_top_k(n_db, top_k)
+    k = min(k, n_db)
+    lo, hi = shard_range(query_desc.shape[0], rank, world)
+    if hi > lo:
+        _, ind = (topk_fn or retrieval_topk)(db_desc, query_desc[lo:hi], k)
+        hits, one_pct, evaluated = recall_counts(ind.cpu().numpy(), positives[lo:hi], top_k, threshold)
+    else:
+        hits, one_pct, evaluated = np.zeros(top_k, dtype=np.int64), 0, 0
+    counters = torch.tensor(list(hits) + [one_pct, evaluated], dtype=torch.int64, device=db_desc.device)
+    if world > 1:
+        dist.all_reduce(counters, group=group)
+    counters = counters.cpu().numpy()
+    evaluated = int(counters[-1])
+    recall = np.cumsum(counters[:top_k]) / float(max(evaluated, 1)) * 100.0           # :1095
+    return dict(recall=recall, one_percent_recall=counters[-2] / float(max(evaluated, 1)) * 100.0, evaluated=evaluated,
+                k=k, threshold=threshold)

@@ -1,0 +1,108 @@
+"""CPU tier: host-side logic — BN folding, sharding, recall bookkeeping, and the 2-rank (gloo) shard + all-gather +
+recall path, which must reproduce the 1-rank result exactly."""
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import util
+from patchaugnet_b200 import retrieval
+from patchaugnet_b200.engine import _Layers, _fold_bn
+
+
+def test_folded_shared_mlp_equals_eval_forward():
+    net = util.build_network()
+    mlp = net.backbone.SA_modules[1].mlps[0]                 # [67, 64, 64, 256]
+    layers = _Layers(mlp, "cpu")
+    x = torch.randn(50, 67)
+    y = x
+    for i in range(layers.n):
+        wt, sh = layers.tensors[2 * i], layers.tensors[2 * i + 1]
+        assert wt.shape[0] % 4 == 0 and (wt[layers.spec[i][0]:] == 0).all()
+        y = torch.relu(torch.nn.functional.pad(y, (0, wt.shape[0] - y.shape[1])) @ wt + sh)
+    ref = mlp(x.t()[None, :, :, None]).squeeze(-1)[0].t()
+    assert torch.allclose(y, ref, atol=1e-5, rtol=1e-5)
+    # folding must not touch the module's own parameters (state_dict is API)
+    assert "layer0.conv.weight" in mlp.state_dict() and mlp.layer0.conv.weight.shape == (64, 67, 1, 1)
+
+
+def test_fold_bn_matches_batchnorm_eval():
+    bn = torch.nn.BatchNorm1d(8).eval()
+    bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 2); bn.weight.data.normal_(); bn.bias.data.normal_()
+    x = torch.randn(5, 8)
+    s, t = _fold_bn(bn)
+    assert torch.allclose(x * s + t, bn(x), atol=1e-6)
+
+
+def test_shard_range_partitions_exactly():
+    for n in (0, 1, 7, 10000, 10001):
+        for w in (1, 2, 4, 8):
+            spans = [retrieval.shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_real_top_k_rule():
+    assert retrieval.real_top_k(10000, 25) == (101, 100)      # max(26, round(N/100)+1), scene_dataset.py:1026-1029
+    assert retrieval.real_top_k(300, 25) == (26, 3)
+    assert retrieval.real_top_k(10, 25) == (26, 1)
+
+
+def test_recall_counts_first_hit_rule():
+    ind = np.array([[5, 3, 9, 1], [2, 2, 2, 2], [7, 8, 9, 0]])
+    pos = [{9, 1}, set(), {0}]
+    hits, one_pct, ev = retrieval.recall_counts(ind, pos, top_k=3, threshold=2)
+    assert ev == 2 and hits.tolist() == [0, 0, 1] and one_pct == 0            # query 2's positive sits at rank 4 > top_k
+    hits, one_pct, ev = retrieval.recall_counts(ind, pos, top_k=4, threshold=3)
+    assert hits.tolist() == [0, 0, 1, 1] and one_pct == 1
+
+
+def _cpu_topk(db, q, k):
+    d = torch.cdist(q.double(), db.double())
+    order = torch.argsort(d, dim=1, stable=True)[:, :k]
+    return torch.gather(d, 1, order).float(), order.int()
+
+
+def _fake_extract(x):                      # deterministic stand-in for the network: (b,1,N,3) -> (b,8)
+    x = x.squeeze(1)
+    feats = torch.cat([x.mean(1), x.std(1), x.abs().max(1)[0][:, :2]], 1)
+    return torch.nn.functional.normalize(feats)
+
+
+def _world(rank, world, port, clouds, queries, positives, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        db = retrieval.extract_descriptors(_fake_extract, clouds, batch_size=3, dim=8)
+        qd = retrieval.extract_descriptors(_fake_extract, queries, batch_size=3, dim=8)
+        res = retrieval.evaluate_recall(db, qd, positives, top_k=5, topk_fn=_cpu_topk)
+        if rank == 0:
+            out.put((db.numpy(), res["recall"], res["one_percent_recall"], res["evaluated"]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_matches_single_rank():
+    g = torch.Generator().manual_seed(0)
+    clouds = torch.rand(11, 64, 3, generator=g)                       # 11 places: uneven shards on 2 ranks
+    queries = clouds[:7] + 0.01 * torch.randn(7, 64, 3, generator=g)
+    positives = [{i} for i in range(7)]
+    db1 = retrieval.extract_descriptors(_fake_extract, clouds, batch_size=3, dim=8)
+    q1 = retrieval.extract_descriptors(_fake_extract, queries, batch_size=3, dim=8)
+    res1 = retrieval.evaluate_recall(db1, q1, positives, top_k=5, topk_fn=_cpu_topk)
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_world, args=(r, 2, port, clouds, queries, positives, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    db2, recall2, one2, ev2 = out.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert np.array_equal(db2, db1.numpy())                           # gathered database identical to the 1-rank run
+    assert np.array_equal(recall2, res1["recall"]) and one2 == res1["one_percent_recall"] and ev2 == res1["evaluated"] == 7

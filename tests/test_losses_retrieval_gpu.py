@@ -1,0 +1,98 @@
+"""GPU tier: chamfer, KNN_CUDA drop-in, retrieval top-k and EMD through the C ABI against the CPU oracle,
+the reference's KDTree known-answer property, and domain invariants."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ops
+from patchaugnet_b200 import chamfer_dist, emd_module, knn_cuda, retrieval
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _g(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+@pytest.mark.parametrize("B,n,m", [(3000, 20, 20), (7, 20, 13), (2, 4096, 4096), (3, 600, 2500), (1, 1, 1)])
+def test_chamfer_forward_backward(B, n, m):
+    rng = np.random.default_rng(B + n)
+    a = rng.uniform(-1, 1, (B, n, 3)).astype(np.float32)
+    b = rng.uniform(-1, 1, (B, m, 3)).astype(np.float32)
+    if m >= 4:
+        b[:, m // 2:] = b[:, : m - m // 2]                            # duplicates: first minimum must win
+    d1, d2, i1, i2 = ops.chamfer_forward(a, b)
+    g1, g2, gi1, gi2 = chamfer_dist.forward(_g(a), _g(b))
+    assert torch.equal(gi1.cpu(), torch.from_numpy(i1)) and torch.equal(gi2.cpu(), torch.from_numpy(i2))
+    assert torch.equal(g1.cpu(), torch.from_numpy(d1)) and torch.equal(g2.cpu(), torch.from_numpy(d2))
+    gd1 = rng.normal(size=d1.shape).astype(np.float32); gd2 = rng.normal(size=d2.shape).astype(np.float32)
+    wx1, wx2 = ops.chamfer_backward(a, b, i1, i2, gd1, gd2)
+    gx1, gx2 = chamfer_dist.backward(_g(a), _g(b), gi1, gi2, _g(gd1), _g(gd2))
+    assert torch.allclose(gx1.cpu(), torch.from_numpy(wx1), atol=1e-4, rtol=1e-4)
+    assert torch.allclose(gx2.cpu(), torch.from_numpy(wx2), atol=1e-4, rtol=1e-4)
+
+
+def test_chamfer_l1_module_autograd():
+    rng = np.random.default_rng(1)
+    a = _g(rng.uniform(-1, 1, (64, 20, 3)).astype(np.float32)).requires_grad_(True)
+    b = _g(rng.uniform(-1, 1, (64, 20, 3)).astype(np.float32))
+    loss = chamfer_dist.ChamferDistanceL1()(a, b)
+    d1, d2, _, _ = ops.chamfer_forward(a.detach().cpu().numpy(), b.cpu().numpy())
+    assert abs(loss.item() - (np.sqrt(d1).mean() + np.sqrt(d2).mean()) / 2) < 1e-5
+    loss.backward()
+    assert a.grad is not None and torch.isfinite(a.grad).all() and a.grad.abs().sum() > 0
+    assert chamfer_dist.ChamferDistanceL2()(a, a).item() == 0.0
+
+
+@pytest.mark.parametrize("k,n,dim", [(10, 100, 5), (2, 11, 5), (400, 1001, 5), (33, 300, 3), (101, 2000, 256), (600, 700, 4)])
+def test_knn_cuda_dropin(k, n, dim):
+    from sklearn.neighbors import KDTree
+    rng = np.random.default_rng(k + n)
+    x = rng.random((2, n, dim)).astype(np.float32)
+    D, I = knn_cuda.KNN(k, transpose_mode=True)(_g(x), _g(x))
+    wD, wI = ops.knn_cuda(x, x, k, transpose_mode=True)
+    assert I.dtype == torch.int64 and torch.equal(I.cpu(), torch.from_numpy(wI))
+    assert torch.equal(D.cpu(), torch.from_numpy(wD))                       # same fma chain -> bit-exact distances
+    if dim <= 5:                                                            # the reference's own test (test_knn_cuda.py:32-47)
+        dist, _ = KDTree(x[0], leaf_size=100).query(x[0], k=k)
+        np.testing.assert_almost_equal(D[0].cpu().numpy(), dist, decimal=3)
+    xt = _g(np.ascontiguousarray(x.transpose(0, 2, 1)))
+    D2, I2 = knn_cuda.KNN(k, transpose_mode=False)(xt, xt)
+    assert torch.equal(D2.transpose(1, 2), D) and torch.equal(I2.transpose(1, 2), I)
+    raw_d, raw_i = knn_cuda._knn.knn(xt[0].contiguous(), xt[0].contiguous(), k)
+    assert raw_i.min().item() == 1                                          # raw binding is 1-based (knn.cpp / __init__.py:41-44)
+
+
+def test_retrieval_topk_matches_kdtree_distances():
+    from sklearn.neighbors import KDTree
+    rng = np.random.default_rng(3)
+    db = rng.normal(size=(3000, 256)).astype(np.float32)
+    db /= np.linalg.norm(db, axis=1, keepdims=True)
+    q = db[:200] + 0.05 * rng.normal(size=(200, 256)).astype(np.float32)
+    d, i = retrieval.retrieval_topk(_g(db), _g(q), 31)
+    kd, ki = KDTree(db).query(q, k=31)                                      # place_recognition_dataset.py:60
+    assert np.abs(d.cpu().numpy() - kd).max() < 1e-4
+    assert (i.cpu().numpy() == ki).mean() > 0.999                           # ties at fp32 resolution may swap
+    assert (np.diff(d.cpu().numpy(), axis=1) >= 0).all()
+
+
+def test_emd_small_runs_match_reference_semantics():
+    rng = np.random.default_rng(4)
+    a = rng.random((2, 1024, 3)).astype(np.float32)
+    b = rng.random((2, 1024, 3)).astype(np.float32)
+    dist, assignment = emd_module.emdModule()(_g(a), _g(b), 0.05, 100)
+    asg = assignment.cpu().numpy().astype(np.int64)
+    assert asg.min() >= 0 and asg.max() < 1024
+    # dist is the squared distance to the assigned point (CalcDist, emd_cuda.cu:217-226)
+    want = ((a - np.take_along_axis(b, asg[..., None], 1)) ** 2).sum(-1)
+    assert np.allclose(dist.cpu().numpy(), want, atol=1e-6)
+    # auction quality: mostly one-to-one and much better than a random matching
+    assert all(len(set(asg[i].tolist())) > 900 for i in range(2))
+    assert np.sqrt(want).mean() < 0.25 * np.sqrt(((a - b) ** 2).sum(-1)).mean()
+    with pytest.raises(ValueError):
+        emd_module.emdModule()(_g(a[:, :1000]), _g(b[:, :1000]), 0.05, 10)   # n % 1024 != 0 (emd_cuda.cu:246-249)
+    xa = _g(a).requires_grad_(True)
+    d, _ = emd_module.emdModule()(xa, _g(b), 0.05, 50)
+    d.sum().backward()
+    assert torch.isfinite(xa.grad).all() and xa.grad.abs().sum() > 0

@@ -1,0 +1,138 @@
+"""GPU tier: the fused PatchAugNet descriptor path against the oracle forward, the golden vectors produced by the
+reference's own nn.Module code, the op-by-op (reference-shaped) path on the same kernels, and size-independent
+properties at the BASELINE.json workload size (B=32 x 4096 points)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import util
+from oracle import model
+from patchaugnet_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 1e-4        # north star: descriptors within 1e-4 (fp32) of the reference forward
+
+
+@pytest.fixture(scope="module")
+def net():
+    return util.build_network(DEV)
+
+
+def test_fused_forward_matches_reference_golden(net):
+    g = np.load(os.path.join(util.GOLDEN, "patchaugnet_ref_forward.npz"))
+    x = torch.cat([util.synthetic_batch(1, 4096, 0), util.tie_stress_cloud(0)[None, None]], 0).to(DEV)
+    before = L.lib().pab_num_launches()
+    with torch.no_grad():
+        desc, fp_features, center_idx = net(x)
+    assert L.lib().pab_num_launches() - before == net.engine().launches_per_forward()   # the CUDA library did the work
+    for i in range(3):
+        assert torch.equal(center_idx[i].cpu(), torch.from_numpy(g[f"center_idx{i}"]))   # FPS indices bit-exact
+    assert np.abs(desc.cpu().numpy() - g["desc"]).max() < TOL
+    for i, f in enumerate(fp_features):
+        assert tuple(f.shape) == (2, 256, (128, 1024, 4096)[i], 1)
+        assert np.abs(f[:, :, :8, 0].cpu().numpy() - g[f"fp{i}_head"]).max() < TOL
+        assert np.allclose(f.sum(dim=(2, 3)).double().cpu().numpy(), g[f"fp{i}_sum"], rtol=1e-4, atol=1e-2)
+
+
+def test_fused_forward_matches_oracle_on_fresh_inputs(net):
+    x = util.synthetic_batch(3, 4096, start=50)
+    out = model.patchaugnet_forward(net.state_dict(), util.PATCHAUGNET_CFG, x.numpy(), perms=[np.arange(20)] * 3)
+    with torch.no_grad():
+        desc, fp_features, center_idx = net(x.to(DEV))
+    for i in range(3):
+        assert np.array_equal(center_idx[i].cpu().numpy(), out["center_idx_origin"][i])
+        assert np.abs(fp_features[i].cpu().numpy() - out["fp_features"][i].numpy()).max() < 5e-4 * max(1.0, out["fp_features"][i].abs().max().item())
+    assert np.abs(desc.cpu().numpy() - out["desc"].numpy()).max() < TOL
+    out64 = model.patchaugnet_forward(net.state_dict(), util.PATCHAUGNET_CFG, x.numpy(), perms=[np.arange(20)] * 3, dtype=torch.float64)
+    assert np.abs(desc.cpu().numpy() - out64["desc"].numpy()).max() < TOL
+
+
+def test_op_by_op_path_matches_fused_path(net):
+    x = util.synthetic_batch(2, 4096, start=80).to(DEV)
+    with torch.no_grad():
+        d_fused, f_fused, c_fused = net(x)
+        net.use_fused = False
+        try:
+            d_ops, f_ops, c_ops = net(x)
+        finally:
+            net.use_fused = True
+    for a, b in zip(c_fused, c_ops):
+        assert torch.equal(a, b)
+    assert (d_fused - d_ops).abs().max().item() < TOL
+    for a, b in zip(f_fused, f_ops):
+        assert a.shape == b.shape and (a - b).abs().max().item() < 5e-4 * max(1.0, b.abs().max().item())
+
+
+def test_training_path_backward_runs(net):
+    net.train()
+    try:
+        x = util.synthetic_batch(2, 1024, start=90).to(DEV).requires_grad_(True)
+        cfg = dict(util.PATCHAUGNET_CFG, SAMPLING=[256, 64, 16], MAX_SAMPLES=[64, 256, 1024])
+        small = util.build_network(DEV, cfg=cfg).train()
+        nn_dict = {(0, 1): [[0, 1]]}
+        (desc, recon), fp_features, center_idx = small(x, nn_dict)
+        from patchaugnet_b200.chamfer_dist import ChamferDistanceL1
+        loss = desc.pow(2).sum() + ChamferDistanceL1()(torch.cat(recon["origin_patches"]), torch.cat(recon["reconstructed_patches"]))
+        loss.backward()
+        grads = [p.grad for p in small.parameters() if p.grad is not None]
+        assert len(grads) > 50 and all(torch.isfinite(g).all() for g in grads)
+        assert x.grad is not None and torch.isfinite(x.grad).all()
+    finally:
+        net.eval()
+
+
+def test_full_size_properties(net):
+    """BASELINE.json config 2: batch 32 x 4096 points."""
+    x = util.synthetic_batch(32, 4096, start=100).to(DEV)
+    with torch.no_grad():
+        desc, fp_features, center_idx = net(x)
+        assert desc.shape == (32, 256) and torch.isfinite(desc).all()
+        assert torch.allclose(desc.norm(dim=1), torch.ones(32, device=DEV), atol=1e-5)           # F.normalize at the end
+        # every cloud is an independent unit: reversing the batch reverses the outputs, bit for bit
+        d2, f2, c2 = net(x.flip(0))
+        assert torch.equal(d2.flip(0), desc) and torch.equal(c2[0].flip(0), center_idx[0])
+        # determinism
+        d3, _, _ = net(x)
+        assert torch.equal(d3, desc)
+        # FPS picks distinct points, first pick is index 0, deeper levels index into the original cloud
+        c0 = center_idx[0].cpu().numpy()
+        assert (c0[:, 0] == 0).all() and all(len(set(r.tolist())) == 1024 for r in c0)
+        assert all(set(center_idx[1][i].tolist()) <= set(center_idx[0][i].tolist()) for i in range(32))
+        # single-cloud batches give the same descriptors as the big batch
+        d1, _, _ = net(x[5:6])
+        assert torch.equal(d1[0], desc[5])
+
+
+def test_cuda_graph_replay_matches_eager(net):
+    x = util.synthetic_batch(4, 4096, start=200).to(DEV)
+    with torch.no_grad():
+        eager, _, ce = net(x)
+        eng = net.engine()
+        eng.capture_graph(4, 4096)
+        try:
+            replay, _, cr = net(x)
+            y = util.synthetic_batch(4, 4096, start=300).to(DEV)
+            r2, _, _ = net(y)
+        finally:
+            eng._graphs.clear()
+        e2, _, _ = net(y)
+    assert torch.equal(eager, replay) and torch.equal(ce[2], cr[2]) and torch.equal(r2, e2)
+
+
+def test_state_dict_roundtrip_keeps_reference_layout(net):
+    sd = net.state_dict()
+    assert "backbone.SA_modules.0.mlps.0.layer0.conv.weight" in sd and "aggregation.afa.fc.weight" in sd
+    assert "aggregation.vlads.2.hidden1_weights" in sd and "aggregation.afa.mlpa.trans_conv.weight" in sd
+    ckpt = {"state_dict_encoder": sd}                       # train_place_recognition.py:183-184 checkpoint layout
+    other = util.build_network(DEV, seed=999)
+    x = util.synthetic_batch(1, 4096, 7).to(DEV)
+    with torch.no_grad():
+        a, _, _ = other(x)
+        other.load_state_dict(ckpt["state_dict_encoder"])
+        other.eval()
+        b, _, _ = other(x)
+        c, _, _ = net(x)
+    assert not torch.equal(a, b) and torch.equal(b, c)      # engine refolds after load_state_dict

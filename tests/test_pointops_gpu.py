@@ -1,0 +1,179 @@
+"""GPU tier: every hand-written kernel, called through the C ABI (patchaugnet_b200.pointops_cuda -> libpatchaug_b200.so),
+against the CPU oracle on the same seeded inputs — bit-exact for indices, exact or 1e-6 for copied/accumulated floats —
+including tie-heavy clouds (duplicates, zero padding), ragged sizes and the reference's edge behaviours."""
+import numpy as np
+import pytest
+import torch
+
+import util
+from oracle import ops
+from patchaugnet_b200 import _lib as L
+from patchaugnet_b200 import pointops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _clouds(b, n, seed=0, dup=False, zero_tail=0):
+    rng = np.random.default_rng(seed)
+    xyz = rng.uniform(-1, 1, (b, n, 3)).astype(np.float32)
+    if dup:
+        xyz[:, n // 2:] = xyz[:, : n - n // 2]
+    if zero_tail:
+        xyz[:, n - zero_tail:] = 0
+    return xyz
+
+
+def _g(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+@pytest.mark.parametrize("n,m", [(4096, 1024), (1024, 128), (128, 16), (16, 16), (100, 37), (5000, 64), (1, 1), (9000, 33)])
+def test_fps_bit_exact(n, m):
+    for kw in (dict(), dict(dup=True), dict(zero_tail=max(1, n // 50))):
+        xyz = _clouds(3, n, seed=n + m, **kw)
+        want = ops.furthestsampling(xyz, m)
+        got = pointops.furthestsampling(_g(xyz), m)
+        assert got.dtype == torch.int32 and torch.equal(got.cpu(), torch.from_numpy(want)), (n, m, kw)
+
+
+def test_fps_thread_layout_does_not_change_result():
+    xyz = _clouds(2, 4096, 5, dup=True)
+    want = ops.furthestsampling(xyz, 256)
+    for threads in (128, 256, 512, 1024):           # tie-break is defined by the reference's block size, not ours
+        L.lib().pab_tune_fps_threads(threads)
+        try:
+            got = pointops.furthestsampling(_g(xyz), 256)
+        finally:
+            L.lib().pab_tune_fps_threads(0)
+        assert torch.equal(got.cpu(), torch.from_numpy(want)), threads
+
+
+def test_fps_temp_is_updated_like_the_reference():
+    from patchaugnet_b200 import pointops_cuda as K
+    xyz = _clouds(2, 300, 6)
+    temp = np.full((2, 300), 1e10, np.float32)
+    want = ops.furthestsampling(xyz, 20, temp)          # oracle updates its copy in place
+    t = torch.full((2, 300), 1e10, device=DEV)
+    idx = torch.zeros(2, 20, dtype=torch.int32, device=DEV)
+    K.furthestsampling_cuda(2, 300, 20, _g(xyz), t, idx)
+    assert torch.equal(idx.cpu(), torch.from_numpy(want)) and torch.equal(t.cpu(), torch.from_numpy(temp))
+
+
+@pytest.mark.parametrize("n,m,k", [(4096, 1024, 40), (1024, 128, 20), (128, 16, 40), (300, 300, 1), (257, 31, 33), (50, 7, 64),
+                                   (700, 40, 200), (5000, 64, 20), (5, 5, 8)])
+def test_knnquery_bit_exact(n, m, k):
+    for kw in (dict(), dict(dup=True)):
+        xyz = _clouds(2, n, seed=n + k, **kw)
+        q = np.ascontiguousarray(xyz[:, :: max(1, n // m)][:, :m])
+        want = ops.knnquery(k, xyz, q)
+        got = pointops.knnquery(k, _g(xyz), _g(q))
+        assert torch.equal(got.cpu(), torch.from_numpy(want)), (n, m, k, kw)
+
+
+def test_knnquery_dist2_and_limits():
+    from patchaugnet_b200 import pointops_cuda as K
+    xyz = _clouds(1, 64, 7)
+    idx = torch.zeros(1, 64, 5, dtype=torch.int32, device=DEV)
+    d2 = torch.zeros(1, 64, 5, device=DEV)
+    K.knnquery_cuda(1, 64, 64, 5, _g(xyz), _g(xyz), idx, d2)
+    wi, wd = ops.knnquery(5, xyz, xyz, return_dist=True)
+    assert torch.equal(idx.cpu(), torch.from_numpy(wi)) and torch.equal(d2.cpu(), torch.from_numpy(wd))
+    with pytest.raises(ValueError):
+        pointops.knnquery(201, _g(xyz), _g(xyz))        # the reference's fixed best[200] (knnquery_cuda_kernel.cu:21-22)
+
+
+@pytest.mark.parametrize("n,m", [(4096, 1024), (1024, 128), (128, 16), (37, 3), (100, 2500)])
+def test_three_nn_bit_exact_and_weights(n, m):
+    for kw in (dict(), dict(dup=True)):
+        unknown, known = _clouds(2, n, n, **kw), _clouds(2, m, m + 1, **kw)
+        if kw:
+            known[:, : min(n, m)] = unknown[:, : min(n, m)]          # zero distances -> the 1e-8 guard matters
+        d2, idx = ops.nearestneighbor(unknown, known)
+        dist, gi = pointops.nearestneighbor(_g(unknown), _g(known))
+        assert torch.equal(gi.cpu(), torch.from_numpy(idx))
+        assert torch.equal(dist.cpu(), torch.sqrt(torch.from_numpy(d2)))
+        # fused weights = patch_aug_net.py:351-353 on the same distances
+        wi = torch.empty(2, n, 3, dtype=torch.int32, device=DEV)
+        w = torch.empty(2, n, 3, device=DEV)
+        L.check(L.lib().pab_three_nn_weights(2, n, m, L.ptr(_g(unknown)), L.ptr(_g(known)), L.ptr(wi), L.ptr(w), L.stream_ptr()), "3nn")
+        r = 1.0 / (torch.sqrt(torch.from_numpy(d2)) + 1e-8)
+        want_w = r / r.sum(2, keepdim=True)
+        assert torch.equal(wi.cpu(), torch.from_numpy(idx))
+        assert torch.allclose(w.cpu(), want_w, rtol=2e-6, atol=0)
+
+
+def test_gather_group_interp_forward_backward():
+    rng = np.random.default_rng(11)
+    b, c, n, m, k = 2, 19, 333, 47, 6
+    f = rng.normal(size=(b, c, n)).astype(np.float32)
+    idx = rng.integers(0, n, (b, m)).astype(np.int32)
+    gidx = rng.integers(0, n, (b, m, k)).astype(np.int32)
+    ft = _g(f).requires_grad_(True)
+    out = pointops.gathering(ft, _g(idx))
+    assert torch.equal(out.detach().cpu(), torch.from_numpy(ops.gathering(f, idx)))
+    g = rng.normal(size=out.shape).astype(np.float32)
+    out.backward(_g(g))
+    assert torch.allclose(ft.grad.cpu(), torch.from_numpy(ops.gathering_backward(g, idx, n)), atol=1e-5)
+    ft = _g(f).requires_grad_(True)
+    out = pointops.grouping(ft, _g(gidx))
+    assert torch.equal(out.detach().cpu(), torch.from_numpy(ops.grouping(f, gidx)))
+    g = rng.normal(size=out.shape).astype(np.float32)
+    out.backward(_g(g))
+    assert torch.allclose(ft.grad.cpu(), torch.from_numpy(ops.grouping_backward(g, gidx, n)), atol=1e-5)
+    li = rng.integers(0, 2 ** 40, (b, 3, n))
+    assert torch.equal(pointops.grouping_int(_g(li), _g(gidx)).cpu(), torch.from_numpy(ops.grouping_int(li, gidx)))
+    i3 = rng.integers(0, n, (b, m, 3)).astype(np.int32)
+    w = rng.uniform(0, 1, (b, m, 3)).astype(np.float32)
+    ft = _g(f).requires_grad_(True)
+    out = pointops.interpolation(ft, _g(i3), _g(w))
+    assert torch.equal(out.detach().cpu(), torch.from_numpy(ops.interpolation(f, i3, w)))     # same fma order -> bit-exact
+    g = rng.normal(size=out.shape).astype(np.float32)
+    out.backward(_g(g))
+    assert torch.allclose(ft.grad.cpu(), torch.from_numpy(ops.interpolation_backward(g, i3, w, n)), atol=1e-5)
+
+
+def test_ballquery_labelstat_featuredistribute():
+    xyz = _clouds(2, 3000, 12)
+    q = np.ascontiguousarray(xyz[:, ::29])
+    for r, ns in ((0.2, 16), (0.05, 4), (1e-6, 3), (5.0, 32)):
+        assert torch.equal(pointops.ballquery(r, ns, _g(xyz), _g(q)).cpu(), torch.from_numpy(ops.ballquery(r, ns, xyz, q)))
+    far = (q + 10).astype(np.float32)
+    assert (pointops.ballquery(0.1, 5, _g(xyz), _g(far)) == 0).all()
+    rng = np.random.default_rng(13)
+    ls = rng.integers(0, 4, (2, 3000, 7)).astype(np.int32)
+    stat, idx = pointops.labelstat_and_ballquery(0.2, 16, _g(xyz), _g(q), _g(ls))
+    ws, wi = ops.labelstat_and_ballquery(0.2, 16, xyz, q, ls)
+    assert torch.equal(stat.cpu(), torch.from_numpy(ws)) and torch.equal(idx.cpu(), torch.from_numpy(wi))
+    assert torch.equal(pointops.labelstat_idx(16, _g(ls), idx).cpu(), torch.from_numpy(ops.labelstat_idx(16, ls, wi)))
+    assert torch.equal(pointops.labelstat_ballrange(0.2, _g(xyz), _g(q), _g(ls)).cpu(),
+                       torch.from_numpy(ops.labelstat_ballrange(0.2, xyz, q, ls)))
+    centres = _clouds(2, 40, 14)
+    di = pointops.featuredistribute(_g(centres), _g(xyz))
+    assert torch.equal(di.cpu(), torch.from_numpy(ops.featuredistribute(centres, xyz)))
+    mf = rng.normal(size=(2, 9, 40)).astype(np.float32)
+    mft = _g(mf).requires_grad_(True)
+    out = pointops.featuregather(mft, di)
+    assert torch.equal(out.detach().cpu(), torch.from_numpy(ops.featuregather(mf, di.cpu().numpy())))
+    out.sum().backward()
+    assert torch.allclose(mft.grad.cpu(), torch.from_numpy(ops.featuregather_backward(np.ones_like(out.detach().cpu().numpy()), di.cpu().numpy(), 40)))
+
+
+def test_query_and_group_edge_consumes_rng_like_the_reference():
+    xyz = _g(_clouds(2, 512, 15))
+    new_xyz = xyz[:, :32].contiguous()
+    feats = xyz.transpose(1, 2).contiguous()
+    centre = feats[:, :, :32].contiguous()
+    grouper = pointops.QueryAndGroup_Edge(None, 8, knn_dilation=2, use_xyz=True, ret_sample_idx=True)
+    torch.manual_seed(3)
+    nf, idx = grouper(xyz, new_xyz, feats, centre)
+    torch.manual_seed(3)
+    perm = torch.randperm(8)
+    after = torch.rand(1)
+    torch.manual_seed(3)
+    grouper(xyz, new_xyz, feats, centre)
+    assert torch.equal(torch.rand(1), after)                           # exactly one randperm(nsample) draw
+    cand = torch.from_numpy(ops.knnquery(16, xyz.cpu().numpy(), new_xyz.cpu().numpy()))
+    assert torch.equal(idx.cpu(), cand[:, :, perm])                    # pointops.py:553-555
+    assert nf.shape == (2, 6, 32, 8)
+    assert torch.allclose(nf[:, :3], nf[:, 3:])                        # features are xyz here: both halves are xyz_j - xyz_i
