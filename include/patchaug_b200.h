@@ -123,6 +123,12 @@ typedef struct {
     const float *wt;    /* (c_in_pad, c_out) */
     const float *shift; /* (c_out) */
     int c_in, c_in_pad, c_out, relu;
+    /* Optional tensor-core operands (NULL -> the layer runs on the fp32 SIMT path).  The same folded weight, restricted
+     * to input channels [tc_k0, tc_k0 + tc_k), split as W = hi + lo with hi = bf16(W), lo = bf16(W - hi), each stored
+     * K-major as (c_out, tc_k) bf16.  tc_k must be a multiple of 64; the (at most 3) remaining input channels of
+     * layer 0 — the xyz part — are applied from `wt` as a rank-n update in the epilogue. */
+    const void *w_hi, *w_lo;
+    int tc_k0, tc_k;
 } pab_layer_t;
 
 /* Fused set-abstraction module (patch_aug_net.py:203-243 + pointops.py:533-582, eval mode):
@@ -158,6 +164,9 @@ int pab_netvlad_forward(int b, int n, int c, int K, const float *x, const float 
 size_t pab_afa_workspace_bytes(int b, int c, int K, int c_out);
 int pab_afa_forward(int b, int c, int K, int c_out, const float *v, const float *w_att_t, const float *fc_wt,
                     const float *fc_scale, const float *fc_shift, int l2_norm, float *desc, void *workspace, pab_stream_t s);
+
+/* Tuning hook: enable (1, default) / disable (0) the tcgen05 tensor-core path of the fused SharedMLP kernels. */
+void pab_tune_tensor_core(int enable);
 
 /* Tuning hook: force the FPS CTA size (power of two, 32..1024; 0 = automatic). */
 void pab_tune_fps_threads(int threads);

@@ -22,7 +22,8 @@ _SZ = C.c_size_t
 
 class PabLayer(C.Structure):
     """pab_layer_t"""
-    _fields_ = [("wt", _P), ("shift", _P), ("c_in", _I), ("c_in_pad", _I), ("c_out", _I), ("relu", _I)]
+    _fields_ = [("wt", _P), ("shift", _P), ("c_in", _I), ("c_in_pad", _I), ("c_out", _I), ("relu", _I),
+                ("w_hi", _P), ("w_lo", _P), ("tc_k0", _I), ("tc_k", _I)]
 
 
 # name -> (restype, argtypes); every symbol include/patchaug_b200.h declares
@@ -31,6 +32,7 @@ SIGNATURES = {
     "pab_num_launches": (_I, []),
     "pab_reset_launch_counter": (None, []),
     "pab_tune_fps_threads": (None, [_I]),
+    "pab_tune_tensor_core": (None, [_I]),
     "pab_furthestsampling": (_I, [_I, _I, _I, _P, _P, _P, _P]),
     "pab_gathering_forward": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),
     "pab_gathering_backward": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),

@@ -154,7 +154,8 @@ int g_fps_threads_override = 0;
 template <int PPT>
 int launch_fps(int b, int n, int m, int threads, int log2bs, const float *xyz, float *temp, int *idx, cudaStream_t st) {
     const size_t smem = (size_t)n * 3 * sizeof(float);
-    if (smem > 48 * 1024) PAB_CUDA(cudaFuncSetAttribute(fps_kernel<PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // static smem (candidate slots) counts against the 48 KB default too: opt in whenever we are near it
+    if (smem > 40 * 1024) PAB_CUDA(cudaFuncSetAttribute(fps_kernel<PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     fps_kernel<PPT><<<b, threads, smem, st>>>(n, m, log2bs, xyz, temp, idx);
     PAB_LAUNCH_CHECK();
     return 0;

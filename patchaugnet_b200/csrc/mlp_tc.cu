@@ -1,0 +1,517 @@
+// mlp_tc.cu — fused SharedMLP on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+// Same fusion as mlp.cu (neighbour gather / 3-NN interpolation -> every MLP layer -> max over K or row store, tile
+// resident on chip), but the layer GEMMs run as tcgen05.mma with fp32 accumulators in tensor memory:
+//
+//   * a persistent CTA owns 128-row tiles; the layer input lives in shared memory as TWO bf16 planes
+//     (x = hi + lo, hi = bf16(x), lo = bf16(x - hi)) in the canonical K-major SWIZZLE_128B layout; the folded weights
+//     are split the same way on the host.  Each 16-wide k-step issues three MMAs
+//         D += hi(A) * hi(W)  +  lo(A) * hi(W)  +  hi(A) * lo(W)
+//     which carries ~16 mantissa bits through every product (error ~2^-17 per term, fp32 accumulation) — the
+//     descriptors stay within the 1e-4 contract where a single TF32/bf16 pass does not.
+//   * warp 0 streams weight blocks (128 output channels x 64 k, hi+lo) with TMA (cp.async.bulk.tensor, mbarrier
+//     complete_tx) through a ring of stages, running ahead across layers and tiles; warp 1 (one elected thread)
+//     issues the MMAs and frees stages with tcgen05.commit; warps 2..9 (256 threads) gather the tile, and after
+//     each layer read the accumulators with tcgen05.ld, add the folded BN shift (+ the rank-3 xyz update of
+//     layer 0, whose K would otherwise not be a multiple of 64), ReLU, split to bf16 hi/lo and write the next layer's
+//     operand in place.  The last layer is staged as fp32 in the (now free) operand region and either max-pooled
+//     over the K neighbours (SA) or stored as coalesced rows (FP).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace {
+
+constexpr int TM = 128;                       // rows per tile (UMMA M)
+constexpr int KCH = 64;                       // bf16 per K chunk = one 128-byte swizzle row
+constexpr int NBLK = 128;                     // output channels per weight stage (UMMA N)
+constexpr int NWORK = 256;                    // worker threads
+constexpr int TC_THREADS = 64 + NWORK;
+constexpr int A_CHUNK = TM * 128;             // bytes of one K chunk of one plane
+constexpr int STAGE = 2 * NBLK * 128;         // hi + lo weight block
+constexpr int MAX_STAGES = 6;
+constexpr int MAX_LAYERS = 3;
+
+enum { TC_SA = 1, TC_FP = 2 };
+
+struct alignas(64) TcArgs {
+    CUtensorMap tm[MAX_LAYERS][2];
+    const float *shift[MAX_LAYERS];
+    int K[MAX_LAYERS], N[MAX_LAYERS], relu[MAX_LAYERS];
+    int n_layers, n_stages, kchunks_max, mode;
+    long rows;                                 // SA: centres, FP: points
+    int ntiles;
+    // layer-0 "extra" channels (the xyz part), applied as a rank-n update from the fp32 weight rows
+    const float *w_extra;                      // layers[0].wt + extra_row0 * N0
+    int n_extra;
+    // SA
+    int n, m, k, nbr_stride, c;
+    const float *xyz, *feat;
+    const int *center_idx, *nbr_idx;
+    // FP
+    int c_known, c_skip;
+    const float *known_feat, *skip_feat;
+    const int *idx3;
+    const float *w3;
+    float *out;
+};
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in [0,14),
+// LBO (unused for swizzled K-major) = 1 in [16,30), SBO = 1024 B (8 rows x 128 B) >> 4 in [32,46), version 1 in [46,48),
+// layout type SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D = f32 [4,6)=1, A = B = bf16 [7,10)=[10,13)=1,
+// both K-major, N>>3 in [17,23), M>>4 in [24,29).
+__device__ __forceinline__ uint32_t umma_idesc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// x = hi + lo with hi = bf16_rn(x), lo = bf16_rn(x - hi); packs element pairs (low half = lower index)
+__device__ __forceinline__ void split_pack(float a, float b, uint32_t &hi, uint32_t &lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
+
+// byte offset of the 16-byte unit holding channels [8*j, 8*j+8) of row r inside the operand planes
+__device__ __forceinline__ uint32_t a_unit_offset(int r, int j) {
+    return (uint32_t)((j >> 3) * A_CHUNK + r * 128 + (((j & 7) ^ (r & 7)) << 4));
+}
+// fp32 staging of the last layer in the operand region: [128 rows][256 cols], 16-byte units XOR-swizzled by row
+__device__ __forceinline__ uint32_t stage_offset(int r, int c) {
+    return (uint32_t)(r * 1024 + ((((c >> 2) ^ (r & 7)) & 63) << 4) + ((c & 3) << 2));
+}
+
+__device__ __forceinline__ void store_units(uint8_t *a1, uint8_t *a2, int r, int j, const float (&v)[8]) {
+    uint4 h, l;
+    split_pack(v[0], v[1], h.x, l.x);
+    split_pack(v[2], v[3], h.y, l.y);
+    split_pack(v[4], v[5], h.z, l.z);
+    split_pack(v[6], v[7], h.w, l.w);
+    const uint32_t off = a_unit_offset(r, j);
+    *reinterpret_cast<uint4 *>(a1 + off) = h;
+    *reinterpret_cast<uint4 *>(a2 + off) = l;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_constant__ TcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *a1 = smem;
+    uint8_t *a2 = a1 + (size_t)a.kchunks_max * A_CHUNK;
+    uint8_t *stages = a2 + (size_t)a.kchunks_max * A_CHUNK;
+    uint8_t *misc = stages + (size_t)a.n_stages * STAGE;
+    uint64_t *full = reinterpret_cast<uint64_t *>(misc);
+    uint64_t *empty = full + MAX_STAGES;
+    uint64_t *a_ready = empty + MAX_STAGES;
+    uint64_t *d_ready = a_ready + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d_ready + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int s = 0; s < a.n_stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(a_ready, NWORK);
+        mbar_init(d_ready, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer: weight blocks, in (tile, layer, n-block, k-chunk) order =================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+                for (int l = 0; l < a.n_layers; ++l) {
+                    const int nkc = a.K[l] / KCH, nbr = min(NBLK, a.N[l]), nnb = a.N[l] / nbr;
+                    for (int nb = 0; nb < nnb; ++nb)
+                        for (int kc = 0; kc < nkc; ++kc, ++it) {
+                            const int s = it % a.n_stages;
+                            const uint32_t ph = (it / a.n_stages) & 1;
+                            mbar_wait(empty + s, ph ^ 1);
+                            uint8_t *dst = stages + (size_t)s * STAGE;
+                            mbar_expect_tx(full + s, 2u * nbr * 128u);
+                            tma_load_2d(dst, &a.tm[l][0], kc * KCH, nb * nbr, full + s);
+                            tma_load_2d(dst + nbr * 128, &a.tm[l][1], kc * KCH, nb * nbr, full + s);
+                        }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ================= MMA issuer =============================================================================
+        if (lane == 0) {
+            uint32_t it = 0, lcount = 0;
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+                for (int l = 0; l < a.n_layers; ++l, ++lcount) {
+                    const int nkc = a.K[l] / KCH, nbr = min(NBLK, a.N[l]), nnb = a.N[l] / nbr;
+                    const uint32_t idesc = umma_idesc(nbr);
+                    mbar_wait(a_ready, lcount & 1);
+                    tc_fence_after();
+                    for (int nb = 0; nb < nnb; ++nb) {
+                        const uint32_t d = tmem + (uint32_t)(nb * nbr);
+                        for (int kc = 0; kc < nkc; ++kc, ++it) {
+                            const int s = it % a.n_stages;
+                            mbar_wait(full + s, (it / a.n_stages) & 1);
+                            tc_fence_after();
+                            const uint32_t sa1 = smem_u32(a1 + (size_t)kc * A_CHUNK), sa2 = smem_u32(a2 + (size_t)kc * A_CHUNK);
+                            const uint32_t sb1 = smem_u32(stages + (size_t)s * STAGE), sb2 = sb1 + nbr * 128;
+#pragma unroll
+                            for (int ks = 0; ks < KCH / 16; ++ks) {
+                                const uint64_t da1 = umma_desc(sa1 + ks * 32), da2 = umma_desc(sa2 + ks * 32);
+                                const uint64_t db1 = umma_desc(sb1 + ks * 32), db2 = umma_desc(sb2 + ks * 32);
+                                umma_f16(d, da1, db1, idesc, (kc | ks) != 0);
+                                umma_f16(d, da2, db1, idesc, 1);
+                                umma_f16(d, da1, db2, idesc, 1);
+                            }
+                            umma_commit(empty + s);          // stage reusable once these MMAs have read it
+                        }
+                    }
+                    umma_commit(d_ready);                    // accumulators of this layer complete
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================= workers: gather, epilogues, output ====================================================
+        const int wt = tid - 64;                             // 0..255
+        const int q = warp & 3;                              // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;                    // column half handled by this warp
+        const int row = q * 32 + lane;                       // accumulator row owned in the epilogue
+        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+        uint32_t lcount = 0;
+        const int units0 = a.K[0] / 8;                       // 16-byte units per row of the layer-0 operand
+
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+            // ---- stage the layer-0 operand (hi/lo planes) ---------------------------------------------------------
+            float xe[3] = {0.f, 0.f, 0.f};
+            if (a.mode == TC_SA) {
+                const int G = TM / a.k;
+                for (int u = wt; u < TM * units0; u += NWORK) {
+                    const int r = u / units0, j = u - r * units0;
+                    const int g = r / a.k, s = r - g * a.k;
+                    const long ci = (long)tile * G + g;
+                    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    if (g < G && ci < a.rows) {
+                        const long cloud = ci / a.m;
+                        const long pc = cloud * a.n + __ldg(a.center_idx + ci);
+                        const long pn = cloud * a.n + __ldg(a.nbr_idx + ci * a.nbr_stride + s);
+                        const float4 *fn = reinterpret_cast<const float4 *>(a.feat + pn * a.c) + 2 * j;
+                        const float4 *fc = reinterpret_cast<const float4 *>(a.feat + pc * a.c) + 2 * j;
+                        const float4 n0 = __ldg(fn), n1 = __ldg(fn + 1), c0 = __ldg(fc), c1 = __ldg(fc + 1);
+                        v[0] = n0.x - c0.x; v[1] = n0.y - c0.y; v[2] = n0.z - c0.z; v[3] = n0.w - c0.w;
+                        v[4] = n1.x - c1.x; v[5] = n1.y - c1.y; v[6] = n1.z - c1.z; v[7] = n1.w - c1.w;
+                    }
+                    store_units(a1, a2, r, j, v);
+                }
+                {   // xyz_j - xyz_i of the row this thread owns in the epilogue
+                    const int g = row / a.k, s = row - g * a.k;
+                    const long ci = (long)tile * G + g;
+                    if (g < G && ci < a.rows) {
+                        const long cloud = ci / a.m;
+                        const long pc = cloud * a.n + __ldg(a.center_idx + ci);
+                        const long pn = cloud * a.n + __ldg(a.nbr_idx + ci * a.nbr_stride + s);
+#pragma unroll
+                        for (int e = 0; e < 3; ++e) xe[e] = __ldg(a.xyz + pn * 3 + e) - __ldg(a.xyz + pc * 3 + e);
+                    }
+                }
+            } else {
+                const int ku = a.c_known / 8;
+                for (int u = wt; u < TM * units0; u += NWORK) {
+                    const int r = u / units0, j = u - r * units0;
+                    const long p = (long)tile * TM + r;
+                    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    if (p < a.rows) {
+                        if (j < ku) {
+                            const long base = (p / a.n) * a.m;
+                            const int i0 = __ldg(a.idx3 + p * 3), i1 = __ldg(a.idx3 + p * 3 + 1), i2 = __ldg(a.idx3 + p * 3 + 2);
+                            const float w0 = __ldg(a.w3 + p * 3), w1 = __ldg(a.w3 + p * 3 + 1), w2 = __ldg(a.w3 + p * 3 + 2);
+                            const float4 *f0 = reinterpret_cast<const float4 *>(a.known_feat + (base + i0) * a.c_known) + 2 * j;
+                            const float4 *f1 = reinterpret_cast<const float4 *>(a.known_feat + (base + i1) * a.c_known) + 2 * j;
+                            const float4 *f2 = reinterpret_cast<const float4 *>(a.known_feat + (base + i2) * a.c_known) + 2 * j;
+                            const float4 x0 = __ldg(f0), x1 = __ldg(f0 + 1), y0 = __ldg(f1), y1 = __ldg(f1 + 1), z0 = __ldg(f2), z1 = __ldg(f2 + 1);
+                            // interpolation_forward: fma(w2,p2, fma(w0,p0, w1*p1)) (interpolation_cuda_kernel.cu:194)
+                            v[0] = __fmaf_rn(w2, z0.x, __fmaf_rn(w0, x0.x, __fmul_rn(w1, y0.x)));
+                            v[1] = __fmaf_rn(w2, z0.y, __fmaf_rn(w0, x0.y, __fmul_rn(w1, y0.y)));
+                            v[2] = __fmaf_rn(w2, z0.z, __fmaf_rn(w0, x0.z, __fmul_rn(w1, y0.z)));
+                            v[3] = __fmaf_rn(w2, z0.w, __fmaf_rn(w0, x0.w, __fmul_rn(w1, y0.w)));
+                            v[4] = __fmaf_rn(w2, z1.x, __fmaf_rn(w0, x1.x, __fmul_rn(w1, y1.x)));
+                            v[5] = __fmaf_rn(w2, z1.y, __fmaf_rn(w0, x1.y, __fmul_rn(w1, y1.y)));
+                            v[6] = __fmaf_rn(w2, z1.z, __fmaf_rn(w0, x1.z, __fmul_rn(w1, y1.z)));
+                            v[7] = __fmaf_rn(w2, z1.w, __fmaf_rn(w0, x1.w, __fmul_rn(w1, y1.w)));
+                        } else {
+                            const float4 *sk = reinterpret_cast<const float4 *>(a.skip_feat + p * a.c_skip) + 2 * (j - ku);
+                            const float4 s0 = __ldg(sk), s1 = __ldg(sk + 1);
+                            v[0] = s0.x; v[1] = s0.y; v[2] = s0.z; v[3] = s0.w; v[4] = s1.x; v[5] = s1.y; v[6] = s1.z; v[7] = s1.w;
+                        }
+                    }
+                    store_units(a1, a2, r, j, v);
+                }
+                if (a.n_extra > 0) {
+                    const long p = (long)tile * TM + row;
+                    if (p < a.rows)
+                        for (int e = 0; e < a.n_extra; ++e) xe[e] = __ldg(a.skip_feat + p * a.c_skip + e);
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(a_ready);
+
+            // ---- per-layer epilogues -----------------------------------------------------------------------------
+            for (int l = 0; l < a.n_layers; ++l, ++lcount) {
+                const int N = a.N[l];
+                const bool last = l == a.n_layers - 1;
+                mbar_wait(d_ready, lcount & 1);
+                tc_fence_after();
+                const int npass = last ? (N + 255) / 256 : 1;
+                for (int pass = 0; pass < npass; ++pass) {
+                    const int ncols = min(256, N - pass * 256);        // columns of this pass
+                    const int per = ncols / 2;                         // columns per worker half
+                    for (int cb = 0; cb < per; cb += 32) {
+                        const int col = pass * 256 + half * per + cb;  // first accumulator column of this batch
+                        float v[32];
+                        tmem_ld32(trow + (uint32_t)col, v);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            float x = v[i] + __ldg(a.shift[l] + col + i);
+                            if (l == 0)
+                                for (int e = 0; e < a.n_extra; ++e) x = fmaf(xe[e], __ldg(a.w_extra + (size_t)e * N + col + i), x);
+                            v[i] = a.relu[l] ? fmaxf(x, 0.f) : x;
+                        }
+                        if (!last) {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                float w8[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) w8[i] = v[u * 8 + i];
+                                store_units(a1, a2, row, (col >> 3) + u, w8);
+                            }
+                        } else {
+                            const int c0 = col - pass * 256;
+#pragma unroll
+                            for (int u = 0; u < 8; ++u)
+                                *reinterpret_cast<float4 *>(a1 + stage_offset(row, c0 + 4 * u)) =
+                                    make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+                        }
+                    }
+                    if (last) {
+                        tc_fence_before();
+                        asm volatile("bar.sync 1, %0;" ::"n"(NWORK) : "memory");   // staging complete (workers only)
+                        if (a.mode == TC_SA) {
+                            const int G = TM / a.k;
+                            for (int e = wt; e < G * ncols; e += NWORK) {
+                                const int g = e / ncols, c = e - g * ncols;
+                                const long ci = (long)tile * G + g;
+                                if (ci >= a.rows) continue;
+                                float mx = *reinterpret_cast<const float *>(a1 + stage_offset(g * a.k, c));
+                                for (int s = 1; s < a.k; ++s)
+                                    mx = fmaxf(mx, *reinterpret_cast<const float *>(a1 + stage_offset(g * a.k + s, c)));
+                                a.out[ci * N + pass * 256 + c] = mx;
+                            }
+                        } else {
+                            const int c4 = ncols / 4;
+                            for (int e = wt; e < TM * c4; e += NWORK) {
+                                const int r = e / c4, cq = e - r * c4;
+                                const long p = (long)tile * TM + r;
+                                if (p < a.rows)
+                                    *reinterpret_cast<float4 *>(a.out + p * N + pass * 256 + 4 * cq) =
+                                        *reinterpret_cast<const float4 *>(a1 + stage_offset(r, 4 * cq));
+                            }
+                        }
+                        asm volatile("bar.sync 1, %0;" ::"n"(NWORK) : "memory");   // staging consumed before it is rewritten
+                    }
+                }
+                if (!last) {
+                    tc_fence_before();
+                    fence_proxy_async();
+                    mbar_arrive(a_ready);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// weight plane (N rows, K bf16 contiguous) -> boxes of (64 k) x (box_n rows), 128-byte swizzle
+int make_weight_map(CUtensorMap *map, const void *w, int N, int K, int box_n) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return PAB_EINVAL;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)KCH, (cuuint32_t)box_n};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(w), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : PAB_EINVAL;
+}
+
+int g_tc_enabled = 1;
+
+}  // namespace
+
+PAB_API void pab_tune_tensor_core(int enable) { g_tc_enabled = enable; }
+
+// Can this module run on the tensor-core path?  (every layer split on the host, shapes a multiple of 64, at most
+// 4 "extra" layer-0 channels, operand planes + >= 2 weight stages within 227 KB)
+bool pab_tc_eligible(const pab_layer_t *layers, int n_layers, int k_group) {
+    if (!g_tc_enabled || n_layers < 1 || n_layers > MAX_LAYERS) return false;
+    int kmax = 0;
+    for (int l = 0; l < n_layers; ++l) {
+        const pab_layer_t &L = layers[l];
+        if (!L.w_hi || !L.w_lo || L.tc_k <= 0 || L.tc_k % KCH || L.c_out % 64) return false;
+        if (l > 0 && (L.tc_k0 != 0 || L.tc_k != L.c_in)) return false;
+        if (l < n_layers - 1 && L.c_out > 256) return false;
+        if (L.c_out > 512 || (L.c_out > NBLK && L.c_out % NBLK)) return false;
+        if (L.tc_k > kmax) kmax = L.tc_k;
+    }
+    const int n_extra = layers[0].c_in - layers[0].tc_k;
+    if (n_extra < 0 || n_extra > 3) return false;
+    if (n_extra > 0 && !(layers[0].tc_k0 == 0 || layers[0].tc_k0 == n_extra)) return false;
+    if (k_group > TM) return false;
+    const size_t need = 2 * (size_t)(kmax / KCH) * A_CHUNK + 2 * (size_t)STAGE + 2048;
+    return need <= 227 * 1024;
+}
+
+int pab_tc_launch(int mode, long rows, int k_group, const pab_layer_t *layers, int n_layers, TcArgs &a, cudaStream_t st) {
+    int kmax = 0;
+    for (int l = 0; l < n_layers; ++l) {
+        const pab_layer_t &L = layers[l];
+        const int nbr = L.c_out < NBLK ? L.c_out : NBLK;
+        if (make_weight_map(&a.tm[l][0], L.w_hi, L.c_out, L.tc_k, nbr)) return PAB_EINVAL;
+        if (make_weight_map(&a.tm[l][1], L.w_lo, L.c_out, L.tc_k, nbr)) return PAB_EINVAL;
+        a.shift[l] = L.shift; a.K[l] = L.tc_k; a.N[l] = L.c_out; a.relu[l] = L.relu;
+        if (L.tc_k > kmax) kmax = L.tc_k;
+    }
+    a.n_layers = n_layers; a.mode = mode; a.rows = rows; a.kchunks_max = kmax / KCH;
+    a.n_extra = layers[0].c_in - layers[0].tc_k;
+    // extra channels sit before (SA: xyz first) or after (FP: skip last) the tensor-core part
+    const int extra_row0 = layers[0].tc_k0 == 0 ? layers[0].tc_k : 0;
+    a.w_extra = layers[0].wt + (size_t)extra_row0 * layers[0].c_out;
+    const long per_tile = mode == TC_SA ? (TM / k_group) : TM;
+    a.ntiles = (int)((rows + per_tile - 1) / per_tile);
+    const size_t fixed = 2 * (size_t)a.kchunks_max * A_CHUNK + 2048 + 1024;
+    int ns = (int)((227 * 1024 - fixed) / STAGE);
+    if (ns > MAX_STAGES) ns = MAX_STAGES;
+    if (ns < 2) return PAB_EINVAL;
+    a.n_stages = ns;
+    const size_t smem = fixed + (size_t)ns * STAGE;
+    static int n_sm = 0;
+    if (!n_sm) {
+        int dev = 0;
+        PAB_CUDA(cudaGetDevice(&dev));
+        PAB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    PAB_CUDA(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = a.ntiles < n_sm ? a.ntiles : n_sm;
+    if (grid == 0) return 0;
+    mlp_tc_kernel<<<grid, TC_THREADS, smem, st>>>(a);
+    PAB_LAUNCH_CHECK();
+    return 0;
+}
+
+int pab_tc_sa(int b, int n, int m, int k, int nbr_stride, int c, const float *xyz, const float *feat, const int *center_idx,
+              const int *nbr_idx, const pab_layer_t *layers, int n_layers, float *out, cudaStream_t st) {
+    TcArgs a{};
+    a.n = n; a.m = m; a.k = k; a.nbr_stride = nbr_stride; a.c = c; a.xyz = xyz; a.feat = feat; a.center_idx = center_idx;
+    a.nbr_idx = nbr_idx; a.out = out;
+    return pab_tc_launch(TC_SA, (long)b * m, k, layers, n_layers, a, st);
+}
+
+int pab_tc_fp(int b, int n, int m, int c_known, int c_skip, const float *known_feat, const float *skip_feat, const int *idx,
+              const float *weight, const pab_layer_t *layers, int n_layers, float *out, cudaStream_t st) {
+    TcArgs a{};
+    a.n = n; a.m = m; a.c_known = c_known; a.c_skip = c_skip; a.known_feat = known_feat; a.skip_feat = skip_feat;
+    a.idx3 = idx; a.w3 = weight; a.out = out;
+    return pab_tc_launch(TC_FP, (long)b * n, 0, layers, n_layers, a, st);
+}

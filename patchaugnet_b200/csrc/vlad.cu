@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(tg::THREADS, 1) vlad_partial_kernel(const Vlad
     const int row_end = min(a.n, row_begin + VROWS_PER_CTA);
     const float *xg = a.x + (size_t)cloud * a.n * a.c;
 
-    pab_layer_t L;
+    pab_layer_t L{};
     L.wt = a.wc; L.shift = a.shift; L.c_in = a.c; L.c_in_pad = a.c; L.c_out = a.K; L.relu = 0;
 
     using G2 = tg::Geo<64>;                    // second contraction: 64 "rows" (clusters) x 128-column passes

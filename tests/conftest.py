@@ -10,6 +10,11 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 
 def pytest_configure(config):
+    import torch
+    # parity is defined against the reference's fp32 forward: its cuDNN convs default to TF32 in this torch
+    # (SURVEY.md section 0), which alone is a 1e-3 error — switch it off for every torch-side comparison
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 

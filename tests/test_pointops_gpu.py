@@ -92,11 +92,18 @@ def test_three_nn_bit_exact_and_weights(n, m):
         d2, idx = ops.nearestneighbor(unknown, known)
         dist, gi = pointops.nearestneighbor(_g(unknown), _g(known))
         assert torch.equal(gi.cpu(), torch.from_numpy(idx))
-        assert torch.equal(dist.cpu(), torch.sqrt(torch.from_numpy(d2)))
+        raw_d2 = torch.empty(2, n, 3, device=DEV)
+        raw_i = torch.empty(2, n, 3, dtype=torch.int32, device=DEV)
+        from patchaugnet_b200 import pointops_cuda as K
+        K.nearestneighbor_cuda(2, n, m, _g(unknown), _g(known), raw_d2, raw_i)
+        assert torch.equal(raw_d2.cpu(), torch.from_numpy(d2)) and torch.equal(raw_i, gi)     # squared distances bit-exact
+        assert torch.allclose(dist.cpu(), torch.sqrt(torch.from_numpy(d2)), rtol=1e-6, atol=0)  # pointops.py:76 sqrt in torch
         # fused weights = patch_aug_net.py:351-353 on the same distances
         wi = torch.empty(2, n, 3, dtype=torch.int32, device=DEV)
         w = torch.empty(2, n, 3, device=DEV)
-        L.check(L.lib().pab_three_nn_weights(2, n, m, L.ptr(_g(unknown)), L.ptr(_g(known)), L.ptr(wi), L.ptr(w), L.stream_ptr()), "3nn")
+        gu, gk = _g(unknown), _g(known)            # keep the device tensors alive across the raw C-ABI call
+        L.check(L.lib().pab_three_nn_weights(2, n, m, L.ptr(gu), L.ptr(gk), L.ptr(wi), L.ptr(w), L.stream_ptr()), "3nn")
+        torch.cuda.synchronize()
         r = 1.0 / (torch.sqrt(torch.from_numpy(d2)) + 1e-8)
         want_w = r / r.sum(2, keepdim=True)
         assert torch.equal(wi.cpu(), torch.from_numpy(idx))

@@ -51,7 +51,7 @@ def test_reference_three_nn_interp_group_gather():
     od2, oidx = ops.nearestneighbor(unknown, known)
     assert np.array_equal(ridx.cpu().numpy(), oidx) and np.array_equal(rd2.cpu().numpy(), od2)
     dist, idx = pointops.nearestneighbor(_g(unknown), _g(known))
-    assert torch.equal(idx, ridx) and torch.equal(dist, torch.sqrt(rd2))
+    assert torch.equal(idx, ridx) and torch.allclose(dist, torch.sqrt(rd2), rtol=1e-6, atol=0)
     rng = np.random.default_rng(3)
     feats = rng.normal(size=(2, 64, 1024)).astype(np.float32)
     w = rng.uniform(0, 1, (2, 4096, 3)).astype(np.float32)
