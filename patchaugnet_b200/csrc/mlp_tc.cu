@@ -24,11 +24,10 @@ namespace {
 
 constexpr int TM = 128;                       // rows per tile (UMMA M)
 constexpr int KCH = 64;                       // bf16 per K chunk = one 128-byte swizzle row
-constexpr int NBLK = 128;                     // output channels per weight stage (UMMA N)
+constexpr int NBLK_MAX = 128;                 // max output channels per weight stage (UMMA N); runtime a.nblk is 64 or 128
 constexpr int NWORK = 256;                    // worker threads
 constexpr int TC_THREADS = 64 + NWORK;
 constexpr int A_CHUNK = TM * 128;             // bytes of one K chunk of one plane
-constexpr int STAGE = 2 * NBLK * 128;         // hi + lo weight block
 constexpr int MAX_STAGES = 6;
 constexpr int MAX_LAYERS = 3;
 
@@ -39,6 +38,9 @@ struct alignas(64) TcArgs {
     const float *shift[MAX_LAYERS];
     int K[MAX_LAYERS], N[MAX_LAYERS], relu[MAX_LAYERS];
     int n_layers, n_stages, kchunks_max, mode;
+    int nblk, stage_bytes;                     // output channels per weight stage, bytes per stage (hi + lo)
+    int coff[MAX_LAYERS];                      // offset of each layer's shift vector in the smem constant table
+    int a_region;                              // bytes of the operand region (>= the 128 KB fp32 staging of the last layer)
     long rows;                                 // SA: centres, FP: points
     int ntiles;
     // layer-0 "extra" channels (the xyz part), applied as a rank-n update from the fp32 weight rows
@@ -157,17 +159,17 @@ __device__ __forceinline__ void store_units(uint8_t *a1, uint8_t *a2, int r, int
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_constant__ TcArgs a) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *a1 = smem;
     uint8_t *a2 = a1 + (size_t)a.kchunks_max * A_CHUNK;
-    uint8_t *stages = a2 + (size_t)a.kchunks_max * A_CHUNK;
-    uint8_t *misc = stages + (size_t)a.n_stages * STAGE;
+    uint8_t *stages = a1 + (size_t)a.a_region;
+    uint8_t *misc = stages + (size_t)a.n_stages * a.stage_bytes;
     uint64_t *full = reinterpret_cast<uint64_t *>(misc);
     uint64_t *empty = full + MAX_STAGES;
     uint64_t *a_ready = empty + MAX_STAGES;
     uint64_t *d_ready = a_ready + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d_ready + 1);
+    float *ctab = reinterpret_cast<float *>(misc + 256);   // [shift of every layer | 3 x N0 extra weight rows], 16-byte aligned
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -181,6 +183,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    {
+        int off = 0;
+        for (int l = 0; l < a.n_layers; ++l) {
+            for (int i = tid; i < a.N[l]; i += TC_THREADS) ctab[off + i] = __ldg(a.shift[l] + i);
+            off += a.N[l];
+        }
+        for (int i = tid; i < a.n_extra * a.N[0]; i += TC_THREADS) ctab[off + i] = __ldg(a.w_extra + i);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -192,13 +202,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
                 for (int l = 0; l < a.n_layers; ++l) {
-                    const int nkc = a.K[l] / KCH, nbr = min(NBLK, a.N[l]), nnb = a.N[l] / nbr;
+                    const int nkc = a.K[l] / KCH, nbr = min(a.nblk, a.N[l]), nnb = a.N[l] / nbr;
                     for (int nb = 0; nb < nnb; ++nb)
                         for (int kc = 0; kc < nkc; ++kc, ++it) {
                             const int s = it % a.n_stages;
                             const uint32_t ph = (it / a.n_stages) & 1;
                             mbar_wait(empty + s, ph ^ 1);
-                            uint8_t *dst = stages + (size_t)s * STAGE;
+                            uint8_t *dst = stages + (size_t)s * a.stage_bytes;
                             mbar_expect_tx(full + s, 2u * nbr * 128u);
                             tma_load_2d(dst, &a.tm[l][0], kc * KCH, nb * nbr, full + s);
                             tma_load_2d(dst + nbr * 128, &a.tm[l][1], kc * KCH, nb * nbr, full + s);
@@ -213,7 +223,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             uint32_t it = 0, lcount = 0;
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
                 for (int l = 0; l < a.n_layers; ++l, ++lcount) {
-                    const int nkc = a.K[l] / KCH, nbr = min(NBLK, a.N[l]), nnb = a.N[l] / nbr;
+                    const int nkc = a.K[l] / KCH, nbr = min(a.nblk, a.N[l]), nnb = a.N[l] / nbr;
                     const uint32_t idesc = umma_idesc(nbr);
                     mbar_wait(a_ready, lcount & 1);
                     tc_fence_after();
@@ -224,7 +234,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                             mbar_wait(full + s, (it / a.n_stages) & 1);
                             tc_fence_after();
                             const uint32_t sa1 = smem_u32(a1 + (size_t)kc * A_CHUNK), sa2 = smem_u32(a2 + (size_t)kc * A_CHUNK);
-                            const uint32_t sb1 = smem_u32(stages + (size_t)s * STAGE), sb2 = sb1 + nbr * 128;
+                            const uint32_t sb1 = smem_u32(stages + (size_t)s * a.stage_bytes), sb2 = sb1 + nbr * 128;
 #pragma unroll
                             for (int ks = 0; ks < KCH / 16; ++ks) {
                                 const uint64_t da1 = umma_desc(sa1 + ks * 32), da2 = umma_desc(sa2 + ks * 32);
@@ -244,77 +254,108 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     } else {
         // ================= workers: gather, epilogues, output ====================================================
         const int wt = tid - 64;                             // 0..255
+        const int wwarp = warp - 2;                          // 0..7
         const int q = warp & 3;                              // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;                    // column half handled by this warp
+        const int half = wwarp >> 2;                         // column half handled by this warp
         const int row = q * 32 + lane;                       // accumulator row owned in the epilogue
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
         uint32_t lcount = 0;
         const int units0 = a.K[0] / 8;                       // 16-byte units per row of the layer-0 operand
+        const float *wext = ctab + a.coff[a.n_layers - 1] + a.N[a.n_layers - 1];   // extra weight rows follow the shifts
 
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-            // ---- stage the layer-0 operand (hi/lo planes) ---------------------------------------------------------
+            // ---- stage the layer-0 operand (hi/lo planes): one warp per row, lanes across the row's 16-byte units -----
             float xe[3] = {0.f, 0.f, 0.f};
             if (a.mode == TC_SA) {
                 const int G = TM / a.k;
-                for (int u = wt; u < TM * units0; u += NWORK) {
-                    const int r = u / units0, j = u - r * units0;
-                    const int g = r / a.k, s = r - g * a.k;
+                for (int r = wwarp; r < TM; r += 8) {
+                    const int g = r / a.k, sidx = r - g * a.k;
                     const long ci = (long)tile * G + g;
-                    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    if (g < G && ci < a.rows) {
+                    const bool valid = g < G && ci < a.rows;
+                    long pc = 0, pn = 0;
+                    if (valid) {
                         const long cloud = ci / a.m;
-                        const long pc = cloud * a.n + __ldg(a.center_idx + ci);
-                        const long pn = cloud * a.n + __ldg(a.nbr_idx + ci * a.nbr_stride + s);
-                        const float4 *fn = reinterpret_cast<const float4 *>(a.feat + pn * a.c) + 2 * j;
-                        const float4 *fc = reinterpret_cast<const float4 *>(a.feat + pc * a.c) + 2 * j;
-                        const float4 n0 = __ldg(fn), n1 = __ldg(fn + 1), c0 = __ldg(fc), c1 = __ldg(fc + 1);
-                        v[0] = n0.x - c0.x; v[1] = n0.y - c0.y; v[2] = n0.z - c0.z; v[3] = n0.w - c0.w;
-                        v[4] = n1.x - c1.x; v[5] = n1.y - c1.y; v[6] = n1.z - c1.z; v[7] = n1.w - c1.w;
+                        pc = cloud * a.n + __ldg(a.center_idx + ci);
+                        pn = cloud * a.n + __ldg(a.nbr_idx + ci * a.nbr_stride + sidx);
                     }
-                    store_units(a1, a2, r, j, v);
+                    for (int j = lane; j < units0; j += 32) {
+                        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                        if (valid) {
+                            const float4 *fn = reinterpret_cast<const float4 *>(a.feat + pn * a.c) + 2 * j;
+                            const float4 *fc = reinterpret_cast<const float4 *>(a.feat + pc * a.c) + 2 * j;
+                            const float4 n0 = __ldg(fn), n1 = __ldg(fn + 1), c0 = __ldg(fc), c1 = __ldg(fc + 1);
+                            v[0] = n0.x - c0.x; v[1] = n0.y - c0.y; v[2] = n0.z - c0.z; v[3] = n0.w - c0.w;
+                            v[4] = n1.x - c1.x; v[5] = n1.y - c1.y; v[6] = n1.z - c1.z; v[7] = n1.w - c1.w;
+                        }
+                        store_units(a1, a2, r, j, v);
+                    }
                 }
                 {   // xyz_j - xyz_i of the row this thread owns in the epilogue
-                    const int g = row / a.k, s = row - g * a.k;
+                    const int g = row / a.k, sidx = row - g * a.k;
                     const long ci = (long)tile * G + g;
                     if (g < G && ci < a.rows) {
                         const long cloud = ci / a.m;
                         const long pc = cloud * a.n + __ldg(a.center_idx + ci);
-                        const long pn = cloud * a.n + __ldg(a.nbr_idx + ci * a.nbr_stride + s);
+                        const long pn = cloud * a.n + __ldg(a.nbr_idx + ci * a.nbr_stride + sidx);
 #pragma unroll
                         for (int e = 0; e < 3; ++e) xe[e] = __ldg(a.xyz + pn * 3 + e) - __ldg(a.xyz + pc * 3 + e);
                     }
                 }
             } else {
                 const int ku = a.c_known / 8;
-                for (int u = wt; u < TM * units0; u += NWORK) {
-                    const int r = u / units0, j = u - r * units0;
-                    const long p = (long)tile * TM + r;
-                    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    if (p < a.rows) {
-                        if (j < ku) {
-                            const long base = (p / a.n) * a.m;
-                            const int i0 = __ldg(a.idx3 + p * 3), i1 = __ldg(a.idx3 + p * 3 + 1), i2 = __ldg(a.idx3 + p * 3 + 2);
-                            const float w0 = __ldg(a.w3 + p * 3), w1 = __ldg(a.w3 + p * 3 + 1), w2 = __ldg(a.w3 + p * 3 + 2);
-                            const float4 *f0 = reinterpret_cast<const float4 *>(a.known_feat + (base + i0) * a.c_known) + 2 * j;
-                            const float4 *f1 = reinterpret_cast<const float4 *>(a.known_feat + (base + i1) * a.c_known) + 2 * j;
-                            const float4 *f2 = reinterpret_cast<const float4 *>(a.known_feat + (base + i2) * a.c_known) + 2 * j;
-                            const float4 x0 = __ldg(f0), x1 = __ldg(f0 + 1), y0 = __ldg(f1), y1 = __ldg(f1 + 1), z0 = __ldg(f2), z1 = __ldg(f2 + 1);
-                            // interpolation_forward: fma(w2,p2, fma(w0,p0, w1*p1)) (interpolation_cuda_kernel.cu:194)
-                            v[0] = __fmaf_rn(w2, z0.x, __fmaf_rn(w0, x0.x, __fmul_rn(w1, y0.x)));
-                            v[1] = __fmaf_rn(w2, z0.y, __fmaf_rn(w0, x0.y, __fmul_rn(w1, y0.y)));
-                            v[2] = __fmaf_rn(w2, z0.z, __fmaf_rn(w0, x0.z, __fmul_rn(w1, y0.z)));
-                            v[3] = __fmaf_rn(w2, z0.w, __fmaf_rn(w0, x0.w, __fmul_rn(w1, y0.w)));
-                            v[4] = __fmaf_rn(w2, z1.x, __fmaf_rn(w0, x1.x, __fmul_rn(w1, y1.x)));
-                            v[5] = __fmaf_rn(w2, z1.y, __fmaf_rn(w0, x1.y, __fmul_rn(w1, y1.y)));
-                            v[6] = __fmaf_rn(w2, z1.z, __fmaf_rn(w0, x1.z, __fmul_rn(w1, y1.z)));
-                            v[7] = __fmaf_rn(w2, z1.w, __fmaf_rn(w0, x1.w, __fmul_rn(w1, y1.w)));
-                        } else {
-                            const float4 *sk = reinterpret_cast<const float4 *>(a.skip_feat + p * a.c_skip) + 2 * (j - ku);
-                            const float4 s0 = __ldg(sk), s1 = __ldg(sk + 1);
-                            v[0] = s0.x; v[1] = s0.y; v[2] = s0.z; v[3] = s0.w; v[4] = s1.x; v[5] = s1.y; v[6] = s1.z; v[7] = s1.w;
+                // two rows per iteration so that twelve 16-byte loads are in flight per lane
+                for (int r0 = wwarp * 2; r0 < TM; r0 += 16) {
+                    long pp[2]; bool ok[2]; long base[2]; int i0[2], i1[2], i2[2]; float w0[2], w1[2], w2[2];
+#pragma unroll
+                    for (int t2 = 0; t2 < 2; ++t2) {
+                        pp[t2] = (long)tile * TM + r0 + t2;
+                        ok[t2] = pp[t2] < a.rows;
+                        base[t2] = 0; i0[t2] = i1[t2] = i2[t2] = 0; w0[t2] = w1[t2] = w2[t2] = 0.f;
+                        if (ok[t2]) {
+                            base[t2] = (pp[t2] / a.n) * a.m;
+                            i0[t2] = __ldg(a.idx3 + pp[t2] * 3); i1[t2] = __ldg(a.idx3 + pp[t2] * 3 + 1); i2[t2] = __ldg(a.idx3 + pp[t2] * 3 + 2);
+                            w0[t2] = __ldg(a.w3 + pp[t2] * 3); w1[t2] = __ldg(a.w3 + pp[t2] * 3 + 1); w2[t2] = __ldg(a.w3 + pp[t2] * 3 + 2);
                         }
                     }
-                    store_units(a1, a2, r, j, v);
+                    for (int j = lane; j < units0; j += 32) {
+                        float v[2][8];
+                        if (j < ku) {
+                            float4 x0[2], x1[2], y0[2], y1[2], z0[2], z1[2];
+#pragma unroll
+                            for (int t2 = 0; t2 < 2; ++t2) {
+                                const float4 *f0 = reinterpret_cast<const float4 *>(a.known_feat + (base[t2] + i0[t2]) * a.c_known) + 2 * j;
+                                const float4 *f1 = reinterpret_cast<const float4 *>(a.known_feat + (base[t2] + i1[t2]) * a.c_known) + 2 * j;
+                                const float4 *f2 = reinterpret_cast<const float4 *>(a.known_feat + (base[t2] + i2[t2]) * a.c_known) + 2 * j;
+                                x0[t2] = __ldg(f0); x1[t2] = __ldg(f0 + 1); y0[t2] = __ldg(f1); y1[t2] = __ldg(f1 + 1);
+                                z0[t2] = __ldg(f2); z1[t2] = __ldg(f2 + 1);
+                            }
+#pragma unroll
+                            for (int t2 = 0; t2 < 2; ++t2) {
+                                // interpolation_forward: fma(w2,p2, fma(w0,p0, w1*p1)) (interpolation_cuda_kernel.cu:194)
+                                v[t2][0] = __fmaf_rn(w2[t2], z0[t2].x, __fmaf_rn(w0[t2], x0[t2].x, __fmul_rn(w1[t2], y0[t2].x)));
+                                v[t2][1] = __fmaf_rn(w2[t2], z0[t2].y, __fmaf_rn(w0[t2], x0[t2].y, __fmul_rn(w1[t2], y0[t2].y)));
+                                v[t2][2] = __fmaf_rn(w2[t2], z0[t2].z, __fmaf_rn(w0[t2], x0[t2].z, __fmul_rn(w1[t2], y0[t2].z)));
+                                v[t2][3] = __fmaf_rn(w2[t2], z0[t2].w, __fmaf_rn(w0[t2], x0[t2].w, __fmul_rn(w1[t2], y0[t2].w)));
+                                v[t2][4] = __fmaf_rn(w2[t2], z1[t2].x, __fmaf_rn(w0[t2], x1[t2].x, __fmul_rn(w1[t2], y1[t2].x)));
+                                v[t2][5] = __fmaf_rn(w2[t2], z1[t2].y, __fmaf_rn(w0[t2], x1[t2].y, __fmul_rn(w1[t2], y1[t2].y)));
+                                v[t2][6] = __fmaf_rn(w2[t2], z1[t2].z, __fmaf_rn(w0[t2], x1[t2].z, __fmul_rn(w1[t2], y1[t2].z)));
+                                v[t2][7] = __fmaf_rn(w2[t2], z1[t2].w, __fmaf_rn(w0[t2], x1[t2].w, __fmul_rn(w1[t2], y1[t2].w)));
+                            }
+                        } else {
+#pragma unroll
+                            for (int t2 = 0; t2 < 2; ++t2) {
+                                float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+                                if (ok[t2]) {
+                                    const float4 *sk = reinterpret_cast<const float4 *>(a.skip_feat + pp[t2] * a.c_skip) + 2 * (j - ku);
+                                    s0 = __ldg(sk); s1 = __ldg(sk + 1);
+                                }
+                                v[t2][0] = s0.x; v[t2][1] = s0.y; v[t2][2] = s0.z; v[t2][3] = s0.w;
+                                v[t2][4] = s1.x; v[t2][5] = s1.y; v[t2][6] = s1.z; v[t2][7] = s1.w;
+                            }
+                        }
+#pragma unroll
+                        for (int t2 = 0; t2 < 2; ++t2) store_units(a1, a2, r0 + t2, j, v[t2]);
+                    }
                 }
                 if (a.n_extra > 0) {
                     const long p = (long)tile * TM + row;
@@ -329,6 +370,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             for (int l = 0; l < a.n_layers; ++l, ++lcount) {
                 const int N = a.N[l];
                 const bool last = l == a.n_layers - 1;
+                const bool relu = a.relu[l] != 0;
+                const bool extras = l == 0 && a.n_extra > 0;
+                const float *shl = ctab + a.coff[l];
                 mbar_wait(d_ready, lcount & 1);
                 tc_fence_after();
                 const int npass = last ? (N + 255) / 256 : 1;
@@ -340,11 +384,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                         float v[32];
                         tmem_ld32(trow + (uint32_t)col, v);
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            float x = v[i] + __ldg(a.shift[l] + col + i);
-                            if (l == 0)
-                                for (int e = 0; e < a.n_extra; ++e) x = fmaf(xe[e], __ldg(a.w_extra + (size_t)e * N + col + i), x);
-                            v[i] = a.relu[l] ? fmaxf(x, 0.f) : x;
+                        for (int u = 0; u < 8; ++u) {
+                            const float4 sh = *reinterpret_cast<const float4 *>(shl + col + 4 * u);
+                            v[4 * u] += sh.x; v[4 * u + 1] += sh.y; v[4 * u + 2] += sh.z; v[4 * u + 3] += sh.w;
+                        }
+                        if (extras) {
+#pragma unroll
+                            for (int e = 0; e < 3; ++e) {
+                                if (e < a.n_extra) {
+#pragma unroll
+                                    for (int u = 0; u < 8; ++u) {
+                                        const float4 w = *reinterpret_cast<const float4 *>(wext + e * N + col + 4 * u);
+                                        v[4 * u] = fmaf(xe[e], w.x, v[4 * u]); v[4 * u + 1] = fmaf(xe[e], w.y, v[4 * u + 1]);
+                                        v[4 * u + 2] = fmaf(xe[e], w.z, v[4 * u + 2]); v[4 * u + 3] = fmaf(xe[e], w.w, v[4 * u + 3]);
+                                    }
+                                }
+                            }
+                        }
+                        if (relu) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
                         }
                         if (!last) {
 #pragma unroll
@@ -372,16 +431,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                                 const long ci = (long)tile * G + g;
                                 if (ci >= a.rows) continue;
                                 float mx = *reinterpret_cast<const float *>(a1 + stage_offset(g * a.k, c));
-                                for (int s = 1; s < a.k; ++s)
-                                    mx = fmaxf(mx, *reinterpret_cast<const float *>(a1 + stage_offset(g * a.k + s, c)));
+                                for (int sidx = 1; sidx < a.k; ++sidx)
+                                    mx = fmaxf(mx, *reinterpret_cast<const float *>(a1 + stage_offset(g * a.k + sidx, c)));
                                 a.out[ci * N + pass * 256 + c] = mx;
                             }
                         } else {
-                            const int c4 = ncols / 4;
-                            for (int e = wt; e < TM * c4; e += NWORK) {
-                                const int r = e / c4, cq = e - r * c4;
+                            const int c4 = ncols / 4;                  // one warp per row: 1 KB contiguous per store wave
+                            for (int r = wwarp; r < TM; r += 8) {
                                 const long p = (long)tile * TM + r;
-                                if (p < a.rows)
+                                if (p >= a.rows) break;
+                                for (int cq = lane; cq < c4; cq += 32)
                                     *reinterpret_cast<float4 *>(a.out + p * N + pass * 256 + 4 * cq) =
                                         *reinterpret_cast<const float4 *>(a1 + stage_offset(r, 4 * cq));
                             }
@@ -442,60 +501,79 @@ int g_tc_enabled = 1;
 
 PAB_API void pab_tune_tensor_core(int enable) { g_tc_enabled = enable; }
 
+// Shared-memory plan of one launch: operand region, constant table, weight-stage granularity and count.
+struct TcPlan { int kchunks_max, a_region, nblk, stage_bytes, n_stages, coff[MAX_LAYERS]; size_t misc, smem; };
+
+bool tc_plan(const pab_layer_t *layers, int n_layers, TcPlan *p) {
+    int kmax = 0, ctab = 0;
+    for (int l = 0; l < n_layers; ++l) {
+        if (layers[l].tc_k > kmax) kmax = layers[l].tc_k;
+        p->coff[l] = ctab;
+        ctab += layers[l].c_out;
+    }
+    ctab += (layers[0].c_in - layers[0].tc_k) * layers[0].c_out;
+    p->kchunks_max = kmax / KCH;
+    p->a_region = 2 * p->kchunks_max * A_CHUNK;
+    if (p->a_region < TM * 256 * 4) p->a_region = TM * 256 * 4;      // last-layer fp32 staging [128][256]
+    p->misc = 256 + (size_t)ctab * 4 + 64;
+    const long budget = 227L * 1024 - p->a_region - (long)p->misc;
+    if (budget < 2 * 2 * 64 * 128) return false;
+    // 128 output channels per stage when at least 3 such stages fit, else 64
+    p->nblk = (budget / (2 * 128 * 128) >= 3) ? 128 : 64;
+    p->stage_bytes = 2 * p->nblk * 128;
+    p->n_stages = (int)(budget / p->stage_bytes);
+    if (p->n_stages > MAX_STAGES) p->n_stages = MAX_STAGES;
+    p->smem = (size_t)p->a_region + (size_t)p->n_stages * p->stage_bytes + p->misc;
+    return p->n_stages >= 2;
+}
+
 // Can this module run on the tensor-core path?  (every layer split on the host, shapes a multiple of 64, at most
-// 4 "extra" layer-0 channels, operand planes + >= 2 weight stages within 227 KB)
+// 3 "extra" layer-0 channels, operand planes + >= 2 weight stages within 227 KB)
 bool pab_tc_eligible(const pab_layer_t *layers, int n_layers, int k_group) {
     if (!g_tc_enabled || n_layers < 1 || n_layers > MAX_LAYERS) return false;
-    int kmax = 0;
     for (int l = 0; l < n_layers; ++l) {
         const pab_layer_t &L = layers[l];
         if (!L.w_hi || !L.w_lo || L.tc_k <= 0 || L.tc_k % KCH || L.c_out % 64) return false;
         if (l > 0 && (L.tc_k0 != 0 || L.tc_k != L.c_in)) return false;
         if (l < n_layers - 1 && L.c_out > 256) return false;
-        if (L.c_out > 512 || (L.c_out > NBLK && L.c_out % NBLK)) return false;
-        if (L.tc_k > kmax) kmax = L.tc_k;
+        if (L.c_out > 512 || (L.c_out > 64 && L.c_out % 128)) return false;
     }
     const int n_extra = layers[0].c_in - layers[0].tc_k;
     if (n_extra < 0 || n_extra > 3) return false;
     if (n_extra > 0 && !(layers[0].tc_k0 == 0 || layers[0].tc_k0 == n_extra)) return false;
     if (k_group > TM) return false;
-    const size_t need = 2 * (size_t)(kmax / KCH) * A_CHUNK + 2 * (size_t)STAGE + 2048;
-    return need <= 227 * 1024;
+    TcPlan p;
+    return tc_plan(layers, n_layers, &p);
 }
 
 int pab_tc_launch(int mode, long rows, int k_group, const pab_layer_t *layers, int n_layers, TcArgs &a, cudaStream_t st) {
-    int kmax = 0;
+    TcPlan p;
+    if (!tc_plan(layers, n_layers, &p)) return PAB_EINVAL;
+    a.kchunks_max = p.kchunks_max; a.a_region = p.a_region; a.nblk = p.nblk; a.stage_bytes = p.stage_bytes; a.n_stages = p.n_stages;
     for (int l = 0; l < n_layers; ++l) {
         const pab_layer_t &L = layers[l];
-        const int nbr = L.c_out < NBLK ? L.c_out : NBLK;
+        const int nbr = L.c_out < a.nblk ? L.c_out : a.nblk;
         if (make_weight_map(&a.tm[l][0], L.w_hi, L.c_out, L.tc_k, nbr)) return PAB_EINVAL;
         if (make_weight_map(&a.tm[l][1], L.w_lo, L.c_out, L.tc_k, nbr)) return PAB_EINVAL;
-        a.shift[l] = L.shift; a.K[l] = L.tc_k; a.N[l] = L.c_out; a.relu[l] = L.relu;
-        if (L.tc_k > kmax) kmax = L.tc_k;
+        a.shift[l] = L.shift; a.K[l] = L.tc_k; a.N[l] = L.c_out; a.relu[l] = L.relu; a.coff[l] = p.coff[l];
     }
-    a.n_layers = n_layers; a.mode = mode; a.rows = rows; a.kchunks_max = kmax / KCH;
+    a.n_layers = n_layers; a.mode = mode; a.rows = rows;
     a.n_extra = layers[0].c_in - layers[0].tc_k;
     // extra channels sit before (SA: xyz first) or after (FP: skip last) the tensor-core part
     const int extra_row0 = layers[0].tc_k0 == 0 ? layers[0].tc_k : 0;
     a.w_extra = layers[0].wt + (size_t)extra_row0 * layers[0].c_out;
     const long per_tile = mode == TC_SA ? (TM / k_group) : TM;
     a.ntiles = (int)((rows + per_tile - 1) / per_tile);
-    const size_t fixed = 2 * (size_t)a.kchunks_max * A_CHUNK + 2048 + 1024;
-    int ns = (int)((227 * 1024 - fixed) / STAGE);
-    if (ns > MAX_STAGES) ns = MAX_STAGES;
-    if (ns < 2) return PAB_EINVAL;
-    a.n_stages = ns;
-    const size_t smem = fixed + (size_t)ns * STAGE;
     static int n_sm = 0;
     if (!n_sm) {
         int dev = 0;
         PAB_CUDA(cudaGetDevice(&dev));
         PAB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     }
-    PAB_CUDA(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PAB_CUDA(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     const int grid = a.ntiles < n_sm ? a.ntiles : n_sm;
     if (grid == 0) return 0;
-    mlp_tc_kernel<<<grid, TC_THREADS, smem, st>>>(a);
+    mlp_tc_kernel<<<grid, TC_THREADS, p.smem, st>>>(a);
     PAB_LAUNCH_CHECK();
     return 0;
 }

@@ -29,14 +29,27 @@ def _fold_bn(bn):
     return scale, shift
 
 
-class _Layers:
-    """A folded SharedMLP as a ctypes array of pab_layer_t (keeps the device tensors alive)."""
+def _split_bf16(w):
+    """w = hi + lo with hi = bf16(w), lo = bf16(w - hi): the two operand planes of the tensor-core path."""
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.float()).to(torch.bfloat16)
+    return hi.contiguous(), lo.contiguous()
 
-    def __init__(self, shared_mlp, device):
+
+class _Layers:
+    """A folded SharedMLP as a ctypes array of pab_layer_t (keeps the device tensors alive).
+
+    `extra_first` / `extra_last`: number of layer-0 input channels (the xyz part, <= 3) that sit before / after the
+    block of channels eligible for the tensor-core path.  When every layer's remaining K and its N are multiples of
+    64 the bf16 hi/lo weight planes are attached (pab_layer_t.w_hi / w_lo) and the C side picks the tcgen05 kernel.
+    """
+
+    def __init__(self, shared_mlp, device, extra_first=0, extra_last=0):
         self.tensors = []
         blocks = list(shared_mlp.children())
         self.arr = (L.PabLayer * len(blocks))()
         self.spec = []
+        folded = []
         for i, blk in enumerate(blocks):
             w = blk.conv.weight.detach().float().reshape(blk.conv.weight.shape[0], -1)   # (c_out, c_in)
             c_out, c_in = w.shape
@@ -45,12 +58,27 @@ class _Layers:
             else:
                 scale = torch.ones(c_out, device=w.device)
                 shift = blk.conv.bias.detach().float() if blk.conv.bias is not None else torch.zeros(c_out, device=w.device)
+            folded.append(((w * scale[:, None]).to(device), shift.to(device).contiguous(), c_in, c_out, hasattr(blk, "activation")))
+        tc_ok = len(blocks) <= 3
+        for i, (wf, sh, c_in, c_out, act) in enumerate(folded):
+            k0 = extra_first if i == 0 else 0
+            kk = c_in - (extra_first + extra_last if i == 0 else 0)
+            tc_ok = tc_ok and kk > 0 and kk % 64 == 0 and c_out % 64 == 0
+        self.tensor_core = tc_ok
+        for i, (wf, sh, c_in, c_out, act) in enumerate(folded):
             c_in_pad = (c_in + 3) // 4 * 4
             wt = torch.zeros(c_in_pad, c_out, dtype=torch.float32, device=device)
-            wt[:c_in] = (w * scale[:, None]).t().to(device)
-            sh = shift.to(device).contiguous()
+            wt[:c_in] = wf.t()
             self.tensors += [wt, sh]
-            self.arr[i] = L.PabLayer(wt.data_ptr(), sh.data_ptr(), c_in, c_in_pad, c_out, 1 if hasattr(blk, "activation") else 0)
+            hi_p = lo_p = 0
+            k0 = kk = 0
+            if tc_ok:
+                k0 = extra_first if i == 0 else 0
+                kk = c_in - (extra_first + extra_last if i == 0 else 0)
+                hi, lo = _split_bf16(wf[:, k0:k0 + kk].contiguous())
+                self.tensors += [hi, lo]
+                hi_p, lo_p = hi.data_ptr(), lo.data_ptr()
+            self.arr[i] = L.PabLayer(wt.data_ptr(), sh.data_ptr(), c_in, c_in_pad, c_out, 1 if act else 0, hi_p, lo_p, k0, kk)
             self.spec.append((c_in, c_out))
         self.n = len(blocks)
         self.c_out = self.spec[-1][1]
@@ -78,9 +106,12 @@ class FusedPatchAugNet:
         self.sa = []
         for mod in bb.SA_modules:
             g = mod.groupers[0]
-            self.sa.append(dict(npoint=mod.npoint, k=g.nsample, dilation=g.knn_dilation, layers=_Layers(mod.mlps[0], dev)))
-        self.fp = [_Layers(mod.mlp, dev) for mod in bb.FP_modules]
+            self.sa.append(dict(npoint=mod.npoint, k=g.nsample, dilation=g.knn_dilation,
+                                layers=_Layers(mod.mlps[0], dev, extra_first=3)))
         self.use_origin = bb.use_origin_pc_in_fp
+        # FP_modules[0] concatenates the 3 raw xyz channels after the interpolated features (patch_aug_net.py:137, 359)
+        self.fp = [_Layers(mod.mlp, dev, extra_last=3 if (i == 0 and self.use_origin) else 0)
+                   for i, mod in enumerate(bb.FP_modules)]
         agg = net.aggregation
         self.vlad = []
         for v in agg.vlads:

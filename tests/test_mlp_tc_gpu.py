@@ -1,0 +1,92 @@
+"""GPU tier: the tcgen05 tensor-core SharedMLP kernels (mlp_tc.cu) against the fp32 SIMT kernels (mlp.cu, themselves
+checked against the oracle) and against a float64 torch evaluation, through the same C-ABI entry points.
+Tolerance: the bf16 hi/lo split carries ~16 mantissa bits per product -> relative error ~1e-5 per layer."""
+import numpy as np
+import pytest
+import torch
+
+import util
+from patchaugnet_b200 import _lib as L
+from patchaugnet_b200 import pt_util
+from patchaugnet_b200.engine import _Layers
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _mlp(spec, seed):
+    torch.manual_seed(seed)
+    m = pt_util.SharedMLP(list(spec), bn=True)
+    sd = util.fill_state_dict(m.state_dict(), seed)
+    m.load_state_dict(sd)
+    return m.to(DEV).eval()
+
+
+def _run_fp(layers, B, n, m, known, skip, idx, w, tc):
+    out = torch.empty(B, n, layers.c_out, device=DEV)
+    L.lib().pab_tune_tensor_core(1 if tc else 0)
+    try:
+        L.check(L.lib().pab_fp_module_forward(B, n, m, known.shape[2], 0 if skip is None else skip.shape[2], L.ptr(known), L.ptr(skip),
+                                              L.ptr(idx), L.ptr(w), layers.arr, layers.n, L.ptr(out), L.stream_ptr()), "fp")
+        torch.cuda.synchronize()
+    finally:
+        L.lib().pab_tune_tensor_core(1)
+    return out
+
+
+@pytest.mark.parametrize("spec,c_known,c_skip,n,m", [([259, 256, 256, 256], 256, 3, 1000, 300), ([320, 256, 256], 256, 64, 700, 128),
+                                                       ([128, 64, 128], 128, 0, 130, 40)])
+def test_fp_module_tensor_core_matches_simt_and_fp64(spec, c_known, c_skip, n, m):
+    B = 3
+    g = torch.Generator(device="cpu").manual_seed(n)
+    mlp = _mlp(spec, n)
+    layers = _Layers(mlp, DEV, extra_last=c_skip if c_skip <= 3 else 0)
+    assert layers.tensor_core
+    known = torch.randn(B, m, c_known, generator=g).to(DEV)
+    skip = torch.randn(B, n, c_skip, generator=g).to(DEV) if c_skip else None
+    idx = torch.randint(0, m, (B, n, 3), generator=g).int().to(DEV)
+    w = torch.rand(B, n, 3, generator=g)
+    w = (w / w.sum(2, keepdim=True)).to(DEV)
+    simt = _run_fp(layers, B, n, m, known, skip, idx, w, tc=False)
+    before = L.lib().pab_num_launches()
+    tcore = _run_fp(layers, B, n, m, known, skip, idx, w, tc=True)
+    assert L.lib().pab_num_launches() == before + 1
+    # float64 reference of the same module: interpolate, concat, conv/bn/relu
+    gk = torch.gather(known.double(), 1, idx.long().view(B, n * 3, 1).expand(-1, -1, c_known)).view(B, n, 3, c_known)
+    x = (gk * w.double().unsqueeze(-1)).sum(2)
+    if skip is not None:
+        x = torch.cat([x, skip.double()], 2)
+    ref = mlp.double()(x.transpose(1, 2).unsqueeze(-1)).squeeze(-1).transpose(1, 2)
+    scale = ref.abs().max().item()
+    assert (simt.double() - ref).abs().max().item() < 2e-5 * scale
+    assert (tcore.double() - ref).abs().max().item() < 5e-5 * scale
+    assert torch.isfinite(tcore).all()
+
+
+@pytest.mark.parametrize("spec,c,k,n,m", [([259, 256, 256, 512], 256, 20, 128, 16), ([67, 64, 64, 256], 64, 20, 1024, 128),
+                                           ([131, 128, 128, 256], 128, 7, 300, 50)])
+def test_sa_module_tensor_core_matches_simt(spec, c, k, n, m):
+    B = 4
+    g = torch.Generator(device="cpu").manual_seed(n + k)
+    mlp = _mlp(spec, n + 1)
+    layers = _Layers(mlp, DEV, extra_first=3)
+    assert layers.tensor_core
+    xyz = (torch.rand(B, n, 3, generator=g) * 2 - 1).to(DEV)
+    feat = torch.randn(B, n, c, generator=g).to(DEV)
+    cidx = torch.stack([torch.randperm(n, generator=g)[:m] for _ in range(B)]).int().to(DEV)
+    nbr = torch.randint(0, n, (B, m, k), generator=g).int().to(DEV)
+    outs = []
+    for tc in (False, True):
+        out = torch.empty(B, m, layers.c_out, device=DEV)
+        L.lib().pab_tune_tensor_core(1 if tc else 0)
+        try:
+            L.check(L.lib().pab_sa_module_forward(B, n, m, k, k, c, L.ptr(xyz), L.ptr(feat), L.ptr(cidx), L.ptr(nbr), layers.arr,
+                                                  layers.n, L.ptr(out), L.ptr(None), L.stream_ptr()), "sa")
+            torch.cuda.synchronize()
+        finally:
+            L.lib().pab_tune_tensor_core(1)
+        outs.append(out)
+    simt, tcore = outs
+    scale = simt.abs().max().item()
+    assert torch.isfinite(tcore).all()
+    assert (simt - tcore).abs().max().item() < 5e-5 * scale
