@@ -144,10 +144,14 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--graph", type=int, default=1, help="replay the step from a CUDA graph (1) or launch eagerly (0)")
+    ap.add_argument("--mode", default="stream", choices=["stream", "graph", "eager"],
+                    help="stream: 2-stream pipelined throughput mode (default); graph: one CUDA graph per step; eager")
+    ap.add_argument("--graph", type=int, default=None, help="deprecated alias: 1 -> --mode graph, 0 -> --mode eager")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.graph is not None:
+        args.mode = "graph" if args.graph else "eager"
 
     import torch.distributed as dist
     import util
@@ -175,7 +179,6 @@ def main():
     base = base - base.mean(1, keepdim=True)
     base = base / base.norm(dim=2).max(dim=1)[0][:, None, None]
     pool = base.to(dev).view(pool_batches, B, NPTS, 3)
-    host_pool = base.view(pool_batches, B, NPTS, 3)[:8].contiguous().pin_memory()
 
     def sync_all():
         torch.cuda.synchronize()
@@ -195,12 +198,15 @@ def main():
     dominant = max(stage_ms, key=stage_ms.get)
     work = eng.stage_work(B, NPTS)
 
-    use_graph = bool(args.graph)
-    if use_graph:
+    mode = args.mode
+    if mode == "graph":
         eng.capture_graph(B, NPTS)
         with torch.no_grad():
             for i in range(2):
-                eng(pool[i], clone=False)
+                eng(pool[i], clone=False, return_feat=False)
+    elif mode == "stream":
+        with torch.no_grad():
+            eng.forward_stream([pool[i] for i in range(4)])          # creates the side streams / second workspace
     gathered = torch.empty(world * K * B, 256, device=dev) if world > 1 else None
     local_desc = torch.empty(K * B, 256, device=dev)
 
@@ -213,16 +219,19 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     with torch.no_grad():
-        for i in range(K):
-            desc = eng(pool[(W + i) % pool_batches], clone=False, return_feat=False)
-            local_desc[i * B:(i + 1) * B].copy_(desc)
+        if mode == "stream":     # throughput mode: batch i+1's geometry overlaps batch i's dense kernels (2 streams)
+            eng.forward_stream([pool[(W + i) % pool_batches] for i in range(K)], out=local_desc)
+        else:
+            for i in range(K):
+                desc = eng(pool[(W + i) % pool_batches], clone=False, return_feat=False)
+                local_desc[i * B:(i + 1) * B].copy_(desc)
         if world > 1:   # the one collective of the path: all-gather of the 256-D descriptors before retrieval
             dist.all_gather_into_tensor(gathered, local_desc)
     e1.record()
     sync_all()
     elapsed_ms = e0.elapsed_time(e1)
     launches = lib.pab_num_launches()
-    if use_graph:
+    if mode == "graph":
         launches = K * eng.launches_per_forward()        # graph replays do not pass through the C ABI counter
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
@@ -255,28 +264,27 @@ def main():
                     share_of_step=dom_ms / sum(stage_ms.values()), peak_source=f"{pk['src']} copy bandwidth",
                     note="latency/issue-bound scan: " + str(wk.get("units", "")) + " " + wk.get("unit", ""))
 
-    # ---- end to end through the public API: pinned host input -> net(x) -> descriptors on the host --------------
-    xdev = torch.empty(B, 1, NPTS, 3, device=dev)
-    out_host = torch.empty(B, 256).pin_memory()
-    e2e_steps = K
+    # ---- end to end through the public API: pinned host clouds -> extract_descriptors(net, ...) -> host descriptors ----
+    from patchaugnet_b200 import retrieval
+    # weak scaling: every rank extracts K*B clouds of a common (world*K*B)-cloud database, then one all-gather
+    g2 = torch.Generator(device="cpu").manual_seed(999)
+    host_clouds = (torch.rand(world * K * B, NPTS, 3, generator=g2) * 2 - 1).mul_(0.57).contiguous().pin_memory()
+    out_host = torch.empty(world * K * B, 256).pin_memory()
     with torch.no_grad():
-        for i in range(3):
-            xdev.copy_(host_pool[i % 8].unsqueeze(1), non_blocking=True)
-            net(xdev, return_feat=False)
+        retrieval.extract_descriptors(net, host_clouds[: world * 4 * B], batch_size=B, device=dev)     # warm-up
     sync_all()
     t0 = time.perf_counter()
     with torch.no_grad():
-        for i in range(e2e_steps):
-            xdev.copy_(host_pool[i % 8].unsqueeze(1), non_blocking=True)       # H2D of this step's clouds
-            desc = net(xdev, return_feat=False)                                # public nn.Module call
-            out_host.copy_(desc, non_blocking=False)                           # D2H read of the result
+        d = retrieval.extract_descriptors(net, host_clouds, batch_size=B, device=dev)   # H2D + K steps per rank + all-gather
+        out_host.copy_(d)                                                               # D2H of the result
     sync_all()
     e2e_s = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = t.item()
-    e2e = dict(value=world * B * e2e_steps / e2e_s, unit=UNIT, h2d_bytes_per_step=B * NPTS * 3 * 4, d2h_bytes_per_step=B * 256 * 4)
+    e2e = dict(value=world * K * B / e2e_s, unit=UNIT, h2d_bytes_per_step=B * NPTS * 3 * 4, d2h_bytes_per_step=world * B * 256 * 4,
+               api="patchaugnet_b200.retrieval.extract_descriptors(net, pinned_host_clouds) + .cpu()")
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -292,7 +300,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"PatchAugNet descriptor extraction, batch {B} x {NPTS}-pt synthetic clouds per GPU, fp32, eval "
                                    "(BASELINE.json configs[1])", "global_batch": world * B, "l2": "inputs_larger_than_l2 (164 MB rotating pool)",
-                       "launch": "cuda_graph" if use_graph else "eager", "parallelism": f"dp{world}, shard-by-submap, one all_gather of descriptors"},
+                       "launch": mode, "parallelism": f"dp{world}, shard-by-submap, one all_gather of descriptors"},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "stage_ms": {k: round(v, 4) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1])}}))
     if world > 1:

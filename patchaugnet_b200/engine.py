@@ -96,6 +96,7 @@ class FusedPatchAugNet:
         self._graphs = {}
         self._events = None
         self._event_filter = None
+        self._streams = None
         self.refold()
 
     # ---- weights -------------------------------------------------------------------------------------------------
@@ -132,8 +133,8 @@ class FusedPatchAugNet:
         self._graphs.clear()
 
     # ---- workspace -----------------------------------------------------------------------------------------------
-    def _workspace(self, B, N):
-        key = (B, N)
+    def _workspace(self, B, N, slot=0):
+        key = (B, N, slot)
         ws = self._ws.get(key)
         if ws is not None:
             return ws
@@ -164,8 +165,7 @@ class FusedPatchAugNet:
         return ws
 
     # ---- forward -------------------------------------------------------------------------------------------------
-    def _launch(self, xyz0, ws):
-        lib, st, p = L.lib(), L.stream_ptr(), L.ptr
+    def _runner(self):
         ev = self._events
 
         def run(stage, rc_fn):
@@ -178,9 +178,14 @@ class FusedPatchAugNet:
                 ev.setdefault(stage, []).append((e0, e1))
             else:
                 L.check(rc_fn(), stage)
+        return run
 
-        B, N, _ = xyz0.shape
-        xyz, feat, c = xyz0, xyz0, 3
+    def _launch_geo(self, xyz0, ws, first_knn_event=None):
+        """Geometry of every level — FPS, centre gather, kNN, 3-NN weights.  Depends on xyz only, never on features,
+        so it can run ahead of (and concurrently with) the dense part on another stream."""
+        lib, st, p, run = L.lib(), L.stream_ptr(), L.ptr, self._runner()
+        B = xyz0.shape[0]
+        xyz = xyz0
         for i, (sa, lv) in enumerate(zip(self.sa, ws["levels"])):
             n, m, k = lv["n"], lv["m"], sa["k"]
             temp = None                      # register-resident FPS initialises its own 1e10 distances
@@ -190,17 +195,34 @@ class FusedPatchAugNet:
             run(f"fps{i}", lambda: lib.pab_furthestsampling(B, n, m, p(xyz), p(temp), p(lv["cidx"]), st))
             run(f"gather{i}", lambda: lib.pab_gather_rows(B, n, m, 3, p(xyz), p(lv["cidx"]), p(lv["new_xyz"]), st))
             run(f"knn{i}", lambda: lib.pab_knnquery(B, n, m, k, p(xyz), p(lv["new_xyz"]), p(lv["nbr"]), p(None), st))
-            run(f"sa{i}", lambda: lib.pab_sa_module_forward(B, n, m, k, k, c, p(xyz), p(feat), p(lv["cidx"]), p(lv["nbr"]),
-                                                            sa["layers"].arr, sa["layers"].n, p(lv["feat"]), p(None), st))
-            xyz, feat, c = lv["new_xyz"], lv["feat"], sa["layers"].c_out
+            if i == 0 and first_knn_event is not None:
+                first_knn_event.record()      # the first SA module can start; deeper geometry overlaps with it
+            xyz = lv["new_xyz"]
         xyzs = [xyz0] + [lv["new_xyz"] for lv in ws["levels"]]
-        feats = [xyz0] + [lv["feat"] for lv in ws["levels"]]      # skip features per level (level 0 = raw xyz)
-        known_feat = feats[-1]
-        for li in range(len(self.fp) - 1, -1, -1):                # FP_modules[-1] first (patch_aug_net.py:183-187)
+        for li in range(len(self.fp) - 1, -1, -1):
             f = ws["fp"][li]
             unknown, known = xyzs[li], xyzs[li + 1]
             n, m = unknown.shape[1], known.shape[1]
             run(f"three_nn{li}", lambda: lib.pab_three_nn_weights(B, n, m, p(unknown), p(known), p(f["idx"]), p(f["w"]), st))
+
+    def _launch_dense(self, xyz0, ws, after_first_sa=None):
+        """Feature path — fused SA modules, fused FP modules, NetVLAD levels, AFA head."""
+        lib, st, p, run = L.lib(), L.stream_ptr(), L.ptr, self._runner()
+        B = xyz0.shape[0]
+        xyz, feat, c = xyz0, xyz0, 3
+        for i, (sa, lv) in enumerate(zip(self.sa, ws["levels"])):
+            n, m, k = lv["n"], lv["m"], sa["k"]
+            run(f"sa{i}", lambda: lib.pab_sa_module_forward(B, n, m, k, k, c, p(xyz), p(feat), p(lv["cidx"]), p(lv["nbr"]),
+                                                            sa["layers"].arr, sa["layers"].n, p(lv["feat"]), p(None), st))
+            if i == 0 and after_first_sa is not None:
+                after_first_sa()
+            xyz, feat, c = lv["new_xyz"], lv["feat"], sa["layers"].c_out
+        feats = [xyz0] + [lv["feat"] for lv in ws["levels"]]      # skip features per level (level 0 = raw xyz)
+        ns = [xyz0.shape[1]] + [lv["m"] for lv in ws["levels"]]
+        known_feat = feats[-1]
+        for li in range(len(self.fp) - 1, -1, -1):                # FP_modules[-1] first (patch_aug_net.py:183-187)
+            f = ws["fp"][li]
+            n, m = ns[li], ns[li + 1]
             skip = feats[li]
             c_skip = skip.shape[2]
             if li == 0 and not self.use_origin:
@@ -220,6 +242,62 @@ class FusedPatchAugNet:
         run("afa", lambda: lib.pab_afa_forward(B, self.vlad[0]["C"], self.sumK, self.c_out, p(v), p(self.w_att_t), p(self.fc_wt),
                                                p(self.fc_scale), p(self.fc_shift), self.l2_norm, p(ws["desc"]), p(ws["scratch"]), st))
         return fp_out
+
+    def _launch(self, xyz0, ws):
+        """One forward on the current stream (also the body captured into a CUDA graph)."""
+        self._launch_geo(xyz0, ws)
+        return self._launch_dense(xyz0, ws)
+
+    @torch.no_grad()
+    def forward_stream(self, batches, out=None):
+        """Throughput mode: descriptors of a sequence of equally shaped (B,N,3) / (B,1,N,3) CUDA batches.
+
+        Submaps are independent, and the geometry of a batch (FPS is a serial m-step chain that occupies only B SMs)
+        depends on nothing the dense path produces.  So batch i+1's geometry runs on a second stream while batch i's
+        SharedMLP / NetVLAD kernels fill the rest of the machine; two workspaces ping-pong, events order the reuse.
+        Returns (len(batches)*B, c_out) descriptors on the device.
+        """
+        batches = list(batches)
+        if not batches:
+            return torch.empty(0, self.c_out, device=self.device)
+        x0 = batches[0].squeeze(1) if batches[0].dim() == 4 else batches[0]
+        B, N, _ = x0.shape
+        if out is None:
+            out = torch.empty(len(batches) * B, self.c_out, dtype=torch.float32, device=self.device)
+        cur = torch.cuda.current_stream()
+        if self._streams is None:
+            self._streams = (torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device))
+        s_geo, s_dense = self._streams
+        s_geo.wait_stream(cur)
+        s_dense.wait_stream(cur)
+        slots = [self._workspace(B, N, slot) for slot in (0, 1)]
+        geo_done = [None, None]
+        dense_done = [None, None]
+        for i, x in enumerate(batches):
+            L.require_cuda(x)
+            xyz0 = (x.squeeze(1) if x.dim() == 4 else x).contiguous().float()
+            for sa in self.sa:                # keep the CPU RNG in lock-step with the reference (see forward)
+                if sa["dilation"] > 1:
+                    torch.randperm(sa["k"])
+            slot = i & 1
+            ws = slots[slot]
+            with torch.cuda.stream(s_geo):
+                if dense_done[slot] is not None:
+                    s_geo.wait_event(dense_done[slot])          # workspace free again
+                self._launch_geo(xyz0, ws)
+                geo_done[slot] = torch.cuda.Event()
+                geo_done[slot].record()
+            with torch.cuda.stream(s_dense):
+                s_dense.wait_event(geo_done[slot])
+                self._launch_dense(xyz0, ws)
+                out[i * B:(i + 1) * B].copy_(ws["desc"], non_blocking=True)
+                dense_done[slot] = torch.cuda.Event()
+                dense_done[slot].record()
+            xyz0.record_stream(s_geo)
+            xyz0.record_stream(s_dense)
+        cur.wait_stream(s_dense)
+        cur.wait_stream(s_geo)
+        return out
 
     # ---- per-stage timing and algorithmic work (bench.py roofline) ---------------------------------------------
     def enable_stage_timing(self, stages=None):

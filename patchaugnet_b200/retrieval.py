@@ -32,21 +32,42 @@ def _dist_info(group=None):
     return 0, 1
 
 
-def extract_descriptors(extract_fn, clouds, batch_size=32, device=None, dim=256, group=None, out_device=None):
-    """Run ``extract_fn(x (b,1,N,3) on device) -> (b,dim)`` over this rank's shard of ``clouds`` (M,N,3) and all-gather.
+def extract_descriptors(extract_fn, clouds, batch_size=32, device=None, dim=256, group=None, out_device=None,
+                        super_chunk=64):
+    """Descriptors of this rank's shard of ``clouds`` (M,N,3), all-gathered so every rank returns the full (M, dim).
 
-    ``clouds`` may live on the host (pinned memory recommended: copies are issued non-blocking) or on the device.
-    Returns the full (M, dim) descriptor matrix on every rank.
+    ``extract_fn`` is either a ``patchaugnet_b200.patch_aug_net.Network`` in eval mode on CUDA — then the shard runs
+    through the fused engine in throughput mode (``FusedPatchAugNet.forward_stream``: geometry of batch i+1 overlapped
+    with the dense kernels of batch i) — or any callable ``x (b,1,N,3) on device -> (b,dim)``.
+    ``clouds`` may live on the host (pinned memory recommended: the copies are issued non-blocking, ``super_chunk``
+    batches at a time) or on the device.
     """
     rank, world = _dist_info(group)
     M = clouds.shape[0]
     lo, hi = shard_range(M, rank, world)
     device = device if device is not None else (clouds.device if clouds.is_cuda else torch.device("cpu"))
     local = torch.empty(hi - lo, dim, dtype=torch.float32, device=device)
-    for s in range(lo, hi, batch_size):
-        e = min(hi, s + batch_size)
-        x = clouds[s:e].to(device, non_blocking=True).unsqueeze(1)
-        local[s - lo:e - lo] = extract_fn(x)
+    engine = None
+    if hasattr(extract_fn, "engine") and hasattr(extract_fn, "fusable") and torch.device(device).type == "cuda" \
+            and not extract_fn.training and extract_fn.fusable():
+        engine = extract_fn.engine()
+    if engine is not None:
+        step = batch_size * super_chunk
+        for s in range(lo, hi, step):
+            e = min(hi, s + step)
+            dev_chunk = clouds[s:e].to(device, non_blocking=True)
+            full = (e - s) // batch_size * batch_size
+            if full:
+                engine.forward_stream([dev_chunk[i:i + batch_size] for i in range(0, full, batch_size)],
+                                      out=local[s - lo:s - lo + full])
+            if full < e - s:                                   # ragged tail batch
+                local[s - lo + full:e - lo] = engine(dev_chunk[full:], return_feat=False, clone=False)
+    else:
+        for s in range(lo, hi, batch_size):
+            e = min(hi, s + batch_size)
+            x = clouds[s:e].to(device, non_blocking=True).unsqueeze(1)
+            out = extract_fn(x)
+            local[s - lo:e - lo] = out[0] if isinstance(out, (tuple, list)) else out
     if world == 1:
         return local if out_device is None else local.to(out_device)
     # equal-size shards are required by all_gather_into_tensor: pad to the largest shard, trim after

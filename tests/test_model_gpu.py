@@ -136,3 +136,19 @@ def test_state_dict_roundtrip_keeps_reference_layout(net):
         b, _, _ = other(x)
         c, _, _ = net(x)
     assert not torch.equal(a, b) and torch.equal(b, c)      # engine refolds after load_state_dict
+
+
+def test_pipelined_forward_stream_matches_per_batch_forward(net):
+    """Throughput mode (two streams, ping-pong workspaces) must give exactly the per-batch results, in order."""
+    batches = [util.synthetic_batch(4, 4096, start=400 + 4 * i).to(DEV) for i in range(5)]
+    with torch.no_grad():
+        want = torch.cat([net(b, return_feat=False) for b in batches])
+        got = net.engine().forward_stream(batches)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want)
+        # through the retrieval API with host clouds and a ragged tail batch
+        from patchaugnet_b200 import retrieval
+        host = torch.cat([b.squeeze(1) for b in batches]).cpu()[:18].pin_memory()
+        d = retrieval.extract_descriptors(net, host, batch_size=4, device=torch.device(DEV))
+        torch.cuda.synchronize()
+    assert torch.equal(d, want[:18])
