@@ -151,3 +151,61 @@ def patchaugnet_forward(sd, cfg, x, perms=None, dtype=torch.float32):
     desc = afa(v, sd, "aggregation.afa")
     return dict(desc=desc, fp_features=fp_features, center_idx_origin=c_origin, sample_idx_origin=s_origin,
                 sa_features=sa_features, xyz=l_xyz, vlad=v)
+
+
+# ---- PPT-Net -------------------------------------------------------------------------------------------------------
+# place_recognition/pptnet_origin/models/pptnet.py:46-62, 90-134, 145-183, 246-282, 313-330
+# place_recognition/pptnet_origin/models/loupe.py:39-71, 94-105, 124-136
+
+def sa_layer(x, sd, prefix, gp):
+    """SA_Layer.forward (pptnet.py:261-282), eval mode.  x (B,C,N).  q and k share one weight (pptnet.py:254)."""
+    B, C, N = x.shape
+    wk = sd[prefix + ".k_conv.weight"].to(x.dtype)
+    q = F.conv1d(x, wk, groups=gp).reshape(B, gp, C // gp, N).permute(0, 1, 3, 2)
+    k = F.conv1d(x, wk, groups=gp).reshape(B, gp, C // gp, N)
+    v = F.conv1d(x, sd[prefix + ".v_conv.weight"].to(x.dtype), sd[prefix + ".v_conv.bias"].to(x.dtype))
+    energy = torch.matmul(q, k).sum(dim=1)
+    attn = torch.softmax(energy, dim=-1)
+    attn = attn / (1e-9 + attn.sum(dim=1, keepdim=True))
+    x_r = torch.matmul(v, attn)
+    t = F.conv1d(x - x_r, sd[prefix + ".trans_conv.weight"].to(x.dtype), sd[prefix + ".trans_conv.bias"].to(x.dtype))
+    return x + F.relu(_bn(t, sd, prefix + ".after_norm", 1))
+
+
+def gating_context(x, sd, prefix):
+    """GatingContext.forward, pptnet_origin/models/loupe.py:124-136 (add_batch_norm=True)."""
+    gates = torch.matmul(x, sd[prefix + ".gating_weights"].to(x.dtype))
+    gates = _bn(gates, sd, prefix + ".bn1", 1)
+    return x * torch.sigmoid(gates)
+
+
+def pptnet_forward(sd, cfg, x, dtype=torch.float32, use_normalize=True):
+    """pptnet.Network.forward(x), eval mode.  Returns dict(desc, fp_features [4], center_idx_origin [4])."""
+    xyz0 = np.ascontiguousarray(np.asarray(x, dtype=np.float32).reshape(np.asarray(x).shape[0], -1, 3))
+    sd = {k: (v.detach().cpu() if torch.is_tensor(v) else torch.as_tensor(v)) for k, v in sd.items()}
+    sap, knn, gp = cfg["SAMPLING"], cfg["KNN"], cfg["GROUP"]
+    l_xyz = [xyz0]
+    l_feat = [_t(xyz0).transpose(1, 2).contiguous().to(dtype)]
+    cidx = []
+    for i in range(4):
+        nx, ci, si, nf = sa_module(l_xyz[i], l_feat[i], sd, f"backbone.SA_modules.{i}", sap[i], knn[i], 1, None, dtype)
+        nf = sa_layer(nf, sd, f"backbone.SA_modules.{i}.sas.0", gp)
+        l_xyz.append(nx); l_feat.append(nf); cidx.append(ci)
+    c_origin = [cidx[0]]
+    for i in range(1, 4):
+        c_origin.append(np.take_along_axis(c_origin[i - 1], cidx[i].astype(np.int64), -1))
+    for i in range(-1, -5, -1):
+        l_feat[i - 1] = fp_module(l_xyz[i - 1], l_xyz[i], l_feat[i - 1], l_feat[i], sd, f"backbone.FP_modules.{4 + i}", dtype)
+    fp_features = [l_feat[3].unsqueeze(-1), l_feat[2].unsqueeze(-1), l_feat[1].unsqueeze(-1), l_feat[0].unsqueeze(-1)]
+    vs = []
+    for i, f in enumerate(fp_features):
+        v = netvlad(f, sd, f"aggregation.vlad{i}")                       # (B,C,K)
+        vs.append(v.reshape(v.shape[0], -1))                             # view(B, C*K), loupe.py:70
+    vlad = torch.cat(vs, dim=-1)
+    vlad = torch.matmul(vlad, sd["aggregation.hidden_weights"].to(dtype))
+    vlad = _bn(vlad, sd, "aggregation.bn2", 1)
+    if cfg["GATING"]:
+        vlad = gating_context(vlad, sd, "aggregation.context_gating")
+    if use_normalize:
+        vlad = F.normalize(vlad)
+    return dict(desc=vlad, fp_features=fp_features, center_idx_origin=c_origin, xyz=l_xyz)

@@ -1,0 +1,194 @@
+// attention.cu — PPT-Net's grouped self-attention layer (SA_Layer), fused, sm_100a.
+//
+// Reference: place_recognition/pptnet_origin/models/pptnet.py:246-282.  It materialises the (B, 8, N, N) per-group
+// energies (1.07 GB at B=32, N=1024), sums them, softmaxes, renormalises columns, and multiplies — ~12 kernels.
+// Because q_conv and k_conv share one weight (pptnet.py:254) and the per-group dot products add up to the dot product
+// over all channels, energy = Q^T Q is a symmetric Gram matrix of ONE projected tensor.  With
+//     P[n1][n2] = exp(E[n1][n2] - rowmax[n1]) / rowsum[n1]           (softmax over the last dim, pptnet.py:277)
+//     attn      = P / (1e-9 + colsum),  colsum[n2] = sum_n1 P[n1][n2]  (pptnet.py:278)
+//     x_r[:,n2] = (sum_n1 V[:,n1] P[n1][n2]) / (1e-9 + colsum[n2])     (pptnet.py:279)
+// nothing of size N x N ever leaves the SM:
+//   1. pointwise projection  [Q | V] = x [Wq_dense | Wv] + [0 | bv]           (mlp.cu, point-major)
+//   2. attn_stats_kernel:  row max / row sum of E, one CTA per 64-row tile, streaming 128-column tiles
+//   3. attn_apply_kernel:  per 64-column tile of n2, recompute E tiles (E is symmetric, so they are produced
+//      directly as P^T), accumulate U = P^T-tile x V and colsum in registers, write d = x - U / (1e-9 + colsum)
+//   4. pointwise trans_conv + BN + ReLU with residual:  out = x + relu(Wt d + bt)   (mlp.cu)
+// fp32 SIMT tiles (tile_gemm.cuh); all tensors point-major (b, n, c).
+#include <math.h>
+#include "tile_gemm.cuh"
+
+int pab_pointwise_mlp_residual(int rows, const float *x, const pab_layer_t *layers, int n_layers, const float *residual,
+                               float *out, cudaStream_t st);   // mlp.cu
+
+namespace {
+
+constexpr int AT_R = 64;       // rows per CTA tile
+constexpr int AT_C = 128;      // columns per streamed tile (= Geo<64>::CT)
+constexpr int AT_KC = 64;      // channel chunk of the Gram products
+constexpr int SXQ = 68;        // stride of the [64][64] Q chunk
+constexpr int SPT = 132;       // stride of the [64][128] E / P^T tile
+
+using G = tg::Geo<AT_R>;
+
+// E tile [rows r0..r0+64) x [cols c0..c0+128) of Q Q^T into acc (thread tile 8 x 4), K = C in chunks of 64.
+// xq: smem [64][SXQ]; wq: smem [64][AT_C] (chunk of Q^T for the column tile).
+__device__ __forceinline__ void gram_tile(float (&acc)[8][4], const float *__restrict__ q, long ld, int n, int C, int r0, int c0,
+                                          float *xq, float *wq) {
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < C; k0 += AT_KC) {
+        __syncthreads();
+        // rows chunk: coalesced along channels
+        for (int e = t; e < AT_R * AT_KC; e += tg::THREADS) {
+            const int r = e / AT_KC, k = e - r * AT_KC;
+            xq[r * SXQ + k] = (r0 + r < n) ? __ldg(q + (long)(r0 + r) * ld + k0 + k) : 0.f;
+        }
+        // columns chunk, transposed: lane = column (conflict-free smem writes), each warp walks 8 channels
+        for (int cc = lane; cc < AT_C; cc += 32) {
+            const bool ok = c0 + cc < n;
+            const float *src = q + (long)(c0 + cc) * ld + k0;
+            for (int k = warp * 8; k < warp * 8 + 8; ++k) wq[k * AT_C + cc] = ok ? __ldg(src + k) : 0.f;
+        }
+        __syncthreads();
+        tg::fma_block<G::RG>(acc, xq, SXQ, G::rg(), wq, AT_C, G::cg(), AT_KC);
+    }
+}
+
+// rowmax[n1], rowsum[n1] of E = Q Q^T over all n2
+__global__ void __launch_bounds__(tg::THREADS, 1)
+attn_stats_kernel(int n, int C, const float *__restrict__ q, long ld, float *__restrict__ rowmax, float *__restrict__ rowsum) {
+    extern __shared__ __align__(16) float smem[];
+    float *xq = smem, *wq = xq + AT_R * SXQ, *et = wq + AT_KC * AT_C;
+    const int t = threadIdx.x, cloud = blockIdx.y, r0 = blockIdx.x * AT_R;
+    q += (long)cloud * n * ld;
+    float m = -INFINITY, s = 0.f;
+    float acc[8][4];
+    for (int c0 = 0; c0 < n; c0 += AT_C) {
+        gram_tile(acc, q, ld, n, C, r0, c0, xq, wq);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4 *>(et + (G::rg() + G::RG * i) * SPT + 4 * G::cg()) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        __syncthreads();
+        if (t < AT_R) {
+            const float *row = et + t * SPT;
+            const int cn = min(AT_C, n - c0);
+            float tm = m;
+            for (int j = 0; j < cn; ++j) tm = fmaxf(tm, row[j]);
+            float ts = s * expf(m - tm);
+            for (int j = 0; j < cn; ++j) ts += expf(row[j] - tm);
+            m = tm; s = ts;
+        }
+    }
+    if (t < AT_R && r0 + t < n) {
+        rowmax[(long)cloud * n + r0 + t] = m;
+        rowsum[(long)cloud * n + r0 + t] = s;
+    }
+}
+
+// d[n2][c] = x[n2][c] - (sum_n1 P[n1][n2] V[n1][c]) / (1e-9 + sum_n1 P[n1][n2])
+__global__ void __launch_bounds__(tg::THREADS, 1)
+attn_apply_kernel(int n, int C, const float *__restrict__ q, const float *__restrict__ v, long ld, const float *__restrict__ x,
+                  const float *__restrict__ rowmax, const float *__restrict__ rowsum, float *__restrict__ d) {
+    extern __shared__ __align__(16) float smem[];
+    float *xq = smem, *wq = xq + AT_R * SXQ;          // wq: [64][128] Q^T chunk, reused as the [128][128] V tile
+    float *pt = wq + AT_C * AT_C, *st = pt + AT_R * SPT, *csum = st + 2 * AT_C;
+    const int t = threadIdx.x, cloud = blockIdx.y, r0 = blockIdx.x * AT_R;   // r0: first n2 of this tile
+    q += (long)cloud * n * ld; v += (long)cloud * n * ld;
+    x += (long)cloud * n * C; d += (long)cloud * n * C;
+    rowmax += (long)cloud * n; rowsum += (long)cloud * n;
+    const int rg = G::rg(), cg = G::cg();
+
+    for (int cp = 0; cp < C; cp += AT_C) {            // channel pass of the output (recomputes P for C > 128: tiny N there)
+        float u[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) u[i][j] = 0.f;
+        float cs = 0.f;
+        for (int c0 = 0; c0 < n; c0 += AT_C) {        // n1 tile
+            float acc[8][4];
+            gram_tile(acc, q, ld, n, C, r0, c0, xq, wq);     // E'[n2][n1] = E[n1][n2] (symmetric)
+            __syncthreads();
+            for (int j = t; j < AT_C; j += tg::THREADS) {
+                const bool ok = c0 + j < n;
+                st[j] = ok ? rowmax[c0 + j] : 0.f;
+                st[AT_C + j] = ok ? 1.f / rowsum[c0 + j] : 0.f;      // 0 kills the padded columns
+            }
+            // V tile [n1 (128)][c (128)] into wq (Q^T chunk no longer needed)
+            const int cw = min(AT_C, C - cp);
+            for (int e = t; e < AT_C * AT_C; e += tg::THREADS) {
+                const int r = e / AT_C, c = e - r * AT_C;
+                wq[e] = (c0 + r < n && c < cw) ? __ldg(v + (long)(c0 + r) * ld + cp + c) : 0.f;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float4 p;
+                const int c = 4 * cg;
+                p.x = expf(acc[i][0] - st[c]) * st[AT_C + c];
+                p.y = expf(acc[i][1] - st[c + 1]) * st[AT_C + c + 1];
+                p.z = expf(acc[i][2] - st[c + 2]) * st[AT_C + c + 2];
+                p.w = expf(acc[i][3] - st[c + 3]) * st[AT_C + c + 3];
+                *reinterpret_cast<float4 *>(pt + (rg + G::RG * i) * SPT + c) = p;
+            }
+            __syncthreads();
+            if (t < AT_R) {
+                const float *row = pt + t * SPT;
+                float s = 0.f;
+                for (int j = 0; j < AT_C; ++j) s += row[j];
+                cs += s;
+            }
+            tg::fma_block<G::RG>(u, pt, SPT, rg, wq, AT_C, cg, AT_C);
+        }
+        __syncthreads();
+        if (t < AT_R) csum[t] = cs;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = rg + G::RG * i, c = cp + 4 * cg;
+            if (r0 + r < n && c < C) {
+                const float inv = 1.f / (1e-9f + csum[r]);
+                const float4 xv = *reinterpret_cast<const float4 *>(x + (long)(r0 + r) * C + c);
+                *reinterpret_cast<float4 *>(d + (long)(r0 + r) * C + c) =
+                    make_float4(xv.x - u[i][0] * inv, xv.y - u[i][1] * inv, xv.z - u[i][2] * inv, xv.w - u[i][3] * inv);
+            }
+        }
+    }
+}
+
+inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
+
+PAB_API size_t pab_sa_layer_workspace_bytes(int b, int n, int c) {
+    return al(sizeof(float) * (size_t)b * n * 2 * c) + al(sizeof(float) * (size_t)b * n * c) + 2 * al(sizeof(float) * (size_t)b * n);
+}
+
+PAB_API int pab_sa_layer_forward(int b, int n, int c, const float *x, const pab_layer_t *qv_layer, const pab_layer_t *trans_layer,
+                                 float *out, void *workspace, pab_stream_t s) {
+    if (b < 0 || b > 65535 || n <= 0 || c <= 0 || c % 64 || !qv_layer || !trans_layer || !workspace) return PAB_EINVAL;
+    if (qv_layer->c_in != c || qv_layer->c_out != 2 * c || trans_layer->c_in != c || trans_layer->c_out != c) return PAB_EINVAL;
+    if (b == 0) return 0;
+    cudaStream_t st = (cudaStream_t)s;
+    char *w = (char *)workspace;
+    float *qv = (float *)w; w += al(sizeof(float) * (size_t)b * n * 2 * c);
+    float *d = (float *)w; w += al(sizeof(float) * (size_t)b * n * c);
+    float *rmax = (float *)w; w += al(sizeof(float) * (size_t)b * n);
+    float *rsum = (float *)w;
+    int rc = pab_pointwise_mlp_residual(b * n, x, qv_layer, 1, nullptr, qv, st);
+    if (rc) return rc;
+    const long ld = 2L * c;
+    const dim3 grid(pab_divup(n, AT_R), b);
+    const size_t smem_a = sizeof(float) * (AT_R * SXQ + AT_KC * AT_C + AT_R * SPT);
+    const size_t smem_b = sizeof(float) * (AT_R * SXQ + AT_C * AT_C + AT_R * SPT + 2 * AT_C + AT_R);
+    PAB_CUDA(cudaFuncSetAttribute(attn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+    PAB_CUDA(cudaFuncSetAttribute(attn_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    attn_stats_kernel<<<grid, tg::THREADS, smem_a, st>>>(n, c, qv, ld, rmax, rsum);
+    PAB_LAUNCH_CHECK();
+    attn_apply_kernel<<<grid, tg::THREADS, smem_b, st>>>(n, c, qv, qv + c, ld, x, rmax, rsum, d);
+    PAB_LAUNCH_CHECK();
+    return pab_pointwise_mlp_residual(b * n, d, trans_layer, 1, x, out, st);
+}

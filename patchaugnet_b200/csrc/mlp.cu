@@ -29,6 +29,7 @@ struct MlpArgs {
     int sA, sB;         // smem row strides
     // PLAIN
     const float *x;
+    const float *residual;   // optional (rows, c_last): added to the last layer's output
     // SA
     int n, m, k, nbr_stride, c;
     const float *xyz, *feat;
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(tg::THREADS, 1) mlp_kernel(const MlpArgs a) {
         for (int e = t; e < R * cl; e += tg::THREADS) {
             const int r = e / cl, ch = e - r * cl;
             const long j = first + r;
-            if (j < a.rows) a.out[j * cl + ch] = X[(size_t)r * sx + ch];
+            if (j < a.rows) a.out[j * cl + ch] = X[(size_t)r * sx + ch] + (a.residual ? __ldg(a.residual + j * cl + ch) : 0.f);
         }
     }
 }
@@ -244,9 +245,14 @@ PAB_API int pab_fp_module_forward(int b, int n, int m, int c_known, int c_skip, 
     return run(a, layers, n_layers, 0, (cudaStream_t)s);
 }
 
-PAB_API int pab_pointwise_mlp_forward(int rows, const float *x, const pab_layer_t *layers, int n_layers, float *out, pab_stream_t s) {
+int pab_pointwise_mlp_residual(int rows, const float *x, const pab_layer_t *layers, int n_layers, const float *residual,
+                               float *out, cudaStream_t st) {
     if (rows < 0 || !layers) return PAB_EINVAL;
     MlpArgs a{};
-    a.mode = MODE_PLAIN; a.rows = rows; a.x = x; a.out = out;
-    return run(a, layers, n_layers, 0, (cudaStream_t)s);
+    a.mode = MODE_PLAIN; a.rows = rows; a.x = x; a.residual = residual; a.out = out;
+    return run(a, layers, n_layers, 0, st);
+}
+
+PAB_API int pab_pointwise_mlp_forward(int rows, const float *x, const pab_layer_t *layers, int n_layers, float *out, pab_stream_t s) {
+    return pab_pointwise_mlp_residual(rows, x, layers, n_layers, nullptr, out, (cudaStream_t)s);
 }

@@ -93,6 +93,35 @@ def main():
     np.savez_compressed(os.path.join(HERE, "patchaugnet_ref_forward.npz"), **out)
     print("desc[0,:6] =", desc[0, :6].numpy(), " |desc| =", desc.norm(dim=1).numpy())
     print("wrote", os.path.join(HERE, "patchaugnet_ref_forward.npz"))
+    make_pptnet()
+
+
+def make_pptnet():
+    """Same procedure for the reference's PPT-Net (place_recognition/pptnet_origin/models/pptnet.py)."""
+    for m in [k for k in sys.modules if k == "loupe"]:
+        del sys.modules[m]                       # both model dirs ship a top-level module named `loupe`
+    sys.path.insert(0, os.path.join(REF, "place_recognition", "pptnet_origin", "models"))
+    from place_recognition.pptnet_origin.models.pptnet import Network as PPTNet
+    cfg = yaml.safe_load(open(os.path.join(REF, "configs", "pptnet_origin.yaml")))
+    torch.manual_seed(123)
+    net = PPTNet(param=cfg, use_normalize=True)
+    manifest = {k: list(v.shape) for k, v in net.state_dict().items()}
+    json.dump({"n_params": sum(p.numel() for p in net.parameters()), "state_dict": manifest},
+              open(os.path.join(HERE, "pptnet_state_dict.json"), "w"), indent=0)
+    net.load_state_dict(util.fill_state_dict(net.state_dict(), seed=321))
+    net.eval()
+    x = torch.cat([util.synthetic_batch(1, 4096, 10), util.tie_stress_cloud(1)[None, None]], 0)
+    with torch.no_grad():
+        desc, fp_features, center_idx = net(x)
+    out = dict(desc=desc.numpy())
+    for i, c in enumerate(center_idx):
+        out[f"center_idx{i}"] = c.numpy().astype(np.int32)
+    for i, f in enumerate(fp_features):
+        f = f.numpy()
+        out[f"fp{i}_sum"] = f.sum(axis=(2, 3)).astype(np.float64)
+        out[f"fp{i}_head"] = f[:, :, :8, 0].copy()
+    np.savez_compressed(os.path.join(HERE, "pptnet_ref_forward.npz"), **out)
+    print("pptnet desc[0,:6] =", desc[0, :6].numpy(), " |desc| =", desc.norm(dim=1).numpy())
 
 
 if __name__ == "__main__":

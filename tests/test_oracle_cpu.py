@@ -196,3 +196,50 @@ def test_oracle_model_matches_reference_forward_golden():
     # float64 dense path agrees with the fp32 reference within the 1e-4 contract of the north star
     out64 = model.patchaugnet_forward(net.state_dict(), util.PATCHAUGNET_CFG, x.numpy(), perms=list(g["perms"]), dtype=torch.float64)
     assert np.abs(out64["desc"].numpy() - g["desc"]).max() < 1e-5
+
+
+def test_pptnet_state_dict_and_oracle_match_reference_golden():
+    man = json.load(open(os.path.join(util.GOLDEN, "pptnet_state_dict.json")))
+    net = util.build_pptnet()
+    sd = net.state_dict()
+    assert list(sd.keys()) == list(man["state_dict"].keys()) and len(sd) == 258
+    assert all(list(sd[k].shape) == man["state_dict"][k] for k in sd)
+    assert sum(p.numel() for p in net.parameters()) == man["n_params"] == 13389226
+    sa = net.backbone.SA_modules[0].sas[0]
+    assert sa.q_conv.weight is sa.k_conv.weight                                  # tied projection, pptnet.py:254
+    g = np.load(os.path.join(util.GOLDEN, "pptnet_ref_forward.npz"))
+    x = torch.cat([util.synthetic_batch(1, 4096, 10), util.tie_stress_cloud(1)[None, None]], 0)
+    out = model.pptnet_forward(sd, util.PPTNET_CFG, x.numpy())
+    for i in range(4):
+        assert np.array_equal(out["center_idx_origin"][i], g[f"center_idx{i}"])
+    assert np.abs(out["desc"].numpy() - g["desc"]).max() < 1e-6
+
+
+def test_pointnetvlad_cpu_plumbing_config():
+    """BASELINE.json configs[0]: PointNetVLAD forward on one synthetic 4096-pt submap, CPU."""
+    from patchaugnet_b200.pointnet_vlad import PointNetVlad
+    torch.manual_seed(0)
+    net = PointNetVlad(num_points=4096, global_feat=True, feature_transform=True, max_pool=False, output_dim=256).eval()
+    assert len(net.state_dict()) == 78 and sum(p.numel() for p in net.parameters()) == 19779145   # SURVEY.md section 0
+    with torch.no_grad():
+        out = net(util.synthetic_batch(1, 4096, 0))
+    assert out.shape == (1, 256) and torch.isfinite(out).all()
+
+
+def test_losses_match_plain_restatement():
+    from patchaugnet_b200 import losses
+    g = torch.Generator().manual_seed(5)
+    q, pos, neg, other = (torch.randn(4, n, 16, generator=g) for n in (1, 2, 14, 1))
+    got = losses.quadruplet_loss(q, pos, neg, other, 0.5, 0.2, lazy=True)
+    # reference formula (losses/pointnetvlad_loss.py:53-105) written out with broadcasting
+    positive = ((pos - q) ** 2).sum(2).max(1)[0][:, None]
+    first = (0.5 + positive - ((neg - q) ** 2).sum(2)).clamp(min=0).max(1)[0].mean()
+    second = (0.2 + positive - ((neg - other) ** 2).sum(2)).clamp(min=0).max(1)[0].mean()
+    assert torch.allclose(got, first + second)
+    assert torch.allclose(losses.triplet_loss(q, pos, neg, 0.5, lazy=False),
+                          (0.5 + positive - ((neg - q) ** 2).sum(2)).clamp(min=0).sum(1).mean())
+    a, b, c = [torch.randn(16, generator=g) for _ in range(3)], [torch.randn(16, generator=g) for _ in range(3)], \
+              [torch.randn(16, generator=g) for _ in range(3)]
+    want = torch.stack([(x - y + 1e-6).norm() ** 2 for x, y in zip(a, b)]).mean() + \
+        torch.stack([(0.8 - (x - y + 1e-6).norm()).clamp(min=0) ** 2 for x, y in zip(a, c)]).mean()
+    assert torch.allclose(losses.contrastive_loss(a, b, c, 0.8), want, atol=1e-5)

@@ -19,6 +19,12 @@ PATCHAUGNET_CFG = dict(  # configs/patch_aug_net.yaml:1-56 (model keys only)
     KNN_DILATION=2)
 
 
+PPTNET_CFG = dict(  # configs/pptnet_origin.yaml (model keys only)
+    AGGREGATION="spvlad", GROUP=8, NUM_POINTS=4096, FEATURE_OUTPUT_DIM=256, FEATURE_SIZE=[256, 256, 256, 256],
+    MAX_SAMPLES=[64, 256, 1024, 4096], CLUSTER_SIZE=[1, 4, 16, 64], OUTPUT_DIM=[256, 256, 256, 256], GATING=True,
+    SAMPLING=[1024, 256, 64, 16], KNN=[20, 20, 20, 20])
+
+
 def synthetic_cloud(i, n=4096):
     """Cloud i of SURVEY.md section 8d: seed 1234+i, uniform in [-1,1]^3, centred, scaled into the unit ball
     (utils/loading_pointclouds.py:51-63)."""
@@ -74,11 +80,21 @@ def fill_state_dict(sd, seed=123):
         else:
             t = torch.randn(shape, generator=g) * 0.05
         out[k] = t.to(v.dtype)
+    for k in list(out):            # tied projections (pptnet.py:254): q_conv.weight IS k_conv.weight
+        if k.endswith("q_conv.weight") and k[:-len("q_conv.weight")] + "k_conv.weight" in out:
+            out[k] = out[k[:-len("q_conv.weight")] + "k_conv.weight"].clone()
     return out
 
 
 def build_network(device="cpu", seed=123, cfg=None):
     from patchaugnet_b200.patch_aug_net import Network
     net = Network(param=dict(cfg or PATCHAUGNET_CFG), use_a2a_recon=True, use_l2_norm=True)
+    net.load_state_dict(fill_state_dict(net.state_dict(), seed))
+    return net.to(device).eval()
+
+
+def build_pptnet(device="cpu", seed=321, cfg=None):
+    from patchaugnet_b200.pptnet import Network
+    net = Network(param=dict(cfg or PPTNET_CFG), use_normalize=True)
     net.load_state_dict(fill_state_dict(net.state_dict(), seed))
     return net.to(device).eval()
