@@ -151,12 +151,12 @@ int pab_pointwise_mlp_forward(int rows, const float *x, const pab_layer_t *layer
 
 /* PPT-Net SA_Layer.forward (place_recognition/pptnet_origin/models/pptnet.py:261-282), eval: grouped tied q/k projection,
  * Gram-matrix energy, row softmax, column renormalisation, V @ attn, trans_conv + BN + ReLU, residual — without ever
- * materialising an N x N tensor in HBM.  x, out (b,n,c) point-major, c % 64 == 0.  qv_layer: c -> 2c, columns [0,c) =
- * the grouped q/k weight expanded to a dense block-diagonal matrix, [c,2c) = v_conv (shift = [0 | v bias]), no ReLU;
- * trans_layer: c -> c, trans_conv with after_norm folded, ReLU.  workspace >= pab_sa_layer_workspace_bytes(b,n,c). */
+ * materialising an N x N tensor in HBM.  x, out (b,n,c) point-major, c % 64 == 0.  q_layer: c -> c, the grouped tied
+ * q/k weight expanded to a dense block-diagonal matrix, zero shift, no ReLU; v_layer: c -> c, v_conv (shift = bias), no
+ * ReLU; trans_layer: c -> c, trans_conv with after_norm folded, ReLU.  workspace >= pab_sa_layer_workspace_bytes(b,n,c). */
 size_t pab_sa_layer_workspace_bytes(int b, int n, int c);
-int pab_sa_layer_forward(int b, int n, int c, const float *x, const pab_layer_t *qv_layer, const pab_layer_t *trans_layer,
-                         float *out, void *workspace, pab_stream_t s);
+int pab_sa_layer_forward(int b, int n, int c, const float *x, const pab_layer_t *q_layer, const pab_layer_t *v_layer,
+                         const pab_layer_t *trans_layer, float *out, void *workspace, pab_stream_t s);
 
 /* NetVLADBase.forward (patch_aug_net/models/loupe.py:191-222), eval: x (b,n,c) point-major, wc (c,K) with the
  * bn1 scale folded in, shift (K), w2 (c,K) = cluster_weights2; out written at out[b*out_bstride + ch*out_cstride + k]

@@ -62,7 +62,7 @@ SIGNATURES = {
     "pab_fp_module_forward": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, C.POINTER(PabLayer), _I, _P, _P]),
     "pab_pointwise_mlp_forward": (_I, [_I, _P, C.POINTER(PabLayer), _I, _P, _P]),
     "pab_sa_layer_workspace_bytes": (_SZ, [_I, _I, _I]),
-    "pab_sa_layer_forward": (_I, [_I, _I, _I, _P, C.POINTER(PabLayer), C.POINTER(PabLayer), _P, _P, _P]),
+    "pab_sa_layer_forward": (_I, [_I, _I, _I, _P, C.POINTER(PabLayer), C.POINTER(PabLayer), C.POINTER(PabLayer), _P, _P, _P]),
     "pab_netvlad_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
     "pab_netvlad_forward": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P, _L, _L, _P, _P]),
     "pab_afa_workspace_bytes": (_SZ, [_I, _I, _I, _I]),

@@ -18,18 +18,21 @@ def _fold(layer, device):
     for g in range(gp):
         wq_dense[g * cg:(g + 1) * cg, g * cg:(g + 1) * cg] = wk[g * cg:(g + 1) * cg]
     wv = layer.v_conv.weight.detach().float()[:, :, 0]
-    qv_wt = torch.cat([wq_dense.t(), wv.t()], dim=1).contiguous().to(device)            # (C, 2C)
-    qv_shift = torch.cat([torch.zeros(C, device=wk.device), layer.v_conv.bias.detach().float()]).contiguous().to(device)
+    q_wt = wq_dense.t().contiguous().to(device)                                         # (C_in, C_out)
+    q_shift = torch.zeros(C, device=device)
+    v_wt = wv.t().contiguous().to(device)
+    v_shift = layer.v_conv.bias.detach().float().contiguous().to(device)
     bn = layer.after_norm
     scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
     wt = layer.trans_conv.weight.detach().float()[:, :, 0]
     tr_wt = (wt * scale[:, None]).t().contiguous().to(device)                           # (C, C)
     tr_shift = (scale * (layer.trans_conv.bias.detach().float() - bn.running_mean.detach().float())
                 + bn.bias.detach().float()).contiguous().to(device)
-    arr = (L.PabLayer * 2)()
-    arr[0] = L.PabLayer(qv_wt.data_ptr(), qv_shift.data_ptr(), C, C, 2 * C, 0, 0, 0, 0, 0)
-    arr[1] = L.PabLayer(tr_wt.data_ptr(), tr_shift.data_ptr(), C, C, C, 1, 0, 0, 0, 0)
-    return dict(arr=arr, keep=(qv_wt, qv_shift, tr_wt, tr_shift), C=C)
+    arr = (L.PabLayer * 3)()
+    arr[0] = L.PabLayer(q_wt.data_ptr(), q_shift.data_ptr(), C, C, C, 0, 0, 0, 0, 0)
+    arr[1] = L.PabLayer(v_wt.data_ptr(), v_shift.data_ptr(), C, C, C, 0, 0, 0, 0, 0)
+    arr[2] = L.PabLayer(tr_wt.data_ptr(), tr_shift.data_ptr(), C, C, C, 1, 0, 0, 0, 0)
+    return dict(arr=arr, keep=(q_wt, q_shift, v_wt, v_shift, tr_wt, tr_shift), C=C)
 
 
 def _versions(layer):
@@ -50,8 +53,8 @@ def sa_layer_forward(layer, x):
     out = torch.empty_like(xp)
     ws = torch.empty(L.lib().pab_sa_layer_workspace_bytes(B, N, C), dtype=torch.uint8, device=x.device)
     arr = cache["arr"]
-    L.check(L.lib().pab_sa_layer_forward(B, N, C, L.ptr(xp), arr, C_ptr_offset(arr, 1), L.ptr(out), L.ptr(ws), L.stream_ptr()),
-            "sa_layer_forward")
+    L.check(L.lib().pab_sa_layer_forward(B, N, C, L.ptr(xp), arr, C_ptr_offset(arr, 1), C_ptr_offset(arr, 2), L.ptr(out),
+                                         L.ptr(ws), L.stream_ptr()), "sa_layer_forward")
     return out.transpose(1, 2).contiguous()
 
 

@@ -8,7 +8,7 @@
 //     attn      = P / (1e-9 + colsum),  colsum[n2] = sum_n1 P[n1][n2]  (pptnet.py:278)
 //     x_r[:,n2] = (sum_n1 V[:,n1] P[n1][n2]) / (1e-9 + colsum[n2])     (pptnet.py:279)
 // nothing of size N x N ever leaves the SM:
-//   1. pointwise projection  [Q | V] = x [Wq_dense | Wv] + [0 | bv]           (mlp.cu, point-major)
+//   1. pointwise projections Q = x Wq_dense, V = x Wv + bv, interleaved [Q | V] per point   (mlp.cu, point-major)
 //   2. attn_stats_kernel:  row max / row sum of E, one CTA per 64-row tile, streaming 128-column tiles
 //   3. attn_apply_kernel:  per 64-column tile of n2, recompute E tiles (E is symmetric, so they are produced
 //      directly as P^T), accumulate U = P^T-tile x V and colsum in registers, write d = x - U / (1e-9 + colsum)
@@ -18,7 +18,7 @@
 #include "tile_gemm.cuh"
 
 int pab_pointwise_mlp_residual(int rows, const float *x, const pab_layer_t *layers, int n_layers, const float *residual,
-                               float *out, cudaStream_t st);   // mlp.cu
+                               float *out, long out_ld, cudaStream_t st);   // mlp.cu
 
 namespace {
 
@@ -167,10 +167,11 @@ PAB_API size_t pab_sa_layer_workspace_bytes(int b, int n, int c) {
     return al(sizeof(float) * (size_t)b * n * 2 * c) + al(sizeof(float) * (size_t)b * n * c) + 2 * al(sizeof(float) * (size_t)b * n);
 }
 
-PAB_API int pab_sa_layer_forward(int b, int n, int c, const float *x, const pab_layer_t *qv_layer, const pab_layer_t *trans_layer,
-                                 float *out, void *workspace, pab_stream_t s) {
-    if (b < 0 || b > 65535 || n <= 0 || c <= 0 || c % 64 || !qv_layer || !trans_layer || !workspace) return PAB_EINVAL;
-    if (qv_layer->c_in != c || qv_layer->c_out != 2 * c || trans_layer->c_in != c || trans_layer->c_out != c) return PAB_EINVAL;
+PAB_API int pab_sa_layer_forward(int b, int n, int c, const float *x, const pab_layer_t *q_layer, const pab_layer_t *v_layer,
+                                 const pab_layer_t *trans_layer, float *out, void *workspace, pab_stream_t s) {
+    if (b < 0 || b > 65535 || n <= 0 || c <= 0 || c % 64 || !q_layer || !v_layer || !trans_layer || !workspace) return PAB_EINVAL;
+    if (q_layer->c_in != c || q_layer->c_out != c || v_layer->c_in != c || v_layer->c_out != c || trans_layer->c_in != c ||
+        trans_layer->c_out != c) return PAB_EINVAL;
     if (b == 0) return 0;
     cudaStream_t st = (cudaStream_t)s;
     char *w = (char *)workspace;
@@ -178,9 +179,11 @@ PAB_API int pab_sa_layer_forward(int b, int n, int c, const float *x, const pab_
     float *d = (float *)w; w += al(sizeof(float) * (size_t)b * n * c);
     float *rmax = (float *)w; w += al(sizeof(float) * (size_t)b * n);
     float *rsum = (float *)w;
-    int rc = pab_pointwise_mlp_residual(b * n, x, qv_layer, 1, nullptr, qv, st);
+    const long ld = 2L * c;                                   // [Q | V] interleaved per point
+    int rc = pab_pointwise_mlp_residual(b * n, x, q_layer, 1, nullptr, qv, ld, st);
     if (rc) return rc;
-    const long ld = 2L * c;
+    rc = pab_pointwise_mlp_residual(b * n, x, v_layer, 1, nullptr, qv + c, ld, st);
+    if (rc) return rc;
     const dim3 grid(pab_divup(n, AT_R), b);
     const size_t smem_a = sizeof(float) * (AT_R * SXQ + AT_KC * AT_C + AT_R * SPT);
     const size_t smem_b = sizeof(float) * (AT_R * SXQ + AT_C * AT_C + AT_R * SPT + 2 * AT_C + AT_R);
@@ -190,5 +193,5 @@ PAB_API int pab_sa_layer_forward(int b, int n, int c, const float *x, const pab_
     PAB_LAUNCH_CHECK();
     attn_apply_kernel<<<grid, tg::THREADS, smem_b, st>>>(n, c, qv, qv + c, ld, x, rmax, rsum, d);
     PAB_LAUNCH_CHECK();
-    return pab_pointwise_mlp_residual(b * n, d, trans_layer, 1, x, out, st);
+    return pab_pointwise_mlp_residual(b * n, d, trans_layer, 1, x, out, 0, st);
 }

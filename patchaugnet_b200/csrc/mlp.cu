@@ -30,6 +30,7 @@ struct MlpArgs {
     // PLAIN
     const float *x;
     const float *residual;   // optional (rows, c_last): added to the last layer's output
+    long out_ld;             // PLAIN: row stride of `out` in floats (0 = c_last)
     // SA
     int n, m, k, nbr_stride, c;
     const float *xyz, *feat;
@@ -159,7 +160,8 @@ __global__ void __launch_bounds__(tg::THREADS, 1) mlp_kernel(const MlpArgs a) {
         for (int e = t; e < R * cl; e += tg::THREADS) {
             const int r = e / cl, ch = e - r * cl;
             const long j = first + r;
-            if (j < a.rows) a.out[j * cl + ch] = X[(size_t)r * sx + ch] + (a.residual ? __ldg(a.residual + j * cl + ch) : 0.f);
+            const long old = a.out_ld ? a.out_ld : cl;
+            if (j < a.rows) a.out[j * old + ch] = X[(size_t)r * sx + ch] + (a.residual ? __ldg(a.residual + j * cl + ch) : 0.f);
         }
     }
 }
@@ -246,13 +248,13 @@ PAB_API int pab_fp_module_forward(int b, int n, int m, int c_known, int c_skip, 
 }
 
 int pab_pointwise_mlp_residual(int rows, const float *x, const pab_layer_t *layers, int n_layers, const float *residual,
-                               float *out, cudaStream_t st) {
+                               float *out, long out_ld, cudaStream_t st) {
     if (rows < 0 || !layers) return PAB_EINVAL;
     MlpArgs a{};
-    a.mode = MODE_PLAIN; a.rows = rows; a.x = x; a.residual = residual; a.out = out;
+    a.mode = MODE_PLAIN; a.rows = rows; a.x = x; a.residual = residual; a.out = out; a.out_ld = out_ld;
     return run(a, layers, n_layers, 0, st);
 }
 
 PAB_API int pab_pointwise_mlp_forward(int rows, const float *x, const pab_layer_t *layers, int n_layers, float *out, pab_stream_t s) {
-    return pab_pointwise_mlp_residual(rows, x, layers, n_layers, nullptr, out, (cudaStream_t)s);
+    return pab_pointwise_mlp_residual(rows, x, layers, n_layers, nullptr, out, 0, (cudaStream_t)s);
 }
