@@ -166,6 +166,11 @@ size_t pab_netvlad_workspace_bytes(int b, int n, int c, int K);
 int pab_netvlad_forward(int b, int n, int c, int K, const float *x, const float *wc, const float *shift, const float *w2,
                         float *out, long out_bstride, long out_cstride, void *workspace, pab_stream_t s);
 
+/* Tensor-core variant of pab_netvlad_forward (c == 256): wc_hi / wc_lo are the bf16 hi/lo planes of the folded cluster
+ * weights TRANSPOSED to (Kp, c) K-major, Kp = K rounded up to 16 with zero rows.  Same outputs and workspace. */
+int pab_netvlad_forward_tc(int b, int n, int c, int K, const float *x, const void *wc_hi, const void *wc_lo, const float *shift,
+                           const float *w2, float *out, long out_bstride, long out_cstride, void *workspace, pab_stream_t s);
+
 /* AdaptiveFeatureAggregator.forward (loupe.py:57-66, 24-41), eval: v (b,c,K) -> desc (b,c_out), L2-normalised.
  * w_att_t (c_in,c_out) = mlpa.mlps.0.weight[:, :, 0] TRANSPOSED; fc_wt (c*K, c_out) = fc.weight TRANSPOSED (so the
  * 22 MB matrix streams coalesced); desc = normalize((fc_wt^T y) * fc_scale + fc_shift) with fc.bias and the

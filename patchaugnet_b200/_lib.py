@@ -65,6 +65,7 @@ SIGNATURES = {
     "pab_sa_layer_forward": (_I, [_I, _I, _I, _P, C.POINTER(PabLayer), C.POINTER(PabLayer), C.POINTER(PabLayer), _P, _P, _P]),
     "pab_netvlad_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
     "pab_netvlad_forward": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P, _L, _L, _P, _P]),
+    "pab_netvlad_forward_tc": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _L, _L, _P, _P]),
     "pab_afa_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
     "pab_afa_forward": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P]),
 }

@@ -298,8 +298,12 @@ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace
 
+// tensor-core partial kernel (vlad_tc.cu)
+int pab_vlad_tc_partial(int b, int n, int c, int K, const float *x, const void *wc_hi, const void *wc_lo, const float *shift,
+                        float *part, float *asum, int *nchunk_out, cudaStream_t st);
+
 PAB_API size_t pab_netvlad_workspace_bytes(int b, int n, int c, int K) {
-    const size_t nchunk = (n + VROWS_PER_CTA - 1) / VROWS_PER_CTA;
+    const size_t nchunk = (n + 255) / 256;      // the tensor-core path uses 256-row items, the SIMT path 512-row chunks
     return align256(sizeof(float) * (size_t)b * nchunk * K * c) + align256(sizeof(float) * (size_t)b * nchunk * K);
 }
 
@@ -318,6 +322,22 @@ PAB_API int pab_netvlad_forward(int b, int n, int c, int K, const float *x, cons
     vlad_partial_kernel<<<dim3(nchunk, b), tg::THREADS, smem, st>>>(a);
     PAB_LAUNCH_CHECK();
     vlad_finalize_kernel<<<b, 256, 0, st>>>(c, K, nchunk, a.part, a.asum, w2, out, out_bstride, out_cstride);
+    PAB_LAUNCH_CHECK();
+    return 0;
+}
+
+PAB_API int pab_netvlad_forward_tc(int b, int n, int c, int K, const float *x, const void *wc_hi, const void *wc_lo, const float *shift,
+                                   const float *w2, float *out, long out_bstride, long out_cstride, void *workspace, pab_stream_t s) {
+    if (b < 0 || n <= 0 || c != 256 || K <= 0 || K > VKMAX || K % 4 || !workspace) return PAB_EINVAL;
+    if (b == 0) return 0;
+    cudaStream_t st = (cudaStream_t)s;
+    const int nchunk_max = (n + 255) / 256;
+    float *part = (float *)workspace;
+    float *asum = (float *)((char *)workspace + align256(sizeof(float) * (size_t)b * nchunk_max * K * c));
+    int nchunk = 0;
+    const int rc = pab_vlad_tc_partial(b, n, c, K, x, wc_hi, wc_lo, shift, part, asum, &nchunk, st);
+    if (rc) return rc;
+    vlad_finalize_kernel<<<b, 256, 0, st>>>(c, K, nchunk, part, asum, w2, out, out_bstride, out_cstride);
     PAB_LAUNCH_CHECK();
     return 0;
 }

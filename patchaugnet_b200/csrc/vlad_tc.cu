@@ -1,0 +1,270 @@
+// vlad_tc.cu — NetVLAD soft-assignment + residual aggregation on tcgen05 tensor cores (sm_100a).
+//
+// Same maths and partial-sum contract as vlad.cu (NetVLADBase.forward, patch_aug_net/models/loupe.py:191-222), with both
+// contractions as tcgen05.mma on bf16 hi/lo operand planes (three MMAs per product, fp32 accumulation in TMEM):
+//
+//   GEMM1  logits[128 pts][K]      = x[128][256] . Wc^T          A = x planes (K-major), B = Wc planes (K-major)
+//   softmax over the K clusters, one thread per point straight out of TMEM (tcgen05.ld), written as act^T planes
+//   GEMM2  vlad^T[256 ch][K]      += x^T[256][128 pts] . act      A = THE SAME x planes read MN-major (no transpose copy:
+//                                                                 a 128-byte swizzled row of 64 channels is a K-major
+//                                                                 row of GEMM1 and an MN-major row of GEMM2),
+//                                                                 B = act^T planes (K-major); accumulated in TMEM over
+//                                                                 all tiles of the CTA's work item
+// A work item is (cloud, 256-row chunk); persistent CTAs loop over items.  Each item writes a partial (K, C) block and
+// partial a_sum (K) exactly like vlad_partial_kernel, so vlad_finalize_kernel (vlad.cu) is shared.
+#include <math.h>
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace tc;
+
+constexpr int VT_WORK = 256;                  // worker threads (8 warps); warp 0: idle helper, warp 1: MMA issuer
+constexpr int VT_THREADS = 64 + VT_WORK;
+constexpr int VT_ROWS_PER_ITEM = 256;
+constexpr int VT_C = 256;                     // channels (4 chunks of 64)
+
+struct VtArgs {
+    int n, K, Kp, nchunk, nitems;
+    const float *x, *shift;
+    const __nv_bfloat16 *wc_hi, *wc_lo;       // (Kp, 256) K-major, bn1 scale folded, rows >= K zero
+    float *part, *asum;
+};
+
+// MN-major SWIZZLE_128B descriptor over the x planes: 64-channel blocks (one K chunk each) are LBO = A_CHUNK bytes apart,
+// groups of 8 points (K direction) are SBO = 1024 bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(A_CHUNK >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+__device__ __forceinline__ uint32_t umma_idesc_amn(int n) {   // as umma_idesc, with A MN-major (bit 15)
+    return umma_idesc(n) | (1u << 15);
+}
+
+__global__ void __launch_bounds__(VT_THREADS, 1) vlad_tc_kernel(const VtArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *x1 = smem, *x2 = x1 + 4 * A_CHUNK;                    // x hi / lo planes: 4 chunks x [128][64] bf16
+    uint8_t *w1 = x2 + 4 * A_CHUNK;                                // Wc hi: 4 chunks x [Kp][64]
+    const int wchunk = a.Kp * 128;
+    uint8_t *w2 = w1 + 4 * wchunk;
+    uint8_t *p1 = w2 + 4 * wchunk;                                 // act^T hi: 2 chunks x [Kp][64 pts]
+    uint8_t *p2 = p1 + 2 * wchunk;
+    uint8_t *misc = p2 + 2 * wchunk;
+    uint64_t *a_ready = reinterpret_cast<uint64_t *>(misc);        // x planes staged            (256 arrivals)
+    uint64_t *d1_ready = a_ready + 1;                              // logits in TMEM             (tcgen05.commit)
+    uint64_t *p_ready = a_ready + 2;                               // act^T planes staged        (128 arrivals)
+    uint64_t *g2_done = a_ready + 3;                               // GEMM2 of the tile finished (tcgen05.commit)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_ready + 4);
+    float *asum_s = reinterpret_cast<float *>(misc + 64);          // [Kp]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        mbar_init(a_ready, VT_WORK); mbar_init(d1_ready, 1); mbar_init(p_ready, 128); mbar_init(g2_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // cluster weights into the K-major swizzled planes (once per CTA)
+    for (int u = tid; u < a.Kp * 32; u += VT_THREADS) {            // 16-byte units: Kp rows x 32 units (256 ch)
+        const int k = u >> 5, j = u & 31;
+        const uint32_t off = (uint32_t)((j >> 3) * wchunk + k * 128 + (((j & 7) ^ (k & 7)) << 4));
+        *reinterpret_cast<uint4 *>(w1 + off) = __ldg(reinterpret_cast<const uint4 *>(a.wc_hi + (size_t)k * VT_C) + j);
+        *reinterpret_cast<uint4 *>(w2 + off) = __ldg(reinterpret_cast<const uint4 *>(a.wc_lo + (size_t)k * VT_C) + j);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t d1 = tmem, d2 = tmem + 64;                      // D2 block cb at d2 + cb*64
+
+    if (warp == 1) {
+        if (lane == 0) {
+            uint32_t tcount = 0;
+            const uint32_t id1 = umma_idesc(a.Kp), id2 = umma_idesc_amn(a.Kp);
+            for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+                const int chunk = item % a.nchunk;
+                const int r_begin = chunk * VT_ROWS_PER_ITEM, r_end = min(a.n, r_begin + VT_ROWS_PER_ITEM);
+                int t_in_item = 0;
+                for (int r0 = r_begin; r0 < r_end; r0 += TM, ++tcount, ++t_in_item) {
+                    mbar_wait(a_ready, tcount & 1);
+                    tc_fence_after();
+                    for (int kc = 0; kc < 4; ++kc)
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint64_t da1 = umma_desc(smem_u32(x1 + kc * A_CHUNK) + ks * 32), da2 = umma_desc(smem_u32(x2 + kc * A_CHUNK) + ks * 32);
+                            const uint64_t db1 = umma_desc(smem_u32(w1 + kc * wchunk) + ks * 32), db2 = umma_desc(smem_u32(w2 + kc * wchunk) + ks * 32);
+                            umma_f16(d1, da1, db1, id1, (kc | ks) != 0);
+                            umma_f16(d1, da2, db1, id1, 1);
+                            umma_f16(d1, da1, db2, id1, 1);
+                        }
+                    umma_commit(d1_ready);
+                    mbar_wait(p_ready, tcount & 1);
+                    tc_fence_after();
+                    for (int cb = 0; cb < 2; ++cb)
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks) {            // 16 points per MMA
+                            const uint64_t da1 = umma_desc_mn(smem_u32(x1 + 2 * cb * A_CHUNK) + ks * 2048);
+                            const uint64_t da2 = umma_desc_mn(smem_u32(x2 + 2 * cb * A_CHUNK) + ks * 2048);
+                            const uint64_t db1 = umma_desc(smem_u32(p1 + (ks >> 2) * wchunk) + (ks & 3) * 32);
+                            const uint64_t db2 = umma_desc(smem_u32(p2 + (ks >> 2) * wchunk) + (ks & 3) * 32);
+                            umma_f16(d2 + cb * 64, da1, db1, id2, (t_in_item | ks) != 0);
+                            umma_f16(d2 + cb * 64, da2, db1, id2, 1);
+                            umma_f16(d2 + cb * 64, da1, db2, id2, 1);
+                        }
+                    umma_commit(g2_done);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 2) {
+        const int wt = tid - 64, wwarp = warp - 2;
+        const int q = warp & 3, half = wwarp >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+        uint32_t tcount = 0;
+        for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+            const int cloud = item / a.nchunk, chunk = item % a.nchunk;
+            const int r_begin = chunk * VT_ROWS_PER_ITEM, r_end = min(a.n, r_begin + VT_ROWS_PER_ITEM);
+            const float *xg = a.x + (size_t)cloud * a.n * VT_C;
+            float asum_k = 0.f;                                    // cluster (wt - 128)'s running sum (threads of half 1)
+            for (int r0 = r_begin; r0 < r_end; r0 += TM, ++tcount) {
+                if (tcount > 0) mbar_wait(g2_done, (tcount - 1) & 1);      // previous tile's GEMM2 no longer reads the planes
+                // four rows per warp per step: eight 16-byte loads in flight per lane before the first use
+                for (int rb = wwarp * 4; rb < TM; rb += 32) {
+                    float4 lo4[4], hi4[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        lo4[u] = hi4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (r0 + rb + u < r_end) {
+                            const float4 *src = reinterpret_cast<const float4 *>(xg + (size_t)(r0 + rb + u) * VT_C) + 2 * lane;
+                            lo4[u] = __ldg(src); hi4[u] = __ldg(src + 1);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float v[8] = {lo4[u].x, lo4[u].y, lo4[u].z, lo4[u].w, hi4[u].x, hi4[u].y, hi4[u].z, hi4[u].w};
+                        store_units(x1, x2, rb + u, lane, v);
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(a_ready);
+                if (half == 0) {
+                    mbar_wait(d1_ready, tcount & 1);
+                    tc_fence_after();
+                    float lg[64];
+                    {
+                        float v[32];
+                        tmem_ld32(trow, v);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) lg[i] = v[i];
+                        if (a.Kp > 32) {
+                            tmem_ld32(trow + 32, v);
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) lg[32 + i] = v[i];
+                        }
+                    }
+                    const bool valid = r0 + row < r_end;
+                    float mx = -INFINITY;
+#pragma unroll
+                    for (int k = 0; k < 64; ++k)
+                        if (k < a.K) { lg[k] += __ldg(a.shift + k); mx = fmaxf(mx, lg[k]); }
+                    float sum = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 64; ++k)
+                        if (k < a.K) { lg[k] = expf(lg[k] - mx); sum += lg[k]; }
+                    const float inv = valid ? 1.f / sum : 0.f;
+                    const uint32_t pbase = (uint32_t)((row >> 6) * wchunk + (((row & 63) >> 3) << 4) + ((row & 7) << 1));
+#pragma unroll
+                    for (int k = 0; k < 64; ++k) {
+                        if (k < a.Kp) {
+                            const float p = k < a.K ? lg[k] * inv : 0.f;
+                            const __nv_bfloat16 h = __float2bfloat16_rn(p);
+                            const __nv_bfloat16 l = __float2bfloat16_rn(p - __bfloat162float(h));
+                            const uint32_t off = (uint32_t)(k * 128) + (pbase ^ (uint32_t)((k & 7) << 4));
+                            *reinterpret_cast<__nv_bfloat16 *>(p1 + off) = h;
+                            *reinterpret_cast<__nv_bfloat16 *>(p2 + off) = l;
+                        }
+                    }
+                    tc_fence_before();
+                    fence_proxy_async();
+                    mbar_arrive(p_ready);
+                } else {
+                    // a_sum[k] += sum over the tile's points of act[.][k], read back from the staged planes in a fixed order
+                    mbar_wait(p_ready, tcount & 1);
+                    const int k = wt - 128;
+                    if (k < a.K) {
+                        float s_hi = 0.f, s_lo = 0.f;
+                        for (int ch2 = 0; ch2 < 2; ++ch2) {
+                            const uint8_t *r1 = p1 + ch2 * wchunk + k * 128, *r2 = p2 + ch2 * wchunk + k * 128;
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) {                      // swizzled 16-byte units; order inside the sum is fixed
+                                const uint4 h = *reinterpret_cast<const uint4 *>(r1 + ((u ^ (k & 7)) << 4));
+                                const uint4 l = *reinterpret_cast<const uint4 *>(r2 + ((u ^ (k & 7)) << 4));
+                                const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+                                for (int w = 0; w < 4; ++w) {
+                                    s_hi += __uint_as_float(hw[w] << 16) + __uint_as_float(hw[w] & 0xffff0000u);
+                                    s_lo += __uint_as_float(lw[w] << 16) + __uint_as_float(lw[w] & 0xffff0000u);
+                                }
+                            }
+                        }
+                        asum_k += s_hi + s_lo;
+                    }
+                }
+            }
+            // ---- item done: accumulators -> partial (K, C) block, a_sum -> partial (K) ------------------------------
+            mbar_wait(g2_done, (tcount - 1) & 1);
+            tc_fence_after();
+            {
+                const int ch = half * 128 + row;                               // D2 block `half`, TMEM lane = channel
+                float *part = a.part + (size_t)item * a.K * VT_C;
+                float v[32];
+                tmem_ld32(trow + 64 + (uint32_t)half * 64, v);
+#pragma unroll
+                for (int k = 0; k < 32; ++k)
+                    if (k < a.K) part[(size_t)k * VT_C + ch] = v[k];
+                if (a.K > 32) {
+                    tmem_ld32(trow + 64 + (uint32_t)half * 64 + 32, v);
+#pragma unroll
+                    for (int k = 0; k < 32; ++k)
+                        if (32 + k < a.K) part[(size_t)(32 + k) * VT_C + ch] = v[k];
+                }
+            }
+            tc_fence_before();
+            if (half == 1 && wt - 128 < a.K) a.asum[(size_t)item * a.K + (wt - 128)] = asum_k;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+    }
+}
+
+}  // namespace
+
+// host entry used by vlad.cu: returns 0 on success, PAB_EINVAL if the shape is not supported (caller falls back to SIMT)
+int pab_vlad_tc_partial(int b, int n, int c, int K, const float *x, const void *wc_hi, const void *wc_lo, const float *shift,
+                        float *part, float *asum, int *nchunk_out, cudaStream_t st) {
+    if (c != VT_C || K <= 0 || K > 64 || !wc_hi || !wc_lo) return PAB_EINVAL;
+    VtArgs a;
+    a.n = n; a.K = K; a.Kp = (K + 15) / 16 * 16; a.nchunk = (n + VT_ROWS_PER_ITEM - 1) / VT_ROWS_PER_ITEM; a.nitems = b * a.nchunk;
+    a.x = x; a.shift = shift; a.wc_hi = (const __nv_bfloat16 *)wc_hi; a.wc_lo = (const __nv_bfloat16 *)wc_lo; a.part = part; a.asum = asum;
+    *nchunk_out = a.nchunk;
+    const size_t smem = 8 * (size_t)A_CHUNK + 12 * (size_t)a.Kp * 128 + 64 + 64 * 4 + 64;
+    static int n_sm = 0;
+    if (!n_sm) {
+        int dev = 0;
+        PAB_CUDA(cudaGetDevice(&dev));
+        PAB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    PAB_CUDA(cudaFuncSetAttribute(vlad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = a.nitems < n_sm ? a.nitems : n_sm;
+    vlad_tc_kernel<<<grid, VT_THREADS, smem, st>>>(a);
+    PAB_LAUNCH_CHECK();
+    return 0;
+}

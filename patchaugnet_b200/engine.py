@@ -97,6 +97,7 @@ class FusedPatchAugNet:
         self._events = None
         self._event_filter = None
         self._streams = None
+        self.vlad_tensor_core = True
         self.refold()
 
     # ---- weights -------------------------------------------------------------------------------------------------
@@ -119,7 +120,12 @@ class FusedPatchAugNet:
             scale, shift = _fold_bn(v.bn1)
             wc = (v.cluster_weights.detach().float() * scale[None, :]).contiguous().to(dev)      # (C, K), bn1 folded
             w2 = v.cluster_weights2.detach().float()[0].contiguous().to(dev)                    # (C, K)
-            self.vlad.append(dict(K=v.cluster_size, C=v.feature_size, wc=wc, shift=shift.contiguous().to(dev), w2=w2))
+            K, Cf = v.cluster_size, v.feature_size
+            Kp = (K + 15) // 16 * 16
+            wct = torch.zeros(Kp, Cf, device=dev)
+            wct[:K] = wc.t()
+            hi, lo = _split_bf16(wct)                                                           # (Kp, C) K-major planes
+            self.vlad.append(dict(K=K, C=Cf, wc=wc, shift=shift.contiguous().to(dev), w2=w2, wc_hi=hi, wc_lo=lo))
         afa = agg.afa
         self.w_att_t = afa.mlpa.mlps[0].weight.detach().float()[:, :, 0].t().contiguous().to(dev)   # (c_in, c_out)
         self.fc_wt = afa.fc.weight.detach().float().t().contiguous().to(dev)                        # (C*K, c_out)
@@ -236,8 +242,13 @@ class FusedPatchAugNet:
         v, koff = ws["v"], 0
         for i, (x, lvl) in enumerate(zip(fp_out, self.vlad)):
             dst = C.c_void_p(v.data_ptr() + 4 * koff)
-            run(f"vlad{i}", lambda: lib.pab_netvlad_forward(B, x.shape[1], lvl["C"], lvl["K"], p(x), p(lvl["wc"]), p(lvl["shift"]),
-                                                            p(lvl["w2"]), dst, v.stride(0), v.stride(1), p(ws["scratch"]), st))
+            if self.vlad_tensor_core and lvl["C"] == 256:
+                run(f"vlad{i}", lambda: lib.pab_netvlad_forward_tc(B, x.shape[1], lvl["C"], lvl["K"], p(x), p(lvl["wc_hi"]),
+                                                                   p(lvl["wc_lo"]), p(lvl["shift"]), p(lvl["w2"]), dst, v.stride(0),
+                                                                   v.stride(1), p(ws["scratch"]), st))
+            else:
+                run(f"vlad{i}", lambda: lib.pab_netvlad_forward(B, x.shape[1], lvl["C"], lvl["K"], p(x), p(lvl["wc"]), p(lvl["shift"]),
+                                                                p(lvl["w2"]), dst, v.stride(0), v.stride(1), p(ws["scratch"]), st))
             koff += lvl["K"]
         run("afa", lambda: lib.pab_afa_forward(B, self.vlad[0]["C"], self.sumK, self.c_out, p(v), p(self.w_att_t), p(self.fc_wt),
                                                p(self.fc_scale), p(self.fc_shift), self.l2_norm, p(ws["desc"]), p(ws["scratch"]), st))

@@ -90,3 +90,36 @@ def test_sa_module_tensor_core_matches_simt(spec, c, k, n, m):
     scale = simt.abs().max().item()
     assert torch.isfinite(tcore).all()
     assert (simt - tcore).abs().max().item() < 5e-5 * scale
+
+
+@pytest.mark.parametrize("n,K", [(4096, 64), (1024, 16), (128, 4), (300, 64)])
+def test_netvlad_tensor_core_matches_simt_and_fp64(n, K):
+    """vlad_tc.cu (GEMM2 reads the x planes MN-major) vs vlad.cu vs the reference formula in float64."""
+    from patchaugnet_b200.engine import _split_bf16
+    B, Cf = 3, 256
+    g = torch.Generator(device="cpu").manual_seed(n + K)
+    x = torch.randn(B, n, Cf, generator=g).to(DEV)
+    wc = (torch.randn(Cf, K, generator=g) / 16).to(DEV)
+    shift = (torch.randn(K, generator=g) * 0.1).to(DEV)
+    w2 = (torch.randn(Cf, K, generator=g) / 16).to(DEV)
+    Kp = (K + 15) // 16 * 16
+    wct = torch.zeros(Kp, Cf, device=DEV)
+    wct[:K] = wc.t()
+    hi, lo = _split_bf16(wct)
+    lib = L.lib()
+    ws = torch.empty(lib.pab_netvlad_workspace_bytes(B, n, Cf, K), dtype=torch.uint8, device=DEV)
+    out_s = torch.empty(B, Cf, K, device=DEV)
+    out_t = torch.empty(B, Cf, K, device=DEV)
+    L.check(lib.pab_netvlad_forward(B, n, Cf, K, L.ptr(x), L.ptr(wc), L.ptr(shift), L.ptr(w2), L.ptr(out_s), Cf * K, K, L.ptr(ws),
+                                    L.stream_ptr()), "vlad simt")
+    torch.cuda.synchronize()
+    L.check(lib.pab_netvlad_forward_tc(B, n, Cf, K, L.ptr(x), L.ptr(hi), L.ptr(lo), L.ptr(shift), L.ptr(w2), L.ptr(out_t), Cf * K, K,
+                                       L.ptr(ws), L.stream_ptr()), "vlad tc")
+    torch.cuda.synchronize()
+    xd = x.double()
+    act = torch.softmax(xd @ wc.double() + shift.double(), dim=-1)
+    vlad = (act.transpose(1, 2) @ xd).transpose(1, 2) - act.sum(1, keepdim=True) * w2.double()[None]
+    ref = torch.nn.functional.normalize(vlad, dim=1, p=2)
+    assert (out_s.double() - ref).abs().max().item() < 2e-5
+    assert torch.isfinite(out_t).all()
+    assert (out_t.double() - ref).abs().max().item() < 5e-5
