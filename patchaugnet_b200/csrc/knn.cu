@@ -4,8 +4,10 @@
 // one thread per query with a 2400-byte local-memory insertion list.  Here one WARP owns a query: reference
 // points are staged in shared memory (SoA, coalesced loads), each lane evaluates one reference per step,
 // a warp ballot against the current k-th best distance filters candidates (after warm-up almost every step is
-// rejected by a single compare), and the sorted top-k list lives in registers spread across the lanes
-// (slot s of lane l = rank 32*s + l), updated with shuffles.  Ordering is the reference's: ascending squared
+// rejected by a single compare), and the running k-best SET lives unsorted in registers spread across the lanes:
+// an insertion overwrites the current lexicographic maximum (found with two redux.sync) and re-derives the
+// threshold with one more; the set is sorted once at the end with a shuffle bitonic network on 64-bit
+// (distance, index) keys.  Ordering is the reference's: ascending squared
 // distance (contracted fp32 order, dx = query - ref), ties to the lower index (strict '<' on insertion, refs are
 // visited in index order).
 //
@@ -18,6 +20,11 @@ namespace {
 
 constexpr int KNN_CHUNK = 4096;   // reference points staged per pass (48 KB SoA)
 constexpr int KNN_WARPS = 16;
+
+// 64-bit sort key: squared distance bits (>= 0, so they order as unsigned) then index
+__device__ __forceinline__ unsigned long long knn_key(float d, int i) {
+    return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)i;
+}
 
 template <int KPL>
 __global__ void __launch_bounds__(KNN_WARPS * 32)
@@ -35,12 +42,14 @@ knn_kernel(int n, int m, int k, const float *__restrict__ xyz, const float *__re
         const float *c = new_xyz + ((size_t)cloud * m + q) * 3;
         qx = __ldg(c); qy = __ldg(c + 1); qz = __ldg(c + 2);
     }
+    // The running k-best SET, unsorted, one element per (slot, lane): element e = 32*s + lane is live iff e < k.
+    // Live slots start at (+inf, 0) like the reference's best[]=1e40 / besti[]=0 (knnquery_cuda_kernel.cu:23-26);
+    // dead slots hold -1 so they can never be the maximum.  tau = max live distance = the k-th best so far.
     float ld[KPL];
     int li[KPL];
 #pragma unroll
-    for (int s = 0; s < KPL; ++s) { ld[s] = INFINITY; li[s] = 0; }
+    for (int s = 0; s < KPL; ++s) { ld[s] = (s * 32 + lane < k) ? INFINITY : -1.f; li[s] = 0; }
     float tau = INFINITY;
-    const int ks = (k - 1) >> 5, kl = (k - 1) & 31;
 
     for (int base0 = 0; base0 < n; base0 += KNN_CHUNK) {
         const int cnt = min(KNN_CHUNK, n - base0);
@@ -61,39 +70,67 @@ knn_kernel(int n, int m, int k, const float *__restrict__ xyz, const float *__re
                 const int src = __ffs(hit) - 1;
                 hit &= hit - 1;
                 const float cd = __shfl_sync(0xffffffffu, d, src);
-                if (!(cd < tau)) continue;  // tau shrank since the ballot (warp-uniform)
+                if (!(cd < tau)) continue;  // tau shrank since the ballot (warp-uniform).  Strict '<': refs are visited in
+                                            // index order, so an equal distance with a higher index never displaces
                 const int ci = base0 + base + src;
-                int pos = 0;
-#pragma unroll
-                for (int s = 0; s < KPL; ++s) pos += __popc(__ballot_sync(0xffffffffu, ld[s] <= cd));
-#pragma unroll
-                for (int s = KPL - 1; s >= 0; --s) {
-                    float ud = __shfl_up_sync(0xffffffffu, ld[s], 1);
-                    int ui = __shfl_up_sync(0xffffffffu, li[s], 1);
-                    if (s > 0) {
-                        const float pd = __shfl_sync(0xffffffffu, ld[s - 1], 31);
-                        const int pi = __shfl_sync(0xffffffffu, li[s - 1], 31);
-                        if (lane == 0) { ud = pd; ui = pi; }
-                    }
-                    const int me = s * 32 + lane;
-                    if (me == pos) { ld[s] = cd; li[s] = ci; }
-                    else if (me > pos) { ld[s] = ud; li[s] = ui; }
-                }
+                // evict the lexicographic maximum (distance == tau, then the largest index)
+                const int tb = __float_as_int(tau);
+                int mi = -1, ms = 0;
 #pragma unroll
                 for (int s = 0; s < KPL; ++s)
-                    if (s == ks) tau = __shfl_sync(0xffffffffu, ld[s], kl);
+                    if (__float_as_int(ld[s]) == tb && li[s] > mi) { mi = li[s]; ms = s; }
+                const int top = __reduce_max_sync(0xffffffffu, mi);
+                const unsigned vb = __ballot_sync(0xffffffffu, mi == top);      // unfilled (+inf, 0) slots tie: lowest lane
+                if (lane == __ffs(vb) - 1) {
+#pragma unroll
+                    for (int s = 0; s < KPL; ++s)
+                        if (s == ms) { ld[s] = cd; li[s] = ci; }
+                }
+                float md = ld[0];
+#pragma unroll
+                for (int s = 1; s < KPL; ++s) md = fmaxf(md, ld[s]);
+                tau = __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(md)));
             }
         }
     }
     if (!active) return;
+    // one bitonic sort of the 32*KPL keys (dead slots sort last), ascending (distance, index)
+    unsigned long long key[KPL];
+#pragma unroll
+    for (int s = 0; s < KPL; ++s) key[s] = (s * 32 + lane < k) ? knn_key(ld[s], li[s]) : ~0ull;
+#pragma unroll
+    for (int size = 2; size <= 32 * KPL; size <<= 1) {
+#pragma unroll
+        for (int j = size >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int s = 0; s < KPL; ++s) {
+                const int e = s * 32 + lane;
+                const bool up = (e & size) == 0;                       // ascending block
+                if (j >= 32) {
+                    const int sp = s ^ (j >> 5);
+                    if (sp > s) {                                       // handle each register pair once
+                        const unsigned long long a = key[s], b = key[sp];
+                        const bool swap = (a > b) == up;
+                        key[s] = swap ? b : a;
+                        key[sp] = swap ? a : b;
+                    }
+                } else {
+                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, key[s], j);
+                    const bool lower = (lane & j) == 0;                 // this lane holds the lower position of the pair
+                    const bool take_min = lower == up;
+                    key[s] = ((key[s] < other) == take_min) ? key[s] : other;
+                }
+            }
+        }
+    }
     int *o = idx + ((size_t)cloud * m + q) * k;
     float *od = dist2 ? dist2 + ((size_t)cloud * m + q) * k : nullptr;
 #pragma unroll
     for (int s = 0; s < KPL; ++s) {
         const int me = s * 32 + lane;
         if (me < k) {
-            o[me] = li[s];
-            if (od) od[me] = ld[s];
+            o[me] = (int)(unsigned)(key[s] & 0xffffffffull);
+            if (od) od[me] = __uint_as_float((unsigned)(key[s] >> 32));
         }
     }
 }
@@ -106,7 +143,7 @@ template <bool WEIGHTS>
 __global__ void __launch_bounds__(256)
 three_nn_kernel(int n, int m, const float *__restrict__ unknown, const float *__restrict__ known,
                 float *__restrict__ out_f, int *__restrict__ idx) {
-    __shared__ float xs[NN3_CHUNK], ys[NN3_CHUNK], zs[NN3_CHUNK];
+    __shared__ float4 pts[NN3_CHUNK];           // one broadcast LDS.128 per known point
     const int t = threadIdx.x, cloud = blockIdx.y;
     const int j = blockIdx.x * blockDim.x + t;
     const bool active = j < n;
@@ -121,20 +158,22 @@ three_nn_kernel(int n, int m, const float *__restrict__ unknown, const float *__
     for (int base0 = 0; base0 < m; base0 += NN3_CHUNK) {
         const int cnt = min(NN3_CHUNK, m - base0);
         __syncthreads();
-        for (int e = t; e < cnt * 3; e += blockDim.x) {
-            const float v = __ldg(kn + (size_t)base0 * 3 + e);
-            const int kk = e / 3, c = e - 3 * kk;
-            (c == 0 ? xs : (c == 1 ? ys : zs))[kk] = v;
+        for (int kk = t; kk < cnt; kk += blockDim.x) {
+            const float *src = kn + (size_t)(base0 + kk) * 3;
+            pts[kk] = make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), 0.f);
         }
         __syncthreads();
         if (!active) continue;
 #pragma unroll 4
         for (int kk = 0; kk < cnt; ++kk) {
-            const float d = ref_sqdist(ux, uy, uz, xs[kk], ys[kk], zs[kk]);
-            const int gi = base0 + kk;
-            if (d < b1) { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = gi; }
-            else if (d < b2) { b3 = b2; i3 = i2; b2 = d; i2 = gi; }
-            else if (d < b3) { b3 = d; i3 = gi; }
+            const float4 pk = pts[kk];
+            const float d = ref_sqdist(ux, uy, uz, pk.x, pk.y, pk.z);
+            if (d < b3) {                         // same strict-'<' cascade as the reference, entered only on a hit
+                const int gi = base0 + kk;
+                if (d < b1) { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = gi; }
+                else if (d < b2) { b3 = b2; i3 = i2; b2 = d; i2 = gi; }
+                else { b3 = d; i3 = gi; }
+            }
         }
     }
     if (!active) return;
@@ -247,13 +286,10 @@ PAB_API int pab_knnquery(int b, int n, int m, int nsample, const float *xyz, con
     cudaStream_t st = (cudaStream_t)s;
     dim3 grid(pab_divup(m, KNN_WARPS), b), block(KNN_WARPS * 32);
     const int kpl = (nsample + 31) / 32;
-    switch (kpl) {
-        case 1: knn_kernel<1><<<grid, block, 0, st>>>(n, m, nsample, xyz, new_xyz, idx, dist2); break;
-        case 2: knn_kernel<2><<<grid, block, 0, st>>>(n, m, nsample, xyz, new_xyz, idx, dist2); break;
-        case 3: knn_kernel<3><<<grid, block, 0, st>>>(n, m, nsample, xyz, new_xyz, idx, dist2); break;
-        case 4: knn_kernel<4><<<grid, block, 0, st>>>(n, m, nsample, xyz, new_xyz, idx, dist2); break;
-        default: knn_kernel<7><<<grid, block, 0, st>>>(n, m, nsample, xyz, new_xyz, idx, dist2); break;
-    }
+    if (kpl <= 1) knn_kernel<1><<<grid, block, 0, st>>>(n, m, nsample, xyz, new_xyz, idx, dist2);
+    else if (kpl <= 2) knn_kernel<2><<<grid, block, 0, st>>>(n, m, nsample, xyz, new_xyz, idx, dist2);
+    else if (kpl <= 4) knn_kernel<4><<<grid, block, 0, st>>>(n, m, nsample, xyz, new_xyz, idx, dist2);
+    else knn_kernel<8><<<grid, block, 0, st>>>(n, m, nsample, xyz, new_xyz, idx, dist2);
     PAB_LAUNCH_CHECK();
     return 0;
 }

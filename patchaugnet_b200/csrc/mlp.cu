@@ -11,8 +11,8 @@
 #include "tile_gemm.cuh"
 
 // tensor-core path (mlp_tc.cu)
-bool pab_tc_eligible(const pab_layer_t *layers, int n_layers, int k_group);
-int pab_tc_sa(int b, int n, int m, int k, int nbr_stride, int c, const float *xyz, const float *feat, const int *center_idx,
+int pab_tc_eligible(const pab_layer_t *layers, int n_layers, int k_group, int allow_pre);
+int pab_tc_sa(int kind, int b, int n, int m, int k, int nbr_stride, int c, const float *xyz, const float *feat, const int *center_idx,
               const int *nbr_idx, const pab_layer_t *layers, int n_layers, float *out, cudaStream_t st);
 int pab_tc_fp(int b, int n, int m, int c_known, int c_skip, const float *known_feat, const float *skip_feat, const int *idx,
               const float *weight, const pab_layer_t *layers, int n_layers, float *out, cudaStream_t st);
@@ -225,8 +225,11 @@ PAB_API int pab_sa_module_forward(int b, int n, int m, int k, int nbr_stride, in
                                   float *out, float *new_xyz, pab_stream_t s) {
     if (b < 0 || n <= 0 || m < 0 || k <= 0 || k > 256 || nbr_stride < k || c < 0 || !layers) return PAB_EINVAL;
     if (layers[0].c_in != c + 3) return PAB_EINVAL;
-    if (!new_xyz && c % 8 == 0 && pab_tc_eligible(layers, n_layers, k) && layers[0].tc_k == c && layers[0].tc_k0 == 3)
-        return pab_tc_sa(b, n, m, k, nbr_stride, c, xyz, feat, center_idx, nbr_idx, layers, n_layers, out, (cudaStream_t)s);
+    if (!new_xyz) {
+        const int kind = pab_tc_eligible(layers, n_layers, k, c <= 5);
+        if ((kind == 1 && c % 8 == 0 && layers[0].tc_k == c && layers[0].tc_k0 == 3) || kind == 2)
+            return pab_tc_sa(kind, b, n, m, k, nbr_stride, c, xyz, feat, center_idx, nbr_idx, layers, n_layers, out, (cudaStream_t)s);
+    }
     MlpArgs a{};
     a.mode = MODE_SA; a.rows = (long)b * m; a.n = n; a.m = m; a.k = k; a.nbr_stride = nbr_stride; a.c = c;
     a.xyz = xyz; a.feat = feat; a.center_idx = center_idx; a.nbr_idx = nbr_idx; a.new_xyz = new_xyz; a.out = out;
@@ -238,7 +241,7 @@ PAB_API int pab_fp_module_forward(int b, int n, int m, int c_known, int c_skip, 
                                   float *out, pab_stream_t s) {
     if (b < 0 || n < 0 || m <= 0 || c_known <= 0 || c_skip < 0 || !layers) return PAB_EINVAL;
     if (layers[0].c_in != c_known + c_skip || (c_skip > 0 && !skip_feat)) return PAB_EINVAL;
-    if (c_known % 8 == 0 && pab_tc_eligible(layers, n_layers, 0) && layers[0].tc_k0 == 0 &&
+    if (c_known % 8 == 0 && pab_tc_eligible(layers, n_layers, 0, 0) == 1 && layers[0].tc_k0 == 0 &&
         ((layers[0].tc_k == c_known && c_skip <= 3) || (layers[0].tc_k == c_known + c_skip && c_skip % 8 == 0)))
         return pab_tc_fp(b, n, m, c_known, c_skip, known_feat, skip_feat, idx, weight, layers, n_layers, out, (cudaStream_t)s);
     MlpArgs a{};

@@ -43,6 +43,11 @@ struct alignas(64) TcArgs {
     // layer-0 "extra" channels (the xyz part), applied as a rank-n update from the fp32 weight rows
     const float *w_extra;                      // layers[0].wt + extra_row0 * N0
     int n_extra;
+    // optional "pre" layer: the module's first layer has so few inputs (<= 8: SA1's [xyz_rel ; feat_rel]) that the loader
+    // evaluates it in fp32 and stages its OUTPUT as the first tensor-core operand (zero-padded to 64 channels)
+    int pre_cin, pre_cout, pre_relu;
+    const float *pre_wt, *pre_shift;           // (pre_cin_pad, pre_cout) fp32 folded weight, shift
+    int pre_off;                               // offset of [weights | shift] in the smem constant table
     // SA
     int n, m, k, nbr_stride, c;
     const float *xyz, *feat;
@@ -87,6 +92,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             off += a.N[l];
         }
         for (int i = tid; i < a.n_extra * a.N[0]; i += TC_THREADS) ctab[off + i] = __ldg(a.w_extra + i);
+        if (a.pre_cout > 0) {
+            for (int i = tid; i < a.pre_cin * a.pre_cout; i += TC_THREADS) ctab[a.pre_off + i] = __ldg(a.pre_wt + i);
+            for (int i = tid; i < a.pre_cout; i += TC_THREADS) ctab[a.pre_off + a.pre_cin * a.pre_cout + i] = __ldg(a.pre_shift + i);
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -163,7 +172,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
             // ---- stage the layer-0 operand (hi/lo planes): one warp per row, lanes across the row's 16-byte units -----
             float xe[3] = {0.f, 0.f, 0.f};
-            if (a.mode == TC_SA) {
+            if (a.mode == TC_SA && a.pre_cout > 0) {
+                // two threads per row: inputs [xyz_j - xyz_i ; f_j - f_i] (pre_cin <= 8 values), each thread evaluates half of
+                // the pre-layer's outputs in fp32 and stages them (hi/lo); the rest of the 64-channel chunk is zeroed
+                const int G = TM / a.k;
+                const int r = wt >> 1, part = wt & 1;
+                const int g = r / a.k, sidx = r - g * a.k;
+                const long ci = (long)tile * G + g;
+                float in[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) in[i] = 0.f;
+                const bool valid = g < G && ci < a.rows;
+                if (valid) {
+                    const long cloud = ci / a.m;
+                    const long pc = cloud * a.n + __ldg(a.center_idx + ci);
+                    const long pn = cloud * a.n + __ldg(a.nbr_idx + ci * a.nbr_stride + sidx);
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) in[i] = __ldg(a.xyz + pn * 3 + i) - __ldg(a.xyz + pc * 3 + i);
+#pragma unroll
+                    for (int i = 0; i < 5; ++i)
+                        if (i < a.c) in[3 + i] = __ldg(a.feat + pn * a.c + i) - __ldg(a.feat + pc * a.c + i);
+                }
+                const float *pw = ctab + a.pre_off, *ps = pw + a.pre_cin * a.pre_cout;
+                const int half_out = a.pre_cout / 2;                           // outputs per thread (multiple of 8)
+                for (int u = 0; u < half_out / 8; ++u) {
+                    float v[8];
+                    const int o0 = part * half_out + u * 8;
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) {
+                        float acc = ps[o0 + o];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if (i < a.pre_cin) acc = fmaf(in[i], pw[i * a.pre_cout + o0 + o], acc);
+                        v[o] = valid ? (a.pre_relu ? fmaxf(acc, 0.f) : acc) : 0.f;
+                    }
+                    store_units(a1, a2, r, o0 >> 3, v);
+                }
+                const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                for (int j = a.pre_cout / 8 + part; j < units0; j += 2) store_units(a1, a2, r, j, z);
+            } else if (a.mode == TC_SA) {
                 const int G = TM / a.k;
                 for (int r = wwarp; r < TM; r += 8) {
                     const int g = r / a.k, sidx = r - g * a.k;
@@ -275,9 +322,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                 const int npass = last ? (N + 255) / 256 : 1;
                 for (int pass = 0; pass < npass; ++pass) {
                     const int ncols = min(256, N - pass * 256);        // columns of this pass
-                    const int per = ncols / 2;                         // columns per worker half
+                    const int per = ncols >= 64 ? ncols / 2 : (half == 0 ? ncols : 0);   // columns per worker half (batches of 32)
                     for (int cb = 0; cb < per; cb += 32) {
-                        const int col = pass * 256 + half * per + cb;  // first accumulator column of this batch
+                        const int col = pass * 256 + (ncols >= 64 ? half * per : 0) + cb;  // first accumulator column of this batch
                         float v[32];
                         tmem_ld32(trow + (uint32_t)col, v);
 #pragma unroll
@@ -394,21 +441,22 @@ int make_weight_map(CUtensorMap *map, const void *w, int N, int K, int box_n) {
 
 int g_tc_enabled = 1;
 
-}  // namespace
-
-PAB_API void pab_tune_tensor_core(int enable) { g_tc_enabled = enable; }
-
 // Shared-memory plan of one launch: operand region, constant table, weight-stage granularity and count.
-struct TcPlan { int kchunks_max, a_region, nblk, stage_bytes, n_stages, coff[MAX_LAYERS]; size_t misc, smem; };
+// `layers` are the TENSOR-CORE layers only (the optional pre-layer is passed separately).
+struct TcPlan { int kchunks_max, a_region, nblk, stage_bytes, n_stages, coff[MAX_LAYERS], pre_off; size_t misc, smem; };
 
-bool tc_plan(const pab_layer_t *layers, int n_layers, TcPlan *p) {
+bool tc_plan(const pab_layer_t *layers, int n_layers, const pab_layer_t *pre, TcPlan *p) {
     int kmax = 0, ctab = 0;
+    bool need64 = false;
     for (int l = 0; l < n_layers; ++l) {
         if (layers[l].tc_k > kmax) kmax = layers[l].tc_k;
         p->coff[l] = ctab;
         ctab += layers[l].c_out;
+        if (layers[l].c_out > 64 && layers[l].c_out % 128) need64 = true;   // e.g. 192: only 64-wide blocks divide it
     }
-    ctab += (layers[0].c_in - layers[0].tc_k) * layers[0].c_out;
+    if (!pre) ctab += (layers[0].c_in - layers[0].tc_k) * layers[0].c_out;
+    p->pre_off = ctab;
+    if (pre) ctab += pre->c_in * pre->c_out + pre->c_out;
     p->kchunks_max = kmax / KCH;
     p->a_region = 2 * p->kchunks_max * A_CHUNK;
     if (p->a_region < TM * 256 * 4) p->a_region = TM * 256 * 4;      // last-layer fp32 staging [128][256]
@@ -416,7 +464,7 @@ bool tc_plan(const pab_layer_t *layers, int n_layers, TcPlan *p) {
     const long budget = 227L * 1024 - p->a_region - (long)p->misc;
     if (budget < 2 * 2 * 64 * 128) return false;
     // 128 output channels per stage when at least 3 such stages fit, else 64
-    p->nblk = (budget / (2 * 128 * 128) >= 3) ? 128 : 64;
+    p->nblk = (!need64 && budget / (2 * 128 * 128) >= 3) ? 128 : 64;
     p->stage_bytes = 2 * p->nblk * 128;
     p->n_stages = (int)(budget / p->stage_bytes);
     if (p->n_stages > MAX_STAGES) p->n_stages = MAX_STAGES;
@@ -424,28 +472,46 @@ bool tc_plan(const pab_layer_t *layers, int n_layers, TcPlan *p) {
     return p->n_stages >= 2;
 }
 
-// Can this module run on the tensor-core path?  (every layer split on the host, shapes a multiple of 64, at most
-// 3 "extra" layer-0 channels, operand planes + >= 2 weight stages within 227 KB)
-bool pab_tc_eligible(const pab_layer_t *layers, int n_layers, int k_group) {
-    if (!g_tc_enabled || n_layers < 1 || n_layers > MAX_LAYERS) return false;
+bool tc_layers_ok(const pab_layer_t *layers, int n_layers, bool first_is_module_input) {
+    if (n_layers < 1 || n_layers > MAX_LAYERS) return false;
     for (int l = 0; l < n_layers; ++l) {
         const pab_layer_t &L = layers[l];
-        if (!L.w_hi || !L.w_lo || L.tc_k <= 0 || L.tc_k % KCH || L.c_out % 64) return false;
-        if (l > 0 && (L.tc_k0 != 0 || L.tc_k != L.c_in)) return false;
+        if (!L.w_hi || !L.w_lo || L.tc_k <= 0 || L.tc_k % KCH) return false;
+        if (!(L.c_out == 32 || L.c_out % 64 == 0) || L.c_out > 512) return false;
         if (l < n_layers - 1 && L.c_out > 256) return false;
-        if (L.c_out > 512 || (L.c_out > 64 && L.c_out % 128)) return false;
+        const bool module_input = l == 0 && first_is_module_input;
+        if (!module_input && (L.tc_k0 != 0 || L.tc_k < L.c_in)) return false;          // K may be zero-padded to 64
+        if (l > 0 && L.c_in != layers[l - 1].c_out) return false;
     }
-    const int n_extra = layers[0].c_in - layers[0].tc_k;
-    if (n_extra < 0 || n_extra > 3) return false;
-    if (n_extra > 0 && !(layers[0].tc_k0 == 0 || layers[0].tc_k0 == n_extra)) return false;
-    if (k_group > TM) return false;
-    TcPlan p;
-    return tc_plan(layers, n_layers, &p);
+    return true;
 }
 
-int pab_tc_launch(int mode, long rows, int k_group, const pab_layer_t *layers, int n_layers, TcArgs &a, cudaStream_t st) {
+}  // namespace
+
+// 0: not eligible; 1: every layer on tensor cores; 2: first layer evaluated by the loader (tiny input), rest on tensor cores
+int pab_tc_eligible(const pab_layer_t *layers, int n_layers, int k_group, int allow_pre) {
+    if (!g_tc_enabled || k_group > TM) return 0;
     TcPlan p;
-    if (!tc_plan(layers, n_layers, &p)) return PAB_EINVAL;
+    if (tc_layers_ok(layers, n_layers, true)) {
+        const int n_extra = layers[0].c_in - layers[0].tc_k;
+        if (n_extra >= 0 && n_extra <= 3 && (n_extra == 0 || layers[0].tc_k0 == 0 || layers[0].tc_k0 == n_extra) &&
+            tc_plan(layers, n_layers, nullptr, &p))
+            return 1;
+    }
+    if (allow_pre && n_layers >= 2 && layers[0].c_in <= 8 && layers[0].c_out % 16 == 0 && layers[0].c_out <= 64 &&
+        tc_layers_ok(layers + 1, n_layers - 1, false) && tc_plan(layers + 1, n_layers - 1, &layers[0], &p))
+        return 2;
+    return 0;
+}
+
+namespace {
+
+int pab_tc_launch(int mode, long rows, int k_group, const pab_layer_t *all_layers, int n_all, int kind, TcArgs &a, cudaStream_t st) {
+    const pab_layer_t *pre = kind == 2 ? &all_layers[0] : nullptr;
+    const pab_layer_t *layers = kind == 2 ? all_layers + 1 : all_layers;
+    const int n_layers = kind == 2 ? n_all - 1 : n_all;
+    TcPlan p;
+    if (!tc_plan(layers, n_layers, pre, &p)) return PAB_EINVAL;
     a.kchunks_max = p.kchunks_max; a.a_region = p.a_region; a.nblk = p.nblk; a.stage_bytes = p.stage_bytes; a.n_stages = p.n_stages;
     for (int l = 0; l < n_layers; ++l) {
         const pab_layer_t &L = layers[l];
@@ -455,10 +521,17 @@ int pab_tc_launch(int mode, long rows, int k_group, const pab_layer_t *layers, i
         a.shift[l] = L.shift; a.K[l] = L.tc_k; a.N[l] = L.c_out; a.relu[l] = L.relu; a.coff[l] = p.coff[l];
     }
     a.n_layers = n_layers; a.mode = mode; a.rows = rows;
-    a.n_extra = layers[0].c_in - layers[0].tc_k;
-    // extra channels sit before (SA: xyz first) or after (FP: skip last) the tensor-core part
-    const int extra_row0 = layers[0].tc_k0 == 0 ? layers[0].tc_k : 0;
-    a.w_extra = layers[0].wt + (size_t)extra_row0 * layers[0].c_out;
+    if (pre) {
+        a.n_extra = 0; a.w_extra = nullptr;
+        a.pre_cin = pre->c_in; a.pre_cout = pre->c_out; a.pre_relu = pre->relu; a.pre_wt = pre->wt; a.pre_shift = pre->shift;
+        a.pre_off = p.pre_off;
+    } else {
+        a.pre_cout = 0;
+        a.n_extra = layers[0].c_in - layers[0].tc_k;
+        // extra channels sit before (SA: xyz first) or after (FP: skip last) the tensor-core part
+        const int extra_row0 = layers[0].tc_k0 == 0 ? layers[0].tc_k : 0;
+        a.w_extra = layers[0].wt + (size_t)extra_row0 * layers[0].c_out;
+    }
     const long per_tile = mode == TC_SA ? (TM / k_group) : TM;
     a.ntiles = (int)((rows + per_tile - 1) / per_tile);
     static int n_sm = 0;
@@ -475,12 +548,16 @@ int pab_tc_launch(int mode, long rows, int k_group, const pab_layer_t *layers, i
     return 0;
 }
 
-int pab_tc_sa(int b, int n, int m, int k, int nbr_stride, int c, const float *xyz, const float *feat, const int *center_idx,
+}  // namespace
+
+PAB_API void pab_tune_tensor_core(int enable) { g_tc_enabled = enable; }
+
+int pab_tc_sa(int kind, int b, int n, int m, int k, int nbr_stride, int c, const float *xyz, const float *feat, const int *center_idx,
               const int *nbr_idx, const pab_layer_t *layers, int n_layers, float *out, cudaStream_t st) {
     TcArgs a{};
     a.n = n; a.m = m; a.k = k; a.nbr_stride = nbr_stride; a.c = c; a.xyz = xyz; a.feat = feat; a.center_idx = center_idx;
     a.nbr_idx = nbr_idx; a.out = out;
-    return pab_tc_launch(TC_SA, (long)b * m, k, layers, n_layers, a, st);
+    return pab_tc_launch(TC_SA, (long)b * m, k, layers, n_layers, kind, a, st);
 }
 
 int pab_tc_fp(int b, int n, int m, int c_known, int c_skip, const float *known_feat, const float *skip_feat, const int *idx,
@@ -488,5 +565,5 @@ int pab_tc_fp(int b, int n, int m, int c_known, int c_skip, const float *known_f
     TcArgs a{};
     a.n = n; a.m = m; a.c_known = c_known; a.c_skip = c_skip; a.known_feat = known_feat; a.skip_feat = skip_feat;
     a.idx3 = idx; a.w3 = weight; a.out = out;
-    return pab_tc_launch(TC_FP, (long)b * n, 0, layers, n_layers, a, st);
+    return pab_tc_launch(TC_FP, (long)b * n, 0, layers, n_layers, 1, a, st);
 }

@@ -59,11 +59,19 @@ class _Layers:
                 scale = torch.ones(c_out, device=w.device)
                 shift = blk.conv.bias.detach().float() if blk.conv.bias is not None else torch.zeros(c_out, device=w.device)
             folded.append(((w * scale[:, None]).to(device), shift.to(device).contiguous(), c_in, c_out, hasattr(blk, "activation")))
-        tc_ok = len(blocks) <= 3
+        # tensor-core plan: "pre" = the first layer has a tiny input (<= 8 channels, SA1) and is evaluated by the kernel's
+        # loader in fp32; every other layer needs K (zero-padded to a multiple of 64) and N in {32, 64k}
+        pre = len(folded) >= 2 and folded[0][2] <= 8
+        first_tc = 1 if pre else 0
+        tc_ok = 1 <= len(folded) - first_tc <= 3
         for i, (wf, sh, c_in, c_out, act) in enumerate(folded):
-            k0 = extra_first if i == 0 else 0
+            if i < first_tc:
+                tc_ok = tc_ok and c_out % 16 == 0 and c_out <= 64
+                continue
             kk = c_in - (extra_first + extra_last if i == 0 else 0)
-            tc_ok = tc_ok and kk > 0 and kk % 64 == 0 and c_out % 64 == 0
+            tc_ok = tc_ok and kk > 0 and (c_out == 32 or c_out % 64 == 0)
+            if i == 0:
+                tc_ok = tc_ok and kk % 64 == 0          # the gather loaders stage exactly K channels
         self.tensor_core = tc_ok
         for i, (wf, sh, c_in, c_out, act) in enumerate(folded):
             c_in_pad = (c_in + 3) // 4 * 4
@@ -71,14 +79,17 @@ class _Layers:
             wt[:c_in] = wf.t()
             self.tensors += [wt, sh]
             hi_p = lo_p = 0
-            k0 = kk = 0
-            if tc_ok:
+            k0 = kpad = 0
+            if tc_ok and i >= first_tc:
                 k0 = extra_first if i == 0 else 0
                 kk = c_in - (extra_first + extra_last if i == 0 else 0)
-                hi, lo = _split_bf16(wf[:, k0:k0 + kk].contiguous())
+                kpad = (kk + 63) // 64 * 64
+                wk = torch.zeros(c_out, kpad, dtype=torch.float32, device=device)
+                wk[:, :kk] = wf[:, k0:k0 + kk]
+                hi, lo = _split_bf16(wk)
                 self.tensors += [hi, lo]
                 hi_p, lo_p = hi.data_ptr(), lo.data_ptr()
-            self.arr[i] = L.PabLayer(wt.data_ptr(), sh.data_ptr(), c_in, c_in_pad, c_out, 1 if act else 0, hi_p, lo_p, k0, kk)
+            self.arr[i] = L.PabLayer(wt.data_ptr(), sh.data_ptr(), c_in, c_in_pad, c_out, 1 if act else 0, hi_p, lo_p, k0, kpad)
             self.spec.append((c_in, c_out))
         self.n = len(blocks)
         self.c_out = self.spec[-1][1]

@@ -64,7 +64,8 @@ def test_fp_module_tensor_core_matches_simt_and_fp64(spec, c_known, c_skip, n, m
 
 
 @pytest.mark.parametrize("spec,c,k,n,m", [([259, 256, 256, 512], 256, 20, 128, 16), ([67, 64, 64, 256], 64, 20, 1024, 128),
-                                           ([131, 128, 128, 256], 128, 7, 300, 50)])
+                                           ([131, 128, 128, 256], 128, 7, 300, 50), ([6, 32, 32, 64], 3, 20, 4096, 1024),
+                                           ([6, 32, 64], 3, 9, 500, 77)])
 def test_sa_module_tensor_core_matches_simt(spec, c, k, n, m):
     B = 4
     g = torch.Generator(device="cpu").manual_seed(n + k)
