@@ -146,6 +146,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="stream", choices=["stream", "graph", "eager"],
                     help="stream: 2-stream pipelined throughput mode (default); graph: one CUDA graph per step; eager")
+    ap.add_argument("--dense-streams", type=int, default=2)
     ap.add_argument("--graph", type=int, default=None, help="deprecated alias: 1 -> --mode graph, 0 -> --mode eager")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -170,6 +171,7 @@ def main():
 
     net = util.build_network(dev)                        # random-init weights of the reference architecture (tests/util.py)
     eng = net.engine()
+    eng.dense_streams = max(1, min(2, args.dense_streams))
     lib = L.lib()
 
     # input pool larger than L2 (126 MB): 104 batches x 1.5 MB = 164 MB, distinct seeded clouds per rank

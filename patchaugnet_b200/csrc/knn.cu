@@ -30,7 +30,7 @@ template <int KPL>
 __global__ void __launch_bounds__(KNN_WARPS * 32)
 knn_kernel(int n, int m, int k, const float *__restrict__ xyz, const float *__restrict__ new_xyz,
            int *__restrict__ idx, float *__restrict__ dist2) {
-    __shared__ float xs[KNN_CHUNK], ys[KNN_CHUNK], zs[KNN_CHUNK];
+    __shared__ float sm[3 * KNN_CHUNK];          // SoA: x at +0, y at +KNN_CHUNK, z at +2*KNN_CHUNK (constant offsets)
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int cloud = blockIdx.y;
     const int q = blockIdx.x * KNN_WARPS + warp;
@@ -51,46 +51,57 @@ knn_kernel(int n, int m, int k, const float *__restrict__ xyz, const float *__re
     for (int s = 0; s < KPL; ++s) { ld[s] = (s * 32 + lane < k) ? INFINITY : -1.f; li[s] = 0; }
     float tau = INFINITY;
 
+    // candidates flagged in `hit` (lane order = index order) against the running set
+    auto absorb = [&](unsigned hit, float d, int first_index) {
+        while (hit) {
+            const int src = __ffs(hit) - 1;
+            hit &= hit - 1;
+            const float cd = __shfl_sync(0xffffffffu, d, src);
+            if (!(cd < tau)) continue;      // tau shrank since the ballot (warp-uniform).  Strict '<': refs are visited in
+                                            // index order, so an equal distance with a higher index never displaces
+            const int ci = first_index + src;
+            // evict the lexicographic maximum (distance == tau, then the largest index)
+            const int tb = __float_as_int(tau);
+            int mi = -1, ms = 0;
+#pragma unroll
+            for (int s = 0; s < KPL; ++s)
+                if (__float_as_int(ld[s]) == tb && li[s] > mi) { mi = li[s]; ms = s; }
+            const int top = __reduce_max_sync(0xffffffffu, mi);
+            const unsigned vb = __ballot_sync(0xffffffffu, mi == top);          // unfilled (+inf, 0) slots tie: lowest lane
+            if (lane == __ffs(vb) - 1) {
+#pragma unroll
+                for (int s = 0; s < KPL; ++s)
+                    if (s == ms) { ld[s] = cd; li[s] = ci; }
+            }
+            float md = ld[0];
+#pragma unroll
+            for (int s = 1; s < KPL; ++s) md = fmaxf(md, ld[s]);
+            tau = __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(md)));
+        }
+    };
+
     for (int base0 = 0; base0 < n; base0 += KNN_CHUNK) {
         const int cnt = min(KNN_CHUNK, n - base0);
+        const int cnt64 = (cnt + 63) & ~63;       // padded with +inf coordinates: their distance is +inf, never < tau
         __syncthreads();
-        for (int e = t; e < cnt * 3; e += KNN_WARPS * 32) {
-            const float v = __ldg(p + (size_t)base0 * 3 + e);
-            const int kk = e / 3, c = e - 3 * kk;
-            (c == 0 ? xs : (c == 1 ? ys : zs))[kk] = v;
+        for (int i = t; i < cnt64; i += KNN_WARPS * 32) {
+            float x = INFINITY, y = INFINITY, z = INFINITY;
+            if (i < cnt) {
+                const float *src = p + (size_t)(base0 + i) * 3;
+                x = __ldg(src); y = __ldg(src + 1); z = __ldg(src + 2);
+            }
+            sm[i] = x; sm[KNN_CHUNK + i] = y; sm[2 * KNN_CHUNK + i] = z;
         }
         __syncthreads();
         if (!active) continue;
-        for (int base = 0; base < cnt; base += 32) {
-            const int i = base + lane;
-            float d = INFINITY;
-            if (i < cnt) d = ref_sqdist(qx, qy, qz, xs[i], ys[i], zs[i]);
-            unsigned hit = __ballot_sync(0xffffffffu, d < tau);
-            while (hit) {
-                const int src = __ffs(hit) - 1;
-                hit &= hit - 1;
-                const float cd = __shfl_sync(0xffffffffu, d, src);
-                if (!(cd < tau)) continue;  // tau shrank since the ballot (warp-uniform).  Strict '<': refs are visited in
-                                            // index order, so an equal distance with a higher index never displaces
-                const int ci = base0 + base + src;
-                // evict the lexicographic maximum (distance == tau, then the largest index)
-                const int tb = __float_as_int(tau);
-                int mi = -1, ms = 0;
-#pragma unroll
-                for (int s = 0; s < KPL; ++s)
-                    if (__float_as_int(ld[s]) == tb && li[s] > mi) { mi = li[s]; ms = s; }
-                const int top = __reduce_max_sync(0xffffffffu, mi);
-                const unsigned vb = __ballot_sync(0xffffffffu, mi == top);      // unfilled (+inf, 0) slots tie: lowest lane
-                if (lane == __ffs(vb) - 1) {
-#pragma unroll
-                    for (int s = 0; s < KPL; ++s)
-                        if (s == ms) { ld[s] = cd; li[s] = ci; }
-                }
-                float md = ld[0];
-#pragma unroll
-                for (int s = 1; s < KPL; ++s) md = fmaxf(md, ld[s]);
-                tau = __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(md)));
-            }
+        const float *sp = sm + lane;
+        for (int base = 0; base < cnt64; base += 64) {
+            const float d0 = ref_sqdist(qx, qy, qz, sp[base], sp[KNN_CHUNK + base], sp[2 * KNN_CHUNK + base]);
+            const float d1 = ref_sqdist(qx, qy, qz, sp[base + 32], sp[KNN_CHUNK + base + 32], sp[2 * KNN_CHUNK + base + 32]);
+            const unsigned h0 = __ballot_sync(0xffffffffu, d0 < tau);
+            if (h0) absorb(h0, d0, base0 + base);
+            const unsigned h1 = __ballot_sync(0xffffffffu, d1 < tau);
+            if (h1) absorb(h1, d1, base0 + base + 32);
         }
     }
     if (!active) return;

@@ -109,6 +109,7 @@ class FusedPatchAugNet:
         self._event_filter = None
         self._streams = None
         self.vlad_tensor_core = True
+        self.dense_streams = 2          # dense kernels of consecutive batches alternate between two streams
         self.refold()
 
     # ---- weights -------------------------------------------------------------------------------------------------
@@ -288,10 +289,11 @@ class FusedPatchAugNet:
             out = torch.empty(len(batches) * B, self.c_out, dtype=torch.float32, device=self.device)
         cur = torch.cuda.current_stream()
         if self._streams is None:
-            self._streams = (torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device))
-        s_geo, s_dense = self._streams
+            self._streams = tuple(torch.cuda.Stream(device=self.device) for _ in range(3))
+        s_geo, dense_streams = self._streams[0], self._streams[1:1 + self.dense_streams]
         s_geo.wait_stream(cur)
-        s_dense.wait_stream(cur)
+        for sd in dense_streams:
+            sd.wait_stream(cur)
         slots = [self._workspace(B, N, slot) for slot in (0, 1)]
         geo_done = [None, None]
         dense_done = [None, None]
@@ -309,6 +311,7 @@ class FusedPatchAugNet:
                 self._launch_geo(xyz0, ws)
                 geo_done[slot] = torch.cuda.Event()
                 geo_done[slot].record()
+            s_dense = dense_streams[i % len(dense_streams)]   # alternate: the tail of one batch's kernels overlaps the next's
             with torch.cuda.stream(s_dense):
                 s_dense.wait_event(geo_done[slot])
                 self._launch_dense(xyz0, ws)
@@ -317,7 +320,8 @@ class FusedPatchAugNet:
                 dense_done[slot].record()
             xyz0.record_stream(s_geo)
             xyz0.record_stream(s_dense)
-        cur.wait_stream(s_dense)
+        for sd in dense_streams:
+            cur.wait_stream(sd)
         cur.wait_stream(s_geo)
         return out
 
