@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d_ready + 1);
     float *ctab = reinterpret_cast<float *>(misc + 256);   // [shift of every layer | 3 x N0 extra weight rows], 16-byte aligned
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
 
     if (tid == 0) {
         for (int s = 0; s < a.n_stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
@@ -100,60 +100,58 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == 0) {
         // ================= TMA producer: weight blocks, in (tile, layer, n-block, k-chunk) order =================
         if (lane == 0) {
-            uint32_t it = 0;
+            uint32_t s = 0, ph = 0;
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
                 for (int l = 0; l < a.n_layers; ++l) {
                     const int nkc = a.K[l] / KCH, nbr = min(a.nblk, a.N[l]), nnb = a.N[l] / nbr;
                     for (int nb = 0; nb < nnb; ++nb)
-                        for (int kc = 0; kc < nkc; ++kc, ++it) {
-                            const int s = it % a.n_stages;
-                            const uint32_t ph = (it / a.n_stages) & 1;
+                        for (int kc = 0; kc < nkc; ++kc) {
                             mbar_wait(empty + s, ph ^ 1);
                             uint8_t *dst = stages + (size_t)s * a.stage_bytes;
                             mbar_expect_tx(full + s, 2u * nbr * 128u);
                             tma_load_2d(dst, &a.tm[l][0], kc * KCH, nb * nbr, full + s);
                             tma_load_2d(dst + nbr * 128, &a.tm[l][1], kc * KCH, nb * nbr, full + s);
+                            if (++s == (uint32_t)a.n_stages) { s = 0; ph ^= 1; }
                         }
                 }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ================= MMA issuer =============================================================================
-        if (lane == 0) {
-            uint32_t it = 0, lcount = 0;
-            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-                for (int l = 0; l < a.n_layers; ++l, ++lcount) {
-                    const int nkc = a.K[l] / KCH, nbr = min(a.nblk, a.N[l]), nnb = a.N[l] / nbr;
-                    const uint32_t idesc = umma_idesc(nbr);
-                    mbar_wait(a_ready, lcount & 1);
-                    tc_fence_after();
-                    for (int nb = 0; nb < nnb; ++nb) {
-                        const uint32_t d = tmem + (uint32_t)(nb * nbr);
-                        for (int kc = 0; kc < nkc; ++kc, ++it) {
-                            const int s = it % a.n_stages;
-                            mbar_wait(full + s, (it / a.n_stages) & 1);
-                            tc_fence_after();
-                            const uint32_t sa1 = smem_u32(a1 + (size_t)kc * A_CHUNK), sa2 = smem_u32(a2 + (size_t)kc * A_CHUNK);
-                            const uint32_t sb1 = smem_u32(stages + (size_t)s * a.stage_bytes), sb2 = sb1 + nbr * 128;
+        // ================= MMA issuer: all lanes run the loops, one elected lane issues ===========================
+        const uint32_t leader = elect_one();
+        const uint32_t a1_lo = umma_desc_lo(smem_u32(a1)), a2_lo = umma_desc_lo(smem_u32(a2));
+        const uint32_t st_lo = umma_desc_lo(smem_u32(stages)), st_step = (uint32_t)a.stage_bytes >> 4;
+        uint32_t s = 0, ph = 0, lcount = 0;
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+            for (int l = 0; l < a.n_layers; ++l, ++lcount) {
+                const int nkc = a.K[l] / KCH, nbr = min(a.nblk, a.N[l]), nnb = a.N[l] / nbr;
+                const uint32_t idesc = umma_idesc(nbr);
+                mbar_wait(a_ready, lcount & 1);
+                tc_fence_after();
+                for (int nb = 0; nb < nnb; ++nb) {
+                    const uint32_t d = tmem + (uint32_t)(nb * nbr);
+                    for (int kc = 0; kc < nkc; ++kc) {
+                        mbar_wait(full + s, ph);
+                        tc_fence_after();
+                        const uint32_t ka = (uint32_t)kc * (A_CHUNK >> 4);
+                        const uint32_t sb1 = st_lo + s * st_step, sb2 = sb1 + (uint32_t)nbr * 8;     // lo plane follows hi (nbr x 128 B)
 #pragma unroll
-                            for (int ks = 0; ks < KCH / 16; ++ks) {
-                                const uint64_t da1 = umma_desc(sa1 + ks * 32), da2 = umma_desc(sa2 + ks * 32);
-                                const uint64_t db1 = umma_desc(sb1 + ks * 32), db2 = umma_desc(sb2 + ks * 32);
-                                umma_f16(d, da1, db1, idesc, (kc | ks) != 0);
-                                umma_f16(d, da2, db1, idesc, 1);
-                                umma_f16(d, da1, db2, idesc, 1);
-                            }
-                            umma_commit(empty + s);          // stage reusable once these MMAs have read it
+                        for (int ks = 0; ks < KCH / 16; ++ks) {
+                            umma_f16_if(leader, d, a1_lo + ka + 2 * ks, UMMA_DESC_HI, sb1 + 2 * ks, UMMA_DESC_HI, idesc, (kc | ks) != 0);
+                            umma_f16_if(leader, d, a2_lo + ka + 2 * ks, UMMA_DESC_HI, sb1 + 2 * ks, UMMA_DESC_HI, idesc, 1);
+                            umma_f16_if(leader, d, a1_lo + ka + 2 * ks, UMMA_DESC_HI, sb2 + 2 * ks, UMMA_DESC_HI, idesc, 1);
                         }
+                        umma_commit_if(leader, empty + s);   // stage reusable once these MMAs have read it
+                        if (++s == (uint32_t)a.n_stages) { s = 0; ph ^= 1; }
                     }
-                    umma_commit(d_ready);                    // accumulators of this layer complete
                 }
+                umma_commit_if(leader, d_ready);             // accumulators of this layer complete
             }
         }
         __syncwarp();

@@ -106,45 +106,47 @@ __global__ void __launch_bounds__(tg::THREADS, 1) vlad_partial_kernel(const Vlad
     if (t < a.K) a.asum[((size_t)cloud * a.nchunk + chunk) * a.K + t] = asum;
 }
 
-// one CTA per cloud, one thread per channel
+// One CTA per (cloud, group of 8 clusters), one warp per cluster, eight channels per lane: the per-chunk partials are
+// summed in chunk order (deterministic), a = a_sum * cluster_weights2 is subtracted, every cluster is L2-normalised over
+// its channels (each cluster is independent), and the (C, K) slice is written as 32-byte runs of consecutive clusters.
+constexpr int VFK = 8;           // clusters per CTA
 __global__ void __launch_bounds__(256) vlad_finalize_kernel(int c, int K, int nchunk, const float *__restrict__ part,
                                                            const float *__restrict__ asum, const float *__restrict__ w2,
                                                            float *__restrict__ out, long out_bstride, long out_cstride) {
-    __shared__ float red[VKMAX][8];
-    __shared__ float as[VKMAX];
-    __shared__ float inv[VKMAX];
-    const int t = threadIdx.x, cloud = blockIdx.x, lane = t & 31, warp = t >> 5;
-    if (t < K) {
-        float s = 0.f;
-        for (int ch = 0; ch < nchunk; ++ch) s += asum[((size_t)cloud * nchunk + ch) * K + t];
-        as[t] = s;
-    }
+    __shared__ float w2s[256][VFK];            // cluster_weights2[t][k0 + kk]
+    __shared__ float res[256][VFK + 1];
+    const int t = threadIdx.x, cloud = blockIdx.y, lane = t & 31, warp = t >> 5;
+    const int k0 = blockIdx.x * VFK, k = k0 + warp;
+    const int kn = min(VFK, K - k0);
+    for (int ch = t; ch < c; ch += 256)
+        for (int kk = 0; kk < kn; ++kk) w2s[ch][kk] = __ldg(w2 + (size_t)ch * K + k0 + kk);
     __syncthreads();
-    float v[VKMAX];
-#pragma unroll
-    for (int k = 0; k < VKMAX; ++k) {
-        v[k] = 0.f;
-        if (k < K && t < c) {
-            float s = 0.f;
-            for (int ch = 0; ch < nchunk; ++ch) s += part[(((size_t)cloud * nchunk + ch) * K + k) * c + t];
-            v[k] = s - as[k] * __ldg(w2 + (size_t)t * K + k);   // vlad - a,  a = a_sum * cluster_weights2
+    if (k < K) {
+        float as = 0.f;
+        for (int ch = 0; ch < nchunk; ++ch) as += __ldg(asum + ((size_t)cloud * nchunk + ch) * K + k);
+        float sq = 0.f;
+        for (int c0 = lane * 4; c0 < c; c0 += 128) {                       // c <= 256: two float4 per lane
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int ch = 0; ch < nchunk; ++ch) {
+                const float4 p4 = __ldg(reinterpret_cast<const float4 *>(part + (((size_t)cloud * nchunk + ch) * K + k) * c + c0));
+                v.x += p4.x; v.y += p4.y; v.z += p4.z; v.w += p4.w;
+            }
+            v.x -= as * w2s[c0][warp]; v.y -= as * w2s[c0 + 1][warp];       // vlad - a,  a = a_sum * cluster_weights2
+            v.z -= as * w2s[c0 + 2][warp]; v.w -= as * w2s[c0 + 3][warp];
+            sq += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+            res[c0][warp] = v.x; res[c0 + 1][warp] = v.y; res[c0 + 2][warp] = v.z; res[c0 + 3][warp] = v.w;
         }
-        float sq = v[k] * v[k];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-        if (lane == 0) red[k][warp] = sq;
-    }
-    __syncthreads();
-    if (t < K) {
-        float s = 0.f;
-        for (int w = 0; w < 8; ++w) s += red[t][w];
-        inv[t] = 1.f / fmaxf(sqrtf(s), 1e-12f);                   // F.normalize(dim=1, p=2, eps=1e-12)
-    }
-    __syncthreads();
-    if (t < c) {
+        const float inv = 1.f / fmaxf(sqrtf(sq), 1e-12f);                   // F.normalize(dim=1, p=2, eps=1e-12)
+        for (int c0 = lane * 4; c0 < c; c0 += 128)
 #pragma unroll
-        for (int k = 0; k < VKMAX; ++k)
-            if (k < K) out[(size_t)cloud * out_bstride + (size_t)t * out_cstride + k] = v[k] * inv[k];
+            for (int j = 0; j < 4; ++j) res[c0 + j][warp] *= inv;
+    }
+    __syncthreads();
+    for (int ch = t; ch < c; ch += 256) {
+        float *dst = out + (size_t)cloud * out_bstride + (size_t)ch * out_cstride + k0;
+        for (int kk = 0; kk < kn; ++kk) dst[kk] = res[ch][kk];
     }
 }
 
@@ -321,7 +323,7 @@ PAB_API int pab_netvlad_forward(int b, int n, int c, int K, const float *x, cons
     PAB_CUDA(cudaFuncSetAttribute(vlad_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     vlad_partial_kernel<<<dim3(nchunk, b), tg::THREADS, smem, st>>>(a);
     PAB_LAUNCH_CHECK();
-    vlad_finalize_kernel<<<b, 256, 0, st>>>(c, K, nchunk, a.part, a.asum, w2, out, out_bstride, out_cstride);
+    vlad_finalize_kernel<<<dim3(pab_divup(K, VFK), b), 256, 0, st>>>(c, K, nchunk, a.part, a.asum, w2, out, out_bstride, out_cstride);
     PAB_LAUNCH_CHECK();
     return 0;
 }
@@ -337,7 +339,7 @@ PAB_API int pab_netvlad_forward_tc(int b, int n, int c, int K, const float *x, c
     int nchunk = 0;
     const int rc = pab_vlad_tc_partial(b, n, c, K, x, wc_hi, wc_lo, shift, part, asum, &nchunk, st);
     if (rc) return rc;
-    vlad_finalize_kernel<<<b, 256, 0, st>>>(c, K, nchunk, part, asum, w2, out, out_bstride, out_cstride);
+    vlad_finalize_kernel<<<dim3(pab_divup(K, VFK), b), 256, 0, st>>>(c, K, nchunk, part, asum, w2, out, out_bstride, out_cstride);
     PAB_LAUNCH_CHECK();
     return 0;
 }

@@ -37,6 +37,8 @@ __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(A_CHUNK >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
            (2ull << 61);
 }
+__device__ __forceinline__ uint32_t umma_desc_mn_lo(uint32_t saddr) { return ((saddr & 0x3FFFF) >> 4) | ((uint32_t)(A_CHUNK >> 4) << 16); }
+constexpr uint32_t UMMA_DESC_MN_HI = UMMA_DESC_HI;            // same SBO / version / swizzle fields as the K-major descriptor
 __device__ __forceinline__ uint32_t umma_idesc_amn(int n) {   // as umma_idesc, with A MN-major (bit 15)
     return umma_idesc(n) | (1u << 15);
 }
@@ -57,7 +59,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vlad_tc_kernel(const VtArgs a) 
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_ready + 4);
     float *asum_s = reinterpret_cast<float *>(misc + 64);          // [Kp]
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
     if (tid == 0) {
         mbar_init(a_ready, VT_WORK); mbar_init(d1_ready, 1); mbar_init(p_ready, 128); mbar_init(g2_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -77,45 +79,49 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vlad_tc_kernel(const VtArgs a) 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     const uint32_t d1 = tmem, d2 = tmem + 64;                      // D2 block cb at d2 + cb*64
 
     if (warp == 1) {
-        if (lane == 0) {
-            uint32_t tcount = 0;
-            const uint32_t id1 = umma_idesc(a.Kp), id2 = umma_idesc_amn(a.Kp);
-            for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
-                const int chunk = item % a.nchunk;
-                const int r_begin = chunk * VT_ROWS_PER_ITEM, r_end = min(a.n, r_begin + VT_ROWS_PER_ITEM);
-                int t_in_item = 0;
-                for (int r0 = r_begin; r0 < r_end; r0 += TM, ++tcount, ++t_in_item) {
-                    mbar_wait(a_ready, tcount & 1);
-                    tc_fence_after();
-                    for (int kc = 0; kc < 4; ++kc)
+        // all lanes run the loops, one elected lane issues (tc_common.cuh: warp-uniform issue path)
+        const uint32_t leader = elect_one();
+        uint32_t tcount = 0;
+        const uint32_t id1 = umma_idesc(a.Kp), id2 = umma_idesc_amn(a.Kp);
+        const uint32_t x1_lo = umma_desc_lo(smem_u32(x1)), x2_lo = umma_desc_lo(smem_u32(x2));
+        const uint32_t w1_lo = umma_desc_lo(smem_u32(w1)), w2_lo = umma_desc_lo(smem_u32(w2));
+        const uint32_t p1_lo = umma_desc_lo(smem_u32(p1)), p2_lo = umma_desc_lo(smem_u32(p2));
+        const uint32_t xm1_lo = umma_desc_mn_lo(smem_u32(x1)), xm2_lo = umma_desc_mn_lo(smem_u32(x2));
+        const uint32_t wstep = (uint32_t)wchunk >> 4;
+        for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+            const int chunk = item % a.nchunk;
+            const int r_begin = chunk * VT_ROWS_PER_ITEM, r_end = min(a.n, r_begin + VT_ROWS_PER_ITEM);
+            int t_in_item = 0;
+            for (int r0 = r_begin; r0 < r_end; r0 += TM, ++tcount, ++t_in_item) {
+                mbar_wait(a_ready, tcount & 1);
+                tc_fence_after();
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            const uint64_t da1 = umma_desc(smem_u32(x1 + kc * A_CHUNK) + ks * 32), da2 = umma_desc(smem_u32(x2 + kc * A_CHUNK) + ks * 32);
-                            const uint64_t db1 = umma_desc(smem_u32(w1 + kc * wchunk) + ks * 32), db2 = umma_desc(smem_u32(w2 + kc * wchunk) + ks * 32);
-                            umma_f16(d1, da1, db1, id1, (kc | ks) != 0);
-                            umma_f16(d1, da2, db1, id1, 1);
-                            umma_f16(d1, da1, db2, id1, 1);
-                        }
-                    umma_commit(d1_ready);
-                    mbar_wait(p_ready, tcount & 1);
-                    tc_fence_after();
-                    for (int cb = 0; cb < 2; ++cb)
+                for (int kc = 0; kc < 4; ++kc)
 #pragma unroll
-                        for (int ks = 0; ks < 8; ++ks) {            // 16 points per MMA
-                            const uint64_t da1 = umma_desc_mn(smem_u32(x1 + 2 * cb * A_CHUNK) + ks * 2048);
-                            const uint64_t da2 = umma_desc_mn(smem_u32(x2 + 2 * cb * A_CHUNK) + ks * 2048);
-                            const uint64_t db1 = umma_desc(smem_u32(p1 + (ks >> 2) * wchunk) + (ks & 3) * 32);
-                            const uint64_t db2 = umma_desc(smem_u32(p2 + (ks >> 2) * wchunk) + (ks & 3) * 32);
-                            umma_f16(d2 + cb * 64, da1, db1, id2, (t_in_item | ks) != 0);
-                            umma_f16(d2 + cb * 64, da2, db1, id2, 1);
-                            umma_f16(d2 + cb * 64, da1, db2, id2, 1);
-                        }
-                    umma_commit(g2_done);
-                }
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint32_t xa = (uint32_t)kc * (A_CHUNK >> 4) + 2 * ks, wb = (uint32_t)kc * wstep + 2 * ks;
+                        umma_f16_if(leader, d1, x1_lo + xa, UMMA_DESC_HI, w1_lo + wb, UMMA_DESC_HI, id1, (kc | ks) != 0);
+                        umma_f16_if(leader, d1, x2_lo + xa, UMMA_DESC_HI, w1_lo + wb, UMMA_DESC_HI, id1, 1);
+                        umma_f16_if(leader, d1, x1_lo + xa, UMMA_DESC_HI, w2_lo + wb, UMMA_DESC_HI, id1, 1);
+                    }
+                umma_commit_if(leader, d1_ready);
+                mbar_wait(p_ready, tcount & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int cb = 0; cb < 2; ++cb)
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {            // 16 points per MMA
+                        const uint32_t xa = (uint32_t)(2 * cb) * (A_CHUNK >> 4) + (uint32_t)ks * (2048 >> 4);
+                        const uint32_t pb = (uint32_t)(ks >> 2) * wstep + 2 * (ks & 3);
+                        umma_f16_if(leader, d2 + cb * 64, xm1_lo + xa, UMMA_DESC_MN_HI, p1_lo + pb, UMMA_DESC_HI, id2, (t_in_item | ks) != 0);
+                        umma_f16_if(leader, d2 + cb * 64, xm2_lo + xa, UMMA_DESC_MN_HI, p1_lo + pb, UMMA_DESC_HI, id2, 1);
+                        umma_f16_if(leader, d2 + cb * 64, xm1_lo + xa, UMMA_DESC_MN_HI, p2_lo + pb, UMMA_DESC_HI, id2, 1);
+                    }
+                umma_commit_if(leader, g2_done);
             }
         }
         __syncwarp();
