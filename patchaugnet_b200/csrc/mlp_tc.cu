@@ -3,30 +3,39 @@
 // Same fusion as mlp.cu (neighbour gather / 3-NN interpolation -> every MLP layer -> max over K or row store, tile
 // resident on chip), but the layer GEMMs run as tcgen05.mma with fp32 accumulators in tensor memory:
 //
-//   * a persistent CTA owns 128-row tiles; the layer input lives in shared memory as TWO bf16 planes
-//     (x = hi + lo, hi = bf16(x), lo = bf16(x - hi)) in the canonical K-major SWIZZLE_128B layout; the folded weights
-//     are split the same way on the host.  Each 16-wide k-step issues three MMAs
+//   * a persistent CTA owns 128-row tiles.  Every layer input is kept as TWO bf16 planes (x = hi + lo, hi = bf16(x),
+//     lo = bf16(x - hi)); the folded weights are split the same way on the host.  Each 16-wide k-step issues
 //         D += hi(A) * hi(W)  +  lo(A) * hi(W)  +  hi(A) * lo(W)
 //     which carries ~16 mantissa bits through every product (error ~2^-17 per term, fp32 accumulation) — the
 //     descriptors stay within the 1e-4 contract where a single TF32/bf16 pass does not.
-//   * warp 0 streams weight blocks (128 output channels x 64 k, hi+lo) with TMA (cp.async.bulk.tensor, mbarrier
-//     complete_tx) through a ring of stages, running ahead across layers and tiles; warp 1 (one elected thread)
-//     issues the MMAs and frees stages with tcgen05.commit; warps 2..9 (256 threads) gather the tile, and after
-//     each layer read the accumulators with tcgen05.ld, add the folded BN shift (+ the rank-3 xyz update of
-//     layer 0, whose K would otherwise not be a multiple of 64), ReLU, split to bf16 hi/lo and write the next layer's
-//     operand in place.  The last layer is staged as fp32 in the (now free) operand region and either max-pooled
-//     over the K neighbours (SA) or stored as coalesced rows (FP).
+//   * the layer-0 operand (gathered rows) lives in shared memory in the canonical K-major SWIZZLE_128B layout and is
+//     written by four dedicated LOADER warps; the operands of layers >= 1 never touch shared memory: the epilogue writes
+//     them straight back into TENSOR MEMORY (tcgen05.st) and the next layer's MMAs read A from TMEM (TS form).  TMEM
+//     holds D (256 fp32 columns) + the hi plane (128 columns of bf16 pairs) + the lo plane (128) = 512 columns.
+//     Shared memory is therefore free again as soon as the layer-0 MMAs have completed, and the loaders gather tile i+1
+//     while layers 1.. of tile i run.
+//   * warp 0 streams weight blocks (<= 128 output channels x 64 k of one plane) with TMA (cp.async.bulk.tensor,
+//     mbarrier complete_tx) through a ring of stages, running ahead across layers and tiles; warp 1 issues the MMAs
+//     (warp-uniform loop, one elected lane) and frees stages with tcgen05.commit; warps 2..9 (256 threads) read the
+//     accumulators with tcgen05.ld, add the folded BN shift (+ the rank-3 xyz update of layer 0, whose K would otherwise
+//     not be a multiple of 64), ReLU, split to bf16 hi/lo.  The last layer is staged as fp32 64 columns at a time and
+//     either max-pooled over the K neighbours (SA) or stored as coalesced rows (FP).
 #include "tc_common.cuh"
 
 namespace {
 
 using namespace tc;
 
-constexpr int NBLK_MAX = 128;                 // max output channels per weight stage (UMMA N); runtime a.nblk is 64 or 128
-constexpr int NWORK = 256;                    // worker threads
-constexpr int TC_THREADS = 64 + NWORK;
-constexpr int MAX_STAGES = 6;
+constexpr int NBLK_MAX = 128;                 // max output channels per weight stage (UMMA N)
+constexpr int NEPI = 256;                     // epilogue threads (warps 2..9)
+constexpr int NLOAD = 128;                    // loader threads (warps 10..13)
+constexpr int TC_THREADS = 64 + NEPI + NLOAD;
+constexpr int MAX_STAGES = 8;
 constexpr int MAX_LAYERS = 3;
+constexpr int D_COLS = 256;                   // accumulator columns; TMEM columns [256,384) = hi plane, [384,512) = lo plane
+constexpr uint32_t AH_COL = 256, AL_COL = 384;
+constexpr int STG_COLS = 64;                  // fp32 staging of the last layer: [128 rows][64 columns]
+constexpr int STG_BYTES = TM * STG_COLS * 4;
 
 enum { TC_SA = 1, TC_FP = 2 };
 
@@ -34,10 +43,10 @@ struct alignas(64) TcArgs {
     CUtensorMap tm[MAX_LAYERS][2];
     const float *shift[MAX_LAYERS];
     int K[MAX_LAYERS], N[MAX_LAYERS], relu[MAX_LAYERS];
-    int n_layers, n_stages, kchunks_max, mode;
-    int nblk, stage_bytes;                     // output channels per weight stage, bytes per stage (hi + lo)
+    int ksteps[MAX_LAYERS];                    // 16-wide k-steps that carry data (the rest of the last 64-chunk is zero padding)
+    int n_layers, n_stages, mode;
     int coff[MAX_LAYERS];                      // offset of each layer's shift vector in the smem constant table
-    int a_region;                              // bytes of the operand region (>= the 128 KB fp32 staging of the last layer)
+    int a_region;                              // bytes of the layer-0 operand region (hi plane, then lo plane)
     long rows;                                 // SA: centres, FP: points
     int ntiles;
     // layer-0 "extra" channels (the xyz part), applied as a rank-n update from the fp32 weight rows
@@ -60,25 +69,55 @@ struct alignas(64) TcArgs {
     float *out;
 };
 
+// A operand from tensor memory (TS form): rows = TMEM lanes, k pairs packed in 32-bit columns
+__device__ __forceinline__ void umma_f16_ts_if(uint32_t issue, uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        ".reg .b64 db;\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "setp.ne.b32 q, %6, 0;\n"
+        "mov.b64 db, {%2, %3};\n"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(issue) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+// staging [128][64] fp32, 16-byte units XOR-swizzled by row
+__device__ __forceinline__ uint32_t stg_offset(int r, int c) {
+    return (uint32_t)(r * (STG_COLS * 4) + ((((c >> 2) ^ (r & 7)) & 15) << 4) + ((c & 3) << 2));
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_constant__ TcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t *a1 = smem;
-    uint8_t *a2 = a1 + (size_t)a.kchunks_max * A_CHUNK;
+    uint8_t *a1 = smem;                                            // layer-0 operand, hi plane
+    uint8_t *a2 = a1 + (size_t)(a.a_region >> 1);                  //                  lo plane
     uint8_t *stages = a1 + (size_t)a.a_region;
-    uint8_t *misc = stages + (size_t)a.n_stages * a.stage_bytes;
+    uint8_t *stg = stages + (size_t)a.n_stages * (NBLK_MAX * 128);
+    uint8_t *misc = stg + STG_BYTES;
     uint64_t *full = reinterpret_cast<uint64_t *>(misc);
     uint64_t *empty = full + MAX_STAGES;
-    uint64_t *a_ready = empty + MAX_STAGES;
-    uint64_t *d_ready = a_ready + 1;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d_ready + 1);
-    float *ctab = reinterpret_cast<float *>(misc + 256);   // [shift of every layer | 3 x N0 extra weight rows], 16-byte aligned
+    uint64_t *a_full = empty + MAX_STAGES;                         // loaders -> MMA: layer-0 operand of the tile staged
+    uint64_t *a_empty = a_full + 1;                                // MMA -> loaders: layer-0 MMAs of the tile completed
+    uint64_t *d_ready = a_full + 2;                                // MMA -> epilogue: accumulators of the phase complete
+    uint64_t *t_ready = a_full + 3;                                // epilogue -> MMA: D drained (+ next operand in TMEM)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_full + 4);
+    float *ctab = reinterpret_cast<float *>(misc + 256);           // [shift of every layer | 3 x N0 extra weight rows | pre layer]
 
     const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
 
     if (tid == 0) {
         for (int s = 0; s < a.n_stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        mbar_init(a_ready, NWORK);
+        mbar_init(a_full, NLOAD);
+        mbar_init(a_empty, 1);
         mbar_init(d_ready, 1);
+        mbar_init(t_ready, NEPI);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -103,21 +142,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == 0) {
-        // ================= TMA producer: weight blocks, in (tile, layer, n-block, k-chunk) order =================
+        // ================= TMA producer: weight blocks in (tile, layer, n-block, k-chunk, plane) order ==============
         if (lane == 0) {
             uint32_t s = 0, ph = 0;
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
                 for (int l = 0; l < a.n_layers; ++l) {
-                    const int nkc = a.K[l] / KCH, nbr = min(a.nblk, a.N[l]), nnb = a.N[l] / nbr;
+                    const int nkc = (a.ksteps[l] + 3) >> 2, nbr = min(NBLK_MAX, a.N[l]), nnb = a.N[l] / nbr;
                     for (int nb = 0; nb < nnb; ++nb)
-                        for (int kc = 0; kc < nkc; ++kc) {
-                            mbar_wait(empty + s, ph ^ 1);
-                            uint8_t *dst = stages + (size_t)s * a.stage_bytes;
-                            mbar_expect_tx(full + s, 2u * nbr * 128u);
-                            tma_load_2d(dst, &a.tm[l][0], kc * KCH, nb * nbr, full + s);
-                            tma_load_2d(dst + nbr * 128, &a.tm[l][1], kc * KCH, nb * nbr, full + s);
-                            if (++s == (uint32_t)a.n_stages) { s = 0; ph ^= 1; }
-                        }
+                        for (int kc = 0; kc < nkc; ++kc)
+                            for (int pl = 0; pl < 2; ++pl) {
+                                mbar_wait(empty + s, ph ^ 1);
+                                mbar_expect_tx(full + s, (uint32_t)nbr * 128u);
+                                tma_load_2d(stages + (size_t)s * (NBLK_MAX * 128), &a.tm[l][pl], kc * KCH, nb * nbr, full + s);
+                                if (++s == (uint32_t)a.n_stages) { s = 0; ph ^= 1; }
+                            }
                 }
             }
         }
@@ -126,55 +164,213 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         // ================= MMA issuer: all lanes run the loops, one elected lane issues ===========================
         const uint32_t leader = elect_one();
         const uint32_t a1_lo = umma_desc_lo(smem_u32(a1)), a2_lo = umma_desc_lo(smem_u32(a2));
-        const uint32_t st_lo = umma_desc_lo(smem_u32(stages)), st_step = (uint32_t)a.stage_bytes >> 4;
-        uint32_t s = 0, ph = 0, lcount = 0;
-        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-            for (int l = 0; l < a.n_layers; ++l, ++lcount) {
-                const int nkc = a.K[l] / KCH, nbr = min(a.nblk, a.N[l]), nnb = a.N[l] / nbr;
+        const uint32_t st_lo = umma_desc_lo(smem_u32(stages));
+        constexpr uint32_t st_step = (NBLK_MAX * 128) >> 4;
+        uint32_t s = 0, ph = 0, pcount = 0, tcount = 0;
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tcount) {
+            for (int l = 0; l < a.n_layers; ++l) {
+                const int ksteps = a.ksteps[l], nkc = (ksteps + 3) >> 2;
+                const int nbr = min(NBLK_MAX, a.N[l]), nnb = a.N[l] / nbr, nb_pass = D_COLS / nbr;   // n-blocks per accumulator pass
                 const uint32_t idesc = umma_idesc(nbr);
-                mbar_wait(a_ready, lcount & 1);
-                tc_fence_after();
+                if (l == 0) mbar_wait(a_full, tcount & 1);
                 for (int nb = 0; nb < nnb; ++nb) {
-                    const uint32_t d = tmem + (uint32_t)(nb * nbr);
+                    const int nbp = nb % nb_pass;
+                    if (nbp == 0) {                              // new pass: the epilogue must have drained D (and written A)
+                        if (pcount > 0) mbar_wait(t_ready, (pcount - 1) & 1);
+                        tc_fence_after();
+                    }
+                    const uint32_t d = tmem + (uint32_t)(nbp * nbr);
                     for (int kc = 0; kc < nkc; ++kc) {
+                        const int kn = min(4, ksteps - 4 * kc);
+                        const uint32_t ka = (uint32_t)kc * (A_CHUNK >> 4);
+                        // hi weight plane: hi(A) * hi(W) + lo(A) * hi(W)
                         mbar_wait(full + s, ph);
                         tc_fence_after();
-                        const uint32_t ka = (uint32_t)kc * (A_CHUNK >> 4);
-                        const uint32_t sb1 = st_lo + s * st_step, sb2 = sb1 + (uint32_t)nbr * 8;     // lo plane follows hi (nbr x 128 B)
+                        uint32_t sb = st_lo + s * st_step;
 #pragma unroll
-                        for (int ks = 0; ks < KCH / 16; ++ks) {
-                            umma_f16_if(leader, d, a1_lo + ka + 2 * ks, UMMA_DESC_HI, sb1 + 2 * ks, UMMA_DESC_HI, idesc, (kc | ks) != 0);
-                            umma_f16_if(leader, d, a2_lo + ka + 2 * ks, UMMA_DESC_HI, sb1 + 2 * ks, UMMA_DESC_HI, idesc, 1);
-                            umma_f16_if(leader, d, a1_lo + ka + 2 * ks, UMMA_DESC_HI, sb2 + 2 * ks, UMMA_DESC_HI, idesc, 1);
+                        for (int ks = 0; ks < 4; ++ks) {
+                            if (ks < kn) {
+                                if (l == 0) {
+                                    umma_f16_if(leader, d, a1_lo + ka + 2 * ks, UMMA_DESC_HI, sb + 2 * ks, UMMA_DESC_HI, idesc, (kc | ks) != 0);
+                                    umma_f16_if(leader, d, a2_lo + ka + 2 * ks, UMMA_DESC_HI, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
+                                } else {
+                                    umma_f16_ts_if(leader, d, tmem + AH_COL + kc * 32 + ks * 8, sb + 2 * ks, UMMA_DESC_HI, idesc, (kc | ks) != 0);
+                                    umma_f16_ts_if(leader, d, tmem + AL_COL + kc * 32 + ks * 8, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
+                                }
+                            }
                         }
-                        umma_commit_if(leader, empty + s);   // stage reusable once these MMAs have read it
+                        umma_commit_if(leader, empty + s);
+                        if (++s == (uint32_t)a.n_stages) { s = 0; ph ^= 1; }
+                        // lo weight plane: hi(A) * lo(W)
+                        mbar_wait(full + s, ph);
+                        tc_fence_after();
+                        sb = st_lo + s * st_step;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            if (ks < kn) {
+                                if (l == 0) umma_f16_if(leader, d, a1_lo + ka + 2 * ks, UMMA_DESC_HI, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
+                                else umma_f16_ts_if(leader, d, tmem + AH_COL + kc * 32 + ks * 8, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
+                            }
+                        }
+                        umma_commit_if(leader, empty + s);
                         if (++s == (uint32_t)a.n_stages) { s = 0; ph ^= 1; }
                     }
+                    if (nbp == nb_pass - 1 || nb == nnb - 1) {
+                        umma_commit_if(leader, d_ready);         // accumulators of this pass complete
+                        ++pcount;
+                    }
                 }
-                umma_commit_if(leader, d_ready);             // accumulators of this layer complete
+                if (l == 0) umma_commit_if(leader, a_empty);     // shared-memory operand consumed: loaders may stage the next tile
             }
         }
         __syncwarp();
-    } else {
-        // ================= workers: gather, epilogues, output ====================================================
-        const int wt = tid - 64;                             // 0..255
-        const int wwarp = warp - 2;                          // 0..7
+    } else if (warp < 2 + NEPI / 32) {
+        // ================= epilogue warps ===========================================================================
+        const int et = tid - 64;                             // 0..255
+        const int ewarp = warp - 2;                          // 0..7
         const int q = warp & 3;                              // TMEM lane quarter this warp may access
-        const int half = wwarp >> 2;                         // column half handled by this warp
-        const int row = q * 32 + lane;                       // accumulator row owned in the epilogue
+        const int half = ewarp >> 2;                         // column half handled by this warp
+        const int row = q * 32 + lane;                       // accumulator row owned by this thread
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
-        uint32_t lcount = 0;
-        const int units0 = a.K[0] / 8;                       // 16-byte units per row of the layer-0 operand
+        uint32_t pcount = 0;
         const float *wext = ctab + a.coff[a.n_layers - 1] + a.N[a.n_layers - 1];   // extra weight rows follow the shifts
+        const int G = a.mode == TC_SA ? TM / a.k : 0;
 
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-            // ---- stage the layer-0 operand (hi/lo planes): one warp per row, lanes across the row's 16-byte units -----
+            // the rank-3 part of layer 0 for the row this thread owns (loads overlap the wait for the first accumulators)
             float xe[3] = {0.f, 0.f, 0.f};
+            if (a.n_extra > 0) {
+                if (a.mode == TC_SA) {
+                    const int g = row / a.k, sidx = row - g * a.k;
+                    const long ci = (long)tile * G + g;
+                    if (g < G && ci < a.rows) {
+                        const long cloud = ci / a.m;
+                        const long pc = cloud * a.n + __ldg(a.center_idx + ci);
+                        const long pn = cloud * a.n + __ldg(a.nbr_idx + ci * a.nbr_stride + sidx);
+#pragma unroll
+                        for (int e = 0; e < 3; ++e) xe[e] = __ldg(a.xyz + pn * 3 + e) - __ldg(a.xyz + pc * 3 + e);
+                    }
+                } else {
+                    const long p = (long)tile * TM + row;
+                    if (p < a.rows)
+                        for (int e = 0; e < a.n_extra; ++e) xe[e] = __ldg(a.skip_feat + p * a.c_skip + e);
+                }
+            }
+            for (int l = 0; l < a.n_layers; ++l) {
+                const int N = a.N[l];
+                const bool last = l == a.n_layers - 1;
+                const bool relu = a.relu[l] != 0;
+                const bool extras = l == 0 && a.n_extra > 0;
+                const float *shl = ctab + a.coff[l];
+                const int npass = (N + D_COLS - 1) / D_COLS;
+                for (int pass = 0; pass < npass; ++pass, ++pcount) {
+                    const int ncols = min(D_COLS, N - pass * D_COLS);  // accumulator columns of this pass
+                    const int per = ncols >= 64 ? ncols / 2 : ncols;    // columns per worker half (batches of 32)
+                    const bool active = ncols >= 64 || half == 0;
+                    mbar_wait(d_ready, pcount & 1);
+                    tc_fence_after();
+                    for (int cb = 0; cb < per; cb += 32) {
+                        const int dcol = (ncols >= 64 ? half * per : 0) + cb;          // first accumulator column of this batch
+                        const int col = pass * D_COLS + dcol;                          // output channel
+                        float v[32];
+                        if (active) {
+                            tmem_ld32(trow + (uint32_t)dcol, v);
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                const float4 sh = *reinterpret_cast<const float4 *>(shl + col + 4 * u);
+                                v[4 * u] += sh.x; v[4 * u + 1] += sh.y; v[4 * u + 2] += sh.z; v[4 * u + 3] += sh.w;
+                            }
+                            if (extras) {
+#pragma unroll
+                                for (int e = 0; e < 3; ++e) {
+                                    if (e < a.n_extra) {
+#pragma unroll
+                                        for (int u = 0; u < 8; ++u) {
+                                            const float4 w = *reinterpret_cast<const float4 *>(wext + e * N + col + 4 * u);
+                                            v[4 * u] = fmaf(xe[e], w.x, v[4 * u]); v[4 * u + 1] = fmaf(xe[e], w.y, v[4 * u + 1]);
+                                            v[4 * u + 2] = fmaf(xe[e], w.z, v[4 * u + 2]); v[4 * u + 3] = fmaf(xe[e], w.w, v[4 * u + 3]);
+                                        }
+                                    }
+                                }
+                            }
+                            if (relu) {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                            }
+                        }
+                        if (!last) {
+                            if (active) {                       // next layer's operand: bf16 pairs into the TMEM planes
+                                uint32_t hi[16], lo[16];
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) split_pack(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+                                tmem_st16(trow + AH_COL + (uint32_t)(dcol >> 1), hi);
+                                tmem_st16(trow + AL_COL + (uint32_t)(dcol >> 1), lo);
+                            }
+                        } else {
+                            // one staging round: 32 columns of each half -> [128][64] fp32 -> pooled / stored rows
+                            const bool final_batch = cb + 32 >= per;
+                            if (final_batch) {                   // every accumulator column of the pass has been read
+                                tc_fence_before();
+                                mbar_arrive(t_ready);
+                            }
+                            if (active) {
+                                const int sc0 = ncols >= 64 ? half * 32 : 0;
+#pragma unroll
+                                for (int u = 0; u < 8; ++u)
+                                    *reinterpret_cast<float4 *>(stg + stg_offset(row, sc0 + 4 * u)) =
+                                        make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+                            }
+                            asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");   // staging complete (epilogue warps only)
+                            const int rcols = ncols >= 64 ? 64 : ncols;            // staged columns this round (32 or 64)
+                            if (a.mode == TC_SA) {
+                                for (int e = et; e < G * rcols; e += NEPI) {
+                                    const int g = e / rcols, c = e - g * rcols;
+                                    const long ci = (long)tile * G + g;
+                                    if (ci >= a.rows) continue;
+                                    float mx = *reinterpret_cast<const float *>(stg + stg_offset(g * a.k, c));
+                                    for (int sidx = 1; sidx < a.k; ++sidx)
+                                        mx = fmaxf(mx, *reinterpret_cast<const float *>(stg + stg_offset(g * a.k + sidx, c)));
+                                    const int oc = pass * D_COLS + (c >> 5) * per + cb + (c & 31);
+                                    a.out[ci * N + oc] = mx;
+                                }
+                            } else {
+                                // 16 lanes per row: 8 x 16 B of half 0's columns, 8 x 16 B of half 1's
+                                const int sub = lane >> 4, l16 = lane & 15;
+                                const int hsel = l16 >> 3, u = l16 & 7;
+                                if (l16 * 4 < rcols) {
+                                    for (int r = ewarp * 2 + sub; r < TM; r += 16) {
+                                        const long p = (long)tile * TM + r;
+                                        if (p >= a.rows) break;
+                                        const int oc = pass * D_COLS + hsel * per + cb + 4 * u;
+                                        *reinterpret_cast<float4 *>(a.out + p * N + oc) =
+                                            *reinterpret_cast<const float4 *>(stg + stg_offset(r, hsel * 32 + 4 * u));
+                                    }
+                                }
+                            }
+                            asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");   // staging consumed before it is rewritten
+                        }
+                    }
+                    if (!last) {
+                        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                        tc_fence_before();
+                        mbar_arrive(t_ready);
+                    }
+                }
+            }
+        }
+    } else {
+        // ================= loader warps: stage the layer-0 operand (hi/lo planes) of the next tile =================
+        const int lt = tid - 64 - NEPI;                      // 0..127
+        const int lwarp = lt >> 5;                           // 0..3, rows [32*lwarp, 32*lwarp + 32)
+        const int units0 = ((a.ksteps[0] + 3) >> 2) * 8;     // 16-byte units per operand row (whole 64-chunks)
+        uint32_t tcount = 0;
+        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tcount) {
+            if (tcount > 0) mbar_wait(a_empty, (tcount - 1) & 1);
             if (a.mode == TC_SA && a.pre_cout > 0) {
-                // two threads per row: inputs [xyz_j - xyz_i ; f_j - f_i] (pre_cin <= 8 values), each thread evaluates half of
-                // the pre-layer's outputs in fp32 and stages them (hi/lo); the rest of the 64-channel chunk is zeroed
+                // one thread per row: inputs [xyz_j - xyz_i ; f_j - f_i] (pre_cin <= 8 values), the pre-layer evaluated in
+                // fp32 and staged (hi/lo); the rest of the 64-channel chunk is zeroed
                 const int G = TM / a.k;
-                const int r = wt >> 1, part = wt & 1;
+                const int r = lt;
                 const int g = r / a.k, sidx = r - g * a.k;
                 const long ci = (long)tile * G + g;
                 float in[8];
@@ -192,210 +388,140 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                         if (i < a.c) in[3 + i] = __ldg(a.feat + pn * a.c + i) - __ldg(a.feat + pc * a.c + i);
                 }
                 const float *pw = ctab + a.pre_off, *ps = pw + a.pre_cin * a.pre_cout;
-                const int half_out = a.pre_cout / 2;                           // outputs per thread (multiple of 8)
-                for (int u = 0; u < half_out / 8; ++u) {
+                for (int u = 0; u < a.pre_cout / 8; ++u) {
                     float v[8];
-                    const int o0 = part * half_out + u * 8;
 #pragma unroll
                     for (int o = 0; o < 8; ++o) {
-                        float acc = ps[o0 + o];
+                        float acc = ps[u * 8 + o];
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
-                            if (i < a.pre_cin) acc = fmaf(in[i], pw[i * a.pre_cout + o0 + o], acc);
+                            if (i < a.pre_cin) acc = fmaf(in[i], pw[i * a.pre_cout + u * 8 + o], acc);
                         v[o] = valid ? (a.pre_relu ? fmaxf(acc, 0.f) : acc) : 0.f;
                     }
-                    store_units(a1, a2, r, o0 >> 3, v);
+                    store_units(a1, a2, r, u, v);
                 }
                 const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                for (int j = a.pre_cout / 8 + part; j < units0; j += 2) store_units(a1, a2, r, j, z);
+                for (int j = a.pre_cout / 8; j < units0; ++j) store_units(a1, a2, r, j, z);
             } else if (a.mode == TC_SA) {
+                // lane r of the warp looks up the (centre, neighbour) point of row 32*lwarp + r once; rows are then staged
+                // four at a time with the indices broadcast by shuffles
                 const int G = TM / a.k;
-                for (int r = wwarp; r < TM; r += 8) {
+                long my_pc = -1, my_pn = -1;
+                {
+                    const int r = lwarp * 32 + lane;
                     const int g = r / a.k, sidx = r - g * a.k;
-                    const long ci = (long)tile * G + g;
-                    const bool valid = g < G && ci < a.rows;
-                    long pc = 0, pn = 0;
-                    if (valid) {
-                        const long cloud = ci / a.m;
-                        pc = cloud * a.n + __ldg(a.center_idx + ci);
-                        pn = cloud * a.n + __ldg(a.nbr_idx + ci * a.nbr_stride + sidx);
-                    }
-                    for (int j = lane; j < units0; j += 32) {
-                        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                        if (valid) {
-                            const float4 *fn = reinterpret_cast<const float4 *>(a.feat + pn * a.c) + 2 * j;
-                            const float4 *fc = reinterpret_cast<const float4 *>(a.feat + pc * a.c) + 2 * j;
-                            const float4 n0 = __ldg(fn), n1 = __ldg(fn + 1), c0 = __ldg(fc), c1 = __ldg(fc + 1);
-                            v[0] = n0.x - c0.x; v[1] = n0.y - c0.y; v[2] = n0.z - c0.z; v[3] = n0.w - c0.w;
-                            v[4] = n1.x - c1.x; v[5] = n1.y - c1.y; v[6] = n1.z - c1.z; v[7] = n1.w - c1.w;
-                        }
-                        store_units(a1, a2, r, j, v);
-                    }
-                }
-                {   // xyz_j - xyz_i of the row this thread owns in the epilogue
-                    const int g = row / a.k, sidx = row - g * a.k;
                     const long ci = (long)tile * G + g;
                     if (g < G && ci < a.rows) {
                         const long cloud = ci / a.m;
-                        const long pc = cloud * a.n + __ldg(a.center_idx + ci);
-                        const long pn = cloud * a.n + __ldg(a.nbr_idx + ci * a.nbr_stride + sidx);
+                        my_pc = cloud * a.n + __ldg(a.center_idx + ci);
+                        my_pn = cloud * a.n + __ldg(a.nbr_idx + ci * a.nbr_stride + sidx);
+                    }
+                }
+                for (int rr = 0; rr < 32; rr += 4) {
+                    long pc[4], pn[4];
 #pragma unroll
-                        for (int e = 0; e < 3; ++e) xe[e] = __ldg(a.xyz + pn * 3 + e) - __ldg(a.xyz + pc * 3 + e);
+                    for (int t4 = 0; t4 < 4; ++t4) {
+                        pc[t4] = __shfl_sync(0xffffffffu, my_pc, rr + t4);
+                        pn[t4] = __shfl_sync(0xffffffffu, my_pn, rr + t4);
+                    }
+                    for (int j = lane; j < units0; j += 32) {
+                        float4 n0[4], n1[4], c0[4], c1[4];
+#pragma unroll
+                        for (int t4 = 0; t4 < 4; ++t4) {
+                            n0[t4] = n1[t4] = c0[t4] = c1[t4] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (pc[t4] >= 0 && 8 * j < a.c) {
+                                const float4 *fn = reinterpret_cast<const float4 *>(a.feat + pn[t4] * a.c) + 2 * j;
+                                const float4 *fc = reinterpret_cast<const float4 *>(a.feat + pc[t4] * a.c) + 2 * j;
+                                n0[t4] = __ldg(fn); n1[t4] = __ldg(fn + 1); c0[t4] = __ldg(fc); c1[t4] = __ldg(fc + 1);
+                            }
+                        }
+#pragma unroll
+                        for (int t4 = 0; t4 < 4; ++t4) {
+                            const float v[8] = {n0[t4].x - c0[t4].x, n0[t4].y - c0[t4].y, n0[t4].z - c0[t4].z, n0[t4].w - c0[t4].w,
+                                                n1[t4].x - c1[t4].x, n1[t4].y - c1[t4].y, n1[t4].z - c1[t4].z, n1[t4].w - c1[t4].w};
+                            store_units(a1, a2, lwarp * 32 + rr + t4, j, v);
+                        }
                     }
                 }
             } else {
+                // FP: lane r holds the three neighbour indices / weights of row 32*lwarp + r; rows are staged four at a
+                // time (24 x 16-byte gathers in flight per lane), indices and weights broadcast by shuffles
                 const int ku = a.c_known / 8;
-                // two rows per iteration so that twelve 16-byte loads are in flight per lane
-                for (int r0 = wwarp * 2; r0 < TM; r0 += 16) {
-                    long pp[2]; bool ok[2]; long base[2]; int i0[2], i1[2], i2[2]; float w0[2], w1[2], w2[2];
+                long my_base = -1;
+                int my_i[3] = {0, 0, 0};
+                float my_w[3] = {0.f, 0.f, 0.f};
+                {
+                    const long p = (long)tile * TM + lwarp * 32 + lane;
+                    if (p < a.rows) {
+                        my_base = (p / a.n) * a.m;
 #pragma unroll
-                    for (int t2 = 0; t2 < 2; ++t2) {
-                        pp[t2] = (long)tile * TM + r0 + t2;
-                        ok[t2] = pp[t2] < a.rows;
-                        base[t2] = 0; i0[t2] = i1[t2] = i2[t2] = 0; w0[t2] = w1[t2] = w2[t2] = 0.f;
-                        if (ok[t2]) {
-                            base[t2] = (pp[t2] / a.n) * a.m;
-                            i0[t2] = __ldg(a.idx3 + pp[t2] * 3); i1[t2] = __ldg(a.idx3 + pp[t2] * 3 + 1); i2[t2] = __ldg(a.idx3 + pp[t2] * 3 + 2);
-                            w0[t2] = __ldg(a.w3 + pp[t2] * 3); w1[t2] = __ldg(a.w3 + pp[t2] * 3 + 1); w2[t2] = __ldg(a.w3 + pp[t2] * 3 + 2);
-                        }
+                        for (int e = 0; e < 3; ++e) { my_i[e] = __ldg(a.idx3 + p * 3 + e); my_w[e] = __ldg(a.w3 + p * 3 + e); }
+                    }
+                }
+                for (int rr = 0; rr < 32; rr += 4) {
+                    const float *f0[4], *f1[4], *f2[4];
+                    float w0[4], w1[4], w2[4];
+                    bool ok[4];
+#pragma unroll
+                    for (int t4 = 0; t4 < 4; ++t4) {
+                        const long base = __shfl_sync(0xffffffffu, my_base, rr + t4);
+                        const int i0 = __shfl_sync(0xffffffffu, my_i[0], rr + t4), i1 = __shfl_sync(0xffffffffu, my_i[1], rr + t4),
+                                  i2 = __shfl_sync(0xffffffffu, my_i[2], rr + t4);
+                        w0[t4] = __shfl_sync(0xffffffffu, my_w[0], rr + t4); w1[t4] = __shfl_sync(0xffffffffu, my_w[1], rr + t4);
+                        w2[t4] = __shfl_sync(0xffffffffu, my_w[2], rr + t4);
+                        ok[t4] = base >= 0;
+                        const long b0 = ok[t4] ? base : 0;
+                        f0[t4] = a.known_feat + (b0 + i0) * a.c_known; f1[t4] = a.known_feat + (b0 + i1) * a.c_known;
+                        f2[t4] = a.known_feat + (b0 + i2) * a.c_known;
                     }
                     for (int j = lane; j < units0; j += 32) {
-                        float v[2][8];
+                        float v[4][8];
                         if (j < ku) {
-                            float4 x0[2], x1[2], y0[2], y1[2], z0[2], z1[2];
+                            float4 x0[4], x1[4], y0[4], y1[4], z0[4], z1[4];
 #pragma unroll
-                            for (int t2 = 0; t2 < 2; ++t2) {
-                                const float4 *f0 = reinterpret_cast<const float4 *>(a.known_feat + (base[t2] + i0[t2]) * a.c_known) + 2 * j;
-                                const float4 *f1 = reinterpret_cast<const float4 *>(a.known_feat + (base[t2] + i1[t2]) * a.c_known) + 2 * j;
-                                const float4 *f2 = reinterpret_cast<const float4 *>(a.known_feat + (base[t2] + i2[t2]) * a.c_known) + 2 * j;
-                                x0[t2] = __ldg(f0); x1[t2] = __ldg(f0 + 1); y0[t2] = __ldg(f1); y1[t2] = __ldg(f1 + 1);
-                                z0[t2] = __ldg(f2); z1[t2] = __ldg(f2 + 1);
+                            for (int t4 = 0; t4 < 4; ++t4) {
+                                x0[t4] = __ldg(reinterpret_cast<const float4 *>(f0[t4]) + 2 * j); x1[t4] = __ldg(reinterpret_cast<const float4 *>(f0[t4]) + 2 * j + 1);
+                                y0[t4] = __ldg(reinterpret_cast<const float4 *>(f1[t4]) + 2 * j); y1[t4] = __ldg(reinterpret_cast<const float4 *>(f1[t4]) + 2 * j + 1);
+                                z0[t4] = __ldg(reinterpret_cast<const float4 *>(f2[t4]) + 2 * j); z1[t4] = __ldg(reinterpret_cast<const float4 *>(f2[t4]) + 2 * j + 1);
                             }
 #pragma unroll
-                            for (int t2 = 0; t2 < 2; ++t2) {
+                            for (int t4 = 0; t4 < 4; ++t4) {
                                 // interpolation_forward: fma(w2,p2, fma(w0,p0, w1*p1)) (interpolation_cuda_kernel.cu:194)
-                                v[t2][0] = __fmaf_rn(w2[t2], z0[t2].x, __fmaf_rn(w0[t2], x0[t2].x, __fmul_rn(w1[t2], y0[t2].x)));
-                                v[t2][1] = __fmaf_rn(w2[t2], z0[t2].y, __fmaf_rn(w0[t2], x0[t2].y, __fmul_rn(w1[t2], y0[t2].y)));
-                                v[t2][2] = __fmaf_rn(w2[t2], z0[t2].z, __fmaf_rn(w0[t2], x0[t2].z, __fmul_rn(w1[t2], y0[t2].z)));
-                                v[t2][3] = __fmaf_rn(w2[t2], z0[t2].w, __fmaf_rn(w0[t2], x0[t2].w, __fmul_rn(w1[t2], y0[t2].w)));
-                                v[t2][4] = __fmaf_rn(w2[t2], z1[t2].x, __fmaf_rn(w0[t2], x1[t2].x, __fmul_rn(w1[t2], y1[t2].x)));
-                                v[t2][5] = __fmaf_rn(w2[t2], z1[t2].y, __fmaf_rn(w0[t2], x1[t2].y, __fmul_rn(w1[t2], y1[t2].y)));
-                                v[t2][6] = __fmaf_rn(w2[t2], z1[t2].z, __fmaf_rn(w0[t2], x1[t2].z, __fmul_rn(w1[t2], y1[t2].z)));
-                                v[t2][7] = __fmaf_rn(w2[t2], z1[t2].w, __fmaf_rn(w0[t2], x1[t2].w, __fmul_rn(w1[t2], y1[t2].w)));
+                                v[t4][0] = __fmaf_rn(w2[t4], z0[t4].x, __fmaf_rn(w0[t4], x0[t4].x, __fmul_rn(w1[t4], y0[t4].x)));
+                                v[t4][1] = __fmaf_rn(w2[t4], z0[t4].y, __fmaf_rn(w0[t4], x0[t4].y, __fmul_rn(w1[t4], y0[t4].y)));
+                                v[t4][2] = __fmaf_rn(w2[t4], z0[t4].z, __fmaf_rn(w0[t4], x0[t4].z, __fmul_rn(w1[t4], y0[t4].z)));
+                                v[t4][3] = __fmaf_rn(w2[t4], z0[t4].w, __fmaf_rn(w0[t4], x0[t4].w, __fmul_rn(w1[t4], y0[t4].w)));
+                                v[t4][4] = __fmaf_rn(w2[t4], z1[t4].x, __fmaf_rn(w0[t4], x1[t4].x, __fmul_rn(w1[t4], y1[t4].x)));
+                                v[t4][5] = __fmaf_rn(w2[t4], z1[t4].y, __fmaf_rn(w0[t4], x1[t4].y, __fmul_rn(w1[t4], y1[t4].y)));
+                                v[t4][6] = __fmaf_rn(w2[t4], z1[t4].z, __fmaf_rn(w0[t4], x1[t4].z, __fmul_rn(w1[t4], y1[t4].z)));
+                                v[t4][7] = __fmaf_rn(w2[t4], z1[t4].w, __fmaf_rn(w0[t4], x1[t4].w, __fmul_rn(w1[t4], y1[t4].w)));
                             }
                         } else {
 #pragma unroll
-                            for (int t2 = 0; t2 < 2; ++t2) {
+                            for (int t4 = 0; t4 < 4; ++t4) {
                                 float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
-                                if (ok[t2]) {
-                                    const float4 *sk = reinterpret_cast<const float4 *>(a.skip_feat + pp[t2] * a.c_skip) + 2 * (j - ku);
+                                const long p = (long)tile * TM + lwarp * 32 + rr + t4;
+                                if (ok[t4] && 8 * (j - ku) < a.c_skip) {
+                                    const float4 *sk = reinterpret_cast<const float4 *>(a.skip_feat + p * a.c_skip) + 2 * (j - ku);
                                     s0 = __ldg(sk); s1 = __ldg(sk + 1);
                                 }
-                                v[t2][0] = s0.x; v[t2][1] = s0.y; v[t2][2] = s0.z; v[t2][3] = s0.w;
-                                v[t2][4] = s1.x; v[t2][5] = s1.y; v[t2][6] = s1.z; v[t2][7] = s1.w;
+                                v[t4][0] = s0.x; v[t4][1] = s0.y; v[t4][2] = s0.z; v[t4][3] = s0.w;
+                                v[t4][4] = s1.x; v[t4][5] = s1.y; v[t4][6] = s1.z; v[t4][7] = s1.w;
                             }
                         }
 #pragma unroll
-                        for (int t2 = 0; t2 < 2; ++t2) store_units(a1, a2, r0 + t2, j, v[t2]);
+                        for (int t4 = 0; t4 < 4; ++t4) {
+                            if (!ok[t4]) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[t4][i] = 0.f;
+                            }
+                            store_units(a1, a2, lwarp * 32 + rr + t4, j, v[t4]);
+                        }
                     }
-                }
-                if (a.n_extra > 0) {
-                    const long p = (long)tile * TM + row;
-                    if (p < a.rows)
-                        for (int e = 0; e < a.n_extra; ++e) xe[e] = __ldg(a.skip_feat + p * a.c_skip + e);
                 }
             }
             fence_proxy_async();
-            mbar_arrive(a_ready);
-
-            // ---- per-layer epilogues -----------------------------------------------------------------------------
-            for (int l = 0; l < a.n_layers; ++l, ++lcount) {
-                const int N = a.N[l];
-                const bool last = l == a.n_layers - 1;
-                const bool relu = a.relu[l] != 0;
-                const bool extras = l == 0 && a.n_extra > 0;
-                const float *shl = ctab + a.coff[l];
-                mbar_wait(d_ready, lcount & 1);
-                tc_fence_after();
-                const int npass = last ? (N + 255) / 256 : 1;
-                for (int pass = 0; pass < npass; ++pass) {
-                    const int ncols = min(256, N - pass * 256);        // columns of this pass
-                    const int per = ncols >= 64 ? ncols / 2 : (half == 0 ? ncols : 0);   // columns per worker half (batches of 32)
-                    for (int cb = 0; cb < per; cb += 32) {
-                        const int col = pass * 256 + (ncols >= 64 ? half * per : 0) + cb;  // first accumulator column of this batch
-                        float v[32];
-                        tmem_ld32(trow + (uint32_t)col, v);
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const float4 sh = *reinterpret_cast<const float4 *>(shl + col + 4 * u);
-                            v[4 * u] += sh.x; v[4 * u + 1] += sh.y; v[4 * u + 2] += sh.z; v[4 * u + 3] += sh.w;
-                        }
-                        if (extras) {
-#pragma unroll
-                            for (int e = 0; e < 3; ++e) {
-                                if (e < a.n_extra) {
-#pragma unroll
-                                    for (int u = 0; u < 8; ++u) {
-                                        const float4 w = *reinterpret_cast<const float4 *>(wext + e * N + col + 4 * u);
-                                        v[4 * u] = fmaf(xe[e], w.x, v[4 * u]); v[4 * u + 1] = fmaf(xe[e], w.y, v[4 * u + 1]);
-                                        v[4 * u + 2] = fmaf(xe[e], w.z, v[4 * u + 2]); v[4 * u + 3] = fmaf(xe[e], w.w, v[4 * u + 3]);
-                                    }
-                                }
-                            }
-                        }
-                        if (relu) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-                        }
-                        if (!last) {
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                float w8[8];
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) w8[i] = v[u * 8 + i];
-                                store_units(a1, a2, row, (col >> 3) + u, w8);
-                            }
-                        } else {
-                            const int c0 = col - pass * 256;
-#pragma unroll
-                            for (int u = 0; u < 8; ++u)
-                                *reinterpret_cast<float4 *>(a1 + stage_offset(row, c0 + 4 * u)) =
-                                    make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
-                        }
-                    }
-                    if (last) {
-                        tc_fence_before();
-                        asm volatile("bar.sync 1, %0;" ::"n"(NWORK) : "memory");   // staging complete (workers only)
-                        if (a.mode == TC_SA) {
-                            const int G = TM / a.k;
-                            for (int e = wt; e < G * ncols; e += NWORK) {
-                                const int g = e / ncols, c = e - g * ncols;
-                                const long ci = (long)tile * G + g;
-                                if (ci >= a.rows) continue;
-                                float mx = *reinterpret_cast<const float *>(a1 + stage_offset(g * a.k, c));
-                                for (int sidx = 1; sidx < a.k; ++sidx)
-                                    mx = fmaxf(mx, *reinterpret_cast<const float *>(a1 + stage_offset(g * a.k + sidx, c)));
-                                a.out[ci * N + pass * 256 + c] = mx;
-                            }
-                        } else {
-                            const int c4 = ncols / 4;                  // one warp per row: 1 KB contiguous per store wave
-                            for (int r = wwarp; r < TM; r += 8) {
-                                const long p = (long)tile * TM + r;
-                                if (p >= a.rows) break;
-                                for (int cq = lane; cq < c4; cq += 32)
-                                    *reinterpret_cast<float4 *>(a.out + p * N + pass * 256 + 4 * cq) =
-                                        *reinterpret_cast<const float4 *>(a1 + stage_offset(r, 4 * cq));
-                            }
-                        }
-                        asm volatile("bar.sync 1, %0;" ::"n"(NWORK) : "memory");   // staging consumed before it is rewritten
-                    }
-                }
-                if (!last) {
-                    tc_fence_before();
-                    fence_proxy_async();
-                    mbar_arrive(a_ready);
-                }
-            }
+            mbar_arrive(a_full);
         }
     }
     tc_fence_before();
@@ -439,34 +565,25 @@ int make_weight_map(CUtensorMap *map, const void *w, int N, int K, int box_n) {
 
 int g_tc_enabled = 1;
 
-// Shared-memory plan of one launch: operand region, constant table, weight-stage granularity and count.
+// Shared-memory plan of one launch: layer-0 operand region, staging, weight stages, constant table.
 // `layers` are the TENSOR-CORE layers only (the optional pre-layer is passed separately).
-struct TcPlan { int kchunks_max, a_region, nblk, stage_bytes, n_stages, coff[MAX_LAYERS], pre_off; size_t misc, smem; };
+struct TcPlan { int a_region, n_stages, coff[MAX_LAYERS], pre_off; size_t misc, smem; };
 
 bool tc_plan(const pab_layer_t *layers, int n_layers, const pab_layer_t *pre, TcPlan *p) {
-    int kmax = 0, ctab = 0;
-    bool need64 = false;
+    int ctab = 0;
     for (int l = 0; l < n_layers; ++l) {
-        if (layers[l].tc_k > kmax) kmax = layers[l].tc_k;
         p->coff[l] = ctab;
         ctab += layers[l].c_out;
-        if (layers[l].c_out > 64 && layers[l].c_out % 128) need64 = true;   // e.g. 192: only 64-wide blocks divide it
     }
     if (!pre) ctab += (layers[0].c_in - layers[0].tc_k) * layers[0].c_out;
     p->pre_off = ctab;
     if (pre) ctab += pre->c_in * pre->c_out + pre->c_out;
-    p->kchunks_max = kmax / KCH;
-    p->a_region = 2 * p->kchunks_max * A_CHUNK;
-    if (p->a_region < TM * 256 * 4) p->a_region = TM * 256 * 4;      // last-layer fp32 staging [128][256]
+    p->a_region = 2 * (layers[0].tc_k / KCH) * A_CHUNK;              // hi + lo plane of the gathered rows
     p->misc = 256 + (size_t)ctab * 4 + 64;
-    const long budget = 227L * 1024 - p->a_region - (long)p->misc;
-    if (budget < 2 * 2 * 64 * 128) return false;
-    // 128 output channels per stage when at least 3 such stages fit, else 64
-    p->nblk = (!need64 && budget / (2 * 128 * 128) >= 3) ? 128 : 64;
-    p->stage_bytes = 2 * p->nblk * 128;
-    p->n_stages = (int)(budget / p->stage_bytes);
+    const long budget = 227L * 1024 - p->a_region - STG_BYTES - (long)p->misc;
+    p->n_stages = (int)(budget / (NBLK_MAX * 128));
     if (p->n_stages > MAX_STAGES) p->n_stages = MAX_STAGES;
-    p->smem = (size_t)p->a_region + (size_t)p->n_stages * p->stage_bytes + p->misc;
+    p->smem = (size_t)p->a_region + (size_t)p->n_stages * (NBLK_MAX * 128) + STG_BYTES + p->misc;
     return p->n_stages >= 2;
 }
 
@@ -475,11 +592,11 @@ bool tc_layers_ok(const pab_layer_t *layers, int n_layers, bool first_is_module_
     for (int l = 0; l < n_layers; ++l) {
         const pab_layer_t &L = layers[l];
         if (!L.w_hi || !L.w_lo || L.tc_k <= 0 || L.tc_k % KCH) return false;
-        if (!(L.c_out == 32 || L.c_out % 64 == 0) || L.c_out > 512) return false;
-        if (l < n_layers - 1 && L.c_out > 256) return false;
+        if (!(L.c_out == 32 || L.c_out == 64 || L.c_out % NBLK_MAX == 0) || L.c_out > 512) return false;
+        if (l < n_layers - 1 && L.c_out > D_COLS) return false;       // the next operand must fit the TMEM planes
         const bool module_input = l == 0 && first_is_module_input;
         if (!module_input && (L.tc_k0 != 0 || L.tc_k < L.c_in)) return false;          // K may be zero-padded to 64
-        if (l > 0 && L.c_in != layers[l - 1].c_out) return false;
+        if (l > 0 && (L.c_in != layers[l - 1].c_out || L.c_in % 16)) return false;
     }
     return true;
 }
@@ -510,13 +627,16 @@ int pab_tc_launch(int mode, long rows, int k_group, const pab_layer_t *all_layer
     const int n_layers = kind == 2 ? n_all - 1 : n_all;
     TcPlan p;
     if (!tc_plan(layers, n_layers, pre, &p)) return PAB_EINVAL;
-    a.kchunks_max = p.kchunks_max; a.a_region = p.a_region; a.nblk = p.nblk; a.stage_bytes = p.stage_bytes; a.n_stages = p.n_stages;
+    a.a_region = p.a_region; a.n_stages = p.n_stages;
     for (int l = 0; l < n_layers; ++l) {
         const pab_layer_t &L = layers[l];
-        const int nbr = L.c_out < a.nblk ? L.c_out : a.nblk;
+        const int nbr = L.c_out < NBLK_MAX ? L.c_out : NBLK_MAX;
         if (make_weight_map(&a.tm[l][0], L.w_hi, L.c_out, L.tc_k, nbr)) return PAB_EINVAL;
         if (make_weight_map(&a.tm[l][1], L.w_lo, L.c_out, L.tc_k, nbr)) return PAB_EINVAL;
         a.shift[l] = L.shift; a.K[l] = L.tc_k; a.N[l] = L.c_out; a.relu[l] = L.relu; a.coff[l] = p.coff[l];
+        // k-steps that carry data: the staged layer-0 operand spans whole 64-chunks (only the pre-layer's output is
+        // narrower), the TMEM operand of later layers exactly c_in channels
+        a.ksteps[l] = l == 0 ? (pre ? (pre->c_out + 15) / 16 : L.tc_k / 16) : L.c_in / 16;
     }
     a.n_layers = n_layers; a.mode = mode; a.rows = rows;
     if (pre) {
