@@ -51,6 +51,16 @@ int pab_gathering_backward(int b, int c, int n, int m, const float *grad_out, co
  * nsample <= 200 like the reference's fixed arrays (.cu:21-22), else PAB_EINVAL. */
 int pab_knnquery(int b, int n, int m, int nsample, const float *xyz, const float *new_xyz, int *idx, float *dist2, pab_stream_t s);
 
+/* The same query against a prebuilt spatial index of xyz (a Morton-sorted copy in 64-point chunks with bounding boxes):
+ * chunks are visited in order of their box distance and the scan stops at the first chunk that cannot hold a better
+ * point.  Results are identical to pab_knnquery (which builds a temporary index itself when 256 <= n <= 8192 and there
+ * are enough queries); build the index once when several queries share xyz.  nsample <= 64.
+ * index: pab_knn_index_bytes(b, n) bytes of device memory, 16-byte aligned. */
+size_t pab_knn_index_bytes(int b, int n);
+int pab_knn_build_index(int b, int n, const float *xyz, void *index, pab_stream_t s);
+int pab_knnquery_indexed(int b, int n, int m, int nsample, const void *index, const float *new_xyz, int *idx, float *dist2,
+                         pab_stream_t s);
+
 /* ballquery_cuda_launcher_fast  ballquery/ballquery_cuda_kernel.h, kernel .cu:47-80.  idx caller-zeroed. */
 int pab_ballquery(int b, int n, int m, float radius, int nsample, const float *new_xyz, const float *xyz, int *idx, pab_stream_t s);
 
@@ -116,6 +126,11 @@ int pab_gather_rows(int b, int n, int m, int c, const float *feat, const int *id
 /* Fused 3-NN + inverse-distance weights: pointops.nearestneighbor + patch_aug_net.py:350-353.
  * unknown (b,n,3), known (b,m,3) -> idx (b,n,3) i32, weight (b,n,3) f32. */
 int pab_three_nn_weights(int b, int n, int m, const float *unknown, const float *known, int *idx, float *weight, pab_stream_t s);
+/* The same against prebuilt spatial indices (pab_knn_build_index): known_index over the known points (required,
+ * 256 <= m <= 8192); unknown_index over the unknown points (optional: queries are then processed in Morton order, which
+ * keeps every warp spatially compact; results are written at the original positions).  Identical results. */
+int pab_three_nn_weights_indexed(int b, int n, int m, const float *unknown, const void *unknown_index, const void *known_index,
+                                 int *idx, float *weight, pab_stream_t s);
 
 /* One folded SharedMLP layer: y = relu?(Wt^T x + shift).  Wt is (c_in_pad, c_out) row-major with the
  * BatchNorm scale folded in and rows >= c_in zero; c_in_pad = c_in rounded up to a multiple of 4. */

@@ -37,6 +37,10 @@ SIGNATURES = {
     "pab_gathering_forward": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),
     "pab_gathering_backward": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),
     "pab_knnquery": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "pab_knn_index_bytes": (_SZ, [_I, _I]),
+    "pab_knn_build_index": (_I, [_I, _I, _P, _P, _P]),
+    "pab_knnquery_indexed": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "pab_three_nn_weights_indexed": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "pab_ballquery": (_I, [_I, _I, _I, _F, _I, _P, _P, _P, _P]),
     "pab_grouping_forward": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "pab_grouping_backward": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P]),

@@ -167,7 +167,10 @@ class FusedPatchAugNet:
             ws["levels"].append(dict(
                 n=n, m=m,
                 temp=torch.empty(B, n if n > 8192 else 1, **f32), cidx=torch.empty(B, m, **i32), new_xyz=torch.empty(B, m, 3, **f32),
-                nbr=torch.empty(B, m, sa["k"], **i32), feat=torch.empty(B, m, sa["layers"].c_out, **f32)))
+                nbr=torch.empty(B, m, sa["k"], **i32), feat=torch.empty(B, m, sa["layers"].c_out, **f32),
+                # Morton-sorted spatial index of the level's points (exact pruned kNN); small levels scan brute force
+                index=(torch.empty(lib.pab_knn_index_bytes(B, n), dtype=torch.uint8, device=dev)
+                       if 256 <= n <= 8192 and sa["k"] <= 64 else None)))
             n = m
         ns = [N] + [sa["npoint"] for sa in self.sa]              # points per level 0..3
         for li in range(len(self.fp)):                           # FP_modules[li] lifts level li+1 -> li
@@ -212,7 +215,11 @@ class FusedPatchAugNet:
                 temp.fill_(1e10)
             run(f"fps{i}", lambda: lib.pab_furthestsampling(B, n, m, p(xyz), p(temp), p(lv["cidx"]), st))
             run(f"gather{i}", lambda: lib.pab_gather_rows(B, n, m, 3, p(xyz), p(lv["cidx"]), p(lv["new_xyz"]), st))
-            run(f"knn{i}", lambda: lib.pab_knnquery(B, n, m, k, p(xyz), p(lv["new_xyz"]), p(lv["nbr"]), p(None), st))
+            if lv["index"] is not None:
+                run(f"index{i}", lambda: lib.pab_knn_build_index(B, n, p(xyz), p(lv["index"]), st))
+                run(f"knn{i}", lambda: lib.pab_knnquery_indexed(B, n, m, k, p(lv["index"]), p(lv["new_xyz"]), p(lv["nbr"]), p(None), st))
+            else:
+                run(f"knn{i}", lambda: lib.pab_knnquery(B, n, m, k, p(xyz), p(lv["new_xyz"]), p(lv["nbr"]), p(None), st))
             if i == 0 and first_knn_event is not None:
                 first_knn_event.record()      # the first SA module can start; deeper geometry overlaps with it
             xyz = lv["new_xyz"]
@@ -221,7 +228,13 @@ class FusedPatchAugNet:
             f = ws["fp"][li]
             unknown, known = xyzs[li], xyzs[li + 1]
             n, m = unknown.shape[1], known.shape[1]
-            run(f"three_nn{li}", lambda: lib.pab_three_nn_weights(B, n, m, p(unknown), p(known), p(f["idx"]), p(f["w"]), st))
+            uidx = ws["levels"][li]["index"] if li < len(ws["levels"]) else None
+            kidx = ws["levels"][li + 1]["index"] if li + 1 < len(ws["levels"]) else None
+            if kidx is not None:              # spatial indices of both clouds were built for the kNN of their levels
+                run(f"three_nn{li}", lambda: lib.pab_three_nn_weights_indexed(B, n, m, p(unknown), p(uidx), p(kidx),
+                                                                              p(f["idx"]), p(f["w"]), st))
+            else:
+                run(f"three_nn{li}", lambda: lib.pab_three_nn_weights(B, n, m, p(unknown), p(known), p(f["idx"]), p(f["w"]), st))
 
     def _launch_dense(self, xyz0, ws, after_first_sa=None):
         """Feature path — fused SA modules, fused FP modules, NetVLAD levels, AFA head."""
@@ -350,6 +363,7 @@ class FusedPatchAugNet:
             c_out = sa["layers"].c_out
             work[f"fps{i}"] = dict(flops=0, bytes=B * (12 * n + 4 * m), units=B * n * (m - 1), unit="point-updates")
             work[f"gather{i}"] = dict(flops=0, bytes=B * (4 * m + 24 * m))
+            work[f"index{i}"] = dict(flops=0, bytes=B * (12 * n + 16 * n + n // 2))       # read xyz, write sorted copy + perm + boxes
             work[f"knn{i}"] = dict(flops=0, bytes=B * (12 * n + 12 * m + 4 * m * k), units=B * n * m, unit="distance evals")
             work[f"sa{i}"] = dict(flops=2 * B * m * k * macs, bytes=B * (4 * c * n + 12 * n + 12 * m + 4 * m * k + 4 * c_out * m))
             c = c_out
@@ -425,4 +439,5 @@ class FusedPatchAugNet:
 
     def launches_per_forward(self):
         """Kernels this library launches per forward (for bench.py's gpu_launches)."""
-        return 4 * len(self.sa) + 2 * len(self.fp) + 2 * len(self.vlad) + 4
+        n_index = max((sum(1 for lv in ws["levels"] if lv["index"] is not None) for ws in self._ws.values()), default=0)
+        return 4 * len(self.sa) + n_index + 2 * len(self.fp) + 2 * len(self.vlad) + 4

@@ -71,6 +71,32 @@ def test_knnquery_bit_exact(n, m, k):
         assert torch.equal(got.cpu(), torch.from_numpy(want)), (n, m, k, kw)
 
 
+@pytest.mark.parametrize("n,m,k", [(256, 64, 20), (257, 300, 33), (1000, 77, 1), (4096, 1024, 20), (4096, 200, 64), (8192, 50, 40),
+                                   (5000, 64, 20)])
+def test_knnquery_indexed_bit_exact(n, m, k):
+    """Morton-chunk index + box-distance pruning returns exactly the brute-force answer (distances, ties to the lower index),
+    also on clouds where half the points are exact duplicates, a block of points coincides at the origin, or the queries lie
+    far outside the cloud."""
+    lib = L.lib()
+    b = 2
+    for kw in (dict(), dict(dup=True), dict(zero_tail=n // 3)):
+        xyz = _clouds(b, n, seed=3 * n + k, **kw)
+        q = np.ascontiguousarray(xyz[:, :: max(1, n // m)][:, :m]) if m <= n else _clouds(b, m, seed=n + 1)
+        q[:, -1] += 7.0                                                  # one query far away from every chunk box
+        wi, wd = ops.knnquery(k, xyz, q, return_dist=True)
+        gx, gq = _g(xyz), _g(q)
+        index = torch.empty(lib.pab_knn_index_bytes(b, n), dtype=torch.uint8, device=DEV)
+        idx = torch.full((b, q.shape[1], k), -7, dtype=torch.int32, device=DEV)
+        d2 = torch.zeros(b, q.shape[1], k, device=DEV)
+        L.check(lib.pab_knn_build_index(b, n, L.ptr(gx), L.ptr(index), L.stream_ptr()), "index")
+        L.check(lib.pab_knnquery_indexed(b, n, q.shape[1], k, L.ptr(index), L.ptr(gq), L.ptr(idx), L.ptr(d2), L.stream_ptr()), "knn")
+        torch.cuda.synchronize()
+        assert torch.equal(idx.cpu(), torch.from_numpy(wi)), (n, m, k, kw)
+        assert torch.equal(d2.cpu(), torch.from_numpy(wd)), (n, m, k, kw)
+        # the drop-in entry point picks the same path on its own when there are enough queries
+        assert torch.equal(pointops.knnquery(k, gx, gq).cpu(), torch.from_numpy(wi))
+
+
 def test_knnquery_dist2_and_limits():
     from patchaugnet_b200 import pointops_cuda as K
     xyz = _clouds(1, 64, 7)
@@ -108,6 +134,36 @@ def test_three_nn_bit_exact_and_weights(n, m):
         want_w = r / r.sum(2, keepdim=True)
         assert torch.equal(wi.cpu(), torch.from_numpy(idx))
         assert torch.allclose(w.cpu(), want_w, rtol=2e-6, atol=0)
+
+
+@pytest.mark.parametrize("n,m", [(4096, 1024), (1000, 256), (300, 4096), (5000, 777), (8192, 2048)])
+def test_three_nn_indexed_bit_exact(n, m):
+    """3-NN against the Morton-chunk index of the known points (with and without an index over the unknown points):
+    same indices and weights as the brute-force scan, including duplicate / coincident points."""
+    lib = L.lib()
+    b = 2
+    for kw in (dict(), dict(dup=True), dict(zero_tail=m // 3)):
+        unknown, known = _clouds(b, n, n + 5, **({} if "zero_tail" in kw else kw)), _clouds(b, m, m + 6, **kw)
+        if kw:
+            known[:, : min(n, m) // 2] = unknown[:, : min(n, m) // 2]
+        unknown[:, -1] -= 9.0                                              # a query far outside the known cloud
+        d2, want_i = ops.nearestneighbor(unknown, known)
+        r = 1.0 / (torch.sqrt(torch.from_numpy(d2)) + 1e-8)
+        want_w = r / r.sum(2, keepdim=True)
+        gu, gk = _g(unknown), _g(known)
+        kidx = torch.empty(lib.pab_knn_index_bytes(b, m), dtype=torch.uint8, device=DEV)
+        L.check(lib.pab_knn_build_index(b, m, L.ptr(gk), L.ptr(kidx), L.stream_ptr()), "index")
+        uidx = None
+        if 256 <= n <= 8192:
+            uidx = torch.empty(lib.pab_knn_index_bytes(b, n), dtype=torch.uint8, device=DEV)
+            L.check(lib.pab_knn_build_index(b, n, L.ptr(gu), L.ptr(uidx), L.stream_ptr()), "index")
+        for ui in ([None, uidx] if uidx is not None else [None]):
+            gi = torch.full((b, n, 3), -3, dtype=torch.int32, device=DEV)
+            w = torch.zeros(b, n, 3, device=DEV)
+            L.check(lib.pab_three_nn_weights_indexed(b, n, m, L.ptr(gu), L.ptr(ui), L.ptr(kidx), L.ptr(gi), L.ptr(w), L.stream_ptr()), "3nn")
+            torch.cuda.synchronize()
+            assert torch.equal(gi.cpu(), torch.from_numpy(want_i)), (n, m, kw, ui is not None)
+            assert torch.allclose(w.cpu(), want_w, rtol=2e-6, atol=0)
 
 
 def test_gather_group_interp_forward_backward():
