@@ -561,15 +561,27 @@ template <bool WEIGHTS>
 __global__ void __launch_bounds__(256)
 three_nn_pruned_kernel(int n, int m, const float *__restrict__ unknown, const float *__restrict__ uindex,
                        const float *__restrict__ kindex, float *__restrict__ out_f, int *__restrict__ idx) {
-    extern __shared__ __align__(16) float4 kpts[];           // [mpad] (x, y, z, original index) then the chunk boxes
+    extern __shared__ __align__(16) float4 kpts[];           // [mpad] (x, y, z, original index) then the sub-chunk boxes
     const int t = threadIdx.x, lane = t & 31, cloud = blockIdx.y;
-    const int mpad = idx_npad(m), mch = mpad / IDX_CHUNK;
+    const int mpad = idx_npad(m);
+    // small known clouds are walked in 16-point sub-chunks (still contiguous along the Morton curve): finer boxes prune more
+    const int sub = mpad <= 2048 ? 16 : IDX_CHUNK, mch = mpad / sub;
     float *sbox = reinterpret_cast<float *>(kpts + mpad);
     {
         const float *kx = kindex + (size_t)cloud * idx_stride(m), *ky = kx + mpad, *kz = ky + mpad;
-        const float *kp = kz + mpad, *kb = kp + mpad;
+        const float *kp = kz + mpad;
         for (int i = t; i < mpad; i += 256) kpts[i] = make_float4(__ldg(kx + i), __ldg(ky + i), __ldg(kz + i), __ldg(kp + i));
-        for (int i = t; i < mch * 8; i += 256) sbox[i] = __ldg(kb + i);
+    }
+    __syncthreads();
+    for (int ch = t; ch < mch; ch += 256) {                    // pads (positions >= m) stay outside every box
+        float l[3] = {INFINITY, INFINITY, INFINITY}, h[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int kk = 0; kk < sub && ch * sub + kk < m; ++kk) {
+            const float4 pk = kpts[ch * sub + kk];
+            l[0] = fminf(l[0], pk.x); l[1] = fminf(l[1], pk.y); l[2] = fminf(l[2], pk.z);
+            h[0] = fmaxf(h[0], pk.x); h[1] = fmaxf(h[1], pk.y); h[2] = fmaxf(h[2], pk.z);
+        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { sbox[ch * 8 + d] = l[d]; sbox[ch * 8 + 3 + d] = h[d]; }
     }
     __syncthreads();
     const int j = blockIdx.x * 256 + t;                        // position in the (sorted) unknown cloud
@@ -625,9 +637,9 @@ three_nn_pruned_kernel(int n, int m, const float *__restrict__ unknown, const fl
 #pragma unroll
         for (int s = 0; s < KNNP_SLOTS; ++s)
             if (ck[s] == g) ck[s] = 0xffffffffu;
-        const float4 *cp = kpts + (int)(g & cmask) * IDX_CHUNK;
+        const float4 *cp = kpts + (int)(g & cmask) * sub;
 #pragma unroll 4
-        for (int kk = 0; kk < IDX_CHUNK; ++kk) {
+        for (int kk = 0; kk < sub; ++kk) {
             const float4 pk = cp[kk];
             const float d = ref_sqdist(ux, uy, uz, pk.x, pk.y, pk.z);
             if (d <= b3) {                                     // chunks arrive in arbitrary index order: compare full keys
@@ -832,7 +844,7 @@ namespace {
 template <bool WEIGHTS>
 int launch_three_nn_pruned(int b, int n, int m, const float *unknown, const void *uindex, const void *kindex, float *out_f, int *idx,
                            cudaStream_t st) {
-    const size_t smem = (size_t)idx_npad(m) * 16 + (size_t)(idx_npad(m) / IDX_CHUNK) * 32;
+    const size_t smem = (size_t)idx_npad(m) * 16 + (size_t)(idx_npad(m) / 16) * 32;
     if (smem > 48 * 1024)
         PAB_CUDA(cudaFuncSetAttribute(three_nn_pruned_kernel<WEIGHTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(pab_divup(n, 256), b);
