@@ -637,6 +637,9 @@ three_nn_pruned_kernel(int n, int m, const float *__restrict__ unknown, const fl
 #pragma unroll
         for (int s = 0; s < KNNP_SLOTS; ++s)
             if (ck[s] == g) ck[s] = 0xffffffffu;
+        // the box-to-box bound let this chunk through; skip it all the same unless SOME lane's own point is close enough
+        const float mylb = box_sqdist(ux, uy, uz, sbox + (int)(g & cmask) * 8);
+        if (!__any_sync(0xffffffffu, active && mylb <= b3)) continue;
         const float4 *cp = kpts + (int)(g & cmask) * sub;
 #pragma unroll 4
         for (int kk = 0; kk < sub; ++kk) {

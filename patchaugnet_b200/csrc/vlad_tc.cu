@@ -58,10 +58,13 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vlad_tc_kernel(const VtArgs a) 
     uint64_t *g2_done = a_ready + 3;                               // GEMM2 of the tile finished (tcgen05.commit)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_ready + 4);
     float *asum_s = reinterpret_cast<float *>(misc + 64);          // [Kp]
+    float *xmax = reinterpret_cast<float *>(misc + 64 + 256);      // [2][128] row maxima of the two column halves
+    float *xsum = xmax + 2 * TM;                                   // [2][128] row sums
+    const bool split = a.Kp > 32;
 
     const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
     if (tid == 0) {
-        mbar_init(a_ready, VT_WORK); mbar_init(d1_ready, 1); mbar_init(p_ready, 128); mbar_init(g2_done, 1);
+        mbar_init(a_ready, VT_WORK); mbar_init(d1_ready, 1); mbar_init(p_ready, a.Kp > 32 ? VT_WORK : 128); mbar_init(g2_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -157,39 +160,43 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vlad_tc_kernel(const VtArgs a) 
                 }
                 fence_proxy_async();
                 mbar_arrive(a_ready);
-                if (half == 0) {
+                if (half == 0 || split) {
+                    // softmax over the clusters of this point: with more than 32 clusters the two warps that share a TMEM lane
+                    // quarter take 32 columns each and exchange the row maximum and the row sum through shared memory
                     mbar_wait(d1_ready, tcount & 1);
                     tc_fence_after();
-                    float lg[64];
-                    {
-                        float v[32];
-                        tmem_ld32(trow, v);
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) lg[i] = v[i];
-                        if (a.Kp > 32) {
-                            tmem_ld32(trow + 32, v);
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) lg[32 + i] = v[i];
-                        }
-                    }
+                    float lg[32];
+                    tmem_ld32(trow + (uint32_t)(half * 32), lg);
+                    const int kb = half * 32;
                     const bool valid = r0 + row < r_end;
                     float mx = -INFINITY;
 #pragma unroll
-                    for (int k = 0; k < 64; ++k)
-                        if (k < a.K) { lg[k] += __ldg(a.shift + k); mx = fmaxf(mx, lg[k]); }
+                    for (int k = 0; k < 32; ++k)
+                        if (kb + k < a.K) { lg[k] += __ldg(a.shift + kb + k); mx = fmaxf(mx, lg[k]); }
+                    if (split) {
+                        xmax[half * TM + row] = mx;
+                        asm volatile("bar.sync 2, %0;" ::"n"(VT_WORK) : "memory");
+                        mx = fmaxf(mx, xmax[(half ^ 1) * TM + row]);
+                    }
                     float sum = 0.f;
 #pragma unroll
-                    for (int k = 0; k < 64; ++k)
-                        if (k < a.K) { lg[k] = expf(lg[k] - mx); sum += lg[k]; }
+                    for (int k = 0; k < 32; ++k)
+                        if (kb + k < a.K) { lg[k] = __expf(lg[k] - mx); sum += lg[k]; }
+                    if (split) {
+                        xsum[half * TM + row] = sum;
+                        asm volatile("bar.sync 2, %0;" ::"n"(VT_WORK) : "memory");
+                        sum = xsum[row] + xsum[TM + row];                    // same order in both threads of the row
+                    }
                     const float inv = valid ? 1.f / sum : 0.f;
                     const uint32_t pbase = (uint32_t)((row >> 6) * wchunk + (((row & 63) >> 3) << 4) + ((row & 7) << 1));
 #pragma unroll
-                    for (int k = 0; k < 64; ++k) {
-                        if (k < a.Kp) {
-                            const float p = k < a.K ? lg[k] * inv : 0.f;
+                    for (int k = 0; k < 32; ++k) {
+                        if (kb + k < a.Kp) {
+                            const int kk = kb + k;
+                            const float p = kk < a.K ? lg[k] * inv : 0.f;
                             const __nv_bfloat16 h = __float2bfloat16_rn(p);
                             const __nv_bfloat16 l = __float2bfloat16_rn(p - __bfloat162float(h));
-                            const uint32_t off = (uint32_t)(k * 128) + (pbase ^ (uint32_t)((k & 7) << 4));
+                            const uint32_t off = (uint32_t)(kk * 128) + (pbase ^ (uint32_t)((kk & 7) << 4));
                             *reinterpret_cast<__nv_bfloat16 *>(p1 + off) = h;
                             *reinterpret_cast<__nv_bfloat16 *>(p2 + off) = l;
                         }
@@ -197,7 +204,8 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vlad_tc_kernel(const VtArgs a) 
                     tc_fence_before();
                     fence_proxy_async();
                     mbar_arrive(p_ready);
-                } else {
+                }
+                if (half == 1) {
                     // a_sum[k] += sum over the tile's points of act[.][k], read back from the staged planes in a fixed order
                     mbar_wait(p_ready, tcount & 1);
                     const int k = wt - 128;
@@ -261,7 +269,7 @@ int pab_vlad_tc_partial(int b, int n, int c, int K, const float *x, const void *
     a.n = n; a.K = K; a.Kp = (K + 15) / 16 * 16; a.nchunk = (n + VT_ROWS_PER_ITEM - 1) / VT_ROWS_PER_ITEM; a.nitems = b * a.nchunk;
     a.x = x; a.shift = shift; a.wc_hi = (const __nv_bfloat16 *)wc_hi; a.wc_lo = (const __nv_bfloat16 *)wc_lo; a.part = part; a.asum = asum;
     *nchunk_out = a.nchunk;
-    const size_t smem = 8 * (size_t)A_CHUNK + 12 * (size_t)a.Kp * 128 + 64 + 64 * 4 + 64;
+    const size_t smem = 8 * (size_t)A_CHUNK + 12 * (size_t)a.Kp * 128 + 64 + 64 * 4 + 4 * TM * 4 + 64;
     static int n_sm = 0;
     if (!n_sm) {
         int dev = 0;
