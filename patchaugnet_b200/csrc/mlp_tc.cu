@@ -365,7 +365,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         const int units0 = ((a.ksteps[0] + 3) >> 2) * 8;     // 16-byte units per operand row (whole 64-chunks)
         uint32_t tcount = 0;
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tcount) {
-            if (tcount > 0) mbar_wait(a_empty, (tcount - 1) & 1);
+            // every branch first issues the global loads that do not need the operand region (indices, weights, the pre-layer's
+            // tiny input), THEN waits for the previous tile's layer-0 MMAs to release it: the lookups overlap the wait
             if (a.mode == TC_SA && a.pre_cout > 0) {
                 // one thread per row: inputs [xyz_j - xyz_i ; f_j - f_i] (pre_cin <= 8 values), the pre-layer evaluated in
                 // fp32 and staged (hi/lo); the rest of the 64-channel chunk is zeroed
@@ -387,6 +388,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                     for (int i = 0; i < 5; ++i)
                         if (i < a.c) in[3 + i] = __ldg(a.feat + pn * a.c + i) - __ldg(a.feat + pc * a.c + i);
                 }
+                if (tcount > 0) mbar_wait(a_empty, (tcount - 1) & 1);
                 const float *pw = ctab + a.pre_off, *ps = pw + a.pre_cin * a.pre_cout;
                 for (int u = 0; u < a.pre_cout / 8; ++u) {
                     float v[8];
@@ -417,6 +419,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                         my_pn = cloud * a.n + __ldg(a.nbr_idx + ci * a.nbr_stride + sidx);
                     }
                 }
+                if (tcount > 0) mbar_wait(a_empty, (tcount - 1) & 1);
                 for (int rr = 0; rr < 32; rr += 4) {
                     long pc[4], pn[4];
 #pragma unroll
@@ -458,6 +461,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                         for (int e = 0; e < 3; ++e) { my_i[e] = __ldg(a.idx3 + p * 3 + e); my_w[e] = __ldg(a.w3 + p * 3 + e); }
                     }
                 }
+                if (tcount > 0) mbar_wait(a_empty, (tcount - 1) & 1);
                 for (int rr = 0; rr < 32; rr += 4) {
                     const float *f0[4], *f1[4], *f2[4];
                     float w0[4], w1[4], w2[4];

@@ -154,14 +154,17 @@ __global__ void __launch_bounds__(256) vlad_finalize_kernel(int c, int K, int nc
 
 constexpr int AKC = 28;  // clusters per CTA in the attention kernel
 
-// mx[b][k] = max_c' sum_c w_att_t[c][c'] * v[b][c][k]      (conv1d without bias, then max over channels)
-__global__ void __launch_bounds__(256) afa_att_kernel(int c, int K, const float *__restrict__ v, const float *__restrict__ w_att_t,
+constexpr int ATT_SPLIT = 2;   // CTAs sharing the output channels of one (cloud, cluster group)
+
+// mx[z][b][k] = max over the z-th part of c' of sum_c w_att_t[c][c'] * v[b][c][k]   (conv1d without bias, then max over channels;
+// the softmax kernel takes the maximum over z)
+__global__ void __launch_bounds__(128) afa_att_kernel(int b, int c, int K, const float *__restrict__ v, const float *__restrict__ w_att_t,
                                                      float *__restrict__ mx) {
     extern __shared__ __align__(16) float vs[];  // [c][AKC]
-    __shared__ float red[AKC][8];
-    const int t = threadIdx.x, cloud = blockIdx.y, k0 = blockIdx.x * AKC;
+    __shared__ float red[AKC][4];
+    const int t = threadIdx.x, cloud = blockIdx.y, k0 = blockIdx.x * AKC, z = blockIdx.z;
     const int kn = min(AKC, K - k0);
-    for (int e = t; e < c * AKC; e += 256) {
+    for (int e = t; e < c * AKC; e += 128) {
         const int ci = e / AKC, kk = e - ci * AKC;
         vs[e] = kk < kn ? __ldg(v + ((size_t)cloud * c + ci) * K + k0 + kk) : 0.f;
     }
@@ -169,18 +172,26 @@ __global__ void __launch_bounds__(256) afa_att_kernel(int c, int K, const float 
     float best[AKC];
 #pragma unroll
     for (int kk = 0; kk < AKC; ++kk) best[kk] = -INFINITY;
-    for (int co = t; co < c; co += 256) {
+    const int cpz = (c + ATT_SPLIT - 1) / ATT_SPLIT;
+    for (int co = z * cpz + t; co < min(c, (z + 1) * cpz); co += 128) {
         float acc[AKC];
 #pragma unroll
         for (int kk = 0; kk < AKC; ++kk) acc[kk] = 0.f;
-        for (int ci = 0; ci < c; ++ci) {
-            const float w = __ldg(w_att_t + (size_t)ci * c + co);
-            const float4 *vr = reinterpret_cast<const float4 *>(vs + ci * AKC);
+        for (int ci0 = 0; ci0 < c; ci0 += 4) {
+            float w[4];
 #pragma unroll
-            for (int q = 0; q < AKC / 4; ++q) {
-                const float4 x = vr[q];
-                acc[4 * q + 0] = fmaf(w, x.x, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(w, x.y, acc[4 * q + 1]);
-                acc[4 * q + 2] = fmaf(w, x.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(w, x.w, acc[4 * q + 3]);
+            for (int u = 0; u < 4; ++u) w[u] = ci0 + u < c ? __ldg(w_att_t + (size_t)(ci0 + u) * c + co) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (ci0 + u < c) {
+                    const float4 *vr = reinterpret_cast<const float4 *>(vs + (ci0 + u) * AKC);
+#pragma unroll
+                    for (int q = 0; q < AKC / 4; ++q) {
+                        const float4 x = vr[q];
+                        acc[4 * q + 0] = fmaf(w[u], x.x, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(w[u], x.y, acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(w[u], x.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(w[u], x.w, acc[4 * q + 3]);
+                    }
+                }
             }
         }
 #pragma unroll
@@ -195,23 +206,24 @@ __global__ void __launch_bounds__(256) afa_att_kernel(int c, int K, const float 
         if (lane == 0) red[kk][warp] = m;
     }
     __syncthreads();
-    if (t < kn) {
-        float m = red[t][0];
-        for (int w = 1; w < 8; ++w) m = fmaxf(m, red[t][w]);
-        mx[(size_t)cloud * K + k0 + t] = m;
-    }
+    if (t < kn) mx[((size_t)z * b + cloud) * K + k0 + t] = fmaxf(fmaxf(red[t][0], red[t][1]), fmaxf(red[t][2], red[t][3]));
 }
 
-constexpr int FCH = 128;   // reduction slice per CTA in the fc kernel
+constexpr int FCH = 64;    // reduction slice per CTA in the fc kernel
 constexpr int FB = 32;     // clouds per register pass
 
 // wsm[b][k] = softmax_k(mx[b][:])      (MLPAttentionLayer softmax over the K clusters, loupe.py:31)
-__global__ void __launch_bounds__(128) afa_softmax_kernel(int K, const float *__restrict__ mx, float *__restrict__ wsm) {
+__global__ void __launch_bounds__(128) afa_softmax_kernel(int b, int K, float *__restrict__ mx, float *__restrict__ wsm) {
     __shared__ float red[4];
     const int t = threadIdx.x, cloud = blockIdx.x, lane = t & 31, warp = t >> 5;
-    const float *m = mx + (size_t)cloud * K;
+    float *m = mx + (size_t)cloud * K;
     float mm = -INFINITY;
-    for (int k = t; k < K; k += 128) mm = fmaxf(mm, m[k]);
+    for (int k = t; k < K; k += 128) {                       // combine the attention kernel's channel parts (in place, part 0)
+        float a = m[k];
+        for (int z = 1; z < ATT_SPLIT; ++z) a = fmaxf(a, mx[((size_t)z * b + cloud) * K + k]);
+        m[k] = a;
+        mm = fmaxf(mm, a);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mm = fmaxf(mm, __shfl_xor_sync(0xffffffffu, mm, o));
     if (lane == 0) red[warp] = mm;
@@ -254,14 +266,19 @@ __global__ void __launch_bounds__(256) afa_fc_kernel(int b, int c, int K, int c_
             float acc[FB];
 #pragma unroll
             for (int bb = 0; bb < FB; ++bb) acc[bb] = 0.f;
-            for (int ff = 0; ff < fn; ++ff) {
-                const float w = __ldg(fc_wt + (size_t)(f0 + ff) * c_out + o);
-                const float4 *yr = reinterpret_cast<const float4 *>(&ys[ff][0]);
+            for (int ff0 = 0; ff0 < fn; ff0 += 8) {              // eight weight rows in flight; rows >= fn of ys are zero
+                float w[8];
 #pragma unroll
-                for (int q = 0; q < FB / 4; ++q) {
-                    const float4 y = yr[q];
-                    acc[4 * q + 0] = fmaf(y.x, w, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(y.y, w, acc[4 * q + 1]);
-                    acc[4 * q + 2] = fmaf(y.z, w, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(y.w, w, acc[4 * q + 3]);
+                for (int u = 0; u < 8; ++u) w[u] = ff0 + u < fn ? __ldg(fc_wt + (size_t)(f0 + ff0 + u) * c_out + o) : 0.f;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float4 *yr = reinterpret_cast<const float4 *>(&ys[ff0 + u][0]);
+#pragma unroll
+                    for (int q = 0; q < FB / 4; ++q) {
+                        const float4 y = yr[q];
+                        acc[4 * q + 0] = fmaf(y.x, w[u], acc[4 * q + 0]); acc[4 * q + 1] = fmaf(y.y, w[u], acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(y.z, w[u], acc[4 * q + 2]); acc[4 * q + 3] = fmaf(y.w, w[u], acc[4 * q + 3]);
+                    }
                 }
             }
 #pragma unroll
@@ -272,28 +289,41 @@ __global__ void __launch_bounds__(256) afa_fc_kernel(int b, int c, int K, int c_
 }
 
 // desc[b][o] = normalize( (sum_slices part + ...) * scale[o] + shift[o] )     (fc bias and BN1d folded by the host)
-__global__ void __launch_bounds__(256) afa_finalize_kernel(int b, int c_out, int nslice, const float *__restrict__ part,
-                                                          const float *__restrict__ scale, const float *__restrict__ shift,
-                                                          int l2_norm, float *__restrict__ desc) {
+// 1024 threads: four groups each sum a quarter of the slices of output o = t % 256 (c_out <= 256 per pass), combined in a
+// fixed order.
+__global__ void __launch_bounds__(1024) afa_finalize_kernel(int b, int c_out, int nslice, const float *__restrict__ part,
+                                                           const float *__restrict__ scale, const float *__restrict__ shift,
+                                                           int l2_norm, float *__restrict__ desc) {
+    __shared__ float grp[4][256];
     __shared__ float red[8];
     const int t = threadIdx.x, cloud = blockIdx.x, lane = t & 31, warp = t >> 5;
+    const int g = t >> 8, ot = t & 255;
     float sq = 0.f;
-    for (int o = t; o < c_out; o += 256) {
+    for (int o0 = 0; o0 < c_out; o0 += 256) {
+        const int o = o0 + ot;
         float s = 0.f;
-        for (int sl = 0; sl < nslice; ++sl) s += part[((size_t)sl * b + cloud) * c_out + o];
-        s = fmaf(s, __ldg(scale + o), __ldg(shift + o));
-        desc[(size_t)cloud * c_out + o] = s;
-        sq += s * s;
+        if (o < c_out)
+            for (int sl = g; sl < nslice; sl += 4) s += __ldg(part + ((size_t)sl * b + cloud) * c_out + o);
+        __syncthreads();
+        grp[g][ot] = s;
+        __syncthreads();
+        if (g == 0 && o < c_out) {
+            s = (grp[0][ot] + grp[1][ot]) + (grp[2][ot] + grp[3][ot]);
+            s = fmaf(s, __ldg(scale + o), __ldg(shift + o));
+            desc[(size_t)cloud * c_out + o] = s;
+            sq += s * s;
+        }
     }
     if (!l2_norm) return;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    if (lane == 0) red[warp] = sq;
+    if (warp < 8 && lane == 0) red[warp] = sq;
     __syncthreads();
     float tot = 0.f;
     for (int w = 0; w < 8; ++w) tot += red[w];
     const float inv = 1.f / fmaxf(sqrtf(tot), 1e-12f);
-    for (int o = t; o < c_out; o += 256) desc[(size_t)cloud * c_out + o] *= inv;
+    if (g == 0)
+        for (int o = ot; o < c_out; o += 256) desc[(size_t)cloud * c_out + o] *= inv;
 }
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -346,7 +376,7 @@ PAB_API int pab_netvlad_forward_tc(int b, int n, int c, int K, const float *x, c
 
 PAB_API size_t pab_afa_workspace_bytes(int b, int c, int K, int c_out) {
     const size_t nslice = ((size_t)c * K + FCH - 1) / FCH;
-    return 2 * align256(sizeof(float) * (size_t)b * K) + align256(sizeof(float) * nslice * b * c_out);
+    return (1 + ATT_SPLIT) * align256(sizeof(float) * (size_t)b * K) + align256(sizeof(float) * nslice * b * c_out);
 }
 
 PAB_API int pab_afa_forward(int b, int c, int K, int c_out, const float *v, const float *w_att_t, const float *fc_wt,
@@ -354,19 +384,19 @@ PAB_API int pab_afa_forward(int b, int c, int K, int c_out, const float *v, cons
     if (b < 0 || c <= 0 || K <= 0 || c_out <= 0 || !workspace) return PAB_EINVAL;
     if (b == 0) return 0;
     cudaStream_t st = (cudaStream_t)s;
-    float *mx = (float *)workspace;
-    float *wsm = (float *)((char *)workspace + align256(sizeof(float) * (size_t)b * K));
-    float *part = (float *)((char *)workspace + 2 * align256(sizeof(float) * (size_t)b * K));
+    float *wsm = (float *)workspace;
+    float *mx = (float *)((char *)workspace + align256(sizeof(float) * (size_t)b * K));          // ATT_SPLIT parts of (b, K)
+    float *part = (float *)((char *)workspace + (1 + ATT_SPLIT) * align256(sizeof(float) * (size_t)b * K));
     const int nslice = (c * K + FCH - 1) / FCH;
     const size_t smem = sizeof(float) * (size_t)c * AKC;
     if (smem > 48 * 1024) PAB_CUDA(cudaFuncSetAttribute(afa_att_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    afa_att_kernel<<<dim3(pab_divup(K, AKC), b), 256, smem, st>>>(c, K, v, w_att_t, mx);
+    afa_att_kernel<<<dim3(pab_divup(K, AKC), b, ATT_SPLIT), 128, smem, st>>>(b, c, K, v, w_att_t, mx);
     PAB_LAUNCH_CHECK();
-    afa_softmax_kernel<<<b, 128, 0, st>>>(K, mx, wsm);
+    afa_softmax_kernel<<<b, 128, 0, st>>>(b, K, mx, wsm);
     PAB_LAUNCH_CHECK();
     afa_fc_kernel<<<nslice, 256, 0, st>>>(b, c, K, c_out, v, wsm, fc_wt, part);
     PAB_LAUNCH_CHECK();
-    afa_finalize_kernel<<<b, 256, 0, st>>>(b, c_out, nslice, part, fc_scale, fc_shift, l2_norm, desc);
+    afa_finalize_kernel<<<b, 1024, 0, st>>>(b, c_out, nslice, part, fc_scale, fc_shift, l2_norm, desc);
     PAB_LAUNCH_CHECK();
     return 0;
 }
