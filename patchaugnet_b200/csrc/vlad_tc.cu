@@ -10,7 +10,7 @@
 //                                                                 row of GEMM1 and an MN-major row of GEMM2),
 //                                                                 B = act^T planes (K-major); accumulated in TMEM over
 //                                                                 all tiles of the CTA's work item
-// A work item is (cloud, 256-row chunk); persistent CTAs loop over items.  Each item writes a partial (K, C) block and
+// A work item is (cloud, 256- or 1024-row chunk); persistent CTAs loop over items.  Each item writes a partial (K, C) block and
 // partial a_sum (K) exactly like vlad_partial_kernel, so vlad_finalize_kernel (vlad.cu) is shared.
 #include <math.h>
 #include "tc_common.cuh"
@@ -21,11 +21,11 @@ using namespace tc;
 
 constexpr int VT_WORK = 256;                  // worker threads (8 warps); warp 0: idle helper, warp 1: MMA issuer
 constexpr int VT_THREADS = 64 + VT_WORK;
-constexpr int VT_ROWS_PER_ITEM = 256;
+constexpr int VT_ROWS_MIN = 256;               // smallest work item (rows of one cloud); the workspace is sized for it
 constexpr int VT_C = 256;                     // channels (4 chunks of 64)
 
 struct VtArgs {
-    int n, K, Kp, nchunk, nitems;
+    int n, K, Kp, nchunk, nitems, rows_per_item;
     const float *x, *shift;
     const __nv_bfloat16 *wc_hi, *wc_lo;       // (Kp, 256) K-major, bn1 scale folded, rows >= K zero
     float *part, *asum;
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vlad_tc_kernel(const VtArgs a) 
         const uint32_t wstep = (uint32_t)wchunk >> 4;
         for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
             const int chunk = item % a.nchunk;
-            const int r_begin = chunk * VT_ROWS_PER_ITEM, r_end = min(a.n, r_begin + VT_ROWS_PER_ITEM);
+            const int r_begin = chunk * a.rows_per_item, r_end = min(a.n, r_begin + a.rows_per_item);
             int t_in_item = 0;
             for (int r0 = r_begin; r0 < r_end; r0 += TM, ++tcount, ++t_in_item) {
                 mbar_wait(a_ready, tcount & 1);
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vlad_tc_kernel(const VtArgs a) 
         uint32_t tcount = 0;
         for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
             const int cloud = item / a.nchunk, chunk = item % a.nchunk;
-            const int r_begin = chunk * VT_ROWS_PER_ITEM, r_end = min(a.n, r_begin + VT_ROWS_PER_ITEM);
+            const int r_begin = chunk * a.rows_per_item, r_end = min(a.n, r_begin + a.rows_per_item);
             const float *xg = a.x + (size_t)cloud * a.n * VT_C;
             float asum_k = 0.f;                                    // cluster (wt - 128)'s running sum (threads of half 1)
             for (int r0 = r_begin; r0 < r_end; r0 += TM, ++tcount) {
@@ -266,16 +266,21 @@ int pab_vlad_tc_partial(int b, int n, int c, int K, const float *x, const void *
                         float *part, float *asum, int *nchunk_out, cudaStream_t st) {
     if (c != VT_C || K <= 0 || K > 64 || !wc_hi || !wc_lo) return PAB_EINVAL;
     VtArgs a;
-    a.n = n; a.K = K; a.Kp = (K + 15) / 16 * 16; a.nchunk = (n + VT_ROWS_PER_ITEM - 1) / VT_ROWS_PER_ITEM; a.nitems = b * a.nchunk;
-    a.x = x; a.shift = shift; a.wc_hi = (const __nv_bfloat16 *)wc_hi; a.wc_lo = (const __nv_bfloat16 *)wc_lo; a.part = part; a.asum = asum;
-    *nchunk_out = a.nchunk;
-    const size_t smem = 8 * (size_t)A_CHUNK + 12 * (size_t)a.Kp * 128 + 64 + 64 * 4 + 4 * TM * 4 + 64;
     static int n_sm = 0;
     if (!n_sm) {
         int dev = 0;
         PAB_CUDA(cudaGetDevice(&dev));
         PAB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     }
+    // work items = (cloud, chunk of rows).  Every chunk is another (K, 256) partial block through HBM, so large clouds use
+    // 1024-row chunks.  The chunking depends on n ONLY: the fp32 summation order — and with it every output bit — must not
+    // change with the batch size (a database built in batches of 32 has to match single-cloud queries exactly).
+    const int rpi = n >= 2048 ? 1024 : VT_ROWS_MIN;
+    a.rows_per_item = rpi;
+    a.n = n; a.K = K; a.Kp = (K + 15) / 16 * 16; a.nchunk = (n + rpi - 1) / rpi; a.nitems = b * a.nchunk;
+    a.x = x; a.shift = shift; a.wc_hi = (const __nv_bfloat16 *)wc_hi; a.wc_lo = (const __nv_bfloat16 *)wc_lo; a.part = part; a.asum = asum;
+    *nchunk_out = a.nchunk;
+    const size_t smem = 8 * (size_t)A_CHUNK + 12 * (size_t)a.Kp * 128 + 64 + 64 * 4 + 4 * TM * 4 + 64;
     PAB_CUDA(cudaFuncSetAttribute(vlad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = a.nitems < n_sm ? a.nitems : n_sm;
     vlad_tc_kernel<<<grid, VT_THREADS, smem, st>>>(a);
