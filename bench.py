@@ -276,8 +276,23 @@ def main():
                                     bound_per_s=bound, frac=wk["units"] / (ms * 1e-3) / bound, sms_used=sms)
         return e
 
+    # stages that run on the tensor-core kernels issue 3 bf16 MMAs per algorithmic product
+    tc_stages = {"sa0", "sa1", "sa2", "fp0", "fp1", "vlad0", "vlad1", "vlad2"}
+
+    def traffic_of(stage):
+        """DRAM bytes per launch from the committed `ncu --set full` capture (profiles/r01_traffic.json), B=32 only."""
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                t = json.load(f)["dram_bytes_per_launch"]
+            return int(t[stage]) if B == 32 and stage in t else None
+        except (OSError, KeyError, ValueError):
+            return None
+
     roof = roof_entry(dominant, dom_ms)
-    roof["traffic"] = None
+    roof["traffic"] = traffic_of(dominant)
+    if roof["bound"] == "tensor" and dominant in tc_stages:
+        roof["issued"] = dict(mma_flops_per_launch=3 * work[dominant]["flops"], tensor_pipe_frac=3 * roof["frac"],
+                              note="bf16 hi/lo split: hi*hi + lo*hi + hi*lo per product")
     roof["share_of_step"] = dom_ms / sum(stage_ms.values())
     roof["peak_source"] = (f"{pk['src']} bf16 dense, sustained (kernel timed inside the step); algorithmic fp32-equivalent FLOPs — the "
                            "tcgen05 path issues 3 bf16 MMAs per product") if roof["bound"] == "tensor" else f"{pk['src']} copy bandwidth"

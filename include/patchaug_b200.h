@@ -194,7 +194,9 @@ size_t pab_afa_workspace_bytes(int b, int c, int K, int c_out);
 int pab_afa_forward(int b, int c, int K, int c_out, const float *v, const float *w_att_t, const float *fc_wt,
                     const float *fc_scale, const float *fc_shift, int l2_norm, float *desc, void *workspace, pab_stream_t s);
 
-/* Tuning hook: enable (1, default) / disable (0) the tcgen05 tensor-core path of the fused SharedMLP kernels. */
+/* Tuning hook: bit 0 enables (1, default) / disables (0) the tcgen05 tensor-core path of the fused SharedMLP kernels;
+ * bit 2 set (5) additionally shares the weight stream across CTA pairs (thread-block clusters of 2, TMA multicast;
+ * off by default: measured slower on B200). */
 void pab_tune_tensor_core(int enable);
 
 /* Tuning hook: force the FPS CTA size (power of two, 32..1024; 0 = automatic). */

@@ -45,6 +45,7 @@ struct alignas(64) TcArgs {
     int K[MAX_LAYERS], N[MAX_LAYERS], relu[MAX_LAYERS];
     int ksteps[MAX_LAYERS];                    // 16-wide k-steps that carry data (the rest of the last 64-chunk is zero padding)
     int n_layers, n_stages, mode;
+    int csize, iters;                          // CTAs per cluster sharing the weight stream (1 or 2); tile-loop trips (equal for all CTAs)
     int coff[MAX_LAYERS];                      // offset of each layer's shift vector in the smem constant table
     int a_region;                              // bytes of the layer-0 operand region (hi plane, then lo plane)
     long rows;                                 // SA: centres, FP: points
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
 
     if (tid == 0) {
-        for (int s = 0; s < a.n_stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < a.n_stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, a.csize); }
         mbar_init(a_full, NLOAD);
         mbar_init(a_empty, 1);
         mbar_init(d_ready, 1);
@@ -138,22 +139,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     }
     tc_fence_before();
     __syncthreads();
+    if (a.csize > 1) cluster_sync_all();                          // the peer's barriers exist before anything is multicast
     tc_fence_after();
     const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    const uint32_t crank = a.csize > 1 ? cluster_ctarank() : 0;
+    const uint16_t cmask_all = (uint16_t)((1u << a.csize) - 1);
 
     if (warp == 0) {
         // ================= TMA producer: weight blocks in (tile, layer, n-block, k-chunk, plane) order ==============
         if (lane == 0) {
             uint32_t s = 0, ph = 0;
-            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+            for (int it = 0; it < a.iters; ++it) {
                 for (int l = 0; l < a.n_layers; ++l) {
                     const int nkc = (a.ksteps[l] + 3) >> 2, nbr = min(NBLK_MAX, a.N[l]), nnb = a.N[l] / nbr;
                     for (int nb = 0; nb < nnb; ++nb)
                         for (int kc = 0; kc < nkc; ++kc)
                             for (int pl = 0; pl < 2; ++pl) {
-                                mbar_wait(empty + s, ph ^ 1);
+                                mbar_wait(empty + s, ph ^ 1);                    // released by every CTA of the cluster
                                 mbar_expect_tx(full + s, (uint32_t)nbr * 128u);
-                                tma_load_2d(stages + (size_t)s * (NBLK_MAX * 128), &a.tm[l][pl], kc * KCH, nb * nbr, full + s);
+                                uint8_t *dst = stages + (size_t)s * (NBLK_MAX * 128);
+                                if (a.csize == 1) {
+                                    tma_load_2d(dst, &a.tm[l][pl], kc * KCH, nb * nbr, full + s);
+                                } else {                                         // this CTA's share of the block, delivered to all
+                                    const int share = nbr / a.csize;
+                                    tma_load_2d_mc(dst + (size_t)crank * share * 128, &a.tm[l][pl], kc * KCH, nb * nbr + (int)crank * share,
+                                                   full + s, cmask_all);
+                                }
                                 if (++s == (uint32_t)a.n_stages) { s = 0; ph ^= 1; }
                             }
                 }
@@ -167,7 +178,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         const uint32_t st_lo = umma_desc_lo(smem_u32(stages));
         constexpr uint32_t st_step = (NBLK_MAX * 128) >> 4;
         uint32_t s = 0, ph = 0, pcount = 0, tcount = 0;
-        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tcount) {
+        for (int it = 0; it < a.iters; ++it, ++tcount) {
             for (int l = 0; l < a.n_layers; ++l) {
                 const int ksteps = a.ksteps[l], nkc = (ksteps + 3) >> 2;
                 const int nbr = min(NBLK_MAX, a.N[l]), nnb = a.N[l] / nbr, nb_pass = D_COLS / nbr;   // n-blocks per accumulator pass
@@ -199,7 +210,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                                 }
                             }
                         }
-                        umma_commit_if(leader, empty + s);
+                        if (a.csize == 1) umma_commit_if(leader, empty + s);
+                        else umma_commit_mc_if(leader, empty + s, cmask_all);
                         if (++s == (uint32_t)a.n_stages) { s = 0; ph ^= 1; }
                         // lo weight plane: hi(A) * lo(W)
                         mbar_wait(full + s, ph);
@@ -212,7 +224,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                                 else umma_f16_ts_if(leader, d, tmem + AH_COL + kc * 32 + ks * 8, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
                             }
                         }
-                        umma_commit_if(leader, empty + s);
+                        if (a.csize == 1) umma_commit_if(leader, empty + s);
+                        else umma_commit_mc_if(leader, empty + s, cmask_all);
                         if (++s == (uint32_t)a.n_stages) { s = 0; ph ^= 1; }
                     }
                     if (nbp == nb_pass - 1 || nb == nnb - 1) {
@@ -236,7 +249,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         const float *wext = ctab + a.coff[a.n_layers - 1] + a.N[a.n_layers - 1];   // extra weight rows follow the shifts
         const int G = a.mode == TC_SA ? TM / a.k : 0;
 
-        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        for (int it = 0; it < a.iters; ++it) {
+            const int tile = blockIdx.x + it * gridDim.x;          // tiles >= ntiles are empty (all rows out of range)
             // the rank-3 part of layer 0 for the row this thread owns (loads overlap the wait for the first accumulators)
             float xe[3] = {0.f, 0.f, 0.f};
             if (a.n_extra > 0) {
@@ -364,7 +378,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         const int lwarp = lt >> 5;                           // 0..3, rows [32*lwarp, 32*lwarp + 32)
         const int units0 = ((a.ksteps[0] + 3) >> 2) * 8;     // 16-byte units per operand row (whole 64-chunks)
         uint32_t tcount = 0;
-        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tcount) {
+        for (int it = 0; it < a.iters; ++it, ++tcount) {
+            const int tile = blockIdx.x + it * gridDim.x;
             // every branch first issues the global loads that do not need the operand region (indices, weights, the pre-layer's
             // tiny input), THEN waits for the previous tile's layer-0 MMAs to release it: the lookups overlap the wait
             if (a.mode == TC_SA && a.pre_cout > 0) {
@@ -530,6 +545,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     }
     tc_fence_before();
     __syncthreads();
+    if (a.csize > 1) cluster_sync_all();                          // no CTA leaves while its peer may still signal its barriers
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
@@ -568,6 +584,8 @@ int make_weight_map(CUtensorMap *map, const void *w, int N, int K, int box_n) {
 }
 
 int g_tc_enabled = 1;
+int g_tc_cluster = 0;      // weight multicast across CTA pairs (pab_tune_tensor_core bit 2 sets it): measured slower on
+                           // B200 — the modules are bound by the MMA <-> epilogue hand-offs, not by L2 -> SM weight traffic
 
 // Shared-memory plan of one launch: layer-0 operand region, staging, weight stages, constant table.
 // `layers` are the TENSOR-CORE layers only (the optional pre-layer is passed separately).
@@ -632,11 +650,26 @@ int pab_tc_launch(int mode, long rows, int k_group, const pab_layer_t *all_layer
     TcPlan p;
     if (!tc_plan(layers, n_layers, pre, &p)) return PAB_EINVAL;
     a.a_region = p.a_region; a.n_stages = p.n_stages;
+    const long per_tile = mode == TC_SA ? (TM / k_group) : TM;
+    a.ntiles = (int)((rows + per_tile - 1) / per_tile);
+    if (a.ntiles == 0) return 0;
+    static int n_sm = 0;
+    if (!n_sm) {
+        int dev = 0;
+        PAB_CUDA(cudaGetDevice(&dev));
+        PAB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    // CTA pairs share the weight stream: each CTA fetches half of every weight block and TMA multicasts it to both, which
+    // halves the L2 -> SM weight traffic (the bound of the 256-wide modules: every 128-row tile re-reads all the weights)
+    a.csize = (g_tc_cluster && a.ntiles >= 4) ? 2 : 1;
+    int grid = a.ntiles < n_sm ? a.ntiles : n_sm;
+    if (a.csize == 2) grid = grid / 2 * 2;
+    a.iters = (a.ntiles + grid - 1) / grid;
     for (int l = 0; l < n_layers; ++l) {
         const pab_layer_t &L = layers[l];
         const int nbr = L.c_out < NBLK_MAX ? L.c_out : NBLK_MAX;
-        if (make_weight_map(&a.tm[l][0], L.w_hi, L.c_out, L.tc_k, nbr)) return PAB_EINVAL;
-        if (make_weight_map(&a.tm[l][1], L.w_lo, L.c_out, L.tc_k, nbr)) return PAB_EINVAL;
+        if (make_weight_map(&a.tm[l][0], L.w_hi, L.c_out, L.tc_k, nbr / a.csize)) return PAB_EINVAL;
+        if (make_weight_map(&a.tm[l][1], L.w_lo, L.c_out, L.tc_k, nbr / a.csize)) return PAB_EINVAL;
         a.shift[l] = L.shift; a.K[l] = L.tc_k; a.N[l] = L.c_out; a.relu[l] = L.relu; a.coff[l] = p.coff[l];
         // k-steps that carry data: the staged layer-0 operand spans whole 64-chunks (only the pre-layer's output is
         // narrower), the TMEM operand of later layers exactly c_in channels
@@ -654,25 +687,21 @@ int pab_tc_launch(int mode, long rows, int k_group, const pab_layer_t *all_layer
         const int extra_row0 = layers[0].tc_k0 == 0 ? layers[0].tc_k : 0;
         a.w_extra = layers[0].wt + (size_t)extra_row0 * layers[0].c_out;
     }
-    const long per_tile = mode == TC_SA ? (TM / k_group) : TM;
-    a.ntiles = (int)((rows + per_tile - 1) / per_tile);
-    static int n_sm = 0;
-    if (!n_sm) {
-        int dev = 0;
-        PAB_CUDA(cudaGetDevice(&dev));
-        PAB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    }
     PAB_CUDA(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    const int grid = a.ntiles < n_sm ? a.ntiles : n_sm;
-    if (grid == 0) return 0;
-    mlp_tc_kernel<<<grid, TC_THREADS, p.smem, st>>>(a);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = p.smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = a.csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    PAB_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_kernel, a));
     PAB_LAUNCH_CHECK();
     return 0;
 }
 
 }  // namespace
 
-PAB_API void pab_tune_tensor_core(int enable) { g_tc_enabled = enable; }
+PAB_API void pab_tune_tensor_core(int enable) { g_tc_enabled = enable & 1; g_tc_cluster = (enable & 4) != 0; }
 
 int pab_tc_sa(int kind, int b, int n, int m, int k, int nbr_stride, int c, const float *xyz, const float *feat, const int *center_idx,
               const int *nbr_idx, const pab_layer_t *layers, int n_layers, float *out, cudaStream_t st) {

@@ -10,6 +10,12 @@ using namespace tc;
 // mode 0: one accumulator, every MMA depends on the previous one
 // mode 1: two accumulators alternating
 // mode 2: four accumulators round robin (N <= 128)
+__device__ __forceinline__ void umma_ts(uint32_t issue, uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
+    asm volatile(
+        "{\n.reg .pred q;\n.reg .b64 db;\nsetp.ne.b32 q, %5, 0;\nmov.b64 db, {%2, %3};\n"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, 1;\n}\n" ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(issue) : "memory");
+}
+// mode 3: A operand from tensor memory (TS form), one accumulator; mode 4: TS with a commit + barrier wait every 8 MMAs
 __global__ void __launch_bounds__(128, 1) k(int N, int mode, int iters, int distinct_ab, long long *out) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
@@ -38,7 +44,8 @@ __global__ void __launch_bounds__(128, 1) k(int N, int mode, int iters, int dist
                 const uint32_t d = tmem + (uint32_t)((j % nacc) * N);
                 const uint32_t ao = distinct_ab ? (uint32_t)(j % 4) * 2 + (uint32_t)((j / 4) & 1) * (A_CHUNK >> 4) : 0;
                 const uint32_t bo = distinct_ab ? (uint32_t)(j % 4) * 2 + (uint32_t)((j / 8) & 1) * ((uint32_t)N * 8) : 0;
-                umma_f16_if(leader, d, a_lo + ao, UMMA_DESC_HI, b_lo + bo, UMMA_DESC_HI, idesc, 1);
+                if (mode >= 3) umma_ts(leader, tmem, tmem + 256 + (uint32_t)(j % 4) * 8 + (uint32_t)((j / 4) & 1) * 128, b_lo + bo, UMMA_DESC_HI, idesc);
+                else umma_f16_if(leader, d, a_lo + ao, UMMA_DESC_HI, b_lo + bo, UMMA_DESC_HI, idesc, 1);
             }
         }
         umma_commit_if(leader, &bar);
@@ -62,10 +69,11 @@ int main() {
     const int iters = 200;
     for (int grid : {1, 148})
         for (int N : {64, 128, 256})
-            for (int mode : {0, 1, 2})
+            for (int mode : {0, 1, 2, 3})
                 for (int dab : {0, 1}) {
                     if (mode == 2 && N > 128) continue;
                     if (mode == 1 && N > 256) continue;
+                    if (mode == 3 && (N > 256 || grid == 1)) continue;
                     k<<<grid, 128, 200 * 1024>>>(N, mode, iters, dab, out);
                     cudaError_t e = cudaDeviceSynchronize();
                     if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
