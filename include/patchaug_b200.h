@@ -140,8 +140,10 @@ typedef struct {
     int c_in, c_in_pad, c_out, relu;
     /* Optional tensor-core operands (NULL -> the layer runs on the fp32 SIMT path).  The same folded weight, restricted
      * to input channels [tc_k0, tc_k0 + tc_k), split as W = hi + lo with hi = bf16(W), lo = bf16(W - hi), each stored
-     * K-major as (c_out, tc_k) bf16.  tc_k must be a multiple of 64; the (at most 3) remaining input channels of
-     * layer 0 — the xyz part — are applied from `wt` as a rank-n update in the epilogue. */
+     * K-major bf16.  tc_k must be a multiple of 64 (zero-padded).  A layer whose c_in exceeds the channels covered that
+     * way — layer 0 of a module, whose (at most 3) remaining inputs are the xyz part — stores (c_out, tc_k + 64): the
+     * extra 64-column chunk holds those channels' weights in channel order (rest zero) and is fed to the tensor cores
+     * as one more k-step.  Every other layer stores (c_out, tc_k). */
     const void *w_hi, *w_lo;
     int tc_k0, tc_k;
 } pab_layer_t;
@@ -198,6 +200,11 @@ int pab_afa_forward(int b, int c, int K, int c_out, const float *v, const float 
  * bit 2 set (5) additionally shares the weight stream across CTA pairs (thread-block clusters of 2, TMA multicast;
  * off by default: measured slower on B200). */
 void pab_tune_tensor_core(int enable);
+
+/* Debugging aid: when set to a device buffer of 8*4*8 int64, CTA 0 of every fused-MLP tensor-core launch records clock64
+ * stamps of its first 8 tiles ([tile][layer][event]: 0 MMA issue start, 1 MMA issue end, 2 accumulators seen by the
+ * epilogue, 3 epilogue done, 4 loader start, 5 operand staged, 6 tile output stored).  NULL (default) disables it. */
+void pab_tune_tc_trace(void *device_buffer);
 
 /* Tuning hook: force the FPS CTA size (power of two, 32..1024; 0 = automatic). */
 void pab_tune_fps_threads(int threads);

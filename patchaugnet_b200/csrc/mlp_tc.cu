@@ -35,7 +35,8 @@ constexpr int MAX_LAYERS = 3;
 constexpr int D_COLS = 256;                   // accumulator columns; TMEM columns [256,384) = hi plane, [384,512) = lo plane
 constexpr uint32_t AH_COL = 256, AL_COL = 384;
 constexpr int STG_COLS = 64;                  // fp32 staging of the last layer: [128 rows][64 columns]
-constexpr int STG_BYTES = TM * STG_COLS * 4;
+constexpr int STG_BYTES = TM * STG_COLS * 4;                       // SA: one CTA-wide tile (rows of a group span warps)
+constexpr int STG_BYTES_FP = 8 * 32 * 16 * 4;                      // FP: a private [32 rows][16 cols] tile per epilogue warp
 
 enum { TC_SA = 1, TC_FP = 2 };
 
@@ -51,8 +52,8 @@ struct alignas(64) TcArgs {
     long rows;                                 // SA: centres, FP: points
     int ntiles;
     // layer-0 "extra" channels (the xyz part), applied as a rank-n update from the fp32 weight rows
-    const float *w_extra;                      // layers[0].wt + extra_row0 * N0
-    int n_extra;
+    const float *w_extra;                      // layers[0].wt + extra_row0 * N0 (unused: the extras go through the tensor cores)
+    int n_extra;                               // their weights are the EXTRA 64-column chunk at the end of layer 0's planes
     // optional "pre" layer: the module's first layer has so few inputs (<= 8: SA1's [xyz_rel ; feat_rel]) that the loader
     // evaluates it in fp32 and stages its OUTPUT as the first tensor-core operand (zero-padded to 64 channels)
     int pre_cin, pre_cout, pre_relu;
@@ -68,7 +69,14 @@ struct alignas(64) TcArgs {
     const int *idx3;
     const float *w3;
     float *out;
+    long long *trace;                          // optional timeline of CTA 0 (pab_tune_tc_trace), [tile][phase][event] clock64 stamps
 };
+
+#define TC_TRACE(tile_it, ph, ev)                                                                  \
+    do {                                                                                          \
+        if (a.trace && blockIdx.x == 0 && (tile_it) < 8 && lane == 0)                             \
+            a.trace[(((tile_it)*4 + (ph)) * 8) + (ev)] = clock64();                                \
+    } while (0)
 
 // A operand from tensor memory (TS form): rows = TMEM lanes, k pairs packed in 32-bit columns
 __device__ __forceinline__ void umma_f16_ts_if(uint32_t issue, uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi,
@@ -101,7 +109,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     uint8_t *a2 = a1 + (size_t)(a.a_region >> 1);                  //                  lo plane
     uint8_t *stages = a1 + (size_t)a.a_region;
     uint8_t *stg = stages + (size_t)a.n_stages * (NBLK_MAX * 128);
-    uint8_t *misc = stg + STG_BYTES;
+    uint8_t *misc = stg + (a.mode == TC_SA ? STG_BYTES : STG_BYTES_FP);
     uint64_t *full = reinterpret_cast<uint64_t *>(misc);
     uint64_t *empty = full + MAX_STAGES;
     uint64_t *a_full = empty + MAX_STAGES;                         // loaders -> MMA: layer-0 operand of the tile staged
@@ -131,7 +139,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             for (int i = tid; i < a.N[l]; i += TC_THREADS) ctab[off + i] = __ldg(a.shift[l] + i);
             off += a.N[l];
         }
-        for (int i = tid; i < a.n_extra * a.N[0]; i += TC_THREADS) ctab[off + i] = __ldg(a.w_extra + i);
         if (a.pre_cout > 0) {
             for (int i = tid; i < a.pre_cin * a.pre_cout; i += TC_THREADS) ctab[a.pre_off + i] = __ldg(a.pre_wt + i);
             for (int i = tid; i < a.pre_cout; i += TC_THREADS) ctab[a.pre_off + a.pre_cin * a.pre_cout + i] = __ldg(a.pre_shift + i);
@@ -151,7 +158,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             uint32_t s = 0, ph = 0;
             for (int it = 0; it < a.iters; ++it) {
                 for (int l = 0; l < a.n_layers; ++l) {
-                    const int nkc = (a.ksteps[l] + 3) >> 2, nbr = min(NBLK_MAX, a.N[l]), nnb = a.N[l] / nbr;
+                    // layer 0 with extra channels: one more 64-column chunk (k = K[0]..) holding their weights
+                    const int nkc = ((a.ksteps[l] + 3) >> 2) + (l == 0 && a.n_extra > 0 ? 1 : 0);
+                    const int nbr = min(NBLK_MAX, a.N[l]), nnb = a.N[l] / nbr;
                     for (int nb = 0; nb < nnb; ++nb)
                         for (int kc = 0; kc < nkc; ++kc)
                             for (int pl = 0; pl < 2; ++pl) {
@@ -180,33 +189,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         uint32_t s = 0, ph = 0, pcount = 0, tcount = 0;
         for (int it = 0; it < a.iters; ++it, ++tcount) {
             for (int l = 0; l < a.n_layers; ++l) {
-                const int ksteps = a.ksteps[l], nkc = (ksteps + 3) >> 2;
+                const int ksteps = a.ksteps[l], nkc_main = (ksteps + 3) >> 2;
+                const int nkc = nkc_main + (l == 0 && a.n_extra > 0 ? 1 : 0);        // + the extras' chunk (one k-step, A from TMEM)
                 const int nbr = min(NBLK_MAX, a.N[l]), nnb = a.N[l] / nbr, nb_pass = D_COLS / nbr;   // n-blocks per accumulator pass
                 const uint32_t idesc = umma_idesc(nbr);
                 if (l == 0) mbar_wait(a_full, tcount & 1);
                 for (int nb = 0; nb < nnb; ++nb) {
                     const int nbp = nb % nb_pass;
-                    if (nbp == 0) {                              // new pass: the epilogue must have drained D (and written A)
-                        if (pcount > 0) mbar_wait(t_ready, (pcount - 1) & 1);
+                    if (nbp == 0) {                              // new pass: the epilogue has drained D (and written the operand planes)
+                        mbar_wait(t_ready, pcount & 1);
                         tc_fence_after();
+                        TC_TRACE(it, l, 0);
                     }
                     const uint32_t d = tmem + (uint32_t)(nbp * nbr);
                     for (int kc = 0; kc < nkc; ++kc) {
-                        const int kn = min(4, ksteps - 4 * kc);
+                        const bool xk = kc >= nkc_main;          // the extras' chunk: k-step 0 only, operand in plane columns 0..7
+                        const bool from_smem = l == 0 && !xk;
+                        const int kn = xk ? 1 : min(4, ksteps - 4 * kc);
                         const uint32_t ka = (uint32_t)kc * (A_CHUNK >> 4);
+                        const uint32_t ta = xk ? 0u : (uint32_t)(kc * 32);
                         // hi weight plane: hi(A) * hi(W) + lo(A) * hi(W)
                         mbar_wait(full + s, ph);
-                        tc_fence_after();
                         uint32_t sb = st_lo + s * st_step;
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
                             if (ks < kn) {
-                                if (l == 0) {
+                                if (from_smem) {
                                     umma_f16_if(leader, d, a1_lo + ka + 2 * ks, UMMA_DESC_HI, sb + 2 * ks, UMMA_DESC_HI, idesc, (kc | ks) != 0);
                                     umma_f16_if(leader, d, a2_lo + ka + 2 * ks, UMMA_DESC_HI, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
                                 } else {
-                                    umma_f16_ts_if(leader, d, tmem + AH_COL + kc * 32 + ks * 8, sb + 2 * ks, UMMA_DESC_HI, idesc, (kc | ks) != 0);
-                                    umma_f16_ts_if(leader, d, tmem + AL_COL + kc * 32 + ks * 8, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
+                                    umma_f16_ts_if(leader, d, tmem + AH_COL + ta + ks * 8, sb + 2 * ks, UMMA_DESC_HI, idesc, (kc | ks) != 0);
+                                    umma_f16_ts_if(leader, d, tmem + AL_COL + ta + ks * 8, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
                                 }
                             }
                         }
@@ -215,13 +228,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                         if (++s == (uint32_t)a.n_stages) { s = 0; ph ^= 1; }
                         // lo weight plane: hi(A) * lo(W)
                         mbar_wait(full + s, ph);
-                        tc_fence_after();
                         sb = st_lo + s * st_step;
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
                             if (ks < kn) {
-                                if (l == 0) umma_f16_if(leader, d, a1_lo + ka + 2 * ks, UMMA_DESC_HI, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
-                                else umma_f16_ts_if(leader, d, tmem + AH_COL + kc * 32 + ks * 8, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
+                                if (from_smem) umma_f16_if(leader, d, a1_lo + ka + 2 * ks, UMMA_DESC_HI, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
+                                else umma_f16_ts_if(leader, d, tmem + AH_COL + ta + ks * 8, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
                             }
                         }
                         if (a.csize == 1) umma_commit_if(leader, empty + s);
@@ -231,6 +243,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                     if (nbp == nb_pass - 1 || nb == nnb - 1) {
                         umma_commit_if(leader, d_ready);         // accumulators of this pass complete
                         ++pcount;
+                        TC_TRACE(it, l, 1);
                     }
                 }
                 if (l == 0) umma_commit_if(leader, a_empty);     // shared-memory operand consumed: loaders may stage the next tile
@@ -246,35 +259,56 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         const int row = q * 32 + lane;                       // accumulator row owned by this thread
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
         uint32_t pcount = 0;
-        const float *wext = ctab + a.coff[a.n_layers - 1] + a.N[a.n_layers - 1];   // extra weight rows follow the shifts
         const int G = a.mode == TC_SA ? TM / a.k : 0;
+
+        // The rank-3 part of layer 0 (xyz_j - xyz_i of a neighbour, or the raw xyz of a point) goes through the tensor cores
+        // as one more k-step: the thread that owns a row writes its extras as bf16 hi/lo pairs into columns 0..15 of the
+        // operand planes (free while layer 0 runs), for the first tile here and for every next tile at the end of the
+        // current tile's last layer, each time BEFORE the arrival that lets the MMA warp start that tile's layer 0.
+        auto load_extras = [&](int tile, float (&xe)[3]) {
+            xe[0] = xe[1] = xe[2] = 0.f;
+            if (a.mode == TC_SA) {
+                const int g = row / a.k, sidx = row - g * a.k;
+                const long ci = (long)tile * G + g;
+                if (g < G && ci < a.rows) {
+                    const long cloud = ci / a.m;
+                    const long pc = cloud * a.n + __ldg(a.center_idx + ci);
+                    const long pn = cloud * a.n + __ldg(a.nbr_idx + ci * a.nbr_stride + sidx);
+#pragma unroll
+                    for (int e = 0; e < 3; ++e) xe[e] = __ldg(a.xyz + pn * 3 + e) - __ldg(a.xyz + pc * 3 + e);
+                }
+            } else {
+                const long p = (long)tile * TM + row;
+                if (p < a.rows)
+                    for (int e = 0; e < a.n_extra; ++e) xe[e] = __ldg(a.skip_feat + p * a.c_skip + e);
+            }
+        };
+        auto store_extras = [&](const float (&xe)[3]) {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) hi[i] = lo[i] = 0u;
+            split_pack(xe[0], xe[1], hi[0], lo[0]);
+            split_pack(xe[2], 0.f, hi[1], lo[1]);
+            tmem_st16(trow + AH_COL, hi);
+            tmem_st16(trow + AL_COL, lo);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        };
+        const bool xwriter = a.n_extra > 0 && half == 0;
+        float xe_next[3] = {0.f, 0.f, 0.f};
+        if (xwriter && a.iters > 0) {
+            load_extras(blockIdx.x, xe_next);
+            store_extras(xe_next);
+        }
+        tc_fence_before();
+        mbar_arrive(t_ready);                                  // completion #0: the MMA warp may start the first phase
 
         for (int it = 0; it < a.iters; ++it) {
             const int tile = blockIdx.x + it * gridDim.x;          // tiles >= ntiles are empty (all rows out of range)
-            // the rank-3 part of layer 0 for the row this thread owns (loads overlap the wait for the first accumulators)
-            float xe[3] = {0.f, 0.f, 0.f};
-            if (a.n_extra > 0) {
-                if (a.mode == TC_SA) {
-                    const int g = row / a.k, sidx = row - g * a.k;
-                    const long ci = (long)tile * G + g;
-                    if (g < G && ci < a.rows) {
-                        const long cloud = ci / a.m;
-                        const long pc = cloud * a.n + __ldg(a.center_idx + ci);
-                        const long pn = cloud * a.n + __ldg(a.nbr_idx + ci * a.nbr_stride + sidx);
-#pragma unroll
-                        for (int e = 0; e < 3; ++e) xe[e] = __ldg(a.xyz + pn * 3 + e) - __ldg(a.xyz + pc * 3 + e);
-                    }
-                } else {
-                    const long p = (long)tile * TM + row;
-                    if (p < a.rows)
-                        for (int e = 0; e < a.n_extra; ++e) xe[e] = __ldg(a.skip_feat + p * a.c_skip + e);
-                }
-            }
+            if (xwriter && it + 1 < a.iters) load_extras(tile + gridDim.x, xe_next);     // consumed at the end of this tile
             for (int l = 0; l < a.n_layers; ++l) {
                 const int N = a.N[l];
                 const bool last = l == a.n_layers - 1;
                 const bool relu = a.relu[l] != 0;
-                const bool extras = l == 0 && a.n_extra > 0;
                 const float *shl = ctab + a.coff[l];
                 const int npass = (N + D_COLS - 1) / D_COLS;
                 for (int pass = 0; pass < npass; ++pass, ++pcount) {
@@ -283,6 +317,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                     const bool active = ncols >= 64 || half == 0;
                     mbar_wait(d_ready, pcount & 1);
                     tc_fence_after();
+                    if (ewarp == 0) TC_TRACE(it, l, 2);
                     for (int cb = 0; cb < per; cb += 32) {
                         const int dcol = (ncols >= 64 ? half * per : 0) + cb;          // first accumulator column of this batch
                         const int col = pass * D_COLS + dcol;                          // output channel
@@ -293,19 +328,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                             for (int u = 0; u < 8; ++u) {
                                 const float4 sh = *reinterpret_cast<const float4 *>(shl + col + 4 * u);
                                 v[4 * u] += sh.x; v[4 * u + 1] += sh.y; v[4 * u + 2] += sh.z; v[4 * u + 3] += sh.w;
-                            }
-                            if (extras) {
-#pragma unroll
-                                for (int e = 0; e < 3; ++e) {
-                                    if (e < a.n_extra) {
-#pragma unroll
-                                        for (int u = 0; u < 8; ++u) {
-                                            const float4 w = *reinterpret_cast<const float4 *>(wext + e * N + col + 4 * u);
-                                            v[4 * u] = fmaf(xe[e], w.x, v[4 * u]); v[4 * u + 1] = fmaf(xe[e], w.y, v[4 * u + 1]);
-                                            v[4 * u + 2] = fmaf(xe[e], w.z, v[4 * u + 2]); v[4 * u + 3] = fmaf(xe[e], w.w, v[4 * u + 3]);
-                                        }
-                                    }
-                                }
                             }
                             if (relu) {
 #pragma unroll
@@ -321,22 +343,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                                 tmem_st16(trow + AL_COL + (uint32_t)(dcol >> 1), lo);
                             }
                         } else {
-                            // one staging round: 32 columns of each half -> [128][64] fp32 -> pooled / stored rows
                             const bool final_batch = cb + 32 >= per;
                             if (final_batch) {                   // every accumulator column of the pass has been read
+                                // last pass of the tile: the operand planes are free (this layer's MMAs completed before
+                                // d_ready): stage the next tile's layer-0 extras there before releasing the MMA warp
+                                if (xwriter && pass == npass - 1 && it + 1 < a.iters) store_extras(xe_next);
                                 tc_fence_before();
+                                if (ewarp == 0) TC_TRACE(it, l, 3);
                                 mbar_arrive(t_ready);
                             }
-                            if (active) {
-                                const int sc0 = ncols >= 64 ? half * 32 : 0;
-#pragma unroll
-                                for (int u = 0; u < 8; ++u)
-                                    *reinterpret_cast<float4 *>(stg + stg_offset(row, sc0 + 4 * u)) =
-                                        make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
-                            }
-                            asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");   // staging complete (epilogue warps only)
-                            const int rcols = ncols >= 64 ? 64 : ncols;            // staged columns this round (32 or 64)
                             if (a.mode == TC_SA) {
+                                // one staging round: 32 columns of each half -> [128][64] fp32 -> max over the K rows of a group
+                                if (active) {
+                                    const int sc0 = ncols >= 64 ? half * 32 : 0;
+#pragma unroll
+                                    for (int u = 0; u < 8; ++u)
+                                        *reinterpret_cast<float4 *>(stg + stg_offset(row, sc0 + 4 * u)) =
+                                            make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+                                }
+                                asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");   // staging complete (epilogue warps only)
+                                const int rcols = ncols >= 64 ? 64 : ncols;            // staged columns this round (32 or 64)
                                 for (int e = et; e < G * rcols; e += NEPI) {
                                     const int g = e / rcols, c = e - g * rcols;
                                     const long ci = (long)tile * G + g;
@@ -347,27 +373,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                                     const int oc = pass * D_COLS + (c >> 5) * per + cb + (c & 31);
                                     a.out[ci * N + oc] = mx;
                                 }
-                            } else {
-                                // 16 lanes per row: 8 x 16 B of half 0's columns, 8 x 16 B of half 1's
-                                const int sub = lane >> 4, l16 = lane & 15;
-                                const int hsel = l16 >> 3, u = l16 & 7;
-                                if (l16 * 4 < rcols) {
-                                    for (int r = ewarp * 2 + sub; r < TM; r += 16) {
-                                        const long p = (long)tile * TM + r;
-                                        if (p >= a.rows) break;
-                                        const int oc = pass * D_COLS + hsel * per + cb + 4 * u;
-                                        *reinterpret_cast<float4 *>(a.out + p * N + oc) =
-                                            *reinterpret_cast<const float4 *>(stg + stg_offset(r, hsel * 32 + 4 * u));
+                                asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");   // staging consumed before it is rewritten
+                            } else if (active) {
+                                // FP: this warp's 32 rows x 32 columns leave through its private [32][16] fp32 tile, 16 columns at a
+                                // time: thread = row on the way in, 4 lanes per row (64 contiguous bytes) on the way out
+                                float *ws = reinterpret_cast<float *>(stg) + ewarp * (32 * 16);
+#pragma unroll
+                                for (int sb = 0; sb < 2; ++sb) {
+                                    __syncwarp();                                   // previous read-out finished
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u)                     // 16-byte units XOR-swizzled by row
+                                        *reinterpret_cast<float4 *>(ws + lane * 16 + ((u ^ ((lane >> 1) & 3)) << 2)) =
+                                            make_float4(v[16 * sb + 4 * u], v[16 * sb + 4 * u + 1], v[16 * sb + 4 * u + 2], v[16 * sb + 4 * u + 3]);
+                                    __syncwarp();
+                                    const int u = lane & 3;
+#pragma unroll
+                                    for (int r8 = 0; r8 < 4; ++r8) {
+                                        const int r = r8 * 8 + (lane >> 2);         // row of this warp's quarter
+                                        const long p = (long)tile * TM + q * 32 + r;
+                                        if (p < a.rows)
+                                            *reinterpret_cast<float4 *>(a.out + p * N + col + 16 * sb + 4 * u) =
+                                                *reinterpret_cast<const float4 *>(ws + r * 16 + ((u ^ ((r >> 1) & 3)) << 2));
                                     }
                                 }
                             }
-                            asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");   // staging consumed before it is rewritten
                         }
                     }
                     if (!last) {
                         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                         tc_fence_before();
+                        if (ewarp == 0) TC_TRACE(it, l, 3);
                         mbar_arrive(t_ready);
+                    } else if (ewarp == 0) {
+                        TC_TRACE(it, l, 6);                      // output of the tile stored
                     }
                 }
             }
@@ -380,6 +418,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         uint32_t tcount = 0;
         for (int it = 0; it < a.iters; ++it, ++tcount) {
             const int tile = blockIdx.x + it * gridDim.x;
+            if (lwarp == 0) TC_TRACE(it, 0, 4);
             // every branch first issues the global loads that do not need the operand region (indices, weights, the pre-layer's
             // tiny input), THEN waits for the previous tile's layer-0 MMAs to release it: the lookups overlap the wait
             if (a.mode == TC_SA && a.pre_cout > 0) {
@@ -540,6 +579,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                 }
             }
             fence_proxy_async();
+            if (lwarp == 0) TC_TRACE(it, 0, 5);
             mbar_arrive(a_full);
         }
     }
@@ -584,6 +624,7 @@ int make_weight_map(CUtensorMap *map, const void *w, int N, int K, int box_n) {
 }
 
 int g_tc_enabled = 1;
+long long *g_tc_trace = nullptr;   // device buffer of 8 tiles x 4 phases x 8 events (pab_tune_tc_trace); debugging aid
 int g_tc_cluster = 0;      // weight multicast across CTA pairs (pab_tune_tensor_core bit 2 sets it): measured slower on
                            // B200 — the modules are bound by the MMA <-> epilogue hand-offs, not by L2 -> SM weight traffic
 
@@ -591,21 +632,21 @@ int g_tc_cluster = 0;      // weight multicast across CTA pairs (pab_tune_tensor
 // `layers` are the TENSOR-CORE layers only (the optional pre-layer is passed separately).
 struct TcPlan { int a_region, n_stages, coff[MAX_LAYERS], pre_off; size_t misc, smem; };
 
-bool tc_plan(const pab_layer_t *layers, int n_layers, const pab_layer_t *pre, TcPlan *p) {
+bool tc_plan(const pab_layer_t *layers, int n_layers, const pab_layer_t *pre, int mode, TcPlan *p) {
+    const long stg_bytes = mode == TC_SA ? STG_BYTES : STG_BYTES_FP;
     int ctab = 0;
     for (int l = 0; l < n_layers; ++l) {
         p->coff[l] = ctab;
         ctab += layers[l].c_out;
     }
-    if (!pre) ctab += (layers[0].c_in - layers[0].tc_k) * layers[0].c_out;
     p->pre_off = ctab;
     if (pre) ctab += pre->c_in * pre->c_out + pre->c_out;
     p->a_region = 2 * (layers[0].tc_k / KCH) * A_CHUNK;              // hi + lo plane of the gathered rows
     p->misc = 256 + (size_t)ctab * 4 + 64;
-    const long budget = 227L * 1024 - p->a_region - STG_BYTES - (long)p->misc;
+    const long budget = 227L * 1024 - p->a_region - stg_bytes - (long)p->misc;
     p->n_stages = (int)(budget / (NBLK_MAX * 128));
     if (p->n_stages > MAX_STAGES) p->n_stages = MAX_STAGES;
-    p->smem = (size_t)p->a_region + (size_t)p->n_stages * (NBLK_MAX * 128) + STG_BYTES + p->misc;
+    p->smem = (size_t)p->a_region + (size_t)p->n_stages * (NBLK_MAX * 128) + stg_bytes + p->misc;
     return p->n_stages >= 2;
 }
 
@@ -632,11 +673,11 @@ int pab_tc_eligible(const pab_layer_t *layers, int n_layers, int k_group, int al
     if (tc_layers_ok(layers, n_layers, true)) {
         const int n_extra = layers[0].c_in - layers[0].tc_k;
         if (n_extra >= 0 && n_extra <= 3 && (n_extra == 0 || layers[0].tc_k0 == 0 || layers[0].tc_k0 == n_extra) &&
-            tc_plan(layers, n_layers, nullptr, &p))
+            tc_plan(layers, n_layers, nullptr, k_group > 0 ? TC_SA : TC_FP, &p))
             return 1;
     }
     if (allow_pre && n_layers >= 2 && layers[0].c_in <= 8 && layers[0].c_out % 16 == 0 && layers[0].c_out <= 64 &&
-        tc_layers_ok(layers + 1, n_layers - 1, false) && tc_plan(layers + 1, n_layers - 1, &layers[0], &p))
+        tc_layers_ok(layers + 1, n_layers - 1, false) && tc_plan(layers + 1, n_layers - 1, &layers[0], k_group > 0 ? TC_SA : TC_FP, &p))
         return 2;
     return 0;
 }
@@ -648,7 +689,7 @@ int pab_tc_launch(int mode, long rows, int k_group, const pab_layer_t *all_layer
     const pab_layer_t *layers = kind == 2 ? all_layers + 1 : all_layers;
     const int n_layers = kind == 2 ? n_all - 1 : n_all;
     TcPlan p;
-    if (!tc_plan(layers, n_layers, pre, &p)) return PAB_EINVAL;
+    if (!tc_plan(layers, n_layers, pre, mode, &p)) return PAB_EINVAL;
     a.a_region = p.a_region; a.n_stages = p.n_stages;
     const long per_tile = mode == TC_SA ? (TM / k_group) : TM;
     a.ntiles = (int)((rows + per_tile - 1) / per_tile);
@@ -668,14 +709,16 @@ int pab_tc_launch(int mode, long rows, int k_group, const pab_layer_t *all_layer
     for (int l = 0; l < n_layers; ++l) {
         const pab_layer_t &L = layers[l];
         const int nbr = L.c_out < NBLK_MAX ? L.c_out : NBLK_MAX;
-        if (make_weight_map(&a.tm[l][0], L.w_hi, L.c_out, L.tc_k, nbr / a.csize)) return PAB_EINVAL;
-        if (make_weight_map(&a.tm[l][1], L.w_lo, L.c_out, L.tc_k, nbr / a.csize)) return PAB_EINVAL;
+        // layer 0 of a module with extra (xyz) channels: the planes carry one more 64-column chunk with their weights
+        const int kcols = L.tc_k + ((l == 0 && !pre && L.c_in > L.tc_k) ? KCH : 0);
+        if (make_weight_map(&a.tm[l][0], L.w_hi, L.c_out, kcols, nbr / a.csize)) return PAB_EINVAL;
+        if (make_weight_map(&a.tm[l][1], L.w_lo, L.c_out, kcols, nbr / a.csize)) return PAB_EINVAL;
         a.shift[l] = L.shift; a.K[l] = L.tc_k; a.N[l] = L.c_out; a.relu[l] = L.relu; a.coff[l] = p.coff[l];
         // k-steps that carry data: the staged layer-0 operand spans whole 64-chunks (only the pre-layer's output is
         // narrower), the TMEM operand of later layers exactly c_in channels
         a.ksteps[l] = l == 0 ? (pre ? (pre->c_out + 15) / 16 : L.tc_k / 16) : L.c_in / 16;
     }
-    a.n_layers = n_layers; a.mode = mode; a.rows = rows;
+    a.n_layers = n_layers; a.mode = mode; a.rows = rows; a.trace = g_tc_trace;
     if (pre) {
         a.n_extra = 0; a.w_extra = nullptr;
         a.pre_cin = pre->c_in; a.pre_cout = pre->c_out; a.pre_relu = pre->relu; a.pre_wt = pre->wt; a.pre_shift = pre->shift;
@@ -700,6 +743,8 @@ int pab_tc_launch(int mode, long rows, int k_group, const pab_layer_t *all_layer
 }
 
 }  // namespace
+
+PAB_API void pab_tune_tc_trace(void *device_buffer) { g_tc_trace = (long long *)device_buffer; }
 
 PAB_API void pab_tune_tensor_core(int enable) { g_tc_enabled = enable & 1; g_tc_cluster = (enable & 4) != 0; }
 

@@ -84,8 +84,14 @@ class _Layers:
                 k0 = extra_first if i == 0 else 0
                 kk = c_in - (extra_first + extra_last if i == 0 else 0)
                 kpad = (kk + 63) // 64 * 64
-                wk = torch.zeros(c_out, kpad, dtype=torch.float32, device=device)
+                n_extra = (extra_first + extra_last) if i == 0 else 0
+                # layer 0 with extra (xyz) channels: one more 64-column chunk after the padded block holds their weights, in
+                # channel order — the kernel feeds them to the tensor cores as an additional k-step (mlp_tc.cu)
+                wk = torch.zeros(c_out, kpad + (64 if n_extra else 0), dtype=torch.float32, device=device)
                 wk[:, :kk] = wf[:, k0:k0 + kk]
+                if n_extra:
+                    ex0 = 0 if extra_first else kk
+                    wk[:, kpad:kpad + n_extra] = wf[:, ex0:ex0 + n_extra]
                 hi, lo = _split_bf16(wk)
                 self.tensors += [hi, lo]
                 hi_p, lo_p = hi.data_ptr(), lo.data_ptr()

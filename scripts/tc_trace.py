@@ -1,0 +1,42 @@
+#!/usr/bin/env python
+"""Timeline of CTA 0 of the fused-MLP tensor-core kernel for one stage (debugging aid, see pab_tune_tc_trace)."""
+import os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import util
+from patchaugnet_b200 import _lib as L
+
+stage = sys.argv[1] if len(sys.argv) > 1 else "fp0"
+dev = torch.device("cuda", 0)
+net = util.build_network(dev)
+eng = net.engine()
+x = util.synthetic_batch(32, 4096).to(dev)
+with torch.no_grad():
+    eng(x); eng(x)
+torch.cuda.synchronize()
+buf = torch.zeros(8 * 4 * 8, dtype=torch.int64, device=dev)
+# run the forward with tracing on: every TC launch overwrites the buffer, so snapshot right after the wanted stage
+lib = L.lib()
+orig_run = eng._runner
+snap = {}
+def runner():
+    run = orig_run()
+    def wrapped(st, fn):
+        if st == stage:
+            lib.pab_tune_tc_trace(L.ptr(buf)); buf.zero_()
+        run(st, fn)
+        if st == stage:
+            torch.cuda.synchronize(); snap["t"] = buf.clone(); lib.pab_tune_tc_trace(L.ptr(None))
+    return wrapped
+eng._runner = runner
+with torch.no_grad():
+    eng(x)
+t = snap["t"].cpu().view(8, 4, 8)
+t0 = int(t[t > 0].min())
+names = ["mma_start", "mma_end", "acc_seen", "epi_done", "load_start", "staged", "stored", "-"]
+for tile in range(6):
+    for l in range(4):
+        row = t[tile, l]
+        if (row > 0).any():
+            print(f"tile {tile} layer {l}: " + "  ".join(f"{names[e]}={int(row[e]) - t0:>7d}" for e in range(7) if row[e] > 0))
