@@ -1,0 +1,180 @@
+"""Fused eval-mode forward of PPT-Net (``patchaugnet_b200.pptnet.Network``) on the hand-written kernels.
+
+Same building blocks as ``engine.FusedPatchAugNet`` — point-major features, BatchNorm folded into the weights, one C-ABI
+call per module — arranged as the reference's ``pptnet.py:65-134`` backbone:
+
+    level i (4096 -> 1024 -> 256 -> 64 -> 16 points):
+        FPS -> centre gather -> [Morton-chunk index] -> kNN -> fused SA module (gather, edge features, SharedMLP, max over K,
+        ``mlp_tc_kernel`` / ``mlp_kernel``) -> fused ``SA_Layer`` self-attention (``attention.cu``)
+    4 feature-propagation modules (3-NN weights + fused FP module), deepest first
+    NetVLAD on the four pyramid levels (64 / 256 / 1024 / 4096 points, 1 / 4 / 16 / 64 clusters) written straight into the
+    reference's flattened (B, C*K) layout, then ``hidden_weights`` -> bn2 -> context gating -> L2 (row a14: the 21760 x 256
+    head is one library matmul on (B, 21760); everything before it runs on this repo's kernels)
+
+Numerics follow the module mirror (``pptnet.py``) to fp32 round-off; ``tests/test_pptnet_gpu.py`` checks both against the
+reference golden vectors and against each other.
+"""
+import ctypes as C
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib as L
+from . import attention
+from .engine import _Layers, _fold_bn, _split_bf16
+
+
+class FusedPPTNet:
+    def __init__(self, net):
+        self.net = net
+        self.device = next(net.parameters()).device
+        if self.device.type != "cuda":
+            raise L.PabError("FusedPPTNet needs the network on a CUDA device (there is no CPU fallback)")
+        self._ws = {}
+        self.refold()
+
+    # ---- weights -------------------------------------------------------------------------------------------------
+    def refold(self):
+        net, dev = self.net, self.device
+        bb = net.backbone
+        self.sa = []
+        for mod in bb.SA_modules:
+            g = mod.groupers[0]
+            self.sa.append(dict(npoint=mod.npoint, k=g.nsample, layers=_Layers(mod.mlps[0], dev, extra_first=3),
+                                att=attention._fold(mod.sas[0], dev)))
+        # FP_modules[0] takes the raw xyz (3 channels) as its skip input (pptnet.py:83-90: l_features[0] = xyz^T)
+        self.fp = [_Layers(mod.mlp, dev, extra_last=3 if i == 0 else 0) for i, mod in enumerate(bb.FP_modules)]
+        agg = net.aggregation
+        self.vlad = []
+        for i in range(4):
+            v = getattr(agg, f"vlad{i}")
+            scale, shift = _fold_bn(v.bn1)
+            wc = (v.cluster_weights.detach().float() * scale[None, :]).contiguous().to(dev)      # (C, K), bn1 folded
+            w2 = v.cluster_weights2.detach().float()[0].contiguous().to(dev)                    # (C, K)
+            K, Cf = v.cluster_size, v.feature_size
+            Kp = (K + 15) // 16 * 16
+            wct = torch.zeros(Kp, Cf, device=dev)
+            wct[:K] = wc.t()
+            hi, lo = _split_bf16(wct)
+            self.vlad.append(dict(K=K, C=Cf, n=v.max_samples, wc=wc, shift=shift.contiguous().to(dev), w2=w2, wc_hi=hi, wc_lo=lo))
+        self.flat = sum(v["K"] * v["C"] for v in self.vlad)
+        self._ws.clear()
+
+    # ---- workspace -----------------------------------------------------------------------------------------------
+    def _workspace(self, B, N):
+        key = (B, N)
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        dev, lib = self.device, L.lib()
+        f32 = dict(dtype=torch.float32, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        ws = dict(levels=[], fp=[])
+        n = N
+        att_bytes = 0
+        for sa in self.sa:
+            m, c_out = sa["npoint"], sa["layers"].c_out
+            ws["levels"].append(dict(
+                n=n, m=m, cidx=torch.empty(B, m, **i32), new_xyz=torch.empty(B, m, 3, **f32), nbr=torch.empty(B, m, sa["k"], **i32),
+                pooled=torch.empty(B, m, c_out, **f32), feat=torch.empty(B, m, c_out, **f32),
+                temp=torch.empty(B, n if n > 8192 else 1, **f32),
+                index=(torch.empty(lib.pab_knn_index_bytes(B, n), dtype=torch.uint8, device=dev)
+                       if 256 <= n <= 8192 and sa["k"] <= 64 else None)))
+            att_bytes = max(att_bytes, lib.pab_sa_layer_workspace_bytes(B, m, c_out))
+            n = m
+        ns = [N] + [sa["npoint"] for sa in self.sa]
+        for li in range(len(self.fp)):
+            ws["fp"].append(dict(idx=torch.empty(B, ns[li], 3, **i32), w=torch.empty(B, ns[li], 3, **f32),
+                                 out=torch.empty(B, ns[li], self.fp[li].c_out, **f32)))
+        ws["vlad"] = torch.empty(B, self.flat, **f32)
+        nbytes = max(lib.pab_netvlad_workspace_bytes(B, v["n"], v["C"], max(v["K"], 4)) for v in self.vlad)
+        ws["scratch"] = torch.empty(max(nbytes, att_bytes), dtype=torch.uint8, device=dev)
+        self._ws[key] = ws
+        return ws
+
+    # ---- forward -------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x, return_feat=True):
+        """x: (B,1,N,3) or (B,N,3) float32 CUDA -> (desc (B,256), fp_features [4 x (B,256,n,1)], center_idx_origin [4])."""
+        L.require_cuda(x)
+        net = self.net
+        xyz0 = (x.squeeze(1) if x.dim() == 4 else x).contiguous().float()
+        B, N, _ = xyz0.shape
+        ws = self._workspace(B, N)
+        lib, st, p = L.lib(), L.stream_ptr(), L.ptr
+        chk = L.check
+
+        xyz, feat, c = xyz0, xyz0, 3
+        for i, (sa, lv) in enumerate(zip(self.sa, ws["levels"])):
+            n, m, k = lv["n"], lv["m"], sa["k"]
+            temp = None
+            if n > 8192:
+                temp = lv["temp"]
+                temp.fill_(1e10)
+            chk(lib.pab_furthestsampling(B, n, m, p(xyz), p(temp), p(lv["cidx"]), st), "fps")
+            chk(lib.pab_gather_rows(B, n, m, 3, p(xyz), p(lv["cidx"]), p(lv["new_xyz"]), st), "gather")
+            if lv["index"] is not None:
+                chk(lib.pab_knn_build_index(B, n, p(xyz), p(lv["index"]), st), "index")
+                chk(lib.pab_knnquery_indexed(B, n, m, k, p(lv["index"]), p(lv["new_xyz"]), p(lv["nbr"]), p(None), st), "knn")
+            else:
+                chk(lib.pab_knnquery(B, n, m, k, p(xyz), p(lv["new_xyz"]), p(lv["nbr"]), p(None), st), "knn")
+            chk(lib.pab_sa_module_forward(B, n, m, k, k, c, p(xyz), p(feat), p(lv["cidx"]), p(lv["nbr"]), sa["layers"].arr,
+                                          sa["layers"].n, p(lv["pooled"]), p(None), st), "sa")
+            arr = sa["att"]["arr"]
+            chk(lib.pab_sa_layer_forward(B, m, sa["att"]["C"], p(lv["pooled"]), arr, attention.C_ptr_offset(arr, 1),
+                                         attention.C_ptr_offset(arr, 2), p(lv["feat"]), p(ws["scratch"]), st), "sa_layer")
+            xyz, feat, c = lv["new_xyz"], lv["feat"], sa["layers"].c_out
+
+        xyzs = [xyz0] + [lv["new_xyz"] for lv in ws["levels"]]
+        feats = [xyz0] + [lv["feat"] for lv in ws["levels"]]
+        ns = [N] + [lv["m"] for lv in ws["levels"]]
+        known_feat = feats[-1]
+        for li in range(len(self.fp) - 1, -1, -1):
+            f = ws["fp"][li]
+            n, m = ns[li], ns[li + 1]
+            uidx = ws["levels"][li]["index"] if li < len(ws["levels"]) else None
+            kidx = ws["levels"][li + 1]["index"] if li + 1 < len(ws["levels"]) else None
+            if kidx is not None:
+                chk(lib.pab_three_nn_weights_indexed(B, n, m, p(xyzs[li]), p(uidx), p(kidx), p(f["idx"]), p(f["w"]), st), "3nn")
+            else:
+                chk(lib.pab_three_nn_weights(B, n, m, p(xyzs[li]), p(xyzs[li + 1]), p(f["idx"]), p(f["w"]), st), "3nn")
+            skip = feats[li]
+            chk(lib.pab_fp_module_forward(B, n, m, known_feat.shape[2], skip.shape[2], p(known_feat), p(skip), p(f["idx"]), p(f["w"]),
+                                          self.fp[li].arr, self.fp[li].n, p(f["out"]), st), "fp")
+            known_feat = f["out"]
+
+        # pyramid order of the reference: f0 = level-3 features (64 points) ... f3 = level-0 features (4096 points)
+        fp_out = [ws["fp"][i]["out"] for i in range(len(self.fp) - 1, -1, -1)]
+        flat, off = ws["vlad"], 0
+        for x_l, lvl in zip(fp_out, self.vlad):
+            K, Cf = lvl["K"], lvl["C"]
+            if K % 4 == 0:
+                dst = C.c_void_p(flat.data_ptr() + 4 * off)       # element (c, k) of this level sits at off + c*K + k
+                if Cf == 256:
+                    chk(lib.pab_netvlad_forward_tc(B, x_l.shape[1], Cf, K, p(x_l), p(lvl["wc_hi"]), p(lvl["wc_lo"]), p(lvl["shift"]),
+                                                   p(lvl["w2"]), dst, flat.stride(0), K, p(ws["scratch"]), st), "vlad")
+                else:
+                    chk(lib.pab_netvlad_forward(B, x_l.shape[1], Cf, K, p(x_l), p(lvl["wc"]), p(lvl["shift"]), p(lvl["w2"]), dst,
+                                                flat.stride(0), K, p(ws["scratch"]), st), "vlad")
+            else:
+                # a level with fewer than four clusters (K = 1 on 64 points): a handful of torch ops on (B, 64, 256)
+                act = torch.softmax(x_l @ lvl["wc"] + lvl["shift"], dim=-1)                    # (B, n, K)
+                v = torch.matmul(act.transpose(1, 2), x_l).transpose(1, 2) - act.sum(1, keepdim=True) * lvl["w2"][None]
+                flat[:, off:off + Cf * K] = F.normalize(v, dim=1, p=2).reshape(B, Cf * K)
+            off += Cf * K
+        agg = net.aggregation
+        out = agg.bn2(torch.matmul(flat, agg.hidden_weights))
+        if agg.gating:
+            out = agg.context_gating(out)
+        if net.use_normalize:
+            out = F.normalize(out)
+        if not return_feat:
+            return out
+        cidx = [lv["cidx"] for lv in ws["levels"]]
+        origin = [cidx[0].clone()]
+        for ci in cidx[1:]:
+            origin.append(torch.gather(origin[-1], -1, ci.long()))                    # pptnet.py:109-118
+        fp_features = [f.transpose(1, 2).unsqueeze(-1).clone() for f in fp_out]
+        return out, fp_features, origin
+
+    __call__ = forward

@@ -34,9 +34,28 @@ class Network(nn.Module):
         else:
             print("No aggregation algorithm: ", aggregation)
         self.use_normalize = use_normalize
+        self.use_fused = True          # eval-mode CUDA forward on the fused engine (engine_ppt.FusedPPTNet)
+        self._engine = None
+        self._engine_key = None
+
+    def engine(self, refresh=False):
+        """The fused eval engine; rebuilt when parameters / buffers changed (state_dict load, in-place updates)."""
+        key = tuple(p._version for p in self.parameters()) + tuple(b._version for b in self.buffers())
+        if self._engine is None or refresh or key != self._engine_key:
+            from .engine_ppt import FusedPPTNet
+            self._engine = FusedPPTNet(self)
+            self._engine_key = key
+        return self._engine
+
+    def train(self, mode=True):
+        self._engine = None
+        return super().train(mode)
 
     def forward(self, x, return_feat=True):
         """x: B x 1 x N x 3"""
+        if (self.use_fused and not self.training and x.is_cuda and not torch.is_grad_enabled()
+                and isinstance(self.aggregation, lp.SpatialPyramidNetVLAD)):
+            return self.engine()(x, return_feat=return_feat)
         x = x.squeeze(1)
         res = self.backbone(x)
         f = res["fp_features"]

@@ -43,7 +43,16 @@ def test_pptnet_forward_matches_reference_golden():
         assert tuple(fp_features[i].shape) == (2, 256, (64, 256, 1024, 4096)[i], 1)
         assert np.abs(fp_features[i][:, :, :8, 0].cpu().numpy() - g[f"fp{i}_head"]).max() < 2e-4 * max(1.0, np.abs(g[f"fp{i}_head"]).max())
     assert np.abs(desc.cpu().numpy() - g["desc"]).max() < 1e-4
-    # the non-fused attention path (reference op sequence on torch) agrees too
+    # the module-by-module path (fused attention kernels, cuDNN SharedMLPs) agrees with the fused engine ...
+    net.use_fused = False
+    with torch.no_grad():
+        desc1, fp1, c1 = net(x)
+    assert (desc1 - desc).abs().max().item() < 1e-4
+    for a, b in zip(c1, center_idx):
+        assert torch.equal(a, b)
+    for a, b in zip(fp1, fp_features):
+        assert a.shape == b.shape and (a - b).abs().max().item() < 5e-4 * max(1.0, b.abs().max().item())
+    # ... and so does the reference op sequence on torch for the attention layers
     for m in net.modules():
         if isinstance(m, pptnet.SA_Layer):
             m.use_fused = False
