@@ -49,6 +49,8 @@ struct alignas(64) TcArgs {
     int csize, iters;                          // CTAs per cluster sharing the weight stream (1 or 2); tile-loop trips (equal for all CTAs)
     int coff[MAX_LAYERS];                      // offset of each layer's shift vector in the smem constant table
     int a_region;                              // bytes of the layer-0 operand region (hi plane, then lo plane)
+    int gchunks;                               // 64-channel chunks of the layer-0 operand staged at a time: a wide input (FP2's
+                                               // K = 768) goes through the region in several groups, accumulating in TMEM
     long rows;                                 // SA: centres, FP: points
     int ntiles;
     // layer-0 "extra" channels (the xyz part), applied as a rank-n update from the fp32 weight rows
@@ -158,11 +160,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             uint32_t s = 0, ph = 0;
             for (int it = 0; it < a.iters; ++it) {
                 for (int l = 0; l < a.n_layers; ++l) {
-                    // layer 0 with extra channels: one more 64-column chunk (k = K[0]..) holding their weights
-                    const int nkc = ((a.ksteps[l] + 3) >> 2) + (l == 0 && a.n_extra > 0 ? 1 : 0);
+                    // layer 0 with extra channels: one more 64-column chunk (k = K[0]..) holding their weights; layer 0 staged in
+                    // several operand groups: group-major order (the MMA warp finishes a group for every n-block)
+                    const int nkc_main = (a.ksteps[l] + 3) >> 2;
+                    const int nkc = nkc_main + (l == 0 && a.n_extra > 0 ? 1 : 0);
+                    const int gc = l == 0 ? a.gchunks : nkc, ngroups = l == 0 ? (nkc_main + gc - 1) / gc : 1;
                     const int nbr = min(NBLK_MAX, a.N[l]), nnb = a.N[l] / nbr;
-                    for (int nb = 0; nb < nnb; ++nb)
-                        for (int kc = 0; kc < nkc; ++kc)
+                    for (int g = 0; g < ngroups; ++g)
+                      for (int nb = 0; nb < nnb; ++nb)
+                        for (int kc = g * gc; kc < (g == ngroups - 1 ? nkc : (g + 1) * gc); ++kc)
                             for (int pl = 0; pl < 2; ++pl) {
                                 mbar_wait(empty + s, ph ^ 1);                    // released by every CTA of the cluster
                                 mbar_expect_tx(full + s, (uint32_t)nbr * 128u);
@@ -186,7 +192,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         const uint32_t a1_lo = umma_desc_lo(smem_u32(a1)), a2_lo = umma_desc_lo(smem_u32(a2));
         const uint32_t st_lo = umma_desc_lo(smem_u32(stages));
         constexpr uint32_t st_step = (NBLK_MAX * 128) >> 4;
-        uint32_t s = 0, ph = 0, pcount = 0, tcount = 0;
+        uint32_t s = 0, ph = 0, pcount = 0, tcount = 0, gcount = 0;
         int fine = 0;
         bool ok0 = false, ok1 = false;                             // state of the next slot pair's barriers (stale = wait)
         for (int it = 0; it < a.iters; ++it, ++tcount) {
@@ -195,20 +201,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                 const int nkc = nkc_main + (l == 0 && a.n_extra > 0 ? 1 : 0);        // + the extras' chunk (one k-step, A from TMEM)
                 const int nbr = min(NBLK_MAX, a.N[l]), nnb = a.N[l] / nbr, nb_pass = D_COLS / nbr;   // n-blocks per accumulator pass
                 const uint32_t idesc = umma_idesc(nbr);
-                if (l == 0) mbar_wait(a_full, tcount & 1);
+                const int gc = l == 0 ? a.gchunks : nkc, ngroups = l == 0 ? (nkc_main + gc - 1) / gc : 1;
+                for (int g = 0; g < ngroups; ++g) {
+                if (l == 0) mbar_wait(a_full, gcount & 1);       // this group of layer-0 operand chunks is staged
+                const int kc_lo = g * gc, kc_hi = g == ngroups - 1 ? nkc : (g + 1) * gc;
                 for (int nb = 0; nb < nnb; ++nb) {
                     const int nbp = nb % nb_pass;
-                    if (nbp == 0) {                              // new pass: the epilogue has drained D (and written the operand planes)
+                    if (nbp == 0 && g == 0) {                    // new pass: the epilogue has drained D (and written the operand planes)
                         mbar_wait(t_ready, pcount & 1);
                         tc_fence_after();
                         TC_TRACE(it, l, 0);
                     }
                     const uint32_t d = tmem + (uint32_t)(nbp * nbr);
-                    for (int kc = 0; kc < nkc; ++kc) {
+                    for (int kc = kc_lo; kc < kc_hi; ++kc) {
                         const bool xk = kc >= nkc_main;          // the extras' chunk: k-step 0 only, operand in plane columns 0..7
                         const bool from_smem = l == 0 && !xk;
                         const int kn = xk ? 1 : min(4, ksteps - 4 * kc);
-                        const uint32_t ka = (uint32_t)kc * (A_CHUNK >> 4);
+                        const uint32_t ka = (uint32_t)(kc - kc_lo) * (A_CHUNK >> 4);
                         const uint32_t ta = xk ? 0u : (uint32_t)(kc * 32);
                         // the hi and the lo weight plane of this (n-block, k-chunk) sit in two consecutive ring slots: both
                         // barriers are polled together (one round trip), the twelve MMAs
@@ -244,13 +253,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                             ok1 = mbar_try_wait(full + n1, (n1 == 0) ? (ph ^ 1) : ph);
                         }
                     }
-                    if (nbp == nb_pass - 1 || nb == nnb - 1) {
+                    if (g == ngroups - 1 && (nbp == nb_pass - 1 || nb == nnb - 1)) {
                         umma_commit_if(leader, d_ready);         // accumulators of this pass complete
                         ++pcount;
                         TC_TRACE(it, l, 1);
                     }
                 }
-                if (l == 0) umma_commit_if(leader, a_empty);     // shared-memory operand consumed: loaders may stage the next tile
+                if (l == 0) { umma_commit_if(leader, a_empty); ++gcount; }   // operand group consumed: loaders may stage the next one
+                }
             }
         }
         __syncwarp();
@@ -419,8 +429,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         const int lt = tid - 64 - NEPI;                      // 0..127
         const int lwarp = lt >> 5;                           // 0..3, rows [32*lwarp, 32*lwarp + 32)
         const int units0 = ((a.ksteps[0] + 3) >> 2) * 8;     // 16-byte units per operand row (whole 64-chunks)
-        uint32_t tcount = 0;
-        for (int it = 0; it < a.iters; ++it, ++tcount) {
+        const int gunits = a.gchunks * 8;                    // units per operand group (one group = the whole row unless K is wide)
+        const int ngroups = (units0 + gunits - 1) / gunits;
+        uint32_t gcount = 0;                                 // operand groups staged so far (a_full / a_empty completions)
+        for (int it = 0; it < a.iters; ++it) {
             const int tile = blockIdx.x + it * gridDim.x;
             if (lwarp == 0) TC_TRACE(it, 0, 4);
             // every branch first issues the global loads that do not need the operand region (indices, weights, the pre-layer's
@@ -446,7 +458,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                     for (int i = 0; i < 5; ++i)
                         if (i < a.c) in[3 + i] = __ldg(a.feat + pn * a.c + i) - __ldg(a.feat + pc * a.c + i);
                 }
-                if (tcount > 0) mbar_wait(a_empty, (tcount - 1) & 1);
+                if (gcount > 0) mbar_wait(a_empty, (gcount - 1) & 1);
                 const float *pw = ctab + a.pre_off, *ps = pw + a.pre_cin * a.pre_cout;
                 for (int u = 0; u < a.pre_cout / 8; ++u) {
                     float v[8];
@@ -477,7 +489,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                         my_pn = cloud * a.n + __ldg(a.nbr_idx + ci * a.nbr_stride + sidx);
                     }
                 }
-                if (tcount > 0) mbar_wait(a_empty, (tcount - 1) & 1);
+                for (int g = 0; g < ngroups; ++g) {
+                const int j_lo = g * gunits, j_hi = min(units0, j_lo + gunits);
+                if (gcount > 0) mbar_wait(a_empty, (gcount - 1) & 1);
                 for (int rr = 0; rr < 32; rr += 4) {
                     long pc[4], pn[4];
 #pragma unroll
@@ -485,7 +499,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                         pc[t4] = __shfl_sync(0xffffffffu, my_pc, rr + t4);
                         pn[t4] = __shfl_sync(0xffffffffu, my_pn, rr + t4);
                     }
-                    for (int j = lane; j < units0; j += 32) {
+                    for (int j = j_lo + lane; j < j_hi; j += 32) {
                         float4 n0[4], n1[4], c0[4], c1[4];
 #pragma unroll
                         for (int t4 = 0; t4 < 4; ++t4) {
@@ -500,9 +514,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                         for (int t4 = 0; t4 < 4; ++t4) {
                             const float v[8] = {n0[t4].x - c0[t4].x, n0[t4].y - c0[t4].y, n0[t4].z - c0[t4].z, n0[t4].w - c0[t4].w,
                                                 n1[t4].x - c1[t4].x, n1[t4].y - c1[t4].y, n1[t4].z - c1[t4].z, n1[t4].w - c1[t4].w};
-                            store_units(a1, a2, lwarp * 32 + rr + t4, j, v);
+                            store_units(a1, a2, lwarp * 32 + rr + t4, j - j_lo, v);
                         }
                     }
+                }
+                if (g + 1 < ngroups) {                        // more groups of this tile follow
+                    fence_proxy_async();
+                    mbar_arrive(a_full);
+                    ++gcount;
+                }
                 }
             } else {
                 // FP: lane r holds the three neighbour indices / weights of row 32*lwarp + r; rows are staged four at a
@@ -519,7 +539,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                         for (int e = 0; e < 3; ++e) { my_i[e] = __ldg(a.idx3 + p * 3 + e); my_w[e] = __ldg(a.w3 + p * 3 + e); }
                     }
                 }
-                if (tcount > 0) mbar_wait(a_empty, (tcount - 1) & 1);
+                for (int g = 0; g < ngroups; ++g) {
+                const int j_lo = g * gunits, j_hi = min(units0, j_lo + gunits);
+                if (gcount > 0) mbar_wait(a_empty, (gcount - 1) & 1);
                 for (int rr = 0; rr < 32; rr += 4) {
                     const float *f0[4], *f1[4], *f2[4];
                     float w0[4], w1[4], w2[4];
@@ -536,7 +558,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                         f0[t4] = a.known_feat + (b0 + i0) * a.c_known; f1[t4] = a.known_feat + (b0 + i1) * a.c_known;
                         f2[t4] = a.known_feat + (b0 + i2) * a.c_known;
                     }
-                    for (int j = lane; j < units0; j += 32) {
+                    for (int j = j_lo + lane; j < j_hi; j += 32) {
                         float v[4][8];
                         if (j < ku) {
                             float4 x0[4], x1[4], y0[4], y1[4], z0[4], z1[4];
@@ -577,14 +599,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) v[t4][i] = 0.f;
                             }
-                            store_units(a1, a2, lwarp * 32 + rr + t4, j, v[t4]);
+                            store_units(a1, a2, lwarp * 32 + rr + t4, j - j_lo, v[t4]);
                         }
                     }
+                }
+                if (g + 1 < ngroups) {                        // more groups of this tile follow
+                    fence_proxy_async();
+                    mbar_arrive(a_full);
+                    ++gcount;
+                }
                 }
             }
             fence_proxy_async();
             if (lwarp == 0) TC_TRACE(it, 0, 5);
             mbar_arrive(a_full);
+            ++gcount;
         }
     }
     tc_fence_before();
@@ -634,7 +663,7 @@ int g_tc_cluster = 0;      // weight multicast across CTA pairs (pab_tune_tensor
 
 // Shared-memory plan of one launch: layer-0 operand region, staging, weight stages, constant table.
 // `layers` are the TENSOR-CORE layers only (the optional pre-layer is passed separately).
-struct TcPlan { int a_region, n_stages, coff[MAX_LAYERS], pre_off; size_t misc, smem; };
+struct TcPlan { int a_region, gchunks, n_stages, coff[MAX_LAYERS], pre_off; size_t misc, smem; };
 
 bool tc_plan(const pab_layer_t *layers, int n_layers, const pab_layer_t *pre, int mode, TcPlan *p) {
     const long stg_bytes = mode == TC_SA ? STG_BYTES : STG_BYTES_FP;
@@ -645,7 +674,14 @@ bool tc_plan(const pab_layer_t *layers, int n_layers, const pab_layer_t *pre, in
     }
     p->pre_off = ctab;
     if (pre) ctab += pre->c_in * pre->c_out + pre->c_out;
-    p->a_region = 2 * (layers[0].tc_k / KCH) * A_CHUNK;              // hi + lo plane of the gathered rows
+    // hi + lo plane of the gathered rows; inputs wider than 5 chunks go through a 4-chunk region in groups (needs the whole
+    // layer-0 output in one accumulator pass and no loader-evaluated pre-layer)
+    p->gchunks = layers[0].tc_k / KCH;
+    if (p->gchunks > 5) {
+        if (pre || layers[0].c_out > D_COLS) return false;
+        p->gchunks = 4;
+    }
+    p->a_region = 2 * p->gchunks * A_CHUNK;
     p->misc = 256 + (size_t)ctab * 4 + 64;
     const long budget = 227L * 1024 - p->a_region - stg_bytes - (long)p->misc;
     p->n_stages = (int)(budget / (NBLK_MAX * 128));
@@ -694,7 +730,7 @@ int pab_tc_launch(int mode, long rows, int k_group, const pab_layer_t *all_layer
     const int n_layers = kind == 2 ? n_all - 1 : n_all;
     TcPlan p;
     if (!tc_plan(layers, n_layers, pre, mode, &p)) return PAB_EINVAL;
-    a.a_region = p.a_region; a.n_stages = p.n_stages;
+    a.a_region = p.a_region; a.gchunks = p.gchunks; a.n_stages = p.n_stages;
     const long per_tile = mode == TC_SA ? (TM / k_group) : TM;
     a.ntiles = (int)((rows + per_tile - 1) / per_tile);
     if (a.ntiles == 0) return 0;

@@ -35,7 +35,9 @@ def _run_fp(layers, B, n, m, known, skip, idx, w, tc):
 
 
 @pytest.mark.parametrize("spec,c_known,c_skip,n,m", [([259, 256, 256, 256], 256, 3, 1000, 300), ([320, 256, 256], 256, 64, 700, 128),
-                                                       ([128, 64, 128], 128, 0, 130, 40)])
+                                                       ([128, 64, 128], 128, 0, 130, 40),
+                                                       ([768, 256, 256], 512, 256, 300, 16),      # FP2: 12 chunks in 3 operand groups
+                                                       ([384, 256, 256], 256, 128, 517, 64)])     # PPT-Net FP2: 6 chunks = 4 + 2
 def test_fp_module_tensor_core_matches_simt_and_fp64(spec, c_known, c_skip, n, m):
     B = 3
     g = torch.Generator(device="cpu").manual_seed(n)
