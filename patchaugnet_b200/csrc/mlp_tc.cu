@@ -122,6 +122,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     float *ctab = reinterpret_cast<float *>(misc + 256);           // [shift of every layer | 3 x N0 extra weight rows | pre layer]
 
     const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
+    if (a.trace && tid == 0) {                                     // per-CTA wall clock (ns): start here, end before the exit
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        a.trace[512 + 2 * blockIdx.x] = t;
+    }
 
     if (tid == 0) {
         for (int s = 0; s < a.n_stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, a.csize); }
@@ -193,8 +198,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         const uint32_t st_lo = umma_desc_lo(smem_u32(stages));
         constexpr uint32_t st_step = (NBLK_MAX * 128) >> 4;
         uint32_t s = 0, ph = 0, pcount = 0, tcount = 0, gcount = 0;
-        int fine = 0;
-        bool ok0 = false, ok1 = false;                             // state of the next slot pair's barriers (stale = wait)
         for (int it = 0; it < a.iters; ++it, ++tcount) {
             for (int l = 0; l < a.n_layers; ++l) {
                 const int ksteps = a.ksteps[l], nkc_main = (ksteps + 3) >> 2;
@@ -219,39 +222,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                         const int kn = xk ? 1 : min(4, ksteps - 4 * kc);
                         const uint32_t ka = (uint32_t)(kc - kc_lo) * (A_CHUNK >> 4);
                         const uint32_t ta = xk ? 0u : (uint32_t)(kc * 32);
-                        // the hi and the lo weight plane of this (n-block, k-chunk) sit in two consecutive ring slots: both
-                        // barriers are polled together (one round trip), the twelve MMAs
-                        //     hi(A) * hi(W) + lo(A) * hi(W)  [slot 0]   and   hi(A) * lo(W)  [slot 1]
-                        // are issued back to back, and both slots are released by two adjacent commits
-                        const uint32_t s1 = (s + 1 == (uint32_t)a.n_stages) ? 0u : s + 1, ph1 = (s1 == 0) ? (ph ^ 1) : ph;
-                        if (a.trace && blockIdx.x == 0 && it == 2 && lane == 0 && fine < 120) a.trace[256 + fine++] = clock64();
-                        if (!ok0) mbar_wait(full + s, ph);        // ok0 / ok1: polled right after the previous pair was issued
-                        if (!ok1) mbar_wait(full + s1, ph1);
-                        if (a.trace && blockIdx.x == 0 && it == 2 && lane == 0 && fine < 120) a.trace[256 + fine++] = clock64();
-                        const uint32_t sb = st_lo + s * st_step, sb1 = st_lo + s1 * st_step;
+                        // hi weight plane: hi(A) * hi(W) + lo(A) * hi(W)
+                        mbar_wait(full + s, ph);
+                        uint32_t sb = st_lo + s * st_step;
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
                             if (ks < kn) {
                                 if (from_smem) {
                                     umma_f16_if(leader, d, a1_lo + ka + 2 * ks, UMMA_DESC_HI, sb + 2 * ks, UMMA_DESC_HI, idesc, (kc | ks) != 0);
                                     umma_f16_if(leader, d, a2_lo + ka + 2 * ks, UMMA_DESC_HI, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
-                                    umma_f16_if(leader, d, a1_lo + ka + 2 * ks, UMMA_DESC_HI, sb1 + 2 * ks, UMMA_DESC_HI, idesc, 1);
                                 } else {
                                     umma_f16_ts_if(leader, d, tmem + AH_COL + ta + ks * 8, sb + 2 * ks, UMMA_DESC_HI, idesc, (kc | ks) != 0);
                                     umma_f16_ts_if(leader, d, tmem + AL_COL + ta + ks * 8, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
-                                    umma_f16_ts_if(leader, d, tmem + AH_COL + ta + ks * 8, sb1 + 2 * ks, UMMA_DESC_HI, idesc, 1);
                                 }
                             }
                         }
-                        if (a.csize == 1) { umma_commit_if(leader, empty + s); umma_commit_if(leader, empty + s1); }
-                        else { umma_commit_mc_if(leader, empty + s, cmask_all); umma_commit_mc_if(leader, empty + s1, cmask_all); }
-                        s = (s1 + 1 == (uint32_t)a.n_stages) ? 0u : s1 + 1;
-                        ph = (s == 0) ? (ph1 ^ 1) : ph1;
-                        {   // poll the next pair's barriers now: the round trip hides behind the MMAs just queued
-                            const uint32_t n1 = (s + 1 == (uint32_t)a.n_stages) ? 0u : s + 1;
-                            ok0 = mbar_try_wait(full + s, ph);
-                            ok1 = mbar_try_wait(full + n1, (n1 == 0) ? (ph ^ 1) : ph);
+                        if (a.csize == 1) umma_commit_if(leader, empty + s);
+                        else umma_commit_mc_if(leader, empty + s, cmask_all);
+                        if (++s == (uint32_t)a.n_stages) { s = 0; ph ^= 1; }
+                        // lo weight plane: hi(A) * lo(W)
+                        mbar_wait(full + s, ph);
+                        sb = st_lo + s * st_step;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            if (ks < kn) {
+                                if (from_smem) umma_f16_if(leader, d, a1_lo + ka + 2 * ks, UMMA_DESC_HI, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
+                                else umma_f16_ts_if(leader, d, tmem + AH_COL + ta + ks * 8, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
+                            }
                         }
+                        if (a.csize == 1) umma_commit_if(leader, empty + s);
+                        else umma_commit_mc_if(leader, empty + s, cmask_all);
+                        if (++s == (uint32_t)a.n_stages) { s = 0; ph ^= 1; }
                     }
                     if (g == ngroups - 1 && (nbp == nb_pass - 1 || nb == nnb - 1)) {
                         umma_commit_if(leader, d_ready);         // accumulators of this pass complete
@@ -619,6 +620,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     tc_fence_before();
     __syncthreads();
     if (a.csize > 1) cluster_sync_all();                          // no CTA leaves while its peer may still signal its barriers
+    if (a.trace && tid == 0) {
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        a.trace[512 + 2 * blockIdx.x + 1] = t;
+    }
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");

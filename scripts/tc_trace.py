@@ -15,7 +15,7 @@ x = util.synthetic_batch(32, 4096).to(dev)
 with torch.no_grad():
     eng(x); eng(x)
 torch.cuda.synchronize()
-buf = torch.zeros(8 * 4 * 8 + 128, dtype=torch.int64, device=dev)
+buf = torch.zeros(8 * 4 * 8 + 256 + 2 * 148, dtype=torch.int64, device=dev)
 # run the forward with tracing on: every TC launch overwrites the buffer, so snapshot right after the wanted stage
 lib = L.lib()
 orig_run = eng._runner
@@ -32,7 +32,8 @@ def runner():
 eng._runner = runner
 with torch.no_grad():
     eng(x)
-fine = snap["t"].cpu()[256:]
+cta = snap["t"].cpu()[512:].view(148, 2)
+fine = snap["t"].cpu()[256:512]
 t = snap["t"].cpu()[:256].view(8, 4, 8)
 t0 = int(t[t > 0].min())
 names = ["mma_start", "mma_end", "acc_seen", "epi_done", "load_start", "staged", "stored", "-"]
@@ -42,6 +43,10 @@ for tile in range(6):
         if (row > 0).any():
             print(f"tile {tile} layer {l}: " + "  ".join(f"{names[e]}={int(row[e]) - t0:>7d}" for e in range(7) if row[e] > 0))
 
-f = [int(v) - t0 for v in fine.tolist() if v > 0]
-print("tile 2 MMA loop, (before wait, after wait) per weight stage; deltas:")
-print(" ".join(f"{f[i+1]-f[i]}" for i in range(len(f) - 1)))
+st, en = cta[:, 0], cta[:, 1]
+ok = st > 0
+base = int(st[ok].min())
+dur = (en[ok] - st[ok]).float() / 1000.0
+print(f"per-CTA wall time (us): min {dur.min():.1f} median {dur.median():.1f} max {dur.max():.1f}; start skew max {(int(st[ok].max()) - base) / 1000.0:.1f} us; "
+      f"kernel span {(int(en[ok].max()) - base) / 1000.0:.1f} us")
+print("slowest CTAs:", [(int(i), round(float(d), 1)) for d, i in sorted(zip(dur.tolist(), torch.nonzero(ok).flatten().tolist()))[-6:]])
