@@ -31,6 +31,28 @@ __device__ __forceinline__ float ref_sqdist(float ax, float ay, float az, float 
     return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 
+// Two reference distances at once with Blackwell's packed fp32 pair instructions (sub/mul/fma .f32x2): the same IEEE
+// operations in the same order on each half, so both results are bit-identical to ref_sqdist — at half the issue slots
+// of the fp32 pipe.  a* hold two points (lo, hi halves of a 64-bit register pair), b* the same point in both halves.
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void ref_sqdist_x2(unsigned long long ax, unsigned long long ay, unsigned long long az, unsigned long long bx,
+                                              unsigned long long by, unsigned long long bz, float &d_lo, float &d_hi) {
+    asm("{\n"
+        ".reg .b64 dx, dy, dz, t;\n"
+        "sub.rn.f32x2 dx, %2, %5;\n"
+        "sub.rn.f32x2 dy, %3, %6;\n"
+        "sub.rn.f32x2 dz, %4, %7;\n"
+        "mul.rn.f32x2 t, dy, dy;\n"
+        "fma.rn.f32x2 t, dx, dx, t;\n"
+        "fma.rn.f32x2 t, dz, dz, t;\n"
+        "mov.b64 {%0, %1}, t;\n"
+        "}\n" : "=f"(d_lo), "=f"(d_hi) : "l"(ax), "l"(ay), "l"(az), "l"(bx), "l"(by), "l"(bz));
+}
+
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {

@@ -63,17 +63,37 @@ fps_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, float *__res
             rk[i] = 0xFFFFFFFFu;
         }
     }
+    // points kept as fp32 PAIRS for the packed distance (PPT >= 2)
+    unsigned long long px2[(PPT + 1) / 2], py2[(PPT + 1) / 2], pz2[(PPT + 1) / 2];
+    if (PPT >= 2) {
+#pragma unroll
+        for (int i = 0; i + 1 < PPT; i += 2) {
+            px2[i / 2] = pack_f32x2(px[i], px[i + 1]); py2[i / 2] = pack_f32x2(py[i], py[i + 1]); pz2[i / 2] = pack_f32x2(pz[i], pz[i + 1]);
+        }
+    }
 
     int old = 0;
     if (t == 0) idx[0] = 0;
     for (int j = 1; j < m; ++j) {
         const float x1 = xs[old], y1 = ys[old], z1 = zs[old];
         float best = -1.f;
+        if (PPT >= 2) {
+            const unsigned long long x2 = pack_f32x2(x1, x1), y2 = pack_f32x2(y1, y1), z2 = pack_f32x2(z1, z1);
 #pragma unroll
-        for (int i = 0; i < PPT; ++i) {
-            const float d = ref_sqdist(px[i], py[i], pz[i], x1, y1, z1);
-            td[i] = fminf(d, td[i]);
-            best = fmaxf(best, td[i]);
+            for (int i = 0; i + 1 < PPT; i += 2) {
+                float d0, d1;
+                ref_sqdist_x2(px2[i / 2], py2[i / 2], pz2[i / 2], x2, y2, z2, d0, d1);
+                td[i] = fminf(d0, td[i]);
+                td[i + 1] = fminf(d1, td[i + 1]);
+                best = fmaxf(best, fmaxf(td[i], td[i + 1]));
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < PPT; ++i) {
+                const float d = ref_sqdist(px[i], py[i], pz[i], x1, y1, z1);
+                td[i] = fminf(d, td[i]);
+                best = fmaxf(best, td[i]);
+            }
         }
         // floats >= 0 (and the -1 sentinel) order like their bit patterns read as signed ints
         const int bbits = __float_as_int(best);
