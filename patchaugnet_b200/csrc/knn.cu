@@ -538,8 +538,9 @@ knn_pruned32_kernel(int n, int m, int k, int qpc, const float *__restrict__ inde
             for (int s = 0; s < KNNP_SLOTS; ++s)
                 if (ck[s] == g) ck[s] = 0xffffffffu;
             const int base = (int)(g & cmask) * IDX_CHUNK + lane;
-            const float d0 = ref_sqdist(qx, qy, qz, sx[base], sy[base], sz[base]);
-            const float d1 = ref_sqdist(qx, qy, qz, sx[base + 32], sy[base + 32], sz[base + 32]);
+            float d0, d1;                                      // both halves of the chunk through the packed fp32-pair distance
+            ref_sqdist_x2(pack_f32x2(qx, qx), pack_f32x2(qy, qy), pack_f32x2(qz, qz), pack_f32x2(sx[base], sx[base + 32]),
+                          pack_f32x2(sy[base], sy[base + 32]), pack_f32x2(sz[base], sz[base + 32]), d0, d1);
             const unsigned h0 = __ballot_sync(0xffffffffu, d0 <= tau);
             if (h0) absorb(h0, d0, base);
             const unsigned h1 = __ballot_sync(0xffffffffu, d1 <= tau);
@@ -641,16 +642,21 @@ three_nn_pruned_kernel(int n, int m, const float *__restrict__ unknown, const fl
         const float mylb = box_sqdist(ux, uy, uz, sbox + (int)(g & cmask) * 8);
         if (!__any_sync(0xffffffffu, active && mylb <= b3)) continue;
         const float4 *cp = kpts + (int)(g & cmask) * sub;
-#pragma unroll 4
-        for (int kk = 0; kk < sub; ++kk) {
-            const float4 pk = cp[kk];
-            const float d = ref_sqdist(ux, uy, uz, pk.x, pk.y, pk.z);
-            if (d <= b3) {                                     // chunks arrive in arbitrary index order: compare full keys
-                const int gi = __float_as_int(pk.w);
-                if (d < b1 || (d == b1 && gi < i1)) { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = gi; }
-                else if (d < b2 || (d == b2 && gi < i2)) { b3 = b2; i3 = i2; b2 = d; i2 = gi; }
-                else if (d < b3 || (d == b3 && gi < i3)) { b3 = d; i3 = gi; }
-            }
+        // two known points per step through the packed fp32-pair distance (bit-identical to ref_sqdist, half the fp32-pipe
+        // issue slots); chunks arrive in arbitrary index order, so candidates are compared as full (distance, index) keys
+        auto consider = [&](float d, int gi) {
+            if (d < b1 || (d == b1 && gi < i1)) { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = gi; }
+            else if (d < b2 || (d == b2 && gi < i2)) { b3 = b2; i3 = i2; b2 = d; i2 = gi; }
+            else if (d < b3 || (d == b3 && gi < i3)) { b3 = d; i3 = gi; }
+        };
+        const unsigned long long ux2 = pack_f32x2(ux, ux), uy2 = pack_f32x2(uy, uy), uz2 = pack_f32x2(uz, uz);
+#pragma unroll 2
+        for (int kk = 0; kk < sub; kk += 2) {                  // sub is 16 or 64
+            const float4 pa = cp[kk], pb = cp[kk + 1];
+            float da, db;
+            ref_sqdist_x2(ux2, uy2, uz2, pack_f32x2(pa.x, pb.x), pack_f32x2(pa.y, pb.y), pack_f32x2(pa.z, pb.z), da, db);
+            if (da <= b3) consider(da, __float_as_int(pa.w));
+            if (db <= b3) consider(db, __float_as_int(pb.w));
         }
     }
     if (!active) return;
