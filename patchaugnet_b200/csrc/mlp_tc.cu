@@ -35,7 +35,8 @@ constexpr int MAX_LAYERS = 3;
 constexpr int D_COLS = 256;                   // accumulator columns; TMEM columns [256,384) = hi plane, [384,512) = lo plane
 constexpr uint32_t AH_COL = 256, AL_COL = 384;
 constexpr int STG_COLS = 64;                  // fp32 staging of the last layer: [128 rows][64 columns]
-constexpr int STG_BYTES = TM * STG_COLS * 4;                       // SA: one CTA-wide tile (rows of a group span warps)
+constexpr int STG_PITCH = STG_COLS + 4;        // floats per staged row: 68 = 4 mod 32 keeps row-wise 16-byte writes and column-wise reads conflict-free
+constexpr int STG_BYTES = TM * STG_PITCH * 4;                      // SA: one CTA-wide tile (rows of a group span warps)
 constexpr int STG_BYTES_FP = 8 * 32 * 16 * 4;                      // FP: a private [32 rows][16 cols] tile per epilogue warp
 
 enum { TC_SA = 1, TC_FP = 2 };
@@ -100,11 +101,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
         ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
           "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
-// staging [128][64] fp32, 16-byte units XOR-swizzled by row
-__device__ __forceinline__ uint32_t stg_offset(int r, int c) {
-    return (uint32_t)(r * (STG_COLS * 4) + ((((c >> 2) ^ (r & 7)) & 15) << 4) + ((c & 3) << 2));
-}
-
 __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_constant__ TcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *a1 = smem;                                            // layer-0 operand, hi plane
@@ -175,9 +171,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                       for (int nb = 0; nb < nnb; ++nb)
                         for (int kc = g * gc; kc < (g == ngroups - 1 ? nkc : (g + 1) * gc); ++kc)
                             for (int pl = 0; pl < 2; ++pl) {
-                                mbar_wait(empty + s, ph ^ 1);                    // released by every CTA of the cluster
-                                mbar_expect_tx(full + s, (uint32_t)nbr * 128u);
-                                uint8_t *dst = stages + (size_t)s * (NBLK_MAX * 128);
+                                // narrow layers (<= 64 output channels): both planes share one slot and one barrier round trip
+                                const bool first = pl == 0 || nbr > 64;
+                                uint8_t *dst = stages + (size_t)s * (NBLK_MAX * 128) + (first ? 0 : nbr * 128);
+                                if (first) {
+                                    mbar_wait(empty + s, ph ^ 1);                // released by every CTA of the cluster
+                                    mbar_expect_tx(full + s, (uint32_t)nbr * 128u * (nbr > 64 ? 1u : 2u));
+                                }
                                 if (a.csize == 1) {
                                     tma_load_2d(dst, &a.tm[l][pl], kc * KCH, nb * nbr, full + s);
                                 } else {                                         // this CTA's share of the block, delivered to all
@@ -185,7 +185,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                                     tma_load_2d_mc(dst + (size_t)crank * share * 128, &a.tm[l][pl], kc * KCH, nb * nbr + (int)crank * share,
                                                    full + s, cmask_all);
                                 }
-                                if (++s == (uint32_t)a.n_stages) { s = 0; ph ^= 1; }
+                                if (nbr > 64 || pl == 1) {
+                                    if (++s == (uint32_t)a.n_stages) { s = 0; ph ^= 1; }
+                                }
                             }
                 }
             }
@@ -237,12 +239,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                                 }
                             }
                         }
-                        if (a.csize == 1) umma_commit_if(leader, empty + s);
-                        else umma_commit_mc_if(leader, empty + s, cmask_all);
-                        if (++s == (uint32_t)a.n_stages) { s = 0; ph ^= 1; }
+                        if (nbr > 64) {                          // wide block: the lo plane sits in the next slot
+                            if (a.csize == 1) umma_commit_if(leader, empty + s);
+                            else umma_commit_mc_if(leader, empty + s, cmask_all);
+                            if (++s == (uint32_t)a.n_stages) { s = 0; ph ^= 1; }
+                            mbar_wait(full + s, ph);
+                            sb = st_lo + s * st_step;
+                        } else {                                 // narrow block: the lo plane follows the hi plane in the same slot
+                            sb += (uint32_t)nbr * 8;
+                        }
                         // lo weight plane: hi(A) * lo(W)
-                        mbar_wait(full + s, ph);
-                        sb = st_lo + s * st_step;
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
                             if (ks < kn) {
@@ -371,10 +377,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                                 // one staging round: 32 columns of each half -> [128][64] fp32 -> max over the K rows of a group
                                 if (active) {
                                     const int sc0 = ncols >= 64 ? half * 32 : 0;
+                                    float *srow = reinterpret_cast<float *>(stg) + row * STG_PITCH + sc0;
 #pragma unroll
                                     for (int u = 0; u < 8; ++u)
-                                        *reinterpret_cast<float4 *>(stg + stg_offset(row, sc0 + 4 * u)) =
-                                            make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+                                        *reinterpret_cast<float4 *>(srow + 4 * u) = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
                                 }
                                 asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");   // staging complete (epilogue warps only)
                                 const int rcols = ncols >= 64 ? 64 : ncols;            // staged columns this round (32 or 64)
@@ -382,9 +388,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                                     const int g = e / rcols, c = e - g * rcols;
                                     const long ci = (long)tile * G + g;
                                     if (ci >= a.rows) continue;
-                                    float mx = *reinterpret_cast<const float *>(stg + stg_offset(g * a.k, c));
-                                    for (int sidx = 1; sidx < a.k; ++sidx)
-                                        mx = fmaxf(mx, *reinterpret_cast<const float *>(stg + stg_offset(g * a.k + sidx, c)));
+                                    const float *scol = reinterpret_cast<const float *>(stg) + (g * a.k) * STG_PITCH + c;
+                                    float mx = scol[0];
+                                    for (int sidx = 1; sidx < a.k; ++sidx) mx = fmaxf(mx, scol[sidx * STG_PITCH]);
                                     const int oc = pass * D_COLS + (c >> 5) * per + cb + (c & 31);
                                     a.out[ci * N + oc] = mx;
                                 }
@@ -433,6 +439,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         const int gunits = a.gchunks * 8;                    // units per operand group (one group = the whole row unless K is wide)
         const int ngroups = (units0 + gunits - 1) / gunits;
         uint32_t gcount = 0;                                 // operand groups staged so far (a_full / a_empty completions)
+        // pre-layer mode (one thread per row): pipelined lookups, see the branch below
+        float pre_in[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        long pre_pc = 0, pre_pn = 0;
+        bool pre_valid = false, pre_valid2 = false;
+        auto pre_hop1 = [&](int tile, long &pc, long &pn, bool &valid) {
+            const int G = TM / a.k;
+            const int g = lt / a.k, sidx = lt - g * a.k;
+            const long ci = (long)tile * G + g;
+            valid = g < G && ci < a.rows;
+            pc = pn = 0;
+            if (valid) {
+                const long cloud = ci / a.m;
+                pc = cloud * a.n + __ldg(a.center_idx + ci);
+                pn = cloud * a.n + __ldg(a.nbr_idx + ci * a.nbr_stride + sidx);
+            }
+        };
+        auto pre_hop2 = [&](long pc, long pn, bool valid, float (&in)[8]) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) in[i] = 0.f;
+            if (valid) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) in[i] = __ldg(a.xyz + pn * 3 + i) - __ldg(a.xyz + pc * 3 + i);
+#pragma unroll
+                for (int i = 0; i < 5; ++i)
+                    if (i < a.c) in[3 + i] = __ldg(a.feat + pn * a.c + i) - __ldg(a.feat + pc * a.c + i);
+            }
+        };
+        if (a.mode == TC_SA && a.pre_cout > 0 && a.iters > 0) {
+            pre_hop1(blockIdx.x, pre_pc, pre_pn, pre_valid);
+            pre_hop2(pre_pc, pre_pn, pre_valid, pre_in);
+            if (a.iters > 1) pre_hop1(blockIdx.x + gridDim.x, pre_pc, pre_pn, pre_valid2);
+        }
         for (int it = 0; it < a.iters; ++it) {
             const int tile = blockIdx.x + it * gridDim.x;
             if (lwarp == 0) TC_TRACE(it, 0, 4);
@@ -441,24 +479,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             if (a.mode == TC_SA && a.pre_cout > 0) {
                 // one thread per row: inputs [xyz_j - xyz_i ; f_j - f_i] (pre_cin <= 8 values), the pre-layer evaluated in
                 // fp32 and staged (hi/lo); the rest of the 64-channel chunk is zeroed
-                const int G = TM / a.k;
+                // Two-deep software pipeline over tiles: the row's inputs for tile t+1 (second hop: xyz / feature rows) and
+                // its point indices for tile t+2 (first hop: centre / neighbour tables) are in flight while tile t is evaluated,
+                // so no dependent global-load latency sits between two tiles of this thread.
                 const int r = lt;
-                const int g = r / a.k, sidx = r - g * a.k;
-                const long ci = (long)tile * G + g;
                 float in[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) in[i] = 0.f;
-                const bool valid = g < G && ci < a.rows;
-                if (valid) {
-                    const long cloud = ci / a.m;
-                    const long pc = cloud * a.n + __ldg(a.center_idx + ci);
-                    const long pn = cloud * a.n + __ldg(a.nbr_idx + ci * a.nbr_stride + sidx);
-#pragma unroll
-                    for (int i = 0; i < 3; ++i) in[i] = __ldg(a.xyz + pn * 3 + i) - __ldg(a.xyz + pc * 3 + i);
-#pragma unroll
-                    for (int i = 0; i < 5; ++i)
-                        if (i < a.c) in[3 + i] = __ldg(a.feat + pn * a.c + i) - __ldg(a.feat + pc * a.c + i);
+                for (int i = 0; i < 8; ++i) in[i] = pre_in[i];
+                const bool valid = pre_valid;
+                if (it + 1 < a.iters) {
+                    pre_hop2(pre_pc, pre_pn, pre_valid2, pre_in);
+                    pre_valid = pre_valid2;
                 }
+                if (it + 2 < a.iters) pre_hop1(tile + 2 * (int)gridDim.x, pre_pc, pre_pn, pre_valid2);
                 if (gcount > 0) mbar_wait(a_empty, (gcount - 1) & 1);
                 const float *pw = ctab + a.pre_off, *ps = pw + a.pre_cin * a.pre_cout;
                 for (int u = 0; u < a.pre_cout / 8; ++u) {
