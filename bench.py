@@ -147,6 +147,8 @@ def main():
     ap.add_argument("--mode", default="stream", choices=["stream", "graph", "eager"],
                     help="stream: 2-stream pipelined throughput mode (default); graph: one CUDA graph per step; eager")
     ap.add_argument("--dense-streams", type=int, default=2)
+    ap.add_argument("--tc-ctas", type=int, default=0, help="cap on persistent tensor-core CTAs (0 = one per SM)")
+    ap.add_argument("--prio", default="0,0", help="CUDA stream priorities geometry,dense (lower = higher priority)")
     ap.add_argument("--graph", type=int, default=None, help="deprecated alias: 1 -> --mode graph, 0 -> --mode eager")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -171,7 +173,11 @@ def main():
 
     net = util.build_network(dev)                        # random-init weights of the reference architecture (tests/util.py)
     eng = net.engine()
-    eng.dense_streams = max(1, min(2, args.dense_streams))
+    if args.tc_ctas:
+        eng.reserve_fps_sms = False
+        L.lib().pab_tune_tc_max_ctas(args.tc_ctas)
+    eng.dense_streams = max(1, min(3, args.dense_streams))
+    eng.stream_priorities = tuple(int(v) for v in args.prio.split(","))
     lib = L.lib()
 
     # input pool larger than L2 (126 MB): 104 batches x 1.5 MB = 164 MB, distinct seeded clouds per rank

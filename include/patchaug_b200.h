@@ -201,6 +201,10 @@ int pab_afa_forward(int b, int c, int K, int c_out, const float *v, const float 
  * off by default: measured slower on B200). */
 void pab_tune_tensor_core(int enable);
 
+/* Tuning hook: cap the number of persistent CTAs of the tensor-core kernels (0 = one per SM, default) so that kernels of
+ * other streams keep some SMs. */
+void pab_tune_tc_max_ctas(int n);
+
 /* Debugging aid: when set to a device buffer of 8*4*8 int64, CTA 0 of every fused-MLP tensor-core launch records clock64
  * stamps of its first 8 tiles ([tile][layer][event]: 0 MMA issue start, 1 MMA issue end, 2 accumulators seen by the
  * epilogue, 3 epilogue done, 4 loader start, 5 operand staged, 6 tile output stored).  NULL (default) disables it. */

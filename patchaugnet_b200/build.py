@@ -50,7 +50,9 @@ def build(force=False, verbose=False):
             sys.stdout.write(out)
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    # --no-undefined: an unresolved symbol must fail the build here, not the first dlopen on the GPU box
+    subprocess.check_call([NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
+                                                                  "-Xlinker", "--no-undefined"])
     return LIB
 
 

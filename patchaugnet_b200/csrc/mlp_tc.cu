@@ -22,6 +22,8 @@
 //     either max-pooled over the K neighbours (SA) or stored as coalesced rows (FP).
 #include "tc_common.cuh"
 
+int g_tc_max_ctas = 0;      // 0 = one persistent CTA per SM; otherwise a cap (leaves SMs to kernels of other streams); shared with vlad_tc.cu
+
 namespace {
 
 using namespace tc;
@@ -783,6 +785,7 @@ int pab_tc_launch(int mode, long rows, int k_group, const pab_layer_t *all_layer
     // halves the L2 -> SM weight traffic (the bound of the 256-wide modules: every 128-row tile re-reads all the weights)
     a.csize = (g_tc_cluster && a.ntiles >= 4) ? 2 : 1;
     int grid = a.ntiles < n_sm ? a.ntiles : n_sm;
+    if (g_tc_max_ctas > 0 && grid > g_tc_max_ctas) grid = g_tc_max_ctas;
     if (a.csize == 2) grid = grid / 2 * 2;
     a.iters = (a.ntiles + grid - 1) / grid;
     for (int l = 0; l < n_layers; ++l) {
@@ -822,6 +825,8 @@ int pab_tc_launch(int mode, long rows, int k_group, const pab_layer_t *all_layer
 }
 
 }  // namespace
+
+PAB_API void pab_tune_tc_max_ctas(int n) { g_tc_max_ctas = n; }
 
 PAB_API void pab_tune_tc_trace(void *device_buffer) { g_tc_trace = (long long *)device_buffer; }
 

@@ -15,6 +15,8 @@
 #include <math.h>
 #include "tc_common.cuh"
 
+extern int g_tc_max_ctas;   // mlp_tc.cu
+
 namespace {
 
 using namespace tc;
@@ -282,7 +284,8 @@ int pab_vlad_tc_partial(int b, int n, int c, int K, const float *x, const void *
     *nchunk_out = a.nchunk;
     const size_t smem = 8 * (size_t)A_CHUNK + 12 * (size_t)a.Kp * 128 + 64 + 64 * 4 + 4 * TM * 4 + 64;
     PAB_CUDA(cudaFuncSetAttribute(vlad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = a.nitems < n_sm ? a.nitems : n_sm;
+    int grid = a.nitems < n_sm ? a.nitems : n_sm;
+    if (g_tc_max_ctas > 0 && grid > g_tc_max_ctas) grid = g_tc_max_ctas;
     vlad_tc_kernel<<<grid, VT_THREADS, smem, st>>>(a);
     PAB_LAUNCH_CHECK();
     return 0;

@@ -116,6 +116,8 @@ class FusedPatchAugNet:
         self._streams = None
         self.vlad_tensor_core = True
         self.dense_streams = 2          # dense kernels of consecutive batches alternate between two streams
+        self.stream_priorities = (0, 0)
+        self.reserve_fps_sms = True     # forward_stream: persistent tensor-core kernels leave the FPS CTAs' SMs alone
         self.refold()
 
     # ---- weights -------------------------------------------------------------------------------------------------
@@ -308,12 +310,21 @@ class FusedPatchAugNet:
             out = torch.empty(len(batches) * B, self.c_out, dtype=torch.float32, device=self.device)
         cur = torch.cuda.current_stream()
         if self._streams is None:
-            self._streams = tuple(torch.cuda.Stream(device=self.device) for _ in range(3))
+            # stream_priorities: (geometry, dense) CUDA stream priorities, lower = scheduled first when SMs free up
+            pg, pd = self.stream_priorities
+            self._streams = (torch.cuda.Stream(device=self.device, priority=pg),) + tuple(
+                torch.cuda.Stream(device=self.device, priority=pd) for _ in range(3))
         s_geo, dense_streams = self._streams[0], self._streams[1:1 + self.dense_streams]
         s_geo.wait_stream(cur)
         for sd in dense_streams:
             sd.wait_stream(cur)
         slots = [self._workspace(B, N, slot) for slot in (0, 1)]
+        # FPS holds one SM per cloud for a third of the step.  A persistent tensor-core kernel launched with one CTA per SM
+        # would leave B of its CTAs waiting for those SMs and then run their static share of the tiles alone at the end
+        # (measured: 28.3 k -> 31.2 k submaps/s at B = 32 with the cap; 120 instead of 116 CTAs is already slower than no cap).
+        n_sm = torch.cuda.get_device_properties(self.device).multi_processor_count
+        if self.reserve_fps_sms:
+            L.lib().pab_tune_tc_max_ctas(n_sm - B if 0 < B <= n_sm // 2 else 0)
         geo_done = [None, None]
         dense_done = [None, None]
         for i, x in enumerate(batches):
@@ -342,6 +353,8 @@ class FusedPatchAugNet:
         for sd in dense_streams:
             cur.wait_stream(sd)
         cur.wait_stream(s_geo)
+        if self.reserve_fps_sms:
+            L.lib().pab_tune_tc_max_ctas(0)
         return out
 
     # ---- per-stage timing and algorithmic work (bench.py roofline) ---------------------------------------------
