@@ -213,6 +213,10 @@ void pab_tune_tc_trace(void *device_buffer);
 /* Tuning hook: force the FPS CTA size (power of two, 32..1024; 0 = automatic). */
 void pab_tune_fps_threads(int threads);
 
+/* Tuning hook: 2 = one FPS CTA samples two clouds side by side (independent halves of the CTA; identical results), so the
+ * sampler occupies half as many SMs; 1 (default) = one cloud per CTA. */
+void pab_tune_fps_clouds_per_cta(int n);
+
 #ifdef __cplusplus
 }
 #endif

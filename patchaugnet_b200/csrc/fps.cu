@@ -29,16 +29,23 @@ __device__ __forceinline__ uint32_t fps_unrank(uint32_t rank, int log2bs) {
 
 template <int PPT>
 __global__ void __launch_bounds__(1024, 1)
-fps_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, float *__restrict__ temp, int *__restrict__ idx) {
+fps_kernel(int b, int n, int m, int log2bs, int T, const float *__restrict__ xyz, float *__restrict__ temp, int *__restrict__ idx) {
+    // T threads per cloud; a CTA of 2T threads runs two clouds side by side (independent halves, named barriers): the serial
+    // arg-max chain of one cloud leaves most issue slots of its SM idle, so two clouds share an SM at little cost and the
+    // sampler occupies half as many SMs while the dense kernels of the previous batch run on the rest
     extern __shared__ float sm[];
-    float *xs = sm, *ys = sm + n, *zs = sm + 2 * n;
-    __shared__ int2 cand[2][32];
+    const int sub = threadIdx.x / T, t = threadIdx.x - sub * T;
+    const int cloud = blockIdx.x * (blockDim.x / T) + sub;
+    if (cloud >= b) return;                                        // odd tail: the whole half leaves (its barrier is its own)
+    float *xs = sm + (size_t)sub * 3 * n, *ys = xs + n, *zs = xs + 2 * n;
+    __shared__ int2 cand_all[2][2][32];
+    int2 (*cand)[32] = cand_all[sub];
+    const int bar_id = 1 + sub;
 
-    const int T = blockDim.x, t = threadIdx.x;
     const int lane = t & 31, warp = t >> 5, nw = T >> 5;
-    const float *p = xyz + (size_t)blockIdx.x * n * 3;
-    idx += (size_t)blockIdx.x * m;
-    if (temp) temp += (size_t)blockIdx.x * n;
+    const float *p = xyz + (size_t)cloud * n * 3;
+    idx += (size_t)cloud * m;
+    if (temp) temp += (size_t)cloud * n;
 
     // coalesced staging of the raw (n,3) array, de-interleaved into SoA
     for (int e = t; e < n * 3; e += T) {
@@ -46,7 +53,7 @@ fps_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, float *__res
         const int k = e / 3, c = e - 3 * k;
         (c == 0 ? xs : (c == 1 ? ys : zs))[k] = v;
     }
-    __syncthreads();
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(T) : "memory");
 
     float px[PPT], py[PPT], pz[PPT], td[PPT];
     uint32_t rk[PPT];
@@ -108,7 +115,7 @@ fps_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, float *__res
         uint32_t grank;
         if (nw > 1) {
             if (lane == 0) cand[j & 1][warp] = make_int2(wmax, (int)wrank);
-            __syncthreads();
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(T) : "memory");
             int2 c = lane < nw ? cand[j & 1][lane] : make_int2(INT_MIN, -1);
             const int gmax = __reduce_max_sync(0xffffffffu, c.x);
             grank = __reduce_min_sync(0xffffffffu, c.x == gmax ? (uint32_t)c.y : 0xFFFFFFFFu);
@@ -171,12 +178,15 @@ int ref_log2_block(int n) {  // log2(opt_n_threads(n)), cuda_utils.h:15-18, with
 
 int g_fps_threads_override = 0;
 
+int g_fps_clouds_per_cta = 1;
+
 template <int PPT>
 int launch_fps(int b, int n, int m, int threads, int log2bs, const float *xyz, float *temp, int *idx, cudaStream_t st) {
-    const size_t smem = (size_t)n * 3 * sizeof(float);
+    const int cpc = (g_fps_clouds_per_cta == 2 && threads <= 512 && b > 1) ? 2 : 1;
+    const size_t smem = (size_t)cpc * n * 3 * sizeof(float);
     // static smem (candidate slots) counts against the 48 KB default too: opt in whenever we are near it
     if (smem > 40 * 1024) PAB_CUDA(cudaFuncSetAttribute(fps_kernel<PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fps_kernel<PPT><<<b, threads, smem, st>>>(n, m, log2bs, xyz, temp, idx);
+    fps_kernel<PPT><<<pab_divup(b, cpc), cpc * threads, smem, st>>>(b, n, m, log2bs, threads, xyz, temp, idx);
     PAB_LAUNCH_CHECK();
     return 0;
 }
@@ -184,6 +194,8 @@ int launch_fps(int b, int n, int m, int threads, int log2bs, const float *xyz, f
 }  // namespace
 
 PAB_API void pab_tune_fps_threads(int threads) { g_fps_threads_override = threads; }
+
+PAB_API void pab_tune_fps_clouds_per_cta(int n) { g_fps_clouds_per_cta = n == 2 ? 2 : 1; }
 
 PAB_API int pab_furthestsampling(int b, int n, int m, const float *xyz, float *temp, int *idx, pab_stream_t s) {
     if (b < 0 || n <= 0 || m < 0 || m > n) return PAB_EINVAL;
