@@ -27,8 +27,8 @@ __device__ __forceinline__ uint32_t fps_unrank(uint32_t rank, int log2bs) {
     return ((rank & 0x3FFFFFu) << log2bs) | tid;
 }
 
-template <int PPT>
-__global__ void __launch_bounds__(1024, 1)
+template <int PPT, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
 fps_kernel(int b, int n, int m, int log2bs, int T, const float *__restrict__ xyz, float *__restrict__ temp, int *__restrict__ idx) {
     // T threads per cloud; a CTA of 2T threads runs two clouds side by side (independent halves, named barriers): the serial
     // arg-max chain of one cloud leaves most issue slots of its SM idle, so two clouds share an SM at little cost and the
@@ -180,13 +180,14 @@ int g_fps_threads_override = 0;
 
 int g_fps_clouds_per_cta = 1;
 
-template <int PPT>
+template <int PPT, int MAXT>
 int launch_fps(int b, int n, int m, int threads, int log2bs, const float *xyz, float *temp, int *idx, cudaStream_t st) {
-    const int cpc = (g_fps_clouds_per_cta == 2 && threads <= 512 && b > 1) ? 2 : 1;
+    const int cpc = (g_fps_clouds_per_cta == 2 && 2 * threads <= MAXT && b > 1) ? 2 : 1;
     const size_t smem = (size_t)cpc * n * 3 * sizeof(float);
     // static smem (candidate slots) counts against the 48 KB default too: opt in whenever we are near it
-    if (smem > 40 * 1024) PAB_CUDA(cudaFuncSetAttribute(fps_kernel<PPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fps_kernel<PPT><<<pab_divup(b, cpc), cpc * threads, smem, st>>>(b, n, m, log2bs, threads, xyz, temp, idx);
+    if (smem > 40 * 1024)
+        PAB_CUDA(cudaFuncSetAttribute(fps_kernel<PPT, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fps_kernel<PPT, MAXT><<<pab_divup(b, cpc), cpc * threads, smem, st>>>(b, n, m, log2bs, threads, xyz, temp, idx);
     PAB_LAUNCH_CHECK();
     return 0;
 }
@@ -208,15 +209,18 @@ PAB_API int pab_furthestsampling(int b, int n, int m, const float *xyz, float *t
         PAB_LAUNCH_CHECK();
         return 0;
     }
-    // threads: power of two, 8 points per thread when the cloud is large enough (16 warps at n=4096)
+    // threads: power of two; the per-step cost is the latency of the arg-max chain, not the distance updates, so small
+    // clouds get 2 points per thread (n = 1024: 512 threads, 0.044 -> 0.035 ms), 4096 points 512 x 8, larger ones 1024 x 8
     int threads = 32;
-    while (threads < 1024 && threads * 8 < n) threads <<= 1;
+    while (threads < 512 && threads * 2 < n) threads <<= 1;
+    if (n > 4096) threads = 1024;
     if (g_fps_threads_override >= 32 && g_fps_threads_override <= 1024 &&
-        (g_fps_threads_override & (g_fps_threads_override - 1)) == 0 && g_fps_threads_override * 8 >= n)
+        (g_fps_threads_override & (g_fps_threads_override - 1)) == 0 && g_fps_threads_override * 16 >= n)
         threads = g_fps_threads_override;
     const int ppt = (n + threads - 1) / threads;
-    if (ppt <= 1) return launch_fps<1>(b, n, m, threads, log2bs, xyz, temp, idx, st);
-    if (ppt <= 2) return launch_fps<2>(b, n, m, threads, log2bs, xyz, temp, idx, st);
-    if (ppt <= 4) return launch_fps<4>(b, n, m, threads, log2bs, xyz, temp, idx, st);
-    return launch_fps<8>(b, n, m, threads, log2bs, xyz, temp, idx, st);
+    if (ppt <= 1) return launch_fps<1, 1024>(b, n, m, threads, log2bs, xyz, temp, idx, st);
+    if (ppt <= 2) return launch_fps<2, 1024>(b, n, m, threads, log2bs, xyz, temp, idx, st);
+    if (ppt <= 4) return launch_fps<4, 1024>(b, n, m, threads, log2bs, xyz, temp, idx, st);
+    if (ppt <= 8) return launch_fps<8, 1024>(b, n, m, threads, log2bs, xyz, temp, idx, st);
+    return launch_fps<16, 512>(b, n, m, threads, log2bs, xyz, temp, idx, st);     // 16 points per thread: <= 512 threads (registers)
 }
