@@ -198,7 +198,8 @@ int pab_afa_forward(int b, int c, int K, int c_out, const float *v, const float 
 
 /* Tuning hook: bit 0 enables (1, default) / disables (0) the tcgen05 tensor-core path of the fused SharedMLP kernels;
  * bit 2 set (5) additionally shares the weight stream across CTA pairs (thread-block clusters of 2, TMA multicast;
- * off by default: measured slower on B200). */
+ * off by default: measured slower on B200); bit 3 set (9) turns on dynamic tile scheduling of the persistent CTAs (tiles
+ * drawn from a global counter, so CTAs that start late because another stream's kernel holds their SM take fewer). */
 void pab_tune_tensor_core(int enable);
 
 /* Tuning hook: cap the number of persistent CTAs of the tensor-core kernels (0 = one per SM, default) so that kernels of

@@ -50,6 +50,8 @@ struct alignas(64) TcArgs {
     int ksteps[MAX_LAYERS];                    // 16-wide k-steps that carry data (the rest of the last 64-chunk is zero padding)
     int n_layers, n_stages, mode;
     int csize, iters;                          // CTAs per cluster sharing the weight stream (1 or 2); tile-loop trips (equal for all CTAs)
+    int dynamic;                               // 1: CTAs draw tiles from *counter (atomic) instead of the static blockIdx + i*grid sequence
+    unsigned int *counter;                     // zeroed by the host before the launch
     int coff[MAX_LAYERS];                      // offset of each layer's shift vector in the smem constant table
     int a_region;                              // bytes of the layer-0 operand region (hi plane, then lo plane)
     int gchunks;                               // 64-channel chunks of the layer-0 operand staged at a time: a wide input (FP2's
@@ -117,7 +119,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     uint64_t *d_ready = a_full + 2;                                // MMA -> epilogue: accumulators of the phase complete
     uint64_t *t_ready = a_full + 3;                                // epilogue -> MMA: D drained (+ next operand in TMEM)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_full + 4);
-    float *ctab = reinterpret_cast<float *>(misc + 256);           // [shift of every layer | 3 x N0 extra weight rows | pre layer]
+    uint64_t *tq_full = a_full + 5;                                // dynamic tile queue: entry i published (ring of 8)
+    int *tile_list = reinterpret_cast<int *>(tq_full + 8);         // [8] tile index or -1 (no more tiles)
+    float *ctab = reinterpret_cast<float *>(misc + 384);           // [shift of every layer | pre layer]
 
     const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
     if (a.trace && tid == 0) {                                     // per-CTA wall clock (ns): start here, end before the exit
@@ -132,6 +136,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         mbar_init(a_empty, 1);
         mbar_init(d_ready, 1);
         mbar_init(t_ready, NEPI);
+        for (int i = 0; i < 8; ++i) mbar_init(tq_full + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -156,12 +161,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     const uint32_t crank = a.csize > 1 ? cluster_ctarank() : 0;
     const uint16_t cmask_all = (uint16_t)((1u << a.csize) - 1);
+    // i-th tile of this CTA, or -1 when there is none.  Static: blockIdx + i * grid for i < iters (in a cluster every CTA runs
+    // the same number of trips, trailing ones on empty tiles).  Dynamic: the loader's first thread draws tiles from a global
+    // counter and publishes them through an 8-entry shared-memory ring (one mbarrier per entry); every role reads the same
+    // sequence, so a CTA that starts late — its SM was busy with another stream's kernel — simply takes fewer tiles.
+    auto tile_at = [&](uint32_t i) -> int {
+        if (!a.dynamic) return i < (uint32_t)a.iters ? (int)(blockIdx.x + i * gridDim.x) : -1;
+        mbar_wait(tq_full + (i & 7), (i >> 3) & 1);
+        return tile_list[i & 7];
+    };
 
     if (warp == 0) {
         // ================= TMA producer: weight blocks in (tile, layer, n-block, k-chunk, plane) order ==============
         if (lane == 0) {
             uint32_t s = 0, ph = 0;
-            for (int it = 0; it < a.iters; ++it) {
+            for (uint32_t it = 0; tile_at(it) >= 0; ++it) {
                 for (int l = 0; l < a.n_layers; ++l) {
                     // layer 0 with extra channels: one more 64-column chunk (k = K[0]..) holding their weights; layer 0 staged in
                     // several operand groups: group-major order (the MMA warp finishes a group for every n-block)
@@ -202,7 +216,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         const uint32_t st_lo = umma_desc_lo(smem_u32(stages));
         constexpr uint32_t st_step = (NBLK_MAX * 128) >> 4;
         uint32_t s = 0, ph = 0, pcount = 0, tcount = 0, gcount = 0;
-        for (int it = 0; it < a.iters; ++it, ++tcount) {
+        for (int it = 0; tile_at((uint32_t)it) >= 0; ++it, ++tcount) {
             for (int l = 0; l < a.n_layers; ++l) {
                 const int ksteps = a.ksteps[l], nkc_main = (ksteps + 3) >> 2;
                 const int nkc = nkc_main + (l == 0 && a.n_extra > 0 ? 1 : 0);        // + the extras' chunk (one k-step, A from TMEM)
@@ -318,16 +332,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         };
         const bool xwriter = a.n_extra > 0 && half == 0;
         float xe_next[3] = {0.f, 0.f, 0.f};
-        if (xwriter && a.iters > 0) {
-            load_extras(blockIdx.x, xe_next);
+        int tile = tile_at(0);
+        if (xwriter && tile >= 0) {
+            load_extras(tile, xe_next);
             store_extras(xe_next);
         }
         tc_fence_before();
         mbar_arrive(t_ready);                                  // completion #0: the MMA warp may start the first phase
 
-        for (int it = 0; it < a.iters; ++it) {
-            const int tile = blockIdx.x + it * gridDim.x;          // tiles >= ntiles are empty (all rows out of range)
-            if (xwriter && it + 1 < a.iters) load_extras(tile + gridDim.x, xe_next);     // consumed at the end of this tile
+        for (int it = 0; tile >= 0; ++it) {                        // static cluster mode: trailing tiles >= ntiles are empty
+            const int tile_next = tile_at((uint32_t)it + 1);
+            if (xwriter && tile_next >= 0) load_extras(tile_next, xe_next);              // consumed at the end of this tile
             for (int l = 0; l < a.n_layers; ++l) {
                 const int N = a.N[l];
                 const bool last = l == a.n_layers - 1;
@@ -370,7 +385,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                             if (final_batch) {                   // every accumulator column of the pass has been read
                                 // last pass of the tile: the operand planes are free (this layer's MMAs completed before
                                 // d_ready): stage the next tile's layer-0 extras there before releasing the MMA warp
-                                if (xwriter && pass == npass - 1 && it + 1 < a.iters) store_extras(xe_next);
+                                if (xwriter && pass == npass - 1 && tile_next >= 0) store_extras(xe_next);
                                 tc_fence_before();
                                 if (ewarp == 0) TC_TRACE(it, l, 3);
                                 mbar_arrive(t_ready);
@@ -432,6 +447,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                     }
                 }
             }
+            tile = tile_next;
         }
     } else {
         // ================= loader warps: stage the layer-0 operand (hi/lo planes) of the next tile =================
@@ -468,13 +484,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                     if (i < a.c) in[3 + i] = __ldg(a.feat + pn * a.c + i) - __ldg(a.feat + pc * a.c + i);
             }
         };
-        if (a.mode == TC_SA && a.pre_cout > 0 && a.iters > 0) {
-            pre_hop1(blockIdx.x, pre_pc, pre_pn, pre_valid);
+        // dynamic mode: this thread draws the CTA's tiles from the global counter and publishes them `ahead` entries beyond the
+        // tile being staged (1: the epilogue prefetches the next tile's extras; 2: the pre-layer lookups run two tiles ahead)
+        const bool premode = a.mode == TC_SA && a.pre_cout > 0;
+        const uint32_t ahead = premode ? 2u : 1u;
+        uint32_t published = 0;
+        bool drained = false;
+        auto publish_upto = [&](uint32_t last) {
+            if (!a.dynamic || lt != 0) return;
+            while (published <= last) {
+                int t = -1;
+                if (!drained) {
+                    const unsigned v = atomicAdd(a.counter, 1u);
+                    if (v < (unsigned)a.ntiles) t = (int)v;
+                    else drained = true;
+                }
+                tile_list[published & 7] = t;
+                mbar_arrive(tq_full + (published & 7));
+                ++published;
+            }
+        };
+        publish_upto(ahead);
+        if (premode && tile_at(0) >= 0) {
+            pre_hop1(tile_at(0), pre_pc, pre_pn, pre_valid);
             pre_hop2(pre_pc, pre_pn, pre_valid, pre_in);
-            if (a.iters > 1) pre_hop1(blockIdx.x + gridDim.x, pre_pc, pre_pn, pre_valid2);
+            if (tile_at(1) >= 0) pre_hop1(tile_at(1), pre_pc, pre_pn, pre_valid2);
         }
-        for (int it = 0; it < a.iters; ++it) {
-            const int tile = blockIdx.x + it * gridDim.x;
+        for (int it = 0;; ++it) {
+            publish_upto((uint32_t)it + ahead);
+            const int tile = tile_at((uint32_t)it);
+            if (tile < 0) break;
             if (lwarp == 0) TC_TRACE(it, 0, 4);
             // every branch first issues the global loads that do not need the operand region (indices, weights, the pre-layer's
             // tiny input), THEN waits for the previous tile's layer-0 MMAs to release it: the lookups overlap the wait
@@ -489,11 +528,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
 #pragma unroll
                 for (int i = 0; i < 8; ++i) in[i] = pre_in[i];
                 const bool valid = pre_valid;
-                if (it + 1 < a.iters) {
+                if (tile_at((uint32_t)it + 1) >= 0) {
                     pre_hop2(pre_pc, pre_pn, pre_valid2, pre_in);
                     pre_valid = pre_valid2;
                 }
-                if (it + 2 < a.iters) pre_hop1(tile + 2 * (int)gridDim.x, pre_pc, pre_pn, pre_valid2);
+                {
+                    const int t2 = tile_at((uint32_t)it + 2);
+                    if (t2 >= 0) pre_hop1(t2, pre_pc, pre_pn, pre_valid2);
+                }
                 if (gcount > 0) mbar_wait(a_empty, (gcount - 1) & 1);
                 const float *pw = ctab + a.pre_off, *ps = pw + a.pre_cin * a.pre_cout;
                 for (int u = 0; u < a.pre_cout / 8; ++u) {
@@ -699,6 +741,8 @@ int make_weight_map(CUtensorMap *map, const void *w, int N, int K, int box_n) {
 
 int g_tc_enabled = 1;
 long long *g_tc_trace = nullptr;   // device buffer of 8 tiles x 4 phases x 8 events (pab_tune_tc_trace); debugging aid
+int g_tc_dynamic = 0;      // tiles drawn from a global counter (pab_tune_tensor_core bit 3 = 8 sets it): as fast as the static
+                           // sequence + SM reservation of engine.forward_stream, without needing to know what else is running
 int g_tc_cluster = 0;      // weight multicast across CTA pairs (pab_tune_tensor_core bit 2 sets it): measured slower on
                            // B200 — the modules are bound by the MMA <-> epilogue hand-offs, not by L2 -> SM weight traffic
 
@@ -723,7 +767,7 @@ bool tc_plan(const pab_layer_t *layers, int n_layers, const pab_layer_t *pre, in
         p->gchunks = 4;
     }
     p->a_region = 2 * p->gchunks * A_CHUNK;
-    p->misc = 256 + (size_t)ctab * 4 + 64;
+    p->misc = 384 + (size_t)ctab * 4 + 64;
     const long budget = 227L * 1024 - p->a_region - stg_bytes - (long)p->misc;
     p->n_stages = (int)(budget / (NBLK_MAX * 128));
     if (p->n_stages > MAX_STAGES) p->n_stages = MAX_STAGES;
@@ -812,6 +856,16 @@ int pab_tc_launch(int mode, long rows, int k_group, const pab_layer_t *all_layer
         const int extra_row0 = layers[0].tc_k0 == 0 ? layers[0].tc_k : 0;
         a.w_extra = layers[0].wt + (size_t)extra_row0 * layers[0].c_out;
     }
+    // dynamic tile scheduling (not with CTA pairs: they run in lock-step): one zeroed counter per launch out of a small pool
+    a.dynamic = 0; a.counter = nullptr;
+    if (g_tc_dynamic && a.csize == 1 && a.ntiles > grid) {
+        static unsigned int *pool = nullptr;
+        static unsigned int seq = 0;
+        if (!pool) PAB_CUDA(cudaMalloc(&pool, 256 * sizeof(unsigned int)));
+        a.counter = pool + (seq++ & 255u);
+        PAB_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), st));
+        a.dynamic = 1;
+    }
     PAB_CUDA(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = p.smem; cfg.stream = st;
@@ -830,7 +884,11 @@ PAB_API void pab_tune_tc_max_ctas(int n) { g_tc_max_ctas = n; }
 
 PAB_API void pab_tune_tc_trace(void *device_buffer) { g_tc_trace = (long long *)device_buffer; }
 
-PAB_API void pab_tune_tensor_core(int enable) { g_tc_enabled = enable & 1; g_tc_cluster = (enable & 4) != 0; }
+PAB_API void pab_tune_tensor_core(int enable) {
+    g_tc_enabled = enable & 1;
+    g_tc_cluster = (enable & 4) != 0;
+    g_tc_dynamic = (enable & 8) != 0;
+}
 
 int pab_tc_sa(int kind, int b, int n, int m, int k, int nbr_stride, int c, const float *xyz, const float *feat, const int *center_idx,
               const int *nbr_idx, const pab_layer_t *layers, int n_layers, float *out, cudaStream_t st) {

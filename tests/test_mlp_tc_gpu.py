@@ -65,6 +65,32 @@ def test_fp_module_tensor_core_matches_simt_and_fp64(spec, c_known, c_skip, n, m
     assert torch.isfinite(tcore).all()
 
 
+def test_tensor_core_scheduling_options_do_not_change_results():
+    """Weight multicast across CTA pairs (bit 2) and dynamic tile scheduling (bit 3) only change WHO computes a tile and how
+    the weights reach shared memory: outputs must be bit-identical to the default static single-CTA schedule."""
+    B, n, m, c_known, c_skip = 8, 4096, 1024, 256, 3            # 256 tiles > 148 CTAs
+    g = torch.Generator(device="cpu").manual_seed(5)
+    mlp = _mlp([259, 256, 256, 256], 5)
+    layers = _Layers(mlp, DEV, extra_last=3)
+    known = torch.randn(B, m, c_known, generator=g).to(DEV)
+    skip = torch.randn(B, n, c_skip, generator=g).to(DEV)
+    idx = torch.randint(0, m, (B, n, 3), generator=g).int().to(DEV)
+    w = torch.rand(B, n, 3, generator=g)
+    w = (w / w.sum(2, keepdim=True)).to(DEV)
+    outs = {}
+    for tune in (1, 5, 9):
+        out = torch.empty(B, n, layers.c_out, device=DEV)
+        L.lib().pab_tune_tensor_core(tune)
+        try:
+            L.check(L.lib().pab_fp_module_forward(B, n, m, c_known, c_skip, L.ptr(known), L.ptr(skip), L.ptr(idx), L.ptr(w), layers.arr,
+                                                  layers.n, L.ptr(out), L.stream_ptr()), "fp")
+            torch.cuda.synchronize()
+        finally:
+            L.lib().pab_tune_tensor_core(1)
+        outs[tune] = out
+    assert torch.equal(outs[1], outs[5]) and torch.equal(outs[1], outs[9])
+
+
 @pytest.mark.parametrize("spec,c,k,n,m", [([259, 256, 256, 512], 256, 20, 128, 16), ([67, 64, 64, 256], 64, 20, 1024, 128),
                                            ([131, 128, 128, 256], 128, 7, 300, 50), ([6, 32, 32, 64], 3, 20, 4096, 1024),
                                            ([6, 32, 64], 3, 9, 500, 77)])
