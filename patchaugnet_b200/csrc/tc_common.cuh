@@ -69,14 +69,6 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
 __device__ __forceinline__ uint32_t umma_idesc(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 }
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
 // ---- warp-uniform issue path -----------------------------------------------------------------------------------
 // The MMA warp runs its loops with all 32 lanes converged (warp index broadcast with a shuffle so the compiler treats it
 // as uniform) and predicates only the tcgen05 instructions on an elected lane: the descriptors then live in uniform
@@ -127,9 +119,6 @@ __device__ __forceinline__ void umma_commit_mc_if(uint32_t issue, uint64_t *bar,
         "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %2;\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(issue), "h"(mask) : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
     asm volatile(
@@ -146,28 +135,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// split form: issue the load, do other work, then tmem_ld_wait (the registers are in/out operands of the wait so that no
-// consumer can be scheduled ahead of it)
-__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
-          "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
-          "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
-          "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-        :: "memory");
-}
-
 // x = hi + lo with hi = bf16_rn(x), lo = bf16_rn(x - hi); packs element pairs (low half = lower index)
 __device__ __forceinline__ void split_pack(float a, float b, uint32_t &hi, uint32_t &lo) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -181,11 +148,6 @@ __device__ __forceinline__ void split_pack(float a, float b, uint32_t &hi, uint3
 __device__ __forceinline__ uint32_t a_unit_offset(int r, int j) {
     return (uint32_t)((j >> 3) * A_CHUNK + r * 128 + (((j & 7) ^ (r & 7)) << 4));
 }
-// fp32 staging of the last layer in the operand region: [128 rows][256 cols], 16-byte units XOR-swizzled by row
-__device__ __forceinline__ uint32_t stage_offset(int r, int c) {
-    return (uint32_t)(r * 1024 + ((((c >> 2) ^ (r & 7)) & 63) << 4) + ((c & 3) << 2));
-}
-
 __device__ __forceinline__ void store_units(uint8_t *a1, uint8_t *a2, int r, int j, const float (&v)[8]) {
     uint4 h, l;
     split_pack(v[0], v[1], h.x, l.x);
