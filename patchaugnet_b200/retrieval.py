@@ -160,3 +160,77 @@ def evaluate_recall(db_desc, query_desc, positives, top_k=25, group=None, topk_f
     recall = np.cumsum(counters[:top_k]) / float(max(evaluated, 1)) * 100.0           # :1095
     return dict(recall=recall, one_percent_recall=counters[-2] / float(max(evaluated, 1)) * 100.0, evaluated=evaluated,
                 k=k, threshold=threshold)
+
+
+def hard_negatives(query_desc, ref_desc, negative_indices, num_hard_neg=10):
+    """GPU replacement of ``SceneDataSet.__get_hard_negatives`` (scene_dataset.py:1101-1113) for a batch of queries.
+
+    query_desc (Q,D), ref_desc (N,D) float32 CUDA; negative_indices: per query, the reference indices that are negatives.
+    Returns, per query, the ``num_hard_neg`` negatives nearest in descriptor space (ascending distance, as the KDTree query
+    of the reference returns them) or ``[]`` when the query has fewer than ``num_hard_neg`` negatives.
+    The negative sets are ragged, so each query's negatives are gathered (one index_select) and ranked by one launch of the
+    exact top-k kernel; ties go to the lower position in ``negative_indices``.
+    """
+    L.require_cuda(query_desc, ref_desc)
+    out = []
+    for qi, neg in enumerate(negative_indices):
+        if len(neg) < num_hard_neg:
+            out.append([])
+            continue
+        neg_t = torch.as_tensor(np.asarray(neg, dtype=np.int64), device=ref_desc.device)
+        _, ind = retrieval_topk(ref_desc.index_select(0, neg_t), query_desc[qi:qi + 1], num_hard_neg)
+        out.append(neg_t[ind[0].long()].tolist())
+    return out
+
+
+def top_k_in_feature_space(desc, positions, r_pos, r_neg, top_k=300, k_search=1000):
+    """Training branch of ``SceneDataSet.find_top_k_feat`` (scene_dataset.py:884-921) with the per-record KDTree queries
+    replaced by ONE batched GPU top-k over the whole record set.
+
+    desc (N,D) float32 CUDA global descriptors; positions (N,2) numpy northing/easting (``get_dist`` = Euclidean distance
+    between them, :185-189).  For every record i its ``min(k_search, N)`` nearest records in descriptor space are walked
+    in order: self skipped, geometric distance < r_pos -> positive (state 1), > r_neg -> negative (state 0), otherwise
+    unknown (not used); at most ``top_k // 2`` of each class are kept; when ``top_k`` entries are collected the walk stops,
+    and an entry that filled up with a single class is dropped (:913-916).  Returns (top_k_dict, stats) where
+    stats = dict(n_q, n_p, n_n, n_u, n_valid) are the counters the reference prints.
+    """
+    L.require_cuda(desc)
+    n = desc.shape[0]
+    k = min(k_search, n)
+    _, ind = retrieval_topk(desc, desc, k)
+    ind = ind.cpu().numpy()
+    positions = np.asarray(positions, dtype=np.float64)
+    top_k_dict = {}
+    n_q = n_p = n_n = n_u = n_valid = 0
+    half = top_k // 2
+    for i in range(n):
+        cur_p = cur_n = 0
+        entry = {"top_k": [], "state": []}
+        top_k_dict[i] = entry
+        has_pos = False
+        d = np.linalg.norm(positions[ind[i]] - positions[i], axis=1)
+        for j, dij in zip(ind[i], d):
+            j = int(j)
+            if j == i:
+                continue
+            if dij < r_pos:
+                if cur_p == half:
+                    continue
+                entry["top_k"].append(j); entry["state"].append(1)
+                n_p += 1; cur_p += 1
+                has_pos = True
+            elif dij > r_neg:
+                if cur_n == half:
+                    continue
+                entry["top_k"].append(j); entry["state"].append(0)
+                n_n += 1; cur_n += 1
+            else:
+                n_u += 1
+            if cur_p + cur_n == top_k:
+                if cur_p == 0 or cur_n == 0:
+                    del top_k_dict[i]
+                break
+        n_q += 1
+        if has_pos:
+            n_valid += 1
+    return top_k_dict, dict(n_q=n_q, n_p=n_p, n_n=n_n, n_u=n_u, n_valid=n_valid)

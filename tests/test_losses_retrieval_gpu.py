@@ -96,3 +96,51 @@ def test_emd_small_runs_match_reference_semantics():
     d, _ = emd_module.emdModule()(xa, _g(b), 0.05, 50)
     d.sum().backward()
     assert torch.isfinite(xa.grad).all() and xa.grad.abs().sum() > 0
+
+
+def test_hard_negatives_and_feature_space_top_k_match_kdtree_restating():
+    """the GPU versions of __get_hard_negatives and find_top_k_feat's training branch agree with a direct
+    restatement of the reference loops on sklearn's KDTree (scene_dataset.py:884-921, 1101-1113)."""
+    from sklearn.neighbors import KDTree
+    from patchaugnet_b200 import retrieval
+    rng = np.random.default_rng(3)
+    n, d = 400, 256
+    desc = rng.normal(size=(n, d)).astype(np.float32)
+    desc /= np.linalg.norm(desc, axis=1, keepdims=True)
+    pos_xy = rng.uniform(0, 100, size=(n, 2))
+    g = torch.from_numpy(desc).cuda()
+    # hard negatives
+    negs = [sorted(rng.choice(n, size=int(s), replace=False).tolist()) for s in rng.integers(3, 60, size=12)]
+    got = retrieval.hard_negatives(g[:12], g, negs, num_hard_neg=10)
+    for qi, neg in enumerate(negs):
+        if len(neg) < 10:
+            assert got[qi] == []
+            continue
+        _, ind = KDTree(desc[neg]).query(desc[qi:qi + 1], k=10)
+        assert got[qi] == np.asarray(neg)[ind[0]].tolist()
+    # top k in feature space (training branch)
+    r_pos, r_neg, top_k = 12.0, 30.0, 20
+    got_dict, stats = retrieval.top_k_in_feature_space(g, pos_xy, r_pos, r_neg, top_k=top_k, k_search=1000)
+    tree = KDTree(desc)
+    want = {}
+    for i in range(n):
+        cur_p = cur_n = 0
+        want[i] = {"top_k": [], "state": []}
+        _, indices = tree.query(desc[i:i + 1], k=min(1000, n))
+        for j in indices[0]:
+            if i == j:
+                continue
+            dist = np.linalg.norm(pos_xy[i] - pos_xy[j])
+            if dist < r_pos:
+                if cur_p == top_k // 2:
+                    continue
+                want[i]["top_k"].append(int(j)); want[i]["state"].append(1); cur_p += 1
+            elif dist > r_neg:
+                if cur_n == top_k // 2:
+                    continue
+                want[i]["top_k"].append(int(j)); want[i]["state"].append(0); cur_n += 1
+            if cur_p + cur_n == top_k:
+                if cur_p == 0 or cur_n == 0:
+                    del want[i]
+                break
+    assert got_dict == want and stats["n_q"] == n
