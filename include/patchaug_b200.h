@@ -196,6 +196,17 @@ size_t pab_afa_workspace_bytes(int b, int c, int K, int c_out);
 int pab_afa_forward(int b, int c, int K, int c_out, const float *v, const float *w_att_t, const float *fc_wt,
                     const float *fc_scale, const float *fc_shift, int l2_norm, float *desc, void *workspace, pab_stream_t s);
 
+/* Dense head of the PPT-Net / PointNetVLAD style (pptnet_origin/models/loupe.py:99-136): desc = [normalize]( x * sigmoid(
+ * (x G) * gate_scale + gate_shift) ),  x = (fc_wt^T v) * fc_scale + fc_shift.  v (b, f) row-major (the flattened VLAD);
+ * fc_wt (f, c_out) = hidden_weights; fc_scale/fc_shift = the folded BatchNorm1d after it; gate_wt (c_out, c_out) =
+ * gating_weights with its BatchNorm1d (or gating_biases) folded into gate_scale/gate_shift, or NULL for no gating.
+ * c_out <= 256.  The f x c_out weight is streamed once (split-K over f), partials combined in a fixed order.
+ * workspace >= pab_gated_fc_workspace_bytes(b, f, c_out). */
+size_t pab_gated_fc_workspace_bytes(int b, int f, int c_out);
+int pab_gated_fc_forward(int b, int f, int c_out, const float *v, const float *fc_wt, const float *fc_scale, const float *fc_shift,
+                         const float *gate_wt, const float *gate_scale, const float *gate_shift, int l2_norm, float *desc,
+                         void *workspace, pab_stream_t s);
+
 /* Tuning hook: bit 0 enables (1, default) / disables (0) the tcgen05 tensor-core path of the fused SharedMLP kernels;
  * bit 2 set (5) additionally shares the weight stream across CTA pairs (thread-block clusters of 2, TMA multicast;
  * off by default: measured slower on B200); bit 3 set (9) turns on dynamic tile scheduling of the persistent CTAs (tiles

@@ -74,6 +74,8 @@ SIGNATURES = {
     "pab_netvlad_forward": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P, _L, _L, _P, _P]),
     "pab_netvlad_forward_tc": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _L, _L, _P, _P]),
     "pab_afa_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
+    "pab_gated_fc_workspace_bytes": (_SZ, [_I, _I, _I]),
+    "pab_gated_fc_forward": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P]),
     "pab_afa_forward": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P]),
 }
 

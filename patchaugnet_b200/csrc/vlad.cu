@@ -255,9 +255,9 @@ __global__ void __launch_bounds__(256) afa_fc_kernel(int b, int c, int K, int c_
             float y = 0.f;
             if (bb < bn && ff < fn) {
                 const int cloud = b0 + bb, k = (f0 + ff) % K;
-                const float w = __ldg(wsm + (size_t)cloud * K + k);
                 const float x = __ldg(v + (size_t)cloud * F + f0 + ff);
-                y = fmaxf(x + x * w, 0.f);
+                // wsm == nullptr: plain fc over the flattened vector (PPT-Net / PointNetVLAD head), no attention weighting
+                y = wsm ? fmaxf(x + x * __ldg(wsm + (size_t)cloud * K + k), 0.f) : x;
             }
             ys[ff][bb] = y;
         }
@@ -324,6 +324,45 @@ __global__ void __launch_bounds__(1024) afa_finalize_kernel(int b, int c_out, in
     const float inv = 1.f / fmaxf(sqrtf(tot), 1e-12f);
     if (g == 0)
         for (int o = ot; o < c_out; o += 256) desc[(size_t)cloud * c_out + o] *= inv;
+}
+
+// PPT-Net head after the split-K fc (pptnet_origin/models/loupe.py:99-105, 107-136): x = bn2(sum of the fc partials);
+// gates = sigmoid(bn1(x @ G)) (or + gating_biases, folded into scale/shift by the host); out = x * gates; optional L2.
+// One CTA per cloud, c_out <= 256 (one thread per output).
+__global__ void __launch_bounds__(256) gated_finalize_kernel(int b, int c_out, int nslice, const float *__restrict__ part,
+                                                            const float *__restrict__ scale, const float *__restrict__ shift,
+                                                            const float *__restrict__ gate_wt, const float *__restrict__ gate_scale,
+                                                            const float *__restrict__ gate_shift, int l2_norm, float *__restrict__ desc) {
+    __shared__ float xs[256];
+    __shared__ float red[8];
+    const int t = threadIdx.x, cloud = blockIdx.x, lane = t & 31, warp = t >> 5;
+    float x = 0.f;
+    if (t < c_out) {
+        float s = 0.f;
+        for (int sl = 0; sl < nslice; ++sl) s += __ldg(part + ((size_t)sl * b + cloud) * c_out + t);
+        x = fmaf(s, __ldg(scale + t), __ldg(shift + t));
+    }
+    xs[t] = x;
+    __syncthreads();
+    float y = 0.f;
+    if (t < c_out) {
+        float g = 0.f;
+        if (gate_wt) {
+            for (int i = 0; i < c_out; ++i) g = fmaf(xs[i], __ldg(gate_wt + (size_t)i * c_out + t), g);
+            g = fmaf(g, __ldg(gate_scale + t), __ldg(gate_shift + t));
+            y = x * (1.f / (1.f + expf(-g)));
+        } else {
+            y = x;
+        }
+    }
+    float sq = y * y;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if (lane == 0) red[warp] = sq;
+    __syncthreads();
+    float tot = 0.f;
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    if (t < c_out) desc[(size_t)cloud * c_out + t] = l2_norm ? y / fmaxf(sqrtf(tot), 1e-12f) : y;
 }
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -397,6 +436,28 @@ PAB_API int pab_afa_forward(int b, int c, int K, int c_out, const float *v, cons
     afa_fc_kernel<<<nslice, 256, 0, st>>>(b, c, K, c_out, v, wsm, fc_wt, part);
     PAB_LAUNCH_CHECK();
     afa_finalize_kernel<<<b, 1024, 0, st>>>(b, c_out, nslice, part, fc_scale, fc_shift, l2_norm, desc);
+    PAB_LAUNCH_CHECK();
+    return 0;
+}
+
+PAB_API size_t pab_gated_fc_workspace_bytes(int b, int f, int c_out) {
+    const size_t nslice = ((size_t)f + FCH - 1) / FCH;
+    return align256(sizeof(float) * nslice * b * c_out);
+}
+
+PAB_API int pab_gated_fc_forward(int b, int f, int c_out, const float *v, const float *fc_wt, const float *fc_scale, const float *fc_shift,
+                                 const float *gate_wt, const float *gate_scale, const float *gate_shift, int l2_norm, float *desc,
+                                 void *workspace, pab_stream_t s) {
+    if (b < 0 || f <= 0 || c_out <= 0 || c_out > 256 || !workspace || !v || !fc_wt) return PAB_EINVAL;
+    if (gate_wt && (!gate_scale || !gate_shift)) return PAB_EINVAL;
+    if (b == 0) return 0;
+    cudaStream_t st = (cudaStream_t)s;
+    float *part = (float *)workspace;
+    const int nslice = (f + FCH - 1) / FCH;
+    // the split-K fc kernel of the AFA head with the attention weighting switched off (c = f, K = 1: f = c*K + k)
+    afa_fc_kernel<<<nslice, 256, 0, st>>>(b, f, 1, c_out, v, nullptr, fc_wt, part);
+    PAB_LAUNCH_CHECK();
+    gated_finalize_kernel<<<b, 256, 0, st>>>(b, c_out, nslice, part, fc_scale, fc_shift, gate_wt, gate_scale, gate_shift, l2_norm, desc);
     PAB_LAUNCH_CHECK();
     return 0;
 }

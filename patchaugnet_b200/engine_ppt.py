@@ -8,8 +8,8 @@ call per module — arranged as the reference's ``pptnet.py:65-134`` backbone:
         ``mlp_tc_kernel`` / ``mlp_kernel``) -> fused ``SA_Layer`` self-attention (``attention.cu``)
     4 feature-propagation modules (3-NN weights + fused FP module), deepest first
     NetVLAD on the four pyramid levels (64 / 256 / 1024 / 4096 points, 1 / 4 / 16 / 64 clusters) written straight into the
-    reference's flattened (B, C*K) layout, then ``hidden_weights`` -> bn2 -> context gating -> L2 (row a14: the 21760 x 256
-    head is one library matmul on (B, 21760); everything before it runs on this repo's kernels)
+    reference's flattened (B, C*K) layout, then ``hidden_weights`` -> bn2 -> context gating -> L2 as one split-K fc kernel +
+    one finalize kernel (``pab_gated_fc_forward``, row a14)
 
 Numerics follow the module mirror (``pptnet.py``) to fp32 round-off; ``tests/test_pptnet_gpu.py`` checks both against the
 reference golden vectors and against each other.
@@ -56,8 +56,31 @@ class FusedPPTNet:
             wct = torch.zeros(Kp, Cf, device=dev)
             wct[:K] = wc.t()
             hi, lo = _split_bf16(wct)
-            self.vlad.append(dict(K=K, C=Cf, n=v.max_samples, wc=wc, shift=shift.contiguous().to(dev), w2=w2, wc_hi=hi, wc_lo=lo))
+            lvl = dict(K=K, C=Cf, n=v.max_samples, wc=wc, shift=shift.contiguous().to(dev), w2=w2, wc_hi=hi, wc_lo=lo)
+            if K % 4:
+                # the NetVLAD kernels take cluster counts in multiples of four: pad with clusters that can never be assigned
+                # (logit shift -1e30 -> softmax weight exactly 0), run on the padded problem and keep the real columns
+                K4 = (K + 3) // 4 * 4
+                wc4 = torch.zeros(Cf, K4, device=dev); wc4[:, :K] = wc
+                sh4 = torch.full((K4,), -1e30, device=dev); sh4[:K] = lvl["shift"]
+                w24 = torch.zeros(Cf, K4, device=dev); w24[:, :K] = w2
+                lvl.update(K4=K4, wc4=wc4.contiguous(), shift4=sh4, w24=w24.contiguous())
+            self.vlad.append(lvl)
         self.flat = sum(v["K"] * v["C"] for v in self.vlad)
+        # head: hidden_weights -> bn2 -> context gating (bn1 or biases folded) -> L2, one split-K fc + one finalize kernel
+        self.fc_wt = agg.hidden_weights.detach().float().contiguous().to(dev)                  # (flat, c_out)
+        self.c_out = self.fc_wt.shape[1]
+        sc, sh = _fold_bn(agg.bn2)
+        self.fc_scale, self.fc_shift = sc.contiguous().to(dev), sh.contiguous().to(dev)
+        self.gate = None
+        if agg.gating:
+            cg = agg.context_gating
+            gw = cg.gating_weights.detach().float().contiguous().to(dev)                       # (c_out, c_out): gates = x @ G
+            if cg.add_batch_norm:
+                gs, gb = _fold_bn(cg.bn1)
+            else:
+                gs, gb = torch.ones(self.c_out, device=dev), cg.gating_biases.detach().float()
+            self.gate = (gw, gs.contiguous().to(dev), gb.contiguous().to(dev))
         self._ws.clear()
 
     # ---- workspace -----------------------------------------------------------------------------------------------
@@ -87,7 +110,10 @@ class FusedPPTNet:
             ws["fp"].append(dict(idx=torch.empty(B, ns[li], 3, **i32), w=torch.empty(B, ns[li], 3, **f32),
                                  out=torch.empty(B, ns[li], self.fp[li].c_out, **f32)))
         ws["vlad"] = torch.empty(B, self.flat, **f32)
+        ws["vlad_pad"] = torch.empty(B, self.vlad[0]["C"], 4, **f32)
+        ws["desc"] = torch.empty(B, self.c_out, **f32)
         nbytes = max(lib.pab_netvlad_workspace_bytes(B, v["n"], v["C"], max(v["K"], 4)) for v in self.vlad)
+        nbytes = max(nbytes, lib.pab_gated_fc_workspace_bytes(B, self.flat, self.c_out))
         ws["scratch"] = torch.empty(max(nbytes, att_bytes), dtype=torch.uint8, device=dev)
         self._ws[key] = ws
         return ws
@@ -157,17 +183,16 @@ class FusedPPTNet:
                     chk(lib.pab_netvlad_forward(B, x_l.shape[1], Cf, K, p(x_l), p(lvl["wc"]), p(lvl["shift"]), p(lvl["w2"]), dst,
                                                 flat.stride(0), K, p(ws["scratch"]), st), "vlad")
             else:
-                # a level with fewer than four clusters (K = 1 on 64 points): a handful of torch ops on (B, 64, 256)
-                act = torch.softmax(x_l @ lvl["wc"] + lvl["shift"], dim=-1)                    # (B, n, K)
-                v = torch.matmul(act.transpose(1, 2), x_l).transpose(1, 2) - act.sum(1, keepdim=True) * lvl["w2"][None]
-                flat[:, off:off + Cf * K] = F.normalize(v, dim=1, p=2).reshape(B, Cf * K)
+                # a level with a cluster count that is not a multiple of four (K = 1 on 64 points): padded problem, real columns kept
+                pad = ws["vlad_pad"]
+                chk(lib.pab_netvlad_forward(B, x_l.shape[1], Cf, lvl["K4"], p(x_l), p(lvl["wc4"]), p(lvl["shift4"]), p(lvl["w24"]),
+                                            p(pad), pad.stride(0), pad.stride(1), p(ws["scratch"]), st), "vlad")
+                flat[:, off:off + Cf * K] = pad[:, :, :K].reshape(B, Cf * K)
             off += Cf * K
-        agg = net.aggregation
-        out = agg.bn2(torch.matmul(flat, agg.hidden_weights))
-        if agg.gating:
-            out = agg.context_gating(out)
-        if net.use_normalize:
-            out = F.normalize(out)
+        gw, gs, gb = self.gate if self.gate is not None else (None, None, None)
+        chk(lib.pab_gated_fc_forward(B, self.flat, self.c_out, p(flat), p(self.fc_wt), p(self.fc_scale), p(self.fc_shift), p(gw), p(gs),
+                                     p(gb), 1 if net.use_normalize else 0, p(ws["desc"]), p(ws["scratch"]), st), "head")
+        out = ws["desc"].clone()
         if not return_feat:
             return out
         cidx = [lv["cidx"] for lv in ws["levels"]]
