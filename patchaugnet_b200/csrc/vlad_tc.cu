@@ -10,7 +10,7 @@
 //                                                                 row of GEMM1 and an MN-major row of GEMM2),
 //                                                                 B = act^T planes (K-major); accumulated in TMEM over
 //                                                                 all tiles of the CTA's work item
-// A work item is (cloud, 256- or 1024-row chunk); persistent CTAs loop over items.  Each item writes a partial (K, C) block and
+// A work item is (cloud, 256- or 512-row chunk); persistent CTAs loop over items.  Each item writes a partial (K, C) block and
 // partial a_sum (K) exactly like vlad_partial_kernel, so vlad_finalize_kernel (vlad.cu) is shared.
 #include <math.h>
 #include "tc_common.cuh"
@@ -24,6 +24,9 @@ using namespace tc;
 constexpr int VT_WORK = 256;                  // worker threads (8 warps); warp 0: idle helper, warp 1: MMA issuer
 constexpr int VT_THREADS = 64 + VT_WORK;
 constexpr int VT_ROWS_MIN = 256;               // smallest work item (rows of one cloud); the workspace is sized for it
+#ifndef VT_ROWS_BIG
+#define VT_ROWS_BIG 512                        // work item of large clouds (n >= 2048)
+#endif
 constexpr int VT_C = 256;                     // channels (4 chunks of 64)
 
 struct VtArgs {
@@ -275,9 +278,10 @@ int pab_vlad_tc_partial(int b, int n, int c, int K, const float *x, const void *
         PAB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     }
     // work items = (cloud, chunk of rows).  Every chunk is another (K, 256) partial block through HBM, so large clouds use
-    // 1024-row chunks.  The chunking depends on n ONLY: the fp32 summation order — and with it every output bit — must not
+    // 512-row chunks (1024-row chunks make the kernel itself 6 % faster, but 512 fill the SMs the other streams leave free
+    // better: +1.7 % descriptors/s in stream mode, A/B on the same box).  The chunking depends on n ONLY: the fp32 summation order — and with it every output bit — must not
     // change with the batch size (a database built in batches of 32 has to match single-cloud queries exactly).
-    const int rpi = n >= 2048 ? 1024 : VT_ROWS_MIN;
+    const int rpi = n >= 2048 ? VT_ROWS_BIG : VT_ROWS_MIN;
     a.rows_per_item = rpi;
     a.n = n; a.K = K; a.Kp = (K + 15) / 16 * 16; a.nchunk = (n + rpi - 1) / rpi; a.nitems = b * a.nchunk;
     a.x = x; a.shift = shift; a.wc_hi = (const __nv_bfloat16 *)wc_hi; a.wc_lo = (const __nv_bfloat16 *)wc_lo; a.part = part; a.asum = asum;
