@@ -129,8 +129,8 @@ class FusedPatchAugNet:
         self.sa = []
         for mod in bb.SA_modules:
             g = mod.groupers[0]
-            self.sa.append(dict(npoint=mod.npoint, k=g.nsample, dilation=g.knn_dilation,
-                                layers=_Layers(mod.mlps[0], dev, extra_first=3)))
+            self.sa.append(dict(npoint=mod.npoint, k=g.nsample, dilation=g.knn_dilation if g.radius is None else 1,
+                                radius=g.radius, layers=_Layers(mod.mlps[0], dev, extra_first=3)))
         self.use_origin = bb.use_origin_pc_in_fp
         # FP_modules[0] concatenates the 3 raw xyz channels after the interpolated features (patch_aug_net.py:137, 359)
         self.fp = [_Layers(mod.mlp, dev, extra_last=3 if (i == 0 and self.use_origin) else 0)
@@ -147,6 +147,16 @@ class FusedPatchAugNet:
             wct[:K] = wc.t()
             hi, lo = _split_bf16(wct)                                                           # (Kp, C) K-major planes
             self.vlad.append(dict(K=K, C=Cf, wc=wc, shift=shift.contiguous().to(dev), w2=w2, wc_hi=hi, wc_lo=lo))
+        self.c_out = agg.vlads[0].feature_size if agg.aggregation_type == 3 else agg.vlads[0].output_dim
+        self._tail_shape = None
+        self.sumK = sum(v["K"] for v in self.vlad)
+        # aggregation_type 2 without context gating (the configured variant, patch_aug_net.yaml:9) has fused kernels; the other
+        # variants (loupe.py:289-328) run the module's own tail on the fused NetVLAD outputs — a few tiny (B, 256, <=84) ops
+        self.fused_tail = agg.aggregation_type == 2 and not agg.gating
+        self._ws.clear()
+        self._graphs.clear()
+        if not self.fused_tail:
+            return
         afa = agg.afa
         self.w_att_t = afa.mlpa.mlps[0].weight.detach().float()[:, :, 0].t().contiguous().to(dev)   # (c_in, c_out)
         self.fc_wt = afa.fc.weight.detach().float().t().contiguous().to(dev)                        # (C*K, c_out)
@@ -155,9 +165,6 @@ class FusedPatchAugNet:
         self.fc_shift = (afa.fc.bias.detach().float() * scale + shift).contiguous().to(dev)
         self.l2_norm = 1 if afa.l2_norm else 0
         self.c_out = afa.fc.weight.shape[0]
-        self.sumK = sum(v["K"] for v in self.vlad)
-        self._ws.clear()
-        self._graphs.clear()
 
     # ---- workspace -----------------------------------------------------------------------------------------------
     def _workspace(self, B, N, slot=0):
@@ -188,7 +195,8 @@ class FusedPatchAugNet:
         ws["v"] = torch.empty(B, self.vlad[0]["C"], self.sumK, **f32)
         nbytes = max(lib.pab_netvlad_workspace_bytes(B, n_l, v["C"], v["K"])
                      for n_l, v in zip([ns[2], ns[1], ns[0]], self.vlad))
-        nbytes = max(nbytes, lib.pab_afa_workspace_bytes(B, self.vlad[0]["C"], self.sumK, self.c_out))
+        if self.fused_tail:
+            nbytes = max(nbytes, lib.pab_afa_workspace_bytes(B, self.vlad[0]["C"], self.sumK, self.c_out))
         ws["scratch"] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         ws["desc"] = torch.empty(B, self.c_out, **f32)
         self._ws[key] = ws
@@ -226,6 +234,10 @@ class FusedPatchAugNet:
             run(f"gather{i}", lambda: lib.pab_gather_rows(B, n, m, 3, p(xyz), p(lv["cidx"]), p(lv["new_xyz"]), st))
             if lv["index"] is not None:
                 run(f"index{i}", lambda: lib.pab_knn_build_index(B, n, p(xyz), p(lv["index"]), st))
+            if sa["radius"] is not None:      # ball-query grouper (pointops.py:548-549); idx starts zeroed like BallQuery.forward
+                lv["nbr"].zero_()
+                run(f"knn{i}", lambda: lib.pab_ballquery(B, n, m, float(sa["radius"]), k, p(lv["new_xyz"]), p(xyz), p(lv["nbr"]), st))
+            elif lv["index"] is not None:
                 run(f"knn{i}", lambda: lib.pab_knnquery_indexed(B, n, m, k, p(lv["index"]), p(lv["new_xyz"]), p(lv["nbr"]), p(None), st))
             else:
                 run(f"knn{i}", lambda: lib.pab_knnquery(B, n, m, k, p(xyz), p(lv["new_xyz"]), p(lv["nbr"]), p(None), st))
@@ -284,6 +296,15 @@ class FusedPatchAugNet:
                 run(f"vlad{i}", lambda: lib.pab_netvlad_forward(B, x.shape[1], lvl["C"], lvl["K"], p(x), p(lvl["wc"]), p(lvl["shift"]),
                                                                 p(lvl["w2"]), dst, v.stride(0), v.stride(1), p(ws["scratch"]), st))
             koff += lvl["K"]
+        if not self.fused_tail:
+            per_level, koff = [], 0
+            for lvl in self.vlad:
+                per_level.append(v[:, :, koff:koff + lvl["K"]].contiguous())
+                koff += lvl["K"]
+            out = self.net.aggregation.aggregate(per_level)
+            self._tail_shape = tuple(out.shape[1:])               # (c_out,) — or (c_out, 1): type 5 keeps AFA's last dim
+            ws["desc"].copy_(out.reshape(B, -1))
+            return fp_out
         run("afa", lambda: lib.pab_afa_forward(B, self.vlad[0]["C"], self.sumK, self.c_out, p(v), p(self.w_att_t), p(self.fc_wt),
                                                p(self.fc_scale), p(self.fc_shift), self.l2_norm, p(ws["desc"]), p(ws["scratch"]), st))
         return fp_out
@@ -430,6 +451,8 @@ class FusedPatchAugNet:
         else:
             fp_out = self._launch(xyz0, ws)
         desc = ws["desc"]
+        if self._tail_shape is not None:
+            desc = desc.view(B, *self._tail_shape)
         if not return_feat:
             return desc.clone() if clone else desc
         cidx = [lv["cidx"] for lv in ws["levels"]]
@@ -463,4 +486,4 @@ class FusedPatchAugNet:
     def launches_per_forward(self):
         """Kernels this library launches per forward (for bench.py's gpu_launches)."""
         n_index = max((sum(1 for lv in ws["levels"] if lv["index"] is not None) for ws in self._ws.values()), default=0)
-        return 4 * len(self.sa) + n_index + 2 * len(self.fp) + 2 * len(self.vlad) + 4
+        return 4 * len(self.sa) + n_index + 2 * len(self.fp) + 2 * len(self.vlad) + (4 if self.fused_tail else 0)

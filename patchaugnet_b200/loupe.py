@@ -154,7 +154,11 @@ class SpatialPyramidNetVLAD(nn.Module):
             self.afa = AdaptiveFeatureAggregator(output_dim[0], nl, output_dim[0])
 
     def forward(self, features=None):
-        v = [vlad(f) for vlad, f in zip(self.vlads, features or [])]
+        return self.aggregate([vlad(f) for vlad, f in zip(self.vlads, features or [])])
+
+    def aggregate(self, v):
+        """The aggregation variant over the per-level VLADs v[i] (B, C, K_i) (reference loupe.py:289-328).  Also the tail of
+        the fused engine for every variant but the configured one (type 2 without gating has its own kernels)."""
         t = self.aggregation_type
         if t == 0:
             cat = torch.cat(v, dim=-1)

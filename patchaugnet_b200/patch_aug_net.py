@@ -49,13 +49,13 @@ class Network(nn.Module):
     # ---- fused eval path ---------------------------------------------------------------------------------------
     def fusable(self):
         agg = getattr(self, "aggregation", None)
-        if agg is None or agg.aggregation_type != 2 or agg.gating:
+        if agg is None or agg.aggregation_type not in (0, 1, 2, 3, 4, 5):
             return False
         for mod in self.backbone.SA_modules:
             if len(mod.groupers) != 1 or mod.npoint is None:
                 return False
             g = mod.groupers[0]
-            if not isinstance(g, pointops.QueryAndGroup_Edge) or g.radius is not None or not g.use_xyz:
+            if not isinstance(g, pointops.QueryAndGroup_Edge) or not g.use_xyz:
                 return False
         return len(self.backbone.SA_modules) == 3 and len(self.backbone.FP_modules) == 3
 

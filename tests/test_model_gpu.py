@@ -152,3 +152,46 @@ def test_pipelined_forward_stream_matches_per_batch_forward(net):
         d = retrieval.extract_descriptors(net, host, batch_size=4, device=torch.device(DEV))
         torch.cuda.synchronize()
     assert torch.equal(d, want[:18])
+
+
+@pytest.mark.parametrize("agg_type,gating", [(0, False), (1, False), (3, False), (4, False), (5, False), (2, True), (0, True)])
+def test_other_aggregation_variants_through_the_fused_engine(agg_type, gating):
+    """aggregation_type 0/1/3/4/5 and GATING (reference loupe.py:289-328) — fused backbone + NetVLAD
+    kernels, the variant's own tail — against the op-by-op path."""
+    cfg = dict(util.PATCHAUGNET_CFG, SAMPLING=[256, 64, 16], MAX_SAMPLES=[64, 256, 1024], AGGREGATION_TYPE=agg_type, GATING=gating)
+    small = util.build_network(DEV, cfg=cfg)
+    assert small.fusable() and small.engine().fused_tail == (agg_type == 2 and not gating)
+    x = util.synthetic_batch(3, 1024, start=300).to(DEV)
+    before = L.lib().pab_num_launches()
+    with torch.no_grad():
+        d_fused, f_fused, c_fused = small(x)
+        assert L.lib().pab_num_launches() - before == small.engine().launches_per_forward()
+        small.use_fused = False
+        d_ops, f_ops, c_ops = small(x)
+    assert d_fused.shape == d_ops.shape and torch.isfinite(d_fused).all()
+    assert (d_fused - d_ops).abs().max().item() < TOL
+    for a, b in zip(c_fused, c_ops):
+        assert torch.equal(a, b)
+
+
+def test_ball_query_grouper_through_the_fused_engine():
+    """QueryAndGroup_Edge with a radius (pointops.py:548-549) inside the fused SA modules."""
+    cfg = dict(util.PATCHAUGNET_CFG, SAMPLING=[256, 64, 16], MAX_SAMPLES=[64, 256, 1024])
+    small = util.build_network(DEV, cfg=cfg)
+    for mod, r in zip(small.backbone.SA_modules, (0.25, 0.5, 1.0)):
+        mod.groupers[0].radius = r
+    small._engine = None
+    x = util.synthetic_batch(2, 1024, start=310).to(DEV)
+    with torch.no_grad():
+        d_fused, f_fused, c_fused = small(x)
+        small.use_fused = False
+        d_ops, f_ops, c_ops = small(x)
+        small.use_fused = True
+        for mod in small.backbone.SA_modules:
+            mod.groupers[0].radius = None
+        small._engine = None
+        d_knn, _, _ = small(x)
+    assert (d_fused - d_ops).abs().max().item() < TOL
+    assert (d_fused - d_knn).abs().max().item() > 1e-3          # the grouper really changed
+    for a, b in zip(f_fused, f_ops):
+        assert (a - b).abs().max().item() < 5e-4 * max(1.0, b.abs().max().item())
