@@ -207,6 +207,19 @@ int pab_gated_fc_forward(int b, int f, int c_out, const float *v, const float *f
                          const float *gate_wt, const float *gate_scale, const float *gate_shift, int l2_norm, float *desc,
                          void *workspace, pab_stream_t s);
 
+/* Patch-feature-contrast (a2b) triplet selection of one training step — replaces the per-pair numpy where/isin loop and the
+ * per-triplet index_select + H2D copies of place_recognition/train_place_recognition.py:320-378.
+ * centers (n_clouds, M) int32 level-0 centre indices; pair p = clouds (pair_m[p], pair_n[p]) (rows of `centers`) with overlap
+ * entries [entry_ptr[p], entry_ptr[p+1]) in processing order (<= max_entries_per_pair <= 1024 each; the reference samples 500);
+ * entry e = (entry_idx1[e], near list near_val[near_ptr[e]..near_ptr[e+1]), far list far_val[far_ptr[e]..)).  Output, per pair
+ * p at [p*max_out ..): triplets (position of idx1 among m's centres, position of a positive among n's centres, position of a
+ * negative drawn with replacement by a counter-based generator keyed by seed) in the reference's order; out_count[p] = number
+ * of triplets of the pair — when it exceeds max_out only the first max_out were written (call again with more room). */
+int pab_patch_triplets(int n_pairs, int M, const int *centers, const int *pair_m, const int *pair_n, const int *entry_ptr,
+                       int max_entries_per_pair, const int *entry_idx1, const int *near_ptr, const int *near_val,
+                       const int *far_ptr, const int *far_val, unsigned long long seed, int max_out, int *out_idx1, int *out_pos,
+                       int *out_neg, int *out_count, pab_stream_t s);
+
 /* Tuning hook: bit 0 enables (1, default) / disables (0) the tcgen05 tensor-core path of the fused SharedMLP kernels;
  * bit 2 set (5) additionally shares the weight stream across CTA pairs (thread-block clusters of 2, TMA multicast;
  * off by default: measured slower on B200); bit 3 set (9) turns on dynamic tile scheduling of the persistent CTAs (tiles

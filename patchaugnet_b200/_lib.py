@@ -76,6 +76,7 @@ SIGNATURES = {
     "pab_afa_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
     "pab_gated_fc_workspace_bytes": (_SZ, [_I, _I, _I]),
     "pab_gated_fc_forward": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P]),
+    "pab_patch_triplets": (_I, [_I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, C.c_ulonglong, _I, _P, _P, _P, _P, _P]),
     "pab_afa_forward": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P]),
 }
 

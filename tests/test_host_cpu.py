@@ -106,3 +106,95 @@ def test_two_rank_gloo_matches_single_rank():
         assert p.exitcode == 0
     assert np.array_equal(db2, db1.numpy())                           # gathered database identical to the 1-rank run
     assert np.array_equal(recall2, res1["recall"]) and one2 == res1["one_percent_recall"] and ev2 == res1["evaluated"] == 7
+
+
+# ---- overlap indices (.pb) — SURVEY 8(f) rank 3 --------------------------------------------------------------------
+def _overlap_proto_classes():
+    """QueryOverlapIndices & co. of datasets/query_pos_neg_dataset.proto:14-30, declared through the protobuf runtime's
+    descriptor API (no protoc in the image) — the independent encoder/decoder the hand-written wire parser is pinned to."""
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+    fd = descriptor_pb2.FileDescriptorProto(name="qpn_test.proto", package="p2m.base_type", syntax="proto3")
+    U32, MSG = descriptor_pb2.FieldDescriptorProto.TYPE_UINT32, descriptor_pb2.FieldDescriptorProto.TYPE_MESSAGE
+    OPT, REP = descriptor_pb2.FieldDescriptorProto.LABEL_OPTIONAL, descriptor_pb2.FieldDescriptorProto.LABEL_REPEATED
+    m = fd.message_type.add(name="Uint32Pair")
+    m.field.add(name="idx1", number=1, type=U32, label=OPT)
+    for i, n in enumerate(["near_indices2", "far_indices2", "bad_far_indices2"]):
+        m.field.add(name=n, number=2 + i, type=U32, label=REP)
+    m = fd.message_type.add(name="QueryPosOverlapIndices")
+    m.field.add(name="positive_idx", number=2, type=U32, label=OPT)
+    m.field.add(name="overlap_indices", number=3, type=MSG, label=REP, type_name=".p2m.base_type.Uint32Pair")
+    m.field.add(name="inv_overlap_indices", number=4, type=MSG, label=REP, type_name=".p2m.base_type.Uint32Pair")
+    m = fd.message_type.add(name="QueryOverlapIndices")
+    m.field.add(name="query_idx", number=1, type=U32, label=OPT)
+    m.field.add(name="qp_overlap_indices", number=2, type=MSG, label=REP, type_name=".p2m.base_type.QueryPosOverlapIndices")
+    pool = descriptor_pool.DescriptorPool()
+    pool.Add(fd)
+    return message_factory.GetMessageClass(pool.FindMessageTypeByName("p2m.base_type.QueryOverlapIndices"))
+
+
+def _random_overlap(rng, n_pos=3, n_entries=40, n_points=4096):
+    per_pos = {}
+    for p in rng.choice(5000, n_pos, replace=False):
+        ents = []
+        for _ in range(int(rng.integers(0, n_entries))):
+            ents.append((int(rng.integers(0, n_points)), rng.integers(0, n_points, rng.integers(0, 12)).tolist(),
+                         rng.integers(0, n_points, rng.integers(0, 6)).tolist(), rng.integers(0, n_points, rng.integers(0, 4)).tolist()))
+        per_pos[int(p)] = ents
+    return per_pos
+
+
+def test_overlap_indices_wire_parser_matches_the_protobuf_runtime():
+    from patchaugnet_b200 import overlap_indices as oi
+    Q = _overlap_proto_classes()
+    rng = np.random.default_rng(5)
+    for trial in range(4):
+        per_pos = _random_overlap(rng)
+        if trial == 3:
+            per_pos = {}                                        # empty file body
+        msg = Q(query_idx=17 + trial)
+        for p, ents in per_pos.items():
+            qp = msg.qp_overlap_indices.add(positive_idx=p)
+            for i1, ne, fa, ba in ents:
+                qp.overlap_indices.add(idx1=i1, near_indices2=ne, far_indices2=fa, bad_far_indices2=ba)
+            qp.inv_overlap_indices.add(idx1=3, near_indices2=[1, 2])         # present in real files, skipped by the reader
+        data = msg.SerializeToString()
+        qidx, got = oi.parse_query_overlap_indices(data)
+        assert qidx == 17 + trial and set(got) == set(per_pos)
+        for p, ents in per_pos.items():
+            g = got[p]
+            assert g.idx1.tolist() == [e[0] for e in ents]
+            for k, (i1, ne, fa, ba) in enumerate(ents):
+                assert g.near[g.near_ptr[k]:g.near_ptr[k + 1]].tolist() == ne
+                assert g.far[g.far_ptr[k]:g.far_ptr[k + 1]].tolist() == fa
+                assert g.bad[g.bad_ptr[k]:g.bad_ptr[k + 1]].tolist() == ba
+        # the encoder writes what the runtime parses back to the same message (minus the inverse lists)
+        back = Q()
+        back.ParseFromString(oi.encode_query_overlap_indices(17 + trial, per_pos))
+        assert back.query_idx == 17 + trial
+        assert [q.positive_idx for q in back.qp_overlap_indices] == list(per_pos)
+        for q, ents in zip(back.qp_overlap_indices, per_pos.values()):
+            assert [(e.idx1, list(e.near_indices2), list(e.far_indices2), list(e.bad_far_indices2)) for e in q.overlap_indices] == ents
+        # get_overlap_indices keys (scene_dataset.py:293-296)
+        pos_list = list(per_pos)[::-1]
+        d = oi.get_overlap_indices(data, 17 + trial, pos_list)
+        assert list(d) == [(0, i + 1) for i in range(len(pos_list))]
+
+
+def test_far_list_quirk_and_entry_sampling():
+    from patchaugnet_b200 import overlap_indices as oi
+    ents = oi.OverlapEntries.from_lists([(1, [5], [10, 11, 12], [13]), (2, [6], [], []), (3, [7], [20], []), (4, [], [30, 31], [32, 33, 34])])
+    ptr, val = ents.far_lists(hard_only=False)
+    # reference :352-359: t = far + bad; for far_i in range(0, len(t), 2): list_far_indices = t[far_i]  -> last even-position element
+    want = []
+    for far, bad in [([10, 11, 12], [13]), ([], []), ([20], []), ([30, 31], [32, 33, 34])]:
+        t, lst = far + bad, []
+        for far_i in range(0, len(t), 2):
+            lst = t[far_i]
+        want.append([lst] if t else [])
+    assert [val[ptr[e]:ptr[e + 1]].tolist() for e in range(4)] == want
+    ptr, val = ents.far_lists(hard_only=True)
+    assert [val[ptr[e]:ptr[e + 1]].tolist() for e in range(4)] == [[13], [], [], [32, 33, 34]]
+    rng = np.random.default_rng(0)
+    assert oi.sample_entries(7, rng).tolist() == list(range(7))
+    s = oi.sample_entries(1200, rng)
+    assert len(s) == 500 and len(set(s.tolist())) == 500 and s.max() < 1200

@@ -144,3 +144,91 @@ def test_hard_negatives_and_feature_space_top_k_match_kdtree_restating():
                     del want[i]
                 break
     assert got_dict == want and stats["n_q"] == n
+
+
+def _synthetic_overlap_step(rng, n_clouds=6, M=1024, N=4096, n_entries=(0, 30, 120, 700)):
+    """Centres per cloud (distinct FPS-like picks, one cloud with duplicated centre values), overlap entries per pair built so
+    that every skip rule of train_place_recognition.py:338-362 fires somewhere."""
+    from patchaugnet_b200 import overlap_indices as oi
+    centers = np.stack([rng.choice(N, M, replace=False) for _ in range(n_clouds)]).astype(np.int32)
+    centers[2, 100:110] = centers[2, 5]                                  # duplicated centre values: isin hits several positions
+    nn_dict, raw = {}, {}
+    pairs = [(0, 1), (0, 2), (3, 4), (5, 2)]
+    for (m, n), ne in zip(pairs, n_entries):
+        ents = []
+        for _ in range(ne):
+            kind = rng.integers(0, 10)
+            idx1 = int(rng.choice(centers[m])) if kind != 0 else int(N + 5)              # kind 0: idx1 not a centre of m
+            near = rng.choice(centers[n], rng.integers(1, 6)).tolist() + rng.integers(0, N, 3).tolist() if kind != 1 else [N + 7]
+            far = rng.choice(centers[n], rng.integers(1, 8)).tolist() if kind != 2 else []
+            bad = rng.choice(centers[n], rng.integers(0, 4)).tolist() if kind != 2 else []
+            ents.append((idx1, near, far, bad))
+        nn_dict[m, n] = oi.OverlapEntries.from_lists(ents)
+        raw[m, n] = ents
+    return centers, nn_dict, raw
+
+
+@pytest.mark.parametrize("hard_only", [False, True])
+def test_patch_triplet_selection_matches_the_restated_reference_loop(hard_only):
+    """pab_patch_triplets against oracle/patch_pairs.py (np.where / np.isin as in the reference)."""
+    from oracle import patch_pairs
+    from patchaugnet_b200 import overlap_indices as oi
+    rng = np.random.default_rng(11)
+    centers, nn_dict, raw = _synthetic_overlap_step(rng)
+    rows = {c: c for c in range(len(centers))}
+    batch = oi.TripletBatch(nn_dict, rows, hard_only=hard_only, rng=np.random.default_rng(3), device=DEV)
+    seed = 0x1234ABCD5678
+    i1, ip, ineg, count = oi.select_triplets(batch, torch.from_numpy(centers).to(DEV), seed=seed)
+    order_rng = np.random.default_rng(3)                                  # same entry order as the batch drew
+    total = 0
+    for p, (m, n) in enumerate(batch.pairs):
+        ent = nn_dict[m, n]
+        fptr, fval = ent.far_lists(hard_only)
+        order = oi.sample_entries(len(ent), order_rng)
+        entries = [(int(ent.idx1[e]), ent.near[ent.near_ptr[e]:ent.near_ptr[e + 1]].tolist(), fval[fptr[e]:fptr[e + 1]].tolist()) for e in order]
+        w1, wp, wn = patch_pairs.select_pair(centers[m], centers[n], entries, seed, p)
+        c = int(count[p])
+        assert c == len(w1), (p, c, len(w1))
+        assert i1[p, :c].cpu().tolist() == w1 and ip[p, :c].cpu().tolist() == wp and ineg[p, :c].cpu().tolist() == wn
+        total += c
+    assert int(count[0]) == 0 and total > 500                             # the empty pair yields nothing; the others are busy
+    # too little room: the call grows the output and returns the same triplets
+    j1, jp, jn, c2 = oi.select_triplets(batch, torch.from_numpy(centers).to(DEV), seed=seed, max_out=3)
+    assert torch.equal(c2, count) and torch.equal(j1[1, :int(count[1])], i1[1, :int(count[1])])
+
+
+def test_patch_feature_contrast_loss_matches_the_per_pair_loop():
+    from oracle import patch_pairs
+    from patchaugnet_b200 import losses, overlap_indices as oi
+    rng = np.random.default_rng(12)
+    centers, nn_dict, raw = _synthetic_overlap_step(rng, n_entries=(0, 25, 60, 90))
+    g = torch.Generator().manual_seed(4)
+    feats = [torch.randn(1024, 256, generator=g).to(DEV).requires_grad_(True) for _ in range(len(centers))]
+    cloud_indices = list(range(len(centers)))
+    center_indices = [torch.from_numpy(c[None]).to(DEV) for c in centers]
+    seed, margin = 77, 0.5
+    loss, used = oi.patch_feature_contrast_loss(nn_dict, cloud_indices, center_indices, feats, margin, seed=seed)
+    # the reference loop (:310-385) on the oracle's triplets
+    want, cnt = 0.0, 0
+    for p, (m, n) in enumerate(nn_dict):
+        ent = nn_dict[m, n]
+        fptr, fval = ent.far_lists(False)
+        entries = [(int(ent.idx1[e]), ent.near[ent.near_ptr[e]:ent.near_ptr[e + 1]].tolist(), fval[fptr[e]:fptr[e + 1]].tolist()) for e in range(len(ent))]
+        w1, wp, wn = patch_pairs.select_pair(centers[m], centers[n], entries, seed, p)
+        if not w1:
+            continue
+        q = [feats[m][k] for k in w1]; po = [feats[n][k] for k in wp]; ng = [feats[n][k] for k in wn]
+        want = want + losses.contrastive_loss(q, po, ng, margin)
+        cnt += 1
+    want = want / cnt
+    assert used == cnt == 3
+    assert abs(loss.item() - want.item()) < 1e-4 * max(1.0, abs(want.item()))
+    loss.backward()
+    zero = torch.zeros_like(feats[0])
+    g_new = [zero if f.grad is None else f.grad.clone() for f in feats]
+    for f in feats:
+        f.grad = None
+    want.backward()
+    for a, b in zip(g_new, feats):          # clouds outside every used pair get no gradient on either side
+        assert (a - (zero if b.grad is None else b.grad)).abs().max().item() < 1e-5
+    assert sum(f.grad is not None for f in feats) >= 4
