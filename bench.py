@@ -149,6 +149,7 @@ def main():
     ap.add_argument("--dense-streams", type=int, default=2)
     ap.add_argument("--tc-ctas", type=int, default=0, help="cap on persistent tensor-core CTAs (0 = one per SM)")
     ap.add_argument("--tc-tune", type=int, default=1, help="pab_tune_tensor_core bits (1 on, +4 CTA-pair multicast, +8 static tiles)")
+    ap.add_argument("--fp-order", type=int, default=1, help="FP modules walk their points in Morton order (0 = index order)")
     ap.add_argument("--fps-threads", type=int, default=0, help="force the FPS CTA size (0 = automatic)")
     ap.add_argument("--fps-cpc", type=int, default=1, help="clouds per FPS CTA in stream mode (1 or 2)")
     ap.add_argument("--prio", default="0,0", help="CUDA stream priorities geometry,dense (lower = higher priority)")
@@ -183,6 +184,7 @@ def main():
     L.lib().pab_tune_tensor_core(args.tc_tune)
     L.lib().pab_tune_fps_threads(args.fps_threads)
     eng.dense_streams = max(1, min(3, args.dense_streams))
+    eng.fp_row_order = bool(args.fp_order)
     eng.stream_priorities = tuple(int(v) for v in args.prio.split(","))
     lib = L.lib()
 

@@ -162,6 +162,17 @@ int pab_sa_module_forward(int b, int n, int m, int k, int nbr_stride, int c, con
 int pab_fp_module_forward(int b, int n, int m, int c_known, int c_skip, const float *known_feat, const float *skip_feat,
                           const int *idx, const float *weight, const pab_layer_t *layers, int n_layers,
                           float *out, pab_stream_t s);
+/* Same module with a processing order of each cloud's points: row_order[cloud * order_stride + i] = the point handled as the
+ * cloud's i-th row (a permutation of 0..n-1; NULL = index order).  Scheduling only — every point is computed once and stored at
+ * its own position, results are bit-identical; a spatial order (pab_knn_index_order) makes consecutive rows share their 3-NN
+ * rows of the known cloud in L1. */
+int pab_fp_module_forward_ordered(int b, int n, int m, int c_known, int c_skip, const float *known_feat, const float *skip_feat,
+                                  const int *idx, const float *weight, const int *row_order, long order_stride,
+                                  const pab_layer_t *layers, int n_layers, float *out, pab_stream_t s);
+/* The Morton-order permutation stored inside an index built by pab_knn_build_index (device pointer into `index`;
+ * *stride_ints = ints between consecutive clouds).  NULL when n is not a multiple of 64 (the index then has padding rows). */
+const int *pab_knn_index_order(int n, const void *index, long *stride_ints);
+
 
 /* Plain point-wise SharedMLP over rows: x (rows, c_in) -> out (rows, c_out_last). */
 int pab_pointwise_mlp_forward(int rows, const float *x, const pab_layer_t *layers, int n_layers, float *out, pab_stream_t s);

@@ -67,6 +67,8 @@ SIGNATURES = {
     "pab_three_nn_weights": (_I, [_I, _I, _I, _P, _P, _P, _P, _P]),
     "pab_sa_module_forward": (_I, [_I, _I, _I, _I, _I, _I, _P, _P, _P, _P, C.POINTER(PabLayer), _I, _P, _P, _P]),
     "pab_fp_module_forward": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, C.POINTER(PabLayer), _I, _P, _P]),
+    "pab_fp_module_forward_ordered": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _L, C.POINTER(PabLayer), _I, _P, _P]),
+    "pab_knn_index_order": (_P, [_I, _P, C.POINTER(_L)]),
     "pab_pointwise_mlp_forward": (_I, [_I, _P, C.POINTER(PabLayer), _I, _P, _P]),
     "pab_sa_layer_workspace_bytes": (_SZ, [_I, _I, _I]),
     "pab_sa_layer_forward": (_I, [_I, _I, _I, _P, C.POINTER(PabLayer), C.POINTER(PabLayer), C.POINTER(PabLayer), _P, _P, _P]),

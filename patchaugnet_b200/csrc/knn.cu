@@ -805,6 +805,14 @@ PAB_API size_t pab_knn_index_bytes(int b, int n) {
     return (size_t)b * idx_stride(n) * sizeof(float);
 }
 
+// The Morton permutation inside an index built by pab_knn_build_index: *stride_ints = ints between consecutive clouds.  Only
+// when the index has no padding rows (n a multiple of 64) — otherwise NULL.
+PAB_API const int *pab_knn_index_order(int n, const void *index, long *stride_ints) {
+    if (!index || !knn_index_ok(n) || idx_npad(n) != n) return nullptr;
+    if (stride_ints) *stride_ints = (long)idx_stride(n);
+    return reinterpret_cast<const int *>(index) + 3 * (size_t)idx_npad(n);
+}
+
 PAB_API int pab_knn_build_index(int b, int n, const float *xyz, void *index, pab_stream_t s) {
     if (b < 0 || !knn_index_ok(n) || !xyz || !index) return PAB_EINVAL;
     if (b == 0) return 0;

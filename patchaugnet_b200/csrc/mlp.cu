@@ -15,7 +15,8 @@ int pab_tc_eligible(const pab_layer_t *layers, int n_layers, int k_group, int al
 int pab_tc_sa(int kind, int b, int n, int m, int k, int nbr_stride, int c, const float *xyz, const float *feat, const int *center_idx,
               const int *nbr_idx, const pab_layer_t *layers, int n_layers, float *out, cudaStream_t st);
 int pab_tc_fp(int b, int n, int m, int c_known, int c_skip, const float *known_feat, const float *skip_feat, const int *idx,
-              const float *weight, const pab_layer_t *layers, int n_layers, float *out, cudaStream_t st);
+              const float *weight, const int *row_order, long order_stride, const pab_layer_t *layers, int n_layers, float *out,
+              cudaStream_t st);
 
 namespace {
 
@@ -236,18 +237,27 @@ PAB_API int pab_sa_module_forward(int b, int n, int m, int k, int nbr_stride, in
     return run(a, layers, n_layers, k, (cudaStream_t)s);
 }
 
-PAB_API int pab_fp_module_forward(int b, int n, int m, int c_known, int c_skip, const float *known_feat, const float *skip_feat,
-                                  const int *idx, const float *weight, const pab_layer_t *layers, int n_layers,
-                                  float *out, pab_stream_t s) {
+// row_order (optional): order[cloud * order_stride + i] = the point of the cloud processed as its i-th row; the tensor-core
+// kernel uses it for locality only (every point is computed once and stored at its own position: results are bit-identical)
+PAB_API int pab_fp_module_forward_ordered(int b, int n, int m, int c_known, int c_skip, const float *known_feat, const float *skip_feat,
+                                          const int *idx, const float *weight, const int *row_order, long order_stride,
+                                          const pab_layer_t *layers, int n_layers, float *out, pab_stream_t s) {
     if (b < 0 || n < 0 || m <= 0 || c_known <= 0 || c_skip < 0 || !layers) return PAB_EINVAL;
     if (layers[0].c_in != c_known + c_skip || (c_skip > 0 && !skip_feat)) return PAB_EINVAL;
     if (c_known % 8 == 0 && pab_tc_eligible(layers, n_layers, 0, 0) == 1 && layers[0].tc_k0 == 0 &&
         ((layers[0].tc_k == c_known && c_skip <= 3) || (layers[0].tc_k == c_known + c_skip && c_skip % 8 == 0)))
-        return pab_tc_fp(b, n, m, c_known, c_skip, known_feat, skip_feat, idx, weight, layers, n_layers, out, (cudaStream_t)s);
+        return pab_tc_fp(b, n, m, c_known, c_skip, known_feat, skip_feat, idx, weight, row_order, order_stride, layers, n_layers, out,
+                         (cudaStream_t)s);
     MlpArgs a{};
     a.mode = MODE_FP; a.rows = (long)b * n; a.n = n; a.m = m; a.c_known = c_known; a.c_skip = c_skip;
     a.known_feat = known_feat; a.skip_feat = skip_feat; a.idx3 = idx; a.w3 = weight; a.out = out;
     return run(a, layers, n_layers, 0, (cudaStream_t)s);
+}
+
+PAB_API int pab_fp_module_forward(int b, int n, int m, int c_known, int c_skip, const float *known_feat, const float *skip_feat,
+                                  const int *idx, const float *weight, const pab_layer_t *layers, int n_layers,
+                                  float *out, pab_stream_t s) {
+    return pab_fp_module_forward_ordered(b, n, m, c_known, c_skip, known_feat, skip_feat, idx, weight, nullptr, 0, layers, n_layers, out, s);
 }
 
 int pab_pointwise_mlp_residual(int rows, const float *x, const pab_layer_t *layers, int n_layers, const float *residual,

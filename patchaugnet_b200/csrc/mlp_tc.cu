@@ -30,12 +30,15 @@ using namespace tc;
 
 constexpr int NBLK_MAX = 128;                 // max output channels per weight stage (UMMA N)
 constexpr int NEPI = 256;                     // epilogue threads (warps 2..9)
-constexpr int NLOAD = 128;                    // loader threads (warps 10..13)
+constexpr int NLOAD = 192;                    // loader threads (warps 10..15); the SA gathers use the first four warps only
+constexpr int NLOAD_SA = 128;
 constexpr int TC_THREADS = 64 + NEPI + NLOAD;
 constexpr int MAX_STAGES = 8;
 constexpr int MAX_LAYERS = 3;
 constexpr int D_COLS = 256;                   // accumulator columns; TMEM columns [256,384) = hi plane, [384,512) = lo plane
 constexpr uint32_t AH_COL = 256, AL_COL = 384;
+constexpr uint32_t XTRA_COL = 64;             // plane columns [64,80) hold layer 0's xyz extras: the epilogue of a split pass's first
+                                              // n-block rewrites columns [0,64) while the second n-block's MMAs still read the extras
 constexpr int STG_COLS = 64;                  // fp32 staging of the last layer: [128 rows][64 columns]
 constexpr int STG_PITCH = STG_COLS + 4;        // floats per staged row: 68 = 4 mod 32 keeps row-wise 16-byte writes and column-wise reads conflict-free
 constexpr int STG_BYTES = TM * STG_PITCH * 4;                      // SA: one CTA-wide tile (rows of a group span warps)
@@ -75,6 +78,8 @@ struct alignas(64) TcArgs {
     const float *known_feat, *skip_feat;
     const int *idx3;
     const float *w3;
+    const int *row_order;                      // optional processing order of a cloud's points (NULL: index order)
+    long order_stride;                         // ints between the orders of consecutive clouds
     float *out;
     long long *trace;                          // optional timeline of CTA 0 (pab_tune_tc_trace), [tile][phase][event] clock64 stamps
 };
@@ -116,11 +121,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     uint64_t *empty = full + MAX_STAGES;
     uint64_t *a_full = empty + MAX_STAGES;                         // loaders -> MMA: layer-0 operand of the tile staged
     uint64_t *a_empty = a_full + 1;                                // MMA -> loaders: layer-0 MMAs of the tile completed
-    uint64_t *d_ready = a_full + 2;                                // MMA -> epilogue: accumulators of the phase complete
-    uint64_t *t_ready = a_full + 3;                                // epilogue -> MMA: D drained (+ next operand in TMEM)
+    // MMA <-> epilogue hand-off, per accumulator PASS (<= 256 columns).  A pass made of two 128-column n-blocks is pipelined
+    // at n-block granularity ("split" pass): d_ready[i] = n-block i accumulated, t_ready[i] = its columns drained and (not the
+    // last layer) its half of the next operand written to the TMEM planes, p_free = the MMAs of n-block 1 no longer read the
+    // plane columns n-block 0's epilogue overwrites.  Every pass completes exactly one phase of each of the five barriers.
+    uint64_t *d_ready = a_full + 2;                                // MMA -> epilogue: n-block 0 (or the whole unsplit pass)
+    uint64_t *t_ready = a_full + 3;                                // epilogue -> MMA: D columns [0,128) / plane columns [0,64)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_full + 4);
     uint64_t *tq_full = a_full + 5;                                // dynamic tile queue: entry i published (ring of 8)
     int *tile_list = reinterpret_cast<int *>(tq_full + 8);         // [8] tile index or -1 (no more tiles)
+    uint64_t *d_ready1 = reinterpret_cast<uint64_t *>(misc + 272);  // n-block 1
+    uint64_t *t_ready1 = d_ready1 + 1;                             // D columns [128,256) / plane columns [64,128) (+ next tile's extras)
+    uint64_t *p_free = d_ready1 + 2;
     float *ctab = reinterpret_cast<float *>(misc + 384);           // [shift of every layer | pre layer]
 
     const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
@@ -132,10 +144,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
 
     if (tid == 0) {
         for (int s = 0; s < a.n_stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, a.csize); }
-        mbar_init(a_full, NLOAD);
+        mbar_init(a_full, a.mode == TC_FP ? NLOAD : NLOAD_SA);
         mbar_init(a_empty, 1);
         mbar_init(d_ready, 1);
         mbar_init(t_ready, NEPI);
+        mbar_init(d_ready1, 1);
+        mbar_init(t_ready1, NEPI);
+        mbar_init(p_free, 1);
         for (int i = 0; i < 8; ++i) mbar_init(tq_full + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -169,6 +184,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         if (!a.dynamic) return i < (uint32_t)a.iters ? (int)(blockIdx.x + i * gridDim.x) : -1;
         mbar_wait(tq_full + (i & 7), (i >> 3) & 1);
         return tile_list[i & 7];
+    };
+
+    // FP: the point a global row stands for.  With a row order (the Morton order of the level's spatial index) consecutive
+    // rows are neighbours in space and share their 3-NN rows of the known cloud, so the loaders' gathers hit in L1 instead of
+    // going to L2 one 1-KB row each; every point is still computed exactly once and stored at its own position.
+    auto point_of = [&](long gr) -> long {
+        if (!a.row_order) return gr;
+        const long cloud = gr / a.n;
+        return cloud * a.n + __ldg(a.row_order + cloud * a.order_stride + (gr - cloud * a.n));
     };
 
     if (warp == 0) {
@@ -216,6 +240,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         const uint32_t st_lo = umma_desc_lo(smem_u32(stages));
         constexpr uint32_t st_step = (NBLK_MAX * 128) >> 4;
         uint32_t s = 0, ph = 0, pcount = 0, tcount = 0, gcount = 0;
+        bool t1_pending = false;
         for (int it = 0; tile_at((uint32_t)it) >= 0; ++it, ++tcount) {
             for (int l = 0; l < a.n_layers; ++l) {
                 const int ksteps = a.ksteps[l], nkc_main = (ksteps + 3) >> 2;
@@ -226,20 +251,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                 for (int g = 0; g < ngroups; ++g) {
                 if (l == 0) mbar_wait(a_full, gcount & 1);       // this group of layer-0 operand chunks is staged
                 const int kc_lo = g * gc, kc_hi = g == ngroups - 1 ? nkc : (g + 1) * gc;
+                const bool last_g = g == ngroups - 1;
                 for (int nb = 0; nb < nnb; ++nb) {
                     const int nbp = nb % nb_pass;
-                    if (nbp == 0 && g == 0) {                    // new pass: the epilogue has drained D (and written the operand planes)
+                    const bool split = nbr == NBLK_MAX && nb_pass == 2 && nb - nbp + 2 <= nnb;   // this pass has two 128-column n-blocks
+                    if (nbp == 0 && g == 0) {                    // new pass: the epilogue has drained D[0,128) (and written planes [0,64))
                         mbar_wait(t_ready, pcount & 1);
                         tc_fence_after();
+                        t1_pending = true;
                         TC_TRACE(it, l, 0);
                     }
+                    if (nbp == 1 && t1_pending) {                // second n-block: D[128,256) drained
+                        mbar_wait(t_ready1, pcount & 1);
+                        tc_fence_after();
+                        t1_pending = false;
+                    }
                     const uint32_t d = tmem + (uint32_t)(nbp * nbr);
+                    const int kc_free = min(kc_lo + 1, kc_hi - 1);   // after this chunk of n-block 1 plane columns [0,64) are dead
                     for (int kc = kc_lo; kc < kc_hi; ++kc) {
-                        const bool xk = kc >= nkc_main;          // the extras' chunk: k-step 0 only, operand in plane columns 0..7
+                        const bool xk = kc >= nkc_main;          // the extras' chunk: k-step 0 only, operand in plane columns XTRA_COL..
                         const bool from_smem = l == 0 && !xk;
                         const int kn = xk ? 1 : min(4, ksteps - 4 * kc);
                         const uint32_t ka = (uint32_t)(kc - kc_lo) * (A_CHUNK >> 4);
-                        const uint32_t ta = xk ? 0u : (uint32_t)(kc * 32);
+                        const uint32_t ta = xk ? XTRA_COL : (uint32_t)(kc * 32);
+                        if (!from_smem && ta >= 64 && t1_pending) {  // operand columns the previous pass's second half wrote
+                            mbar_wait(t_ready1, pcount & 1);
+                            tc_fence_after();
+                            t1_pending = false;
+                        }
                         // hi weight plane: hi(A) * hi(W) + lo(A) * hi(W)
                         mbar_wait(full + s, ph);
                         uint32_t sb = st_lo + s * st_step;
@@ -275,11 +314,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                         if (a.csize == 1) umma_commit_if(leader, empty + s);
                         else umma_commit_mc_if(leader, empty + s, cmask_all);
                         if (++s == (uint32_t)a.n_stages) { s = 0; ph ^= 1; }
+                        if (split && last_g && nbp == 1 && kc == kc_free) umma_commit_if(leader, p_free);
                     }
-                    if (g == ngroups - 1 && (nbp == nb_pass - 1 || nb == nnb - 1)) {
-                        umma_commit_if(leader, d_ready);         // accumulators of this pass complete
-                        ++pcount;
-                        TC_TRACE(it, l, 1);
+                    if (last_g) {
+                        const bool pass_end = nbp == nb_pass - 1 || nb == nnb - 1;
+                        if (split) {
+                            umma_commit_if(leader, nbp == 0 ? d_ready : d_ready1);   // this n-block's accumulators complete
+                        } else if (pass_end) {
+                            umma_commit_if(leader, d_ready);
+                            umma_commit_if(leader, d_ready1);
+                            umma_commit_if(leader, p_free);
+                        }
+                        if (pass_end) {
+                            if (t1_pending) {                    // nothing in this pass needed the second half: consume the phase
+                                mbar_wait(t_ready1, pcount & 1);
+                                t1_pending = false;
+                            }
+                            ++pcount;
+                            TC_TRACE(it, l, 1);
+                        }
                     }
                 }
                 if (l == 0) { umma_commit_if(leader, a_empty); ++gcount; }   // operand group consumed: loaders may stage the next one
@@ -315,9 +368,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                     for (int e = 0; e < 3; ++e) xe[e] = __ldg(a.xyz + pn * 3 + e) - __ldg(a.xyz + pc * 3 + e);
                 }
             } else {
-                const long p = (long)tile * TM + row;
-                if (p < a.rows)
+                const long gr = (long)tile * TM + row;
+                if (gr < a.rows) {
+                    const long p = point_of(gr);
                     for (int e = 0; e < a.n_extra; ++e) xe[e] = __ldg(a.skip_feat + p * a.c_skip + e);
+                }
             }
         };
         auto store_extras = [&](const float (&xe)[3]) {
@@ -326,8 +381,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             for (int i = 0; i < 16; ++i) hi[i] = lo[i] = 0u;
             split_pack(xe[0], xe[1], hi[0], lo[0]);
             split_pack(xe[2], 0.f, hi[1], lo[1]);
-            tmem_st16(trow + AH_COL, hi);
-            tmem_st16(trow + AL_COL, lo);
+            tmem_st16(trow + AH_COL + XTRA_COL, hi);
+            tmem_st16(trow + AL_COL + XTRA_COL, lo);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         };
         const bool xwriter = a.n_extra > 0 && half == 0;
@@ -339,10 +394,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         }
         tc_fence_before();
         mbar_arrive(t_ready);                                  // completion #0: the MMA warp may start the first phase
+        mbar_arrive(t_ready1);
 
         for (int it = 0; tile >= 0; ++it) {                        // static cluster mode: trailing tiles >= ntiles are empty
             const int tile_next = tile_at((uint32_t)it + 1);
             if (xwriter && tile_next >= 0) load_extras(tile_next, xe_next);              // consumed at the end of this tile
+            int out_pt[4] = {-1, -1, -1, -1};                     // FP: points of the rows this lane stores (row r8*8 + lane/4 of the quarter)
+            if (a.mode == TC_FP) {
+#pragma unroll
+                for (int r8 = 0; r8 < 4; ++r8) {
+                    const long gr = (long)tile * TM + q * 32 + r8 * 8 + (lane >> 2);
+                    out_pt[r8] = gr < a.rows ? (int)point_of(gr) : -1;
+                }
+            }
             for (int l = 0; l < a.n_layers; ++l) {
                 const int N = a.N[l];
                 const bool last = l == a.n_layers - 1;
@@ -351,13 +415,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                 const int npass = (N + D_COLS - 1) / D_COLS;
                 for (int pass = 0; pass < npass; ++pass, ++pcount) {
                     const int ncols = min(D_COLS, N - pass * D_COLS);  // accumulator columns of this pass
-                    const int per = ncols >= 64 ? ncols / 2 : ncols;    // columns per worker half (batches of 32)
+                    // split pass (two 128-column n-blocks): segment i = n-block i, each half of the workers takes 64 of its columns
+                    // as soon as THAT n-block is accumulated; otherwise one segment, the halves share the pass's columns
+                    const bool split = ncols == D_COLS;
+                    const int nseg = split ? 2 : 1;
+                    const int per = split ? 64 : (ncols >= 64 ? ncols / 2 : ncols);   // columns per worker half and segment (batches of 32)
                     const bool active = ncols >= 64 || half == 0;
-                    mbar_wait(d_ready, pcount & 1);
+                    for (int seg = 0; seg < nseg; ++seg) {
+                    const int segbase = split ? seg * NBLK_MAX : 0;
+                    mbar_wait(seg == 0 ? d_ready : d_ready1, pcount & 1);
+                    if (!split) mbar_wait(d_ready1, pcount & 1);
                     tc_fence_after();
-                    if (ewarp == 0) TC_TRACE(it, l, 2);
+                    if (ewarp == 0) TC_TRACE(it, l, (split && seg == 0) ? 7 : 2);
                     for (int cb = 0; cb < per; cb += 32) {
-                        const int dcol = (ncols >= 64 ? half * per : 0) + cb;          // first accumulator column of this batch
+                        const int dcol = segbase + (ncols >= 64 ? half * per : 0) + cb;  // first accumulator column of this batch
                         const int col = pass * D_COLS + dcol;                          // output channel
                         float v[32];
                         if (active) {
@@ -373,22 +444,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                             }
                         }
                         if (!last) {
-                            if (active) {                       // next layer's operand: bf16 pairs into the TMEM planes
-                                uint32_t hi[16], lo[16];
+                            uint32_t hi[16], lo[16];
+                            if (active) {
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) split_pack(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+                            }
+                            if (seg == 0 && cb == 0) {           // plane columns [0,64) are still read by the second n-block's MMAs
+                                mbar_wait(p_free, pcount & 1);
+                                tc_fence_after();
+                            }
+                            if (active) {                       // next layer's operand: bf16 pairs into the TMEM planes
                                 tmem_st16(trow + AH_COL + (uint32_t)(dcol >> 1), hi);
                                 tmem_st16(trow + AL_COL + (uint32_t)(dcol >> 1), lo);
                             }
                         } else {
                             const bool final_batch = cb + 32 >= per;
-                            if (final_batch) {                   // every accumulator column of the pass has been read
-                                // last pass of the tile: the operand planes are free (this layer's MMAs completed before
+                            if (final_batch) {                   // every accumulator column of the segment has been read
+                                // last segment of the tile: the operand planes are free (this layer's MMAs completed before
                                 // d_ready): stage the next tile's layer-0 extras there before releasing the MMA warp
-                                if (xwriter && pass == npass - 1 && tile_next >= 0) store_extras(xe_next);
+                                if (xwriter && pass == npass - 1 && seg == nseg - 1 && tile_next >= 0) store_extras(xe_next);
                                 tc_fence_before();
                                 if (ewarp == 0) TC_TRACE(it, l, 3);
-                                mbar_arrive(t_ready);
+                                mbar_arrive(seg == 0 ? t_ready : t_ready1);
+                                if (!split) mbar_arrive(t_ready1);
                             }
                             if (a.mode == TC_SA) {
                                 // one staging round: 32 columns of each half -> [128][64] fp32 -> max over the K rows of a group
@@ -408,7 +486,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                                     const float *scol = reinterpret_cast<const float *>(stg) + (g * a.k) * STG_PITCH + c;
                                     float mx = scol[0];
                                     for (int sidx = 1; sidx < a.k; ++sidx) mx = fmaxf(mx, scol[sidx * STG_PITCH]);
-                                    const int oc = pass * D_COLS + (c >> 5) * per + cb + (c & 31);
+                                    const int oc = pass * D_COLS + segbase + (c >> 5) * per + cb + (c & 31);
                                     a.out[ci * N + oc] = mx;
                                 }
                                 asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");   // staging consumed before it is rewritten
@@ -428,8 +506,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
 #pragma unroll
                                     for (int r8 = 0; r8 < 4; ++r8) {
                                         const int r = r8 * 8 + (lane >> 2);         // row of this warp's quarter
-                                        const long p = (long)tile * TM + q * 32 + r;
-                                        if (p < a.rows)
+                                        const long p = out_pt[r8];   // rows < 2^31 (checked by the launcher)
+                                        if (p >= 0)
                                             *reinterpret_cast<float4 *>(a.out + p * N + col + 16 * sb + 4 * u) =
                                                 *reinterpret_cast<const float4 *>(ws + r * 16 + ((u ^ ((r >> 1) & 3)) << 2));
                                     }
@@ -441,18 +519,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                         tc_fence_before();
                         if (ewarp == 0) TC_TRACE(it, l, 3);
-                        mbar_arrive(t_ready);
+                        mbar_arrive(seg == 0 ? t_ready : t_ready1);
+                        if (!split) mbar_arrive(t_ready1);
                     } else if (ewarp == 0) {
                         TC_TRACE(it, l, 6);                      // output of the tile stored
+                    }
                     }
                 }
             }
             tile = tile_next;
         }
-    } else {
+    } else if (a.mode == TC_FP || tid < 64 + NEPI + NLOAD_SA) {
         // ================= loader warps: stage the layer-0 operand (hi/lo planes) of the next tile =================
-        const int lt = tid - 64 - NEPI;                      // 0..127
-        const int lwarp = lt >> 5;                           // 0..3, rows [32*lwarp, 32*lwarp + 32)
+        const int lt = tid - 64 - NEPI;                      // 0..191
+        const int lwarp = lt >> 5;                           // 0..5; SA: rows [32*lwarp, 32*lwarp + 32) of warps 0..3
         const int units0 = ((a.ksteps[0] + 3) >> 2) * 8;     // 16-byte units per operand row (whole 64-chunks)
         const int gunits = a.gchunks * 8;                    // units per operand group (one group = the whole row unless K is wide)
         const int ngroups = (units0 + gunits - 1) / gunits;
@@ -603,16 +683,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                 }
                 }
             } else {
-                // FP: lane r holds the three neighbour indices / weights of row 32*lwarp + r; rows are staged four at a
+                // FP: every lane holds the three neighbour indices / weights of one row of its warp; rows are staged four at a
                 // time (24 x 16-byte gathers in flight per lane), indices and weights broadcast by shuffles
                 const int ku = a.c_known / 8;
-                long my_base = -1;
+                // the 32 batches of four rows are dealt round-robin to the six warps (batch = lwarp + 6*(lane/4)), so at any time the
+                // warps work on 24 consecutive rows: with a spatial row order they share most of their known rows in L1.  The
+                // gathers are latency-bound (registers cap the loads a warp keeps in flight), hence as many warps as the register
+                // file allows: 512 threads x 128 registers
+                int my_base = -1, my_p = -1;
                 int my_i[3] = {0, 0, 0};
                 float my_w[3] = {0.f, 0.f, 0.f};
                 {
-                    const long p = (long)tile * TM + lwarp * 32 + lane;
-                    if (p < a.rows) {
-                        my_base = (p / a.n) * a.m;
+                    constexpr int LW = NLOAD / 32;
+                    const int batch = lwarp + LW * (lane >> 2);
+                    const long gr = (long)tile * TM + 4 * batch + (lane & 3);
+                    if (batch < TM / 4 && gr < a.rows) {
+                        const long p = point_of(gr);
+                        my_p = (int)p;
+                        my_base = (int)((p / a.n) * a.m);
 #pragma unroll
                         for (int e = 0; e < 3; ++e) { my_i[e] = __ldg(a.idx3 + p * 3 + e); my_w[e] = __ldg(a.w3 + p * 3 + e); }
                     }
@@ -620,13 +708,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                 for (int g = 0; g < ngroups; ++g) {
                 const int j_lo = g * gunits, j_hi = min(units0, j_lo + gunits);
                 if (gcount > 0) mbar_wait(a_empty, (gcount - 1) & 1);
-                for (int rr = 0; rr < 32; rr += 4) {
+                for (int rr = 0; 6 * rr + 4 * lwarp < TM; rr += 4) {          // batch = lwarp + 6 * (rr / 4), rows 4 * batch ..
                     const float *f0[4], *f1[4], *f2[4];
                     float w0[4], w1[4], w2[4];
                     bool ok[4];
+                    int pt[4];
 #pragma unroll
                     for (int t4 = 0; t4 < 4; ++t4) {
-                        const long base = __shfl_sync(0xffffffffu, my_base, rr + t4);
+                        const int base = __shfl_sync(0xffffffffu, my_base, rr + t4);
+                        pt[t4] = __shfl_sync(0xffffffffu, my_p, rr + t4);
                         const int i0 = __shfl_sync(0xffffffffu, my_i[0], rr + t4), i1 = __shfl_sync(0xffffffffu, my_i[1], rr + t4),
                                   i2 = __shfl_sync(0xffffffffu, my_i[2], rr + t4);
                         w0[t4] = __shfl_sync(0xffffffffu, my_w[0], rr + t4); w1[t4] = __shfl_sync(0xffffffffu, my_w[1], rr + t4);
@@ -662,9 +752,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
 #pragma unroll
                             for (int t4 = 0; t4 < 4; ++t4) {
                                 float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
-                                const long p = (long)tile * TM + lwarp * 32 + rr + t4;
                                 if (ok[t4] && 8 * (j - ku) < a.c_skip) {
-                                    const float4 *sk = reinterpret_cast<const float4 *>(a.skip_feat + p * a.c_skip) + 2 * (j - ku);
+                                    const float4 *sk = reinterpret_cast<const float4 *>(a.skip_feat + (long)pt[t4] * a.c_skip) + 2 * (j - ku);
                                     s0 = __ldg(sk); s1 = __ldg(sk + 1);
                                 }
                                 v[t4][0] = s0.x; v[t4][1] = s0.y; v[t4][2] = s0.z; v[t4][3] = s0.w;
@@ -677,7 +766,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) v[t4][i] = 0.f;
                             }
-                            store_units(a1, a2, lwarp * 32 + rr + t4, j - j_lo, v[t4]);
+                            store_units(a1, a2, 6 * rr + 4 * lwarp + t4, j - j_lo, v[t4]);
                         }
                     }
                 }
@@ -817,6 +906,7 @@ int pab_tc_launch(int mode, long rows, int k_group, const pab_layer_t *all_layer
     if (!tc_plan(layers, n_layers, pre, mode, &p)) return PAB_EINVAL;
     a.a_region = p.a_region; a.gchunks = p.gchunks; a.n_stages = p.n_stages;
     const long per_tile = mode == TC_SA ? (TM / k_group) : TM;
+    if (rows >= (1L << 31)) return PAB_EINVAL;
     a.ntiles = (int)((rows + per_tile - 1) / per_tile);
     if (a.ntiles == 0) return 0;
     static int n_sm = 0;
@@ -899,8 +989,10 @@ int pab_tc_sa(int kind, int b, int n, int m, int k, int nbr_stride, int c, const
 }
 
 int pab_tc_fp(int b, int n, int m, int c_known, int c_skip, const float *known_feat, const float *skip_feat, const int *idx,
-              const float *weight, const pab_layer_t *layers, int n_layers, float *out, cudaStream_t st) {
+              const float *weight, const int *row_order, long order_stride, const pab_layer_t *layers, int n_layers, float *out,
+              cudaStream_t st) {
     TcArgs a{};
+    a.row_order = row_order; a.order_stride = order_stride;
     a.n = n; a.m = m; a.c_known = c_known; a.c_skip = c_skip; a.known_feat = known_feat; a.skip_feat = skip_feat;
     a.idx3 = idx; a.w3 = weight; a.out = out;
     return pab_tc_launch(TC_FP, (long)b * n, 0, layers, n_layers, 1, a, st);

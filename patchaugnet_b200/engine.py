@@ -115,6 +115,7 @@ class FusedPatchAugNet:
         self._event_filter = None
         self._streams = None
         self.vlad_tensor_core = True
+        self.fp_row_order = True        # FP modules walk their points in the Morton order of the level's spatial index
         self.dense_streams = 2          # dense kernels of consecutive batches alternate between two streams
         self.stream_priorities = (0, 0)
         self.reserve_fps_sms = True     # forward_stream: persistent tensor-core kernels leave the FPS CTAs' SMs alone
@@ -279,9 +280,14 @@ class FusedPatchAugNet:
             c_skip = skip.shape[2]
             if li == 0 and not self.use_origin:
                 skip, c_skip = None, 0
-            run(f"fp{li}", lambda: lib.pab_fp_module_forward(B, n, m, known_feat.shape[2], c_skip, p(known_feat), p(skip),
-                                                             p(f["idx"]), p(f["w"]), self.fp[li].arr, self.fp[li].n,
-                                                             p(f["out"]), st))
+            # rows in the Morton order of the level's spatial index (when it has one): neighbouring rows share their 3-NN rows
+            order, stride = None, C.c_long(0)
+            uindex = ws["levels"][li]["index"] if (self.fp_row_order and li < len(ws["levels"])) else None
+            if uindex is not None:
+                order = lib.pab_knn_index_order(n, p(uindex), C.byref(stride))
+            run(f"fp{li}", lambda: lib.pab_fp_module_forward_ordered(B, n, m, known_feat.shape[2], c_skip, p(known_feat), p(skip),
+                                                                     p(f["idx"]), p(f["w"]), C.c_void_p(order), stride.value,
+                                                                     self.fp[li].arr, self.fp[li].n, p(f["out"]), st))
             known_feat = f["out"]
         # fp_features order of the reference: [l2 (128), l1 (1024), l0 (4096)] <-> vlads[0..2]
         fp_out = [ws["fp"][i]["out"] for i in range(len(self.fp) - 1, -1, -1)]

@@ -36,12 +36,12 @@ cta = snap["t"].cpu()[512:].view(148, 2)
 fine = snap["t"].cpu()[256:512]
 t = snap["t"].cpu()[:256].view(8, 4, 8)
 t0 = int(t[t > 0].min())
-names = ["mma_start", "mma_end", "acc_seen", "epi_done", "load_start", "staged", "stored", "-"]
+names = ["mma_start", "mma_end", "acc_seen", "epi_done", "load_start", "staged", "stored", "acc0_seen"]
 for tile in range(6):
     for l in range(4):
         row = t[tile, l]
         if (row > 0).any():
-            print(f"tile {tile} layer {l}: " + "  ".join(f"{names[e]}={int(row[e]) - t0:>7d}" for e in range(7) if row[e] > 0))
+            print(f"tile {tile} layer {l}: " + "  ".join(f"{names[e]}={int(row[e]) - t0:>7d}" for e in range(8) if row[e] > 0))
 
 st, en = cta[:, 0], cta[:, 1]
 ok = st > 0
