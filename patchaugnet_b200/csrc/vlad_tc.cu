@@ -16,6 +16,7 @@
 #include "tc_common.cuh"
 
 extern int g_tc_max_ctas;   // mlp_tc.cu
+extern long long *g_tc_trace;   // mlp_tc.cu: optional timeline buffer (pab_tune_tc_trace), here [tile < 16][8 events] of CTA 0
 
 namespace {
 
@@ -27,6 +28,10 @@ constexpr int VT_ROWS_MIN = 256;               // smallest work item (rows of on
 #ifndef VT_ROWS_BIG
 #define VT_ROWS_BIG 512                        // work item of large clouds (n >= 2048)
 #endif
+#define VT_TRACE(ev)                                                                             \
+    do {                                                                                         \
+        if (a.trace && blockIdx.x == 0 && tcount < 16 && wt == 0) a.trace[tcount * 8 + (ev)] = clock64(); \
+    } while (0)
 constexpr int VT_C = 256;                     // channels (4 chunks of 64)
 
 struct VtArgs {
@@ -34,6 +39,7 @@ struct VtArgs {
     const float *x, *shift;
     const __nv_bfloat16 *wc_hi, *wc_lo;       // (Kp, 256) K-major, bn1 scale folded, rows >= K zero
     float *part, *asum;
+    long long *trace;
 };
 
 // MN-major SWIZZLE_128B descriptor over the x planes: 64-channel blocks (one K chunk each) are LBO = A_CHUNK bytes apart,
@@ -54,16 +60,17 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vlad_tc_kernel(const VtArgs a) 
     uint8_t *w1 = x2 + 4 * A_CHUNK;                                // Wc hi: 4 chunks x [Kp][64]
     const int wchunk = a.Kp * 128;
     uint8_t *w2 = w1 + 4 * wchunk;
-    uint8_t *p1 = w2 + 4 * wchunk;                                 // act^T hi: 2 chunks x [Kp][64 pts]
-    uint8_t *p2 = p1 + 2 * wchunk;
-    uint8_t *misc = p2 + 2 * wchunk;
+    uint8_t *p1 = w2 + 4 * wchunk;                                 // act hi: [128 pts][64 clusters] bf16, 128-byte swizzled rows —
+    uint8_t *p2 = p1 + A_CHUNK;                                    // GEMM2's B operand read MN-major (a point's clusters are contiguous)
+    uint8_t *misc = p2 + A_CHUNK;
     uint64_t *a_ready = reinterpret_cast<uint64_t *>(misc);        // x planes staged            (256 arrivals)
     uint64_t *d1_ready = a_ready + 1;                              // logits in TMEM             (tcgen05.commit)
     uint64_t *p_ready = a_ready + 2;                               // act^T planes staged        (128 arrivals)
     uint64_t *g2_done = a_ready + 3;                               // GEMM2 of the tile finished (tcgen05.commit)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_ready + 4);
-    float *asum_s = reinterpret_cast<float *>(misc + 64);          // [Kp]
-    float *xmax = reinterpret_cast<float *>(misc + 64 + 256);      // [2][128] row maxima of the two column halves
+    float *shift_s = reinterpret_cast<float *>(misc + 64);         // [64] bn1 shift of the clusters (zero beyond K)
+    float *xmax = reinterpret_cast<float *>(misc + 64 + 256);      // [2][128] row maxima of the two column halves; after the softmax
+    float *psum = xmax;                                            //   [4 lane quarters][64] per-warp column sums of act (a_sum)
     float *xsum = xmax + 2 * TM;                                   // [2][128] row sums
     const bool split = a.Kp > 32;
 
@@ -83,6 +90,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vlad_tc_kernel(const VtArgs a) 
         *reinterpret_cast<uint4 *>(w1 + off) = __ldg(reinterpret_cast<const uint4 *>(a.wc_hi + (size_t)k * VT_C) + j);
         *reinterpret_cast<uint4 *>(w2 + off) = __ldg(reinterpret_cast<const uint4 *>(a.wc_lo + (size_t)k * VT_C) + j);
     }
+    if (tid < 64) shift_s[tid] = tid < a.K ? __ldg(a.shift + tid) : 0.f;
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -94,10 +102,10 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vlad_tc_kernel(const VtArgs a) 
         // all lanes run the loops, one elected lane issues (tc_common.cuh: warp-uniform issue path)
         const uint32_t leader = elect_one();
         uint32_t tcount = 0;
-        const uint32_t id1 = umma_idesc(a.Kp), id2 = umma_idesc_amn(a.Kp);
+        const uint32_t id1 = umma_idesc(a.Kp), id2 = umma_idesc_amn(a.Kp) | (1u << 16);   // GEMM2: A and B MN-major
         const uint32_t x1_lo = umma_desc_lo(smem_u32(x1)), x2_lo = umma_desc_lo(smem_u32(x2));
         const uint32_t w1_lo = umma_desc_lo(smem_u32(w1)), w2_lo = umma_desc_lo(smem_u32(w2));
-        const uint32_t p1_lo = umma_desc_lo(smem_u32(p1)), p2_lo = umma_desc_lo(smem_u32(p2));
+        const uint32_t p1_lo = umma_desc_mn_lo(smem_u32(p1)), p2_lo = umma_desc_mn_lo(smem_u32(p2));
         const uint32_t xm1_lo = umma_desc_mn_lo(smem_u32(x1)), xm2_lo = umma_desc_mn_lo(smem_u32(x2));
         const uint32_t wstep = (uint32_t)wchunk >> 4;
         for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
@@ -124,12 +132,37 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vlad_tc_kernel(const VtArgs a) 
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks) {            // 16 points per MMA
                         const uint32_t xa = (uint32_t)(2 * cb) * (A_CHUNK >> 4) + (uint32_t)ks * (2048 >> 4);
-                        const uint32_t pb = (uint32_t)(ks >> 2) * wstep + 2 * (ks & 3);
-                        umma_f16_if(leader, d2 + cb * 64, xm1_lo + xa, UMMA_DESC_MN_HI, p1_lo + pb, UMMA_DESC_HI, id2, (t_in_item | ks) != 0);
-                        umma_f16_if(leader, d2 + cb * 64, xm2_lo + xa, UMMA_DESC_MN_HI, p1_lo + pb, UMMA_DESC_HI, id2, 1);
-                        umma_f16_if(leader, d2 + cb * 64, xm1_lo + xa, UMMA_DESC_MN_HI, p2_lo + pb, UMMA_DESC_HI, id2, 1);
+                        const uint32_t pb = (uint32_t)ks * (2048 >> 4);   // 16 points = two 8-row swizzle atoms
+                        umma_f16_if(leader, d2 + cb * 64, xm1_lo + xa, UMMA_DESC_MN_HI, p1_lo + pb, UMMA_DESC_MN_HI, id2, (t_in_item | ks) != 0);
+                        umma_f16_if(leader, d2 + cb * 64, xm2_lo + xa, UMMA_DESC_MN_HI, p1_lo + pb, UMMA_DESC_MN_HI, id2, 1);
+                        umma_f16_if(leader, d2 + cb * 64, xm1_lo + xa, UMMA_DESC_MN_HI, p2_lo + pb, UMMA_DESC_MN_HI, id2, 1);
                     }
                 umma_commit_if(leader, g2_done);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 0) {
+        // helper: while tile t is processed, pull tile t+1 of this CTA's sequence (128 contiguous KB of one cloud) into L2 with
+        // one bulk prefetch, so the workers' loads — the longest phase of the per-tile chain — find it there instead of in HBM
+        if (lane == 0) {
+            auto prefetch_tile = [&](int item, int r0) {
+                const int cloud = item / a.nchunk, chunk = item % a.nchunk;
+                const int r_end = min(a.n, chunk * a.rows_per_item + a.rows_per_item);
+                const float *src = a.x + ((size_t)cloud * a.n + r0) * VT_C;
+                const uint32_t bytes = (uint32_t)(min(TM, r_end - r0)) * VT_C * 4;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+            };
+            uint32_t tcount = 0;
+            for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+                const int chunk = item % a.nchunk;
+                const int r_begin = chunk * a.rows_per_item, r_end = min(a.n, r_begin + a.rows_per_item);
+                for (int r0 = r_begin; r0 < r_end; r0 += TM, ++tcount) {
+                    // the tile after (item, r0) in this CTA's sequence
+                    int n_item = item, n_r0 = r0 + TM;
+                    if (n_r0 >= r_end) { n_item = item + gridDim.x; n_r0 = (n_item % a.nchunk) * a.rows_per_item; }
+                    if (tcount > 0) mbar_wait(g2_done, (tcount - 1) & 1);       // pace: one tile ahead of the workers
+                    if (n_item < a.nitems) prefetch_tile(n_item, n_r0);
+                }
             }
         }
         __syncwarp();
@@ -145,12 +178,15 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vlad_tc_kernel(const VtArgs a) 
             const float *xg = a.x + (size_t)cloud * a.n * VT_C;
             float asum_k = 0.f;                                    // cluster (wt - 128)'s running sum (threads of half 1)
             for (int r0 = r_begin; r0 < r_end; r0 += TM, ++tcount) {
+                VT_TRACE(0);
                 if (tcount > 0) mbar_wait(g2_done, (tcount - 1) & 1);      // previous tile's GEMM2 no longer reads the planes
-                // four rows per warp per step: eight 16-byte loads in flight per lane before the first use
-                for (int rb = wwarp * 4; rb < TM; rb += 32) {
-                    float4 lo4[4], hi4[4];
+                VT_TRACE(1);
+                // eight rows per warp per step: sixteen 16-byte loads in flight per lane before the first use (the tile was
+                // prefetched into L2 by the helper warp while the previous tile was processed)
+                for (int rb = wwarp * 8; rb < TM; rb += 64) {
+                    float4 lo4[8], hi4[8];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < 8; ++u) {
                         lo4[u] = hi4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (r0 + rb + u < r_end) {
                             const float4 *src = reinterpret_cast<const float4 *>(xg + (size_t)(r0 + rb + u) * VT_C) + 2 * lane;
@@ -158,18 +194,20 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vlad_tc_kernel(const VtArgs a) 
                         }
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < 8; ++u) {
                         const float v[8] = {lo4[u].x, lo4[u].y, lo4[u].z, lo4[u].w, hi4[u].x, hi4[u].y, hi4[u].z, hi4[u].w};
                         store_units(x1, x2, rb + u, lane, v);
                     }
                 }
                 fence_proxy_async();
+                VT_TRACE(2);
                 mbar_arrive(a_ready);
                 if (half == 0 || split) {
                     // softmax over the clusters of this point: with more than 32 clusters the two warps that share a TMEM lane
                     // quarter take 32 columns each and exchange the row maximum and the row sum through shared memory
                     mbar_wait(d1_ready, tcount & 1);
                     tc_fence_after();
+                    VT_TRACE(3);
                     float lg[32];
                     tmem_ld32(trow + (uint32_t)(half * 32), lg);
                     const int kb = half * 32;
@@ -177,7 +215,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vlad_tc_kernel(const VtArgs a) 
                     float mx = -INFINITY;
 #pragma unroll
                     for (int k = 0; k < 32; ++k)
-                        if (kb + k < a.K) { lg[k] += __ldg(a.shift + kb + k); mx = fmaxf(mx, lg[k]); }
+                        if (kb + k < a.K) { lg[k] += shift_s[kb + k]; mx = fmaxf(mx, lg[k]); }
                     if (split) {
                         xmax[half * TM + row] = mx;
                         asm volatile("bar.sync 2, %0;" ::"n"(VT_WORK) : "memory");
@@ -193,45 +231,56 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vlad_tc_kernel(const VtArgs a) 
                         sum = xsum[row] + xsum[TM + row];                    // same order in both threads of the row
                     }
                     const float inv = valid ? 1.f / sum : 0.f;
-                    const uint32_t pbase = (uint32_t)((row >> 6) * wchunk + (((row & 63) >> 3) << 4) + ((row & 7) << 1));
+                    // this point's probabilities as bf16 hi/lo, eight clusters per 16-byte unit of its 128-byte row; lg[] keeps
+                    // the rounded value hi + lo (exact in fp32): a_sum must add up what the tensor cores add up
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) {
-                        if (kb + k < a.Kp) {
-                            const int kk = kb + k;
-                            const float p = kk < a.K ? lg[k] * inv : 0.f;
-                            const __nv_bfloat16 h = __float2bfloat16_rn(p);
-                            const __nv_bfloat16 l = __float2bfloat16_rn(p - __bfloat162float(h));
-                            const uint32_t off = (uint32_t)(kk * 128) + (pbase ^ (uint32_t)((kk & 7) << 4));
-                            *reinterpret_cast<__nv_bfloat16 *>(p1 + off) = h;
-                            *reinterpret_cast<__nv_bfloat16 *>(p2 + off) = l;
+                    for (int u = 0; u < 4; ++u) {
+                        if (kb + 8 * u < a.Kp) {
+                            uint4 h, l;
+                            uint32_t *hw = &h.x, *lw = &l.x;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int k0 = 8 * u + 2 * i;
+                                const float pa = kb + k0 < a.K ? lg[k0] * inv : 0.f, pb = kb + k0 + 1 < a.K ? lg[k0 + 1] * inv : 0.f;
+                                const __nv_bfloat162 hh = __floats2bfloat162_rn(pa, pb);
+                                const float2 hf = __bfloat1622float2(hh);
+                                const __nv_bfloat162 ll = __floats2bfloat162_rn(pa - hf.x, pb - hf.y);
+                                const float2 lf = __bfloat1622float2(ll);
+                                hw[i] = *reinterpret_cast<const uint32_t *>(&hh);
+                                lw[i] = *reinterpret_cast<const uint32_t *>(&ll);
+                                lg[k0] = hf.x + lf.x; lg[k0 + 1] = hf.y + lf.y;
+                            }
+                            const uint32_t off = (uint32_t)(row * 128 + ((((kb >> 3) + u) ^ (row & 7)) << 4));
+                            *reinterpret_cast<uint4 *>(p1 + off) = h;
+                            *reinterpret_cast<uint4 *>(p2 + off) = l;
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) lg[8 * u + i] = 0.f;
                         }
                     }
                     tc_fence_before();
                     fence_proxy_async();
+                    VT_TRACE(4);
                     mbar_arrive(p_ready);
-                }
-                if (half == 1) {
-                    // a_sum[k] += sum over the tile's points of act[.][k], read back from the staged planes in a fixed order
-                    mbar_wait(p_ready, tcount & 1);
-                    const int k = wt - 128;
-                    if (k < a.K) {
-                        float s_hi = 0.f, s_lo = 0.f;
-                        for (int ch2 = 0; ch2 < 2; ++ch2) {
-                            const uint8_t *r1 = p1 + ch2 * wchunk + k * 128, *r2 = p2 + ch2 * wchunk + k * 128;
+                    // column sums of act over this warp's 32 points: transposing butterfly (31 shuffles), lane k ends up with
+                    // cluster kb + k; fixed tree, so the result depends on the tile only
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) {                      // swizzled 16-byte units; order inside the sum is fixed
-                                const uint4 h = *reinterpret_cast<const uint4 *>(r1 + ((u ^ (k & 7)) << 4));
-                                const uint4 l = *reinterpret_cast<const uint4 *>(r2 + ((u ^ (k & 7)) << 4));
-                                const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+                    for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+                        const bool up = (lane & off) != 0;
 #pragma unroll
-                                for (int w = 0; w < 4; ++w) {
-                                    s_hi += __uint_as_float(hw[w] << 16) + __uint_as_float(hw[w] & 0xffff0000u);
-                                    s_lo += __uint_as_float(lw[w] << 16) + __uint_as_float(lw[w] & 0xffff0000u);
-                                }
-                            }
+                        for (int i = 0; i < n / 2; ++i) {
+                            const float send = up ? lg[i] : lg[i + n / 2];
+                            const float keep = up ? lg[i + n / 2] : lg[i];
+                            lg[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
                         }
-                        asum_k += s_hi + s_lo;
                     }
+                    psum[q * 64 + kb + lane] = lg[0];
+                }
+                asm volatile("bar.sync 3, %0;" ::"n"(VT_WORK) : "memory");       // every warp's column sums are in psum
+                if (half == 1) {
+                    // a_sum[k] += the four lane quarters' column sums, in a fixed order
+                    const int k = wt - 128;
+                    if (k < a.K) asum_k += (psum[k] + psum[64 + k]) + (psum[128 + k] + psum[192 + k]);
                 }
             }
             // ---- item done: accumulators -> partial (K, C) block, a_sum -> partial (K) ------------------------------
@@ -284,9 +333,10 @@ int pab_vlad_tc_partial(int b, int n, int c, int K, const float *x, const void *
     const int rpi = n >= 2048 ? VT_ROWS_BIG : VT_ROWS_MIN;
     a.rows_per_item = rpi;
     a.n = n; a.K = K; a.Kp = (K + 15) / 16 * 16; a.nchunk = (n + rpi - 1) / rpi; a.nitems = b * a.nchunk;
+    a.trace = g_tc_trace;
     a.x = x; a.shift = shift; a.wc_hi = (const __nv_bfloat16 *)wc_hi; a.wc_lo = (const __nv_bfloat16 *)wc_lo; a.part = part; a.asum = asum;
     *nchunk_out = a.nchunk;
-    const size_t smem = 8 * (size_t)A_CHUNK + 12 * (size_t)a.Kp * 128 + 64 + 64 * 4 + 4 * TM * 4 + 64;
+    const size_t smem = 10 * (size_t)A_CHUNK + 8 * (size_t)a.Kp * 128 + 64 + 64 * 4 + 4 * TM * 4 + 64;
     PAB_CUDA(cudaFuncSetAttribute(vlad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = a.nitems < n_sm ? a.nitems : n_sm;
     if (g_tc_max_ctas > 0 && grid > g_tc_max_ctas) grid = g_tc_max_ctas;
