@@ -63,7 +63,10 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vlad_tc_kernel(const VtArgs a) 
     uint8_t *p1 = w2 + 4 * wchunk;                                 // act hi: [128 pts][64 clusters] bf16, 128-byte swizzled rows —
     uint8_t *p2 = p1 + A_CHUNK;                                    // GEMM2's B operand read MN-major (a point's clusters are contiguous)
     uint8_t *misc = p2 + A_CHUNK;
-    uint64_t *a_ready = reinterpret_cast<uint64_t *>(misc);        // x planes staged            (256 arrivals)
+    uint64_t *a_ready = reinterpret_cast<uint64_t *>(misc);        // 64-channel chunk 0 of the x planes staged (256 arrivals)
+    uint64_t *a_ready_c = reinterpret_cast<uint64_t *>(misc + 40) - 1;   // chunks 1..3 at a_ready_c[1..3]: GEMM1 starts on chunk 0
+                                                                   // while the later chunks are still being loaded
+    uint64_t *g2_half = reinterpret_cast<uint64_t *>(misc + 64 + 256 + 4 * TM * 4);   // GEMM2 block 0 done: chunks 0,1 are free
     uint64_t *d1_ready = a_ready + 1;                              // logits in TMEM             (tcgen05.commit)
     uint64_t *p_ready = a_ready + 2;                               // act^T planes staged        (128 arrivals)
     uint64_t *g2_done = a_ready + 3;                               // GEMM2 of the tile finished (tcgen05.commit)
@@ -76,7 +79,9 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vlad_tc_kernel(const VtArgs a) 
 
     const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
     if (tid == 0) {
-        mbar_init(a_ready, VT_WORK); mbar_init(d1_ready, 1); mbar_init(p_ready, a.Kp > 32 ? VT_WORK : 128); mbar_init(g2_done, 1);
+        mbar_init(a_ready, VT_WORK); mbar_init(d1_ready, 1);
+        for (int c = 1; c < 4; ++c) mbar_init(a_ready_c + c, VT_WORK);
+        mbar_init(g2_half, 1); mbar_init(p_ready, a.Kp > 32 ? VT_WORK : 128); mbar_init(g2_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -113,10 +118,10 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vlad_tc_kernel(const VtArgs a) 
             const int r_begin = chunk * a.rows_per_item, r_end = min(a.n, r_begin + a.rows_per_item);
             int t_in_item = 0;
             for (int r0 = r_begin; r0 < r_end; r0 += TM, ++tcount, ++t_in_item) {
-                mbar_wait(a_ready, tcount & 1);
-                tc_fence_after();
 #pragma unroll
-                for (int kc = 0; kc < 4; ++kc)
+                for (int kc = 0; kc < 4; ++kc) {
+                    mbar_wait(kc == 0 ? a_ready : a_ready_c + kc, tcount & 1);
+                    tc_fence_after();
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
                         const uint32_t xa = (uint32_t)kc * (A_CHUNK >> 4) + 2 * ks, wb = (uint32_t)kc * wstep + 2 * ks;
@@ -124,11 +129,12 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vlad_tc_kernel(const VtArgs a) 
                         umma_f16_if(leader, d1, x2_lo + xa, UMMA_DESC_HI, w1_lo + wb, UMMA_DESC_HI, id1, 1);
                         umma_f16_if(leader, d1, x1_lo + xa, UMMA_DESC_HI, w2_lo + wb, UMMA_DESC_HI, id1, 1);
                     }
+                }
                 umma_commit_if(leader, d1_ready);
                 mbar_wait(p_ready, tcount & 1);
                 tc_fence_after();
 #pragma unroll
-                for (int cb = 0; cb < 2; ++cb)
+                for (int cb = 0; cb < 2; ++cb) {
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks) {            // 16 points per MMA
                         const uint32_t xa = (uint32_t)(2 * cb) * (A_CHUNK >> 4) + (uint32_t)ks * (2048 >> 4);
@@ -137,6 +143,8 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vlad_tc_kernel(const VtArgs a) 
                         umma_f16_if(leader, d2 + cb * 64, xm2_lo + xa, UMMA_DESC_MN_HI, p1_lo + pb, UMMA_DESC_MN_HI, id2, 1);
                         umma_f16_if(leader, d2 + cb * 64, xm1_lo + xa, UMMA_DESC_MN_HI, p2_lo + pb, UMMA_DESC_MN_HI, id2, 1);
                     }
+                    if (cb == 0) umma_commit_if(leader, g2_half);      // channels 0..127 = chunks 0,1 of the x planes are free
+                }
                 umma_commit_if(leader, g2_done);
             }
         }
@@ -179,29 +187,44 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vlad_tc_kernel(const VtArgs a) 
             float asum_k = 0.f;                                    // cluster (wt - 128)'s running sum (threads of half 1)
             for (int r0 = r_begin; r0 < r_end; r0 += TM, ++tcount) {
                 VT_TRACE(0);
-                if (tcount > 0) mbar_wait(g2_done, (tcount - 1) & 1);      // previous tile's GEMM2 no longer reads the planes
-                VT_TRACE(1);
-                // eight rows per warp per step: sixteen 16-byte loads in flight per lane before the first use (the tile was
-                // prefetched into L2 by the helper warp while the previous tile was processed)
-                for (int rb = wwarp * 8; rb < TM; rb += 64) {
-                    float4 lo4[8], hi4[8];
+                // The tile is staged one 64-channel chunk at a time (a warp covers 16 rows of a chunk: 4 steps of 4 rows x 256
+                // contiguous bytes), two chunks in flight: chunk c+2 is requested before chunk c is split and stored, and GEMM1
+                // starts on chunk c as soon as all warps have staged it.  Chunks 0,1 may be overwritten once GEMM2's first block
+                // (channels 0..127) of the previous tile has completed, chunks 2,3 after its second block.
+                const int lr = lane >> 3, lu = lane & 7;                     // row within a 4-row step, 32-byte unit within 256 B
+                float4 q0[2][4], q1[2][4];
+                auto request = [&](int c, float4 (&a0)[4], float4 (&a1)[4]) {
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        lo4[u] = hi4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (r0 + rb + u < r_end) {
-                            const float4 *src = reinterpret_cast<const float4 *>(xg + (size_t)(r0 + rb + u) * VT_C) + 2 * lane;
-                            lo4[u] = __ldg(src); hi4[u] = __ldg(src + 1);
+                    for (int st4 = 0; st4 < 4; ++st4) {
+                        const int r = wwarp * 16 + st4 * 4 + lr;
+                        a0[st4] = a1[st4] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (r0 + r < r_end) {
+                            const float4 *src = reinterpret_cast<const float4 *>(xg + (size_t)(r0 + r) * VT_C + c * 64) + 2 * lu;
+                            a0[st4] = __ldg(src); a1[st4] = __ldg(src + 1);
                         }
                     }
+                };
+                auto stage = [&](int c, const float4 (&a0)[4], const float4 (&a1)[4]) {
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const float v[8] = {lo4[u].x, lo4[u].y, lo4[u].z, lo4[u].w, hi4[u].x, hi4[u].y, hi4[u].z, hi4[u].w};
-                        store_units(x1, x2, rb + u, lane, v);
+                    for (int st4 = 0; st4 < 4; ++st4) {
+                        const float v[8] = {a0[st4].x, a0[st4].y, a0[st4].z, a0[st4].w, a1[st4].x, a1[st4].y, a1[st4].z, a1[st4].w};
+                        store_units(x1, x2, wwarp * 16 + st4 * 4 + lr, c * 8 + lu, v);
                     }
-                }
-                fence_proxy_async();
+                    fence_proxy_async();
+                    mbar_arrive(c == 0 ? a_ready : a_ready_c + c);
+                };
+                request(0, q0[0], q1[0]);
+                request(1, q0[1], q1[1]);
+                if (tcount > 0) mbar_wait(g2_half, (tcount - 1) & 1);
+                VT_TRACE(1);
+                stage(0, q0[0], q1[0]);
+                request(2, q0[0], q1[0]);
+                stage(1, q0[1], q1[1]);
+                request(3, q0[1], q1[1]);
+                if (tcount > 0) mbar_wait(g2_done, (tcount - 1) & 1);      // previous tile's GEMM2 no longer reads chunks 2,3
+                stage(2, q0[0], q1[0]);
+                stage(3, q0[1], q1[1]);
                 VT_TRACE(2);
-                mbar_arrive(a_ready);
                 if (half == 0 || split) {
                     // softmax over the clusters of this point: with more than 32 clusters the two warps that share a TMEM lane
                     // quarter take 32 columns each and exchange the row maximum and the row sum through shared memory
