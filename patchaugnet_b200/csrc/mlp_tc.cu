@@ -37,6 +37,8 @@ constexpr int MAX_STAGES = 8;
 constexpr int MAX_LAYERS = 3;
 constexpr int D_COLS = 256;                   // accumulator columns; TMEM columns [256,384) = hi plane, [384,512) = lo plane
 constexpr uint32_t AH_COL = 256, AL_COL = 384;
+constexpr uint32_t XTRA_COL = 64;             // plane columns [64,80) hold layer 0's xyz extras: the epilogue of a split pass's first
+                                              // n-block rewrites columns [0,64) while the second n-block's MMAs still read the extras
 constexpr int STG_COLS = 64;                  // fp32 staging of the last layer: [128 rows][64 columns]
 constexpr int STG_PITCH = STG_COLS + 4;        // floats per staged row: 68 = 4 mod 32 keeps row-wise 16-byte writes and column-wise reads conflict-free
 constexpr int STG_BYTES = TM * STG_PITCH * 4;                      // SA: one CTA-wide tile (rows of a group span warps)
@@ -119,11 +121,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     uint64_t *empty = full + MAX_STAGES;
     uint64_t *a_full = empty + MAX_STAGES;                         // loaders -> MMA: layer-0 operand of the tile staged
     uint64_t *a_empty = a_full + 1;                                // MMA -> loaders: layer-0 MMAs of the tile completed
-    uint64_t *d_ready = a_full + 2;                                // MMA -> epilogue: accumulators of the phase complete
-    uint64_t *t_ready = a_full + 3;                                // epilogue -> MMA: D drained (+ next operand in TMEM)
+    // MMA <-> epilogue hand-off, per accumulator PASS (<= 256 columns).  A pass made of two 128-column n-blocks is pipelined
+    // at n-block granularity ("split" pass): d_ready[i] = n-block i accumulated, t_ready[i] = its columns drained and (not the
+    // last layer) its half of the next operand written to the TMEM planes, p_free = the MMAs of n-block 1 no longer read the
+    // plane columns n-block 0's epilogue overwrites.  Every pass completes exactly one phase of each of the five barriers.
+    uint64_t *d_ready = a_full + 2;                                // MMA -> epilogue: n-block 0 (or the whole unsplit pass)
+    uint64_t *t_ready = a_full + 3;                                // epilogue -> MMA: D columns [0,128) / plane columns [0,64)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_full + 4);
     uint64_t *tq_full = a_full + 5;                                // dynamic tile queue: entry i published (ring of 8)
     int *tile_list = reinterpret_cast<int *>(tq_full + 8);         // [8] tile index or -1 (no more tiles)
+    uint64_t *d_ready1 = reinterpret_cast<uint64_t *>(misc + 272);  // n-block 1
+    uint64_t *t_ready1 = d_ready1 + 1;                             // D columns [128,256) / plane columns [64,128) (+ next tile's extras)
+    uint64_t *p_free = d_ready1 + 2;
     float *ctab = reinterpret_cast<float *>(misc + 384);           // [shift of every layer | pre layer]
 
     const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
@@ -139,6 +148,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         mbar_init(a_empty, 1);
         mbar_init(d_ready, 1);
         mbar_init(t_ready, NEPI);
+        mbar_init(d_ready1, 1);
+        mbar_init(t_ready1, NEPI);
+        mbar_init(p_free, 1);
         for (int i = 0; i < 8; ++i) mbar_init(tq_full + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -228,6 +240,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         const uint32_t st_lo = umma_desc_lo(smem_u32(stages));
         constexpr uint32_t st_step = (NBLK_MAX * 128) >> 4;
         uint32_t s = 0, ph = 0, pcount = 0, tcount = 0, gcount = 0;
+        bool t1_pending = false;
         for (int it = 0; tile_at((uint32_t)it) >= 0; ++it, ++tcount) {
             for (int l = 0; l < a.n_layers; ++l) {
                 const int ksteps = a.ksteps[l], nkc_main = (ksteps + 3) >> 2;
@@ -238,20 +251,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                 for (int g = 0; g < ngroups; ++g) {
                 if (l == 0) mbar_wait(a_full, gcount & 1);       // this group of layer-0 operand chunks is staged
                 const int kc_lo = g * gc, kc_hi = g == ngroups - 1 ? nkc : (g + 1) * gc;
+                const bool last_g = g == ngroups - 1;
                 for (int nb = 0; nb < nnb; ++nb) {
                     const int nbp = nb % nb_pass;
-                    if (nbp == 0 && g == 0) {                    // new pass: the epilogue has drained D (and written the operand planes)
+                    const bool split = nbr == NBLK_MAX && nb_pass == 2 && nb - nbp + 2 <= nnb;   // this pass has two 128-column n-blocks
+                    if (nbp == 0 && g == 0) {                    // new pass: the epilogue has drained D[0,128) (and written planes [0,64))
                         mbar_wait(t_ready, pcount & 1);
                         tc_fence_after();
+                        t1_pending = true;
                         TC_TRACE(it, l, 0);
                     }
+                    if (nbp == 1 && t1_pending) {                // second n-block: D[128,256) drained
+                        mbar_wait(t_ready1, pcount & 1);
+                        tc_fence_after();
+                        t1_pending = false;
+                    }
                     const uint32_t d = tmem + (uint32_t)(nbp * nbr);
+                    const int kc_free = min(kc_lo + 1, kc_hi - 1);   // after this chunk of n-block 1 plane columns [0,64) are dead
                     for (int kc = kc_lo; kc < kc_hi; ++kc) {
-                        const bool xk = kc >= nkc_main;          // the extras' chunk: k-step 0 only, operand in plane columns 0..7
+                        const bool xk = kc >= nkc_main;          // the extras' chunk: k-step 0 only, operand in plane columns XTRA_COL..
                         const bool from_smem = l == 0 && !xk;
                         const int kn = xk ? 1 : min(4, ksteps - 4 * kc);
                         const uint32_t ka = (uint32_t)(kc - kc_lo) * (A_CHUNK >> 4);
-                        const uint32_t ta = xk ? 0u : (uint32_t)(kc * 32);
+                        const uint32_t ta = xk ? XTRA_COL : (uint32_t)(kc * 32);
+                        if (!from_smem && ta >= 64 && t1_pending) {  // operand columns the previous pass's second half wrote
+                            mbar_wait(t_ready1, pcount & 1);
+                            tc_fence_after();
+                            t1_pending = false;
+                        }
                         // hi weight plane: hi(A) * hi(W) + lo(A) * hi(W)
                         mbar_wait(full + s, ph);
                         uint32_t sb = st_lo + s * st_step;
@@ -287,11 +314,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                         if (a.csize == 1) umma_commit_if(leader, empty + s);
                         else umma_commit_mc_if(leader, empty + s, cmask_all);
                         if (++s == (uint32_t)a.n_stages) { s = 0; ph ^= 1; }
+                        if (split && last_g && nbp == 1 && kc == kc_free) umma_commit_if(leader, p_free);
                     }
-                    if (g == ngroups - 1 && (nbp == nb_pass - 1 || nb == nnb - 1)) {
-                        umma_commit_if(leader, d_ready);         // accumulators of this pass complete
-                        ++pcount;
-                        TC_TRACE(it, l, 1);
+                    if (last_g) {
+                        const bool pass_end = nbp == nb_pass - 1 || nb == nnb - 1;
+                        if (pass_end && t1_pending) {
+                            // nothing in this pass needed the second half: consume its phase — BEFORE the commits below.  Once
+                            // d_ready is committed the epilogue may finish this pass and complete the NEXT phase of t_ready1; a
+                            // waiter that then still polls for this one sees the parity of an incomplete phase and never wakes
+                            // (observed: one launch in a few hundred when the issuing warp was delayed after the commits).
+                            mbar_wait(t_ready1, pcount & 1);
+                            t1_pending = false;
+                        }
+                        if (split) {
+                            umma_commit_if(leader, nbp == 0 ? d_ready : d_ready1);   // this n-block's accumulators complete
+                        } else if (pass_end) {
+                            umma_commit_if(leader, d_ready);
+                            umma_commit_if(leader, d_ready1);
+                            umma_commit_if(leader, p_free);
+                        }
+                        if (pass_end) {
+                            ++pcount;
+                            TC_TRACE(it, l, 1);
+                        }
                     }
                 }
                 if (l == 0) { umma_commit_if(leader, a_empty); ++gcount; }   // operand group consumed: loaders may stage the next one
@@ -340,8 +385,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             for (int i = 0; i < 16; ++i) hi[i] = lo[i] = 0u;
             split_pack(xe[0], xe[1], hi[0], lo[0]);
             split_pack(xe[2], 0.f, hi[1], lo[1]);
-            tmem_st16(trow + AH_COL, hi);
-            tmem_st16(trow + AL_COL, lo);
+            tmem_st16(trow + AH_COL + XTRA_COL, hi);
+            tmem_st16(trow + AL_COL + XTRA_COL, lo);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         };
         const bool xwriter = a.n_extra > 0 && half == 0;
@@ -353,11 +398,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         }
         tc_fence_before();
         mbar_arrive(t_ready);                                  // completion #0: the MMA warp may start the first phase
+        mbar_arrive(t_ready1);
 
         for (int it = 0; tile >= 0; ++it) {                        // static cluster mode: trailing tiles >= ntiles are empty
             const int tile_next = tile_at((uint32_t)it + 1);
             if (xwriter && tile_next >= 0) load_extras(tile_next, xe_next);              // consumed at the end of this tile
-            int out_pt[4] = {-1, -1, -1, -1};                      // FP: points of the rows this lane stores (row r8*8 + lane/4 of the quarter)
+            int out_pt[4] = {-1, -1, -1, -1};                     // FP: points of the rows this lane stores (row r8*8 + lane/4 of the quarter)
             if (a.mode == TC_FP) {
 #pragma unroll
                 for (int r8 = 0; r8 < 4; ++r8) {
@@ -373,13 +419,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                 const int npass = (N + D_COLS - 1) / D_COLS;
                 for (int pass = 0; pass < npass; ++pass, ++pcount) {
                     const int ncols = min(D_COLS, N - pass * D_COLS);  // accumulator columns of this pass
-                    const int per = ncols >= 64 ? ncols / 2 : ncols;    // columns per worker half (batches of 32)
+                    // split pass (two 128-column n-blocks): segment i = n-block i, each half of the workers takes 64 of its columns
+                    // as soon as THAT n-block is accumulated; otherwise one segment, the halves share the pass's columns
+                    const bool split = ncols == D_COLS;
+                    const int nseg = split ? 2 : 1;
+                    const int per = split ? 64 : (ncols >= 64 ? ncols / 2 : ncols);   // columns per worker half and segment (batches of 32)
                     const bool active = ncols >= 64 || half == 0;
-                    mbar_wait(d_ready, pcount & 1);
+                    for (int seg = 0; seg < nseg; ++seg) {
+                    const int segbase = split ? seg * NBLK_MAX : 0;
+                    mbar_wait(seg == 0 ? d_ready : d_ready1, pcount & 1);
+                    if (!split) mbar_wait(d_ready1, pcount & 1);
                     tc_fence_after();
-                    if (ewarp == 0) TC_TRACE(it, l, 2);
+                    if (ewarp == 0) TC_TRACE(it, l, (split && seg == 0) ? 7 : 2);
                     for (int cb = 0; cb < per; cb += 32) {
-                        const int dcol = (ncols >= 64 ? half * per : 0) + cb;          // first accumulator column of this batch
+                        const int dcol = segbase + (ncols >= 64 ? half * per : 0) + cb;  // first accumulator column of this batch
                         const int col = pass * D_COLS + dcol;                          // output channel
                         float v[32];
                         if (active) {
@@ -395,22 +448,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                             }
                         }
                         if (!last) {
-                            if (active) {                       // next layer's operand: bf16 pairs into the TMEM planes
-                                uint32_t hi[16], lo[16];
+                            uint32_t hi[16], lo[16];
+                            if (active) {
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) split_pack(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+                            }
+                            if (seg == 0 && cb == 0) {           // plane columns [0,64) are still read by the second n-block's MMAs
+                                mbar_wait(p_free, pcount & 1);
+                                tc_fence_after();
+                            }
+                            if (active) {                       // next layer's operand: bf16 pairs into the TMEM planes
                                 tmem_st16(trow + AH_COL + (uint32_t)(dcol >> 1), hi);
                                 tmem_st16(trow + AL_COL + (uint32_t)(dcol >> 1), lo);
                             }
                         } else {
                             const bool final_batch = cb + 32 >= per;
-                            if (final_batch) {                   // every accumulator column of the pass has been read
-                                // last pass of the tile: the operand planes are free (this layer's MMAs completed before
+                            if (final_batch) {                   // every accumulator column of the segment has been read
+                                // last segment of the tile: the operand planes are free (this layer's MMAs completed before
                                 // d_ready): stage the next tile's layer-0 extras there before releasing the MMA warp
-                                if (xwriter && pass == npass - 1 && tile_next >= 0) store_extras(xe_next);
+                                if (xwriter && pass == npass - 1 && seg == nseg - 1 && tile_next >= 0) store_extras(xe_next);
                                 tc_fence_before();
                                 if (ewarp == 0) TC_TRACE(it, l, 3);
-                                mbar_arrive(t_ready);
+                                mbar_arrive(seg == 0 ? t_ready : t_ready1);
+                                if (!split) mbar_arrive(t_ready1);
                             }
                             if (a.mode == TC_SA) {
                                 // one staging round: 32 columns of each half -> [128][64] fp32 -> max over the K rows of a group
@@ -430,7 +490,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                                     const float *scol = reinterpret_cast<const float *>(stg) + (g * a.k) * STG_PITCH + c;
                                     float mx = scol[0];
                                     for (int sidx = 1; sidx < a.k; ++sidx) mx = fmaxf(mx, scol[sidx * STG_PITCH]);
-                                    const int oc = pass * D_COLS + (c >> 5) * per + cb + (c & 31);
+                                    const int oc = pass * D_COLS + segbase + (c >> 5) * per + cb + (c & 31);
                                     a.out[ci * N + oc] = mx;
                                 }
                                 asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");   // staging consumed before it is rewritten
@@ -463,9 +523,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                         tc_fence_before();
                         if (ewarp == 0) TC_TRACE(it, l, 3);
-                        mbar_arrive(t_ready);
+                        mbar_arrive(seg == 0 ? t_ready : t_ready1);
+                        if (!split) mbar_arrive(t_ready1);
                     } else if (ewarp == 0) {
                         TC_TRACE(it, l, 6);                      // output of the tile stored
+                    }
                     }
                 }
             }
