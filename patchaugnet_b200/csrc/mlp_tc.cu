@@ -634,8 +634,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                     }
                     store_units(a1, a2, r, u, v);
                 }
+                // only whole 16-channel k-steps are read by the MMAs (ksteps = ceil(pre_cout / 16)): zero what is left of the
+                // last one, not the rest of the 64-channel chunk
                 const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                for (int j = a.pre_cout / 8; j < units0; ++j) store_units(a1, a2, r, j, z);
+                for (int j = a.pre_cout / 8; j < 2 * a.ksteps[0]; ++j) store_units(a1, a2, r, j, z);
             } else if (a.mode == TC_SA) {
                 // lane r of the warp looks up the (centre, neighbour) point of row 32*lwarp + r once; rows are then staged
                 // four at a time with the indices broadcast by shuffles

@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vlad_tc_kernel(const VtArgs a) 
     uint64_t *p_ready = a_ready + 2;                               // act^T planes staged        (128 arrivals)
     uint64_t *g2_done = a_ready + 3;                               // GEMM2 of the tile finished (tcgen05.commit)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_ready + 4);
+    volatile int *progress = reinterpret_cast<volatile int *>(misc + 36);   // tile the workers are staging (paces the prefetching helper)
     float *shift_s = reinterpret_cast<float *>(misc + 64);         // [64] bn1 shift of the clusters (zero beyond K)
     float *xmax = reinterpret_cast<float *>(misc + 64 + 256);      // [2][128] row maxima of the two column halves; after the softmax
     float *psum = xmax;                                            //   [4 lane quarters][64] per-warp column sums of act (a_sum)
@@ -81,7 +82,8 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vlad_tc_kernel(const VtArgs a) 
     if (tid == 0) {
         mbar_init(a_ready, VT_WORK); mbar_init(d1_ready, 1);
         for (int c = 1; c < 4; ++c) mbar_init(a_ready_c + c, VT_WORK);
-        mbar_init(g2_half, 1); mbar_init(p_ready, a.Kp > 32 ? VT_WORK : 128); mbar_init(g2_done, 1);
+        mbar_init(g2_half, 1);
+        *progress = -1; mbar_init(p_ready, a.Kp > 32 ? VT_WORK : 128); mbar_init(g2_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -168,7 +170,9 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vlad_tc_kernel(const VtArgs a) 
                     // the tile after (item, r0) in this CTA's sequence
                     int n_item = item, n_r0 = r0 + TM;
                     if (n_r0 >= r_end) { n_item = item + gridDim.x; n_r0 = (n_item % a.nchunk) * a.rows_per_item; }
-                    if (tcount > 0) mbar_wait(g2_done, (tcount - 1) & 1);       // pace: one tile ahead of the workers
+                    // pace: one tile ahead of the workers.  A monotonic counter, not an mbarrier phase: nothing waits for this
+                    // warp, so it may fall a whole tile behind — and a parity wait that is two phases late never wakes
+                    while (*progress < (int)tcount) {}
                     if (n_item < a.nitems) prefetch_tile(n_item, n_r0);
                 }
             }
@@ -216,6 +220,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vlad_tc_kernel(const VtArgs a) 
                 request(0, q0[0], q1[0]);
                 request(1, q0[1], q1[1]);
                 if (tcount > 0) mbar_wait(g2_half, (tcount - 1) & 1);
+                if (wt == 0) *progress = (int)tcount;
                 VT_TRACE(1);
                 stage(0, q0[0], q1[0]);
                 request(2, q0[0], q1[0]);
