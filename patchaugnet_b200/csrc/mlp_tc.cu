@@ -689,21 +689,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                 }
                 }
             } else {
-                // FP: every lane holds the three neighbour indices / weights of one row of its warp; rows are staged four at a
-                // time (24 x 16-byte gathers in flight per lane), indices and weights broadcast by shuffles
+                // FP: every lane holds the three neighbour indices / weights of one row of its warp; rows are staged RB = 2 at a time:
+                // 12 x 16-byte gathers per lane, which the 128-register budget really keeps in flight together (with four rows
+                // the compiler split the 24 loads into three dependent rounds); indices and weights broadcast by shuffles
                 const int ku = a.c_known / 8;
-                // the 32 batches of four rows are dealt round-robin to the six warps (batch = lwarp + 6*(lane/4)), so at any time the
-                // warps work on 24 consecutive rows: with a spatial row order they share most of their known rows in L1.  The
+                // the 64 batches of two rows are dealt round-robin to the six warps (batch = lwarp + 6*(lane/2)), so at any time the
+                // warps work on 12 consecutive rows: with a spatial row order they share most of their known rows in L1.  The
                 // gathers are latency-bound (registers cap the loads a warp keeps in flight), hence as many warps as the register
                 // file allows: 512 threads x 128 registers
+                constexpr int RB = 2, LW = NLOAD / 32;
                 int my_base = -1, my_p = -1;
                 int my_i[3] = {0, 0, 0};
                 float my_w[3] = {0.f, 0.f, 0.f};
                 {
-                    constexpr int LW = NLOAD / 32;
-                    const int batch = lwarp + LW * (lane >> 2);
-                    const long gr = (long)tile * TM + 4 * batch + (lane & 3);
-                    if (batch < TM / 4 && gr < a.rows) {
+                    const int batch = lwarp + LW * (lane / RB);
+                    const long gr = (long)tile * TM + RB * batch + (lane % RB);
+                    if (batch < TM / RB && gr < a.rows) {
                         const long p = point_of(gr);
                         my_p = (int)p;
                         my_base = (int)((p / a.n) * a.m);
@@ -714,13 +715,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                 for (int g = 0; g < ngroups; ++g) {
                 const int j_lo = g * gunits, j_hi = min(units0, j_lo + gunits);
                 if (gcount > 0) mbar_wait(a_empty, (gcount - 1) & 1);
-                for (int rr = 0; 6 * rr + 4 * lwarp < TM; rr += 4) {          // batch = lwarp + 6 * (rr / 4), rows 4 * batch ..
-                    const float *f0[4], *f1[4], *f2[4];
-                    float w0[4], w1[4], w2[4];
-                    bool ok[4];
-                    int pt[4];
+                for (int bi = 0; lwarp + LW * bi < TM / RB; ++bi) {           // batch = lwarp + LW * bi, rows RB * batch ..
+                    const int rr = RB * bi, row0 = RB * (lwarp + LW * bi);       // source lane of the batch's first row, its tile row
+                    const float *f0[RB], *f1[RB], *f2[RB];
+                    float w0[RB], w1[RB], w2[RB];
+                    bool ok[RB];
+                    int pt[RB];
 #pragma unroll
-                    for (int t4 = 0; t4 < 4; ++t4) {
+                    for (int t4 = 0; t4 < RB; ++t4) {
                         const int base = __shfl_sync(0xffffffffu, my_base, rr + t4);
                         pt[t4] = __shfl_sync(0xffffffffu, my_p, rr + t4);
                         const int i0 = __shfl_sync(0xffffffffu, my_i[0], rr + t4), i1 = __shfl_sync(0xffffffffu, my_i[1], rr + t4),
@@ -733,17 +735,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                         f2[t4] = a.known_feat + (b0 + i2) * a.c_known;
                     }
                     for (int j = j_lo + lane; j < j_hi; j += 32) {
-                        float v[4][8];
+                        float v[RB][8];
                         if (j < ku) {
-                            float4 x0[4], x1[4], y0[4], y1[4], z0[4], z1[4];
+                            float4 x0[RB], x1[RB], y0[RB], y1[RB], z0[RB], z1[RB];
 #pragma unroll
-                            for (int t4 = 0; t4 < 4; ++t4) {
+                            for (int t4 = 0; t4 < RB; ++t4) {
                                 x0[t4] = __ldg(reinterpret_cast<const float4 *>(f0[t4]) + 2 * j); x1[t4] = __ldg(reinterpret_cast<const float4 *>(f0[t4]) + 2 * j + 1);
                                 y0[t4] = __ldg(reinterpret_cast<const float4 *>(f1[t4]) + 2 * j); y1[t4] = __ldg(reinterpret_cast<const float4 *>(f1[t4]) + 2 * j + 1);
                                 z0[t4] = __ldg(reinterpret_cast<const float4 *>(f2[t4]) + 2 * j); z1[t4] = __ldg(reinterpret_cast<const float4 *>(f2[t4]) + 2 * j + 1);
                             }
 #pragma unroll
-                            for (int t4 = 0; t4 < 4; ++t4) {
+                            for (int t4 = 0; t4 < RB; ++t4) {
                                 // interpolation_forward: fma(w2,p2, fma(w0,p0, w1*p1)) (interpolation_cuda_kernel.cu:194)
                                 v[t4][0] = __fmaf_rn(w2[t4], z0[t4].x, __fmaf_rn(w0[t4], x0[t4].x, __fmul_rn(w1[t4], y0[t4].x)));
                                 v[t4][1] = __fmaf_rn(w2[t4], z0[t4].y, __fmaf_rn(w0[t4], x0[t4].y, __fmul_rn(w1[t4], y0[t4].y)));
@@ -756,7 +758,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                             }
                         } else {
 #pragma unroll
-                            for (int t4 = 0; t4 < 4; ++t4) {
+                            for (int t4 = 0; t4 < RB; ++t4) {
                                 float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
                                 if (ok[t4] && 8 * (j - ku) < a.c_skip) {
                                     const float4 *sk = reinterpret_cast<const float4 *>(a.skip_feat + (long)pt[t4] * a.c_skip) + 2 * (j - ku);
@@ -767,12 +769,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                             }
                         }
 #pragma unroll
-                        for (int t4 = 0; t4 < 4; ++t4) {
+                        for (int t4 = 0; t4 < RB; ++t4) {
                             if (!ok[t4]) {
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) v[t4][i] = 0.f;
                             }
-                            store_units(a1, a2, 6 * rr + 4 * lwarp + t4, j - j_lo, v[t4]);
+                            store_units(a1, a2, row0 + t4, j - j_lo, v[t4]);
                         }
                     }
                 }
