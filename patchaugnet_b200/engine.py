@@ -321,12 +321,14 @@ class FusedPatchAugNet:
         return self._launch_dense(xyz0, ws)
 
     @torch.no_grad()
-    def forward_stream(self, batches, out=None):
+    def forward_stream(self, batches, out=None, ready_events=None):
         """Throughput mode: descriptors of a sequence of equally shaped (B,N,3) / (B,1,N,3) CUDA batches.
 
         Submaps are independent, and the geometry of a batch (FPS is a serial m-step chain that occupies only B SMs)
         depends on nothing the dense path produces.  So batch i+1's geometry runs on a second stream while batch i's
         SharedMLP / NetVLAD kernels fill the rest of the machine; two workspaces ping-pong, events order the reuse.
+        ``ready_events[i]`` (optional): a CUDA event batch i's geometry waits for — the host-to-device copy of that batch
+        issued on a copy stream, so the upload of later batches overlaps the compute of earlier ones.
         Returns (len(batches)*B, c_out) descriptors on the device.
         """
         batches = list(batches)
@@ -366,6 +368,8 @@ class FusedPatchAugNet:
             slot = i & 1
             ws = slots[slot]
             with torch.cuda.stream(s_geo):
+                if ready_events is not None and ready_events[i] is not None:
+                    s_geo.wait_event(ready_events[i])
                 if dense_done[slot] is not None:
                     s_geo.wait_event(dense_done[slot])          # workspace free again
                 self._launch_geo(xyz0, ws)

@@ -32,6 +32,16 @@ def _dist_info(group=None):
     return 0, 1
 
 
+_COPY_STREAMS = {}
+
+
+def _copy_stream(device):
+    key = torch.device(device)
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device=key)
+    return _COPY_STREAMS[key]
+
+
 def extract_descriptors(extract_fn, clouds, batch_size=32, device=None, dim=256, group=None, out_device=None,
                         super_chunk=64):
     """Descriptors of this rank's shard of ``clouds`` (M,N,3), all-gathered so every rank returns the full (M, dim).
@@ -53,15 +63,37 @@ def extract_descriptors(extract_fn, clouds, batch_size=32, device=None, dim=256,
         engine = extract_fn.engine()
     if engine is not None:
         step = batch_size * super_chunk
+        host_side = not clouds.is_cuda
+        copy_stream = _copy_stream(device) if host_side else None
         for s in range(lo, hi, step):
             e = min(hi, s + step)
-            dev_chunk = clouds[s:e].to(device, non_blocking=True)
             full = (e - s) // batch_size * batch_size
-            if full:
-                engine.forward_stream([dev_chunk[i:i + batch_size] for i in range(0, full, batch_size)],
-                                      out=local[s - lo:s - lo + full])
+            if host_side:
+                # one upload per batch on a copy stream, each followed by an event: batch i's kernels wait for ITS upload only,
+                # so the copies of later batches run under the compute of earlier ones (the make_descs loop of the reference
+                # uploads and computes strictly in turn, scene_dataset.py:672-686)
+                batches, events = [], []
+                copy_stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(copy_stream):
+                    for i in range(s, e, batch_size):
+                        batches.append(clouds[i:min(e, i + batch_size)].to(device, non_blocking=True))
+                        ev = torch.cuda.Event()
+                        ev.record(copy_stream)
+                        events.append(ev)
+                for b in batches:
+                    b.record_stream(torch.cuda.current_stream())
+            else:
+                dev_chunk = clouds[s:e]
+                batches = [dev_chunk[i:min(e - s, i + batch_size)] for i in range(0, e - s, batch_size)]
+                events = None
+            n_full = full // batch_size
+            if n_full:
+                engine.forward_stream(batches[:n_full], out=local[s - lo:s - lo + full],
+                                      ready_events=events[:n_full] if events is not None else None)
             if full < e - s:                                   # ragged tail batch
-                local[s - lo + full:e - lo] = engine(dev_chunk[full:], return_feat=False, clone=False)
+                if events is not None:
+                    torch.cuda.current_stream().wait_event(events[-1])
+                local[s - lo + full:e - lo] = engine(batches[-1], return_feat=False, clone=False)
     else:
         for s in range(lo, hi, batch_size):
             e = min(hi, s + batch_size)
