@@ -177,12 +177,14 @@ __global__ void __launch_bounds__(128) afa_att_kernel(int b, int c, int K, const
         float acc[AKC];
 #pragma unroll
         for (int kk = 0; kk < AKC; ++kk) acc[kk] = 0.f;
-        for (int ci0 = 0; ci0 < c; ci0 += 4) {
-            float w[4];
+        // the weight column of this output channel is a chain of dependent-latency global loads (one L2 round trip per group):
+        // 16 input channels per trip — sixteen loads in flight — instead of four; the accumulation order is unchanged
+        for (int ci0 = 0; ci0 < c; ci0 += 16) {
+            float w[16];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) w[u] = ci0 + u < c ? __ldg(w_att_t + (size_t)(ci0 + u) * c + co) : 0.f;
+            for (int u = 0; u < 16; ++u) w[u] = ci0 + u < c ? __ldg(w_att_t + (size_t)(ci0 + u) * c + co) : 0.f;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 16; ++u) {
                 if (ci0 + u < c) {
                     const float4 *vr = reinterpret_cast<const float4 *>(vs + (ci0 + u) * AKC);
 #pragma unroll
@@ -266,12 +268,12 @@ __global__ void __launch_bounds__(256) afa_fc_kernel(int b, int c, int K, int c_
             float acc[FB];
 #pragma unroll
             for (int bb = 0; bb < FB; ++bb) acc[bb] = 0.f;
-            for (int ff0 = 0; ff0 < fn; ff0 += 8) {              // eight weight rows in flight; rows >= fn of ys are zero
-                float w[8];
+            for (int ff0 = 0; ff0 < fn; ff0 += 16) {             // sixteen weight rows in flight; rows >= fn of ys are zero
+                float w[16];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) w[u] = ff0 + u < fn ? __ldg(fc_wt + (size_t)(f0 + ff0 + u) * c_out + o) : 0.f;
+                for (int u = 0; u < 16; ++u) w[u] = ff0 + u < fn ? __ldg(fc_wt + (size_t)(f0 + ff0 + u) * c_out + o) : 0.f;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < 16; ++u) {
                     const float4 *yr = reinterpret_cast<const float4 *>(&ys[ff0 + u][0]);
 #pragma unroll
                     for (int q = 0; q < FB / 4; ++q) {
