@@ -198,3 +198,39 @@ def test_far_list_quirk_and_entry_sampling():
     assert oi.sample_entries(7, rng).tolist() == list(range(7))
     s = oi.sample_entries(1200, rng)
     assert len(s) == 500 and len(set(s.tolist())) == 500 and s.max() < 1200
+
+
+def test_triplet_batch_flattening_matches_the_per_pair_entry_lists():
+    """overlap_indices.TripletBatch (host side of pab_patch_triplets): CSR arrays of a whole step == the per-pair lists the
+    restated reference loop (oracle/patch_pairs.py) consumes, in processing order, with the far-list rule applied."""
+    from oracle import patch_pairs
+    from patchaugnet_b200 import overlap_indices as oi
+    rng = np.random.default_rng(21)
+    nn_dict = {}
+    for pair, ne in zip([(0, 1), (0, 2), (3, 1)], (5, 0, 620)):
+        ents = [(int(rng.integers(0, 4096)), rng.integers(0, 4096, rng.integers(0, 9)).tolist(),
+                 rng.integers(0, 4096, rng.integers(0, 5)).tolist(), rng.integers(0, 4096, rng.integers(0, 3)).tolist()) for _ in range(ne)]
+        nn_dict[pair] = oi.OverlapEntries.from_lists(ents)
+    for hard in (False, True):
+        batch = oi.TripletBatch(nn_dict, {c: 10 + c for c in range(4)}, hard_only=hard, rng=np.random.default_rng(8), device="cpu")
+        h = batch.host
+        assert h["pair_m"].tolist() == [10, 10, 13] and h["pair_n"].tolist() == [11, 12, 11]
+        assert np.diff(h["entry_ptr"]).tolist() == [5, 0, 500] and batch.max_entries == 500       # 620 entries sampled down to 500
+        order_rng = np.random.default_rng(8)
+        e = 0
+        for (m, n) in batch.pairs:
+            ent = nn_dict[m, n]
+            fptr, fval = ent.far_lists(hard)
+            for k in oi.sample_entries(len(ent), order_rng):
+                assert h["idx1"][e] == ent.idx1[k]
+                assert h["near"][h["near_ptr"][e]:h["near_ptr"][e + 1]].tolist() == ent.near[ent.near_ptr[k]:ent.near_ptr[k + 1]].tolist()
+                assert h["far"][h["far_ptr"][e]:h["far_ptr"][e + 1]].tolist() == fval[fptr[k]:fptr[k + 1]].tolist()
+                e += 1
+        assert e == len(h["idx1"])
+        for k, v in h.items():                                   # the device copies are views of one flat upload
+            assert torch.equal(batch.dev[k], torch.from_numpy(v))
+    # the restated loop and its counter-based draw are deterministic functions of (seed, pair, entry, j)
+    centers = np.arange(1024, dtype=np.int32) * 3
+    a = patch_pairs.select_pair(centers, centers, [(3, [3, 6, 9], [12, 15]), (5, [3], [12])], seed=7, pair=2)
+    assert a == patch_pairs.select_pair(centers, centers, [(3, [3, 6, 9], [12, 15]), (5, [3], [12])], seed=7, pair=2)
+    assert a[0] == [1, 1, 1] and a[1] == [1, 2, 3] and set(a[2]) <= {4, 5}
