@@ -218,6 +218,14 @@ int pab_gated_fc_forward(int b, int f, int c_out, const float *v, const float *f
                          const float *gate_wt, const float *gate_scale, const float *gate_shift, int l2_norm, float *desc,
                          void *workspace, pab_stream_t s);
 
+/* Device side of the input pipeline (SceneDataSet.get_pc + normalize_point_cloud, datasets/scene_dataset.py:713-740,
+ * utils/loading_pointclouds.py:51-63): raw (b,n,3) clouds as stored in the .bin files (float64 when raw_is_f64, else float32;
+ * device memory) minus the host array offset[3] (global_offset, may be NULL), optionally centred on the mean (normalize) and
+ * divided by the largest point norm (zoom), written as the float32 (b,n,3) batch the network takes.  meta (b,4) double, may be
+ * NULL: {scale, trans.x, trans.y, trans.z} = the reference's norm_meta.  float64 arithmetic, n <= 8192. */
+int pab_prepare_clouds(int b, int n, const void *raw, int raw_is_f64, const double *offset, int normalize, int zoom, float *out,
+                       double *meta, pab_stream_t s);
+
 /* Patch-feature-contrast (a2b) triplet selection of one training step — replaces the per-pair numpy where/isin loop and the
  * per-triplet index_select + H2D copies of place_recognition/train_place_recognition.py:320-378.
  * centers (n_clouds, M) int32 level-0 centre indices; pair p = clouds (pair_m[p], pair_n[p]) (rows of `centers`) with overlap

@@ -78,6 +78,7 @@ SIGNATURES = {
     "pab_afa_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
     "pab_gated_fc_workspace_bytes": (_SZ, [_I, _I, _I]),
     "pab_gated_fc_forward": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P]),
+    "pab_prepare_clouds": (_I, [_I, _I, _P, _I, C.POINTER(C.c_double), _I, _I, _P, _P, _P]),
     "pab_patch_triplets": (_I, [_I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, C.c_ulonglong, _I, _P, _P, _P, _P, _P]),
     "pab_afa_forward": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P]),
 }

@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(256) vlad_finalize_kernel(int c, int K, int nc
         float sq = 0.f;
         for (int c0 = lane * 4; c0 < c; c0 += 128) {                       // c <= 256: two float4 per lane
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8                                        // independent loads, additions in chunk order
             for (int ch = 0; ch < nchunk; ++ch) {
                 const float4 p4 = __ldg(reinterpret_cast<const float4 *>(part + (((size_t)cloud * nchunk + ch) * K + k) * c + c0));
                 v.x += p4.x; v.y += p4.y; v.z += p4.z; v.w += p4.w;
@@ -304,8 +305,10 @@ __global__ void __launch_bounds__(1024) afa_finalize_kernel(int b, int c_out, in
     for (int o0 = 0; o0 < c_out; o0 += 256) {
         const int o = o0 + ot;
         float s = 0.f;
-        if (o < c_out)
+        if (o < c_out) {
+#pragma unroll 12                                       // independent loads (latency-bound), the additions stay in slice order
             for (int sl = g; sl < nslice; sl += 4) s += __ldg(part + ((size_t)sl * b + cloud) * c_out + o);
+        }
         __syncthreads();
         grp[g][ot] = s;
         __syncthreads();

@@ -243,3 +243,18 @@ def test_losses_match_plain_restatement():
     want = torch.stack([(x - y + 1e-6).norm() ** 2 for x, y in zip(a, b)]).mean() + \
         torch.stack([(0.8 - (x - y + 1e-6).norm()).clamp(min=0) ** 2 for x, y in zip(a, c)]).mean()
     assert torch.allclose(losses.contrastive_loss(a, b, c, 0.8), want, atol=1e-5)
+
+
+def test_prepare_oracle_reproduces_the_reference_normalisation():
+    """oracle/prepare.py against tests/golden/prepare_ref.npz (the reference's normalize_point_cloud, make_prepare_golden.py)."""
+    import os
+    from oracle import prepare
+    import util
+    g = np.load(os.path.join(util.GOLDEN, "prepare_ref.npz"))
+    for i in range(3):
+        for zoom in (True, False):
+            pc, meta = prepare.get_pc(g[f"raw{i}"], g[f"offset{i}"], normalize=True, zoom=zoom)
+            assert np.array_equal(pc, g[f"pc{i}_zoom{int(zoom)}"])
+            assert meta["scale"] == g[f"scale{i}_zoom{int(zoom)}"] and np.array_equal(meta["trans"], g[f"trans{i}_zoom{int(zoom)}"])
+    pc, meta = prepare.get_pc(g["raw0"], g["offset0"], normalize=False)
+    assert np.array_equal(pc, g["raw0"] - g["offset0"]) and meta["scale"] == 1.0
