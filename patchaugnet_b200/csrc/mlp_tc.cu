@@ -9,7 +9,7 @@
 //     which carries ~16 mantissa bits through every product (error ~2^-17 per term, fp32 accumulation) — the
 //     descriptors stay within the 1e-4 contract where a single TF32/bf16 pass does not.
 //   * the layer-0 operand (gathered rows) lives in shared memory in the canonical K-major SWIZZLE_128B layout and is
-//     written by four dedicated LOADER warps; the operands of layers >= 1 never touch shared memory: the epilogue writes
+//     written by dedicated LOADER warps (6 in FP, 4 in SA mode); the operands of layers >= 1 never touch shared memory: the epilogue writes
 //     them straight back into TENSOR MEMORY (tcgen05.st) and the next layer's MMAs read A from TMEM (TS form).  TMEM
 //     holds D (256 fp32 columns) + the hi plane (128 columns of bf16 pairs) + the lo plane (128) = 512 columns.
 //     Shared memory is therefore free again as soon as the layer-0 MMAs have completed, and the loaders gather tile i+1
