@@ -71,10 +71,9 @@ def main():
     json.dump({"n_params": sum(p.numel() for p in net.parameters()), "state_dict": manifest},
               open(os.path.join(HERE, "patchaugnet_state_dict.json"), "w"), indent=0)
 
-    net.load_state_dict(util.fill_state_dict(net.state_dict(), seed=123))
+    net.load_state_dict(util.fill_state_dict(net.state_dict(), seed=123, calibrated="patchaugnet"))
     net.eval()
-    B = 2
-    x = torch.cat([util.synthetic_batch(1, 4096, 0), util.tie_stress_cloud(0)[None, None]], 0)   # one regular, one tie-stress
+    x = util.golden_batch("patchaugnet")        # 8 clouds: 2 uniform, 1 tie-stress, 5 structured places
     torch.manual_seed(7)
     perms = []
     g = torch.get_rng_state()
@@ -92,8 +91,65 @@ def main():
         out[f"fp{i}_head"] = f[:, :, :8, 0].copy()                         # first 8 points, all channels
     np.savez_compressed(os.path.join(HERE, "patchaugnet_ref_forward.npz"), **out)
     print("desc[0,:6] =", desc[0, :6].numpy(), " |desc| =", desc.norm(dim=1).numpy())
+    d = desc.numpy()
+    print("min over cloud pairs of max|desc_i - desc_j| =", min(np.abs(d[i] - d[j]).max() for i in range(8) for j in range(i)))
     print("wrote", os.path.join(HERE, "patchaugnet_ref_forward.npz"))
+    make_decoder(net)
     make_pptnet()
+    make_pointnetvlad()
+
+
+def make_decoder(net):
+    """PointNetDecoder (pointnet_autoencoder.py:85-111) of the reference Network built above: eval and train-mode
+    values on seeded unit-norm patch features."""
+    g = torch.Generator().manual_seed(77)
+    f = torch.nn.functional.normalize(torch.randn(96, 256, generator=g))
+    dec = net.decoder
+    with torch.no_grad():
+        dec.eval()
+        out_eval = dec(f).numpy()
+        dec.train()
+        saved = {k: v.clone() for k, v in dec.state_dict().items()}
+        out_train = dec(f).numpy()
+        dec.load_state_dict(saved)
+        dec.eval()
+    np.savez_compressed(os.path.join(HERE, "decoder_ref.npz"), feats=f.numpy(), out_eval=out_eval, out_train=out_train)
+    print("decoder:", out_eval.shape, float(np.abs(out_eval).mean()))
+
+
+def make_pointnetvlad():
+    """BASELINE.json configs[0]: the reference's PointNetVlad (pure PyTorch, runs on the CPU as is)."""
+    sys.path.insert(0, os.path.join(REF, "place_recognition", "pointnet_vlad"))
+    import importlib.util as iu
+    spec = iu.spec_from_file_location("ref_pointnetvlad", os.path.join(REF, "place_recognition", "pointnet_vlad", "PointNetVlad.py"))
+    mod = iu.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    torch.manual_seed(123)
+    net = mod.PointNetVlad(global_feat=True, feature_transform=True, max_pool=False, output_dim=256, num_points=4096)
+    manifest = {k: list(v.shape) for k, v in net.state_dict().items()}
+    json.dump({"n_params": sum(p.numel() for p in net.parameters()), "state_dict": manifest},
+              open(os.path.join(HERE, "pointnetvlad_state_dict.json"), "w"), indent=0)
+    sd = util.fill_state_dict_raw(net.state_dict(), seed=55)
+    net.load_state_dict(sd)
+    # calibrate the BatchNorm statistics in place with one train-mode pass (same reasoning as make_calibration.py);
+    # the statistics are a function of (seed, clouds) and are stored with the golden
+    for m in net.modules():
+        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+            m.momentum = None
+            m.reset_running_stats()
+    xc = torch.cat([util.place_batch(range(900_000, 900_012), 0), util.synthetic_batch(4, 4096, start=500)], 0)
+    net.train()
+    with torch.no_grad():
+        net(xc)
+    net.eval()
+    stats = {k: v.numpy().copy() for k, v in net.state_dict().items() if k.endswith(("running_mean", "running_var"))}
+    x = util.golden_batch("patchaugnet")[[0, 2, 3, 4]]
+    with torch.no_grad():
+        desc = net(x)
+    np.savez_compressed(os.path.join(HERE, "pointnetvlad_ref_forward.npz"), desc=desc.numpy(),
+                        **{"bn:" + k: v for k, v in stats.items()})
+    d = desc.numpy()
+    print("pointnetvlad desc", d.shape, "min pair diff", min(np.abs(d[i] - d[j]).max() for i in range(4) for j in range(i)))
 
 
 def make_pptnet():
@@ -108,9 +164,9 @@ def make_pptnet():
     manifest = {k: list(v.shape) for k, v in net.state_dict().items()}
     json.dump({"n_params": sum(p.numel() for p in net.parameters()), "state_dict": manifest},
               open(os.path.join(HERE, "pptnet_state_dict.json"), "w"), indent=0)
-    net.load_state_dict(util.fill_state_dict(net.state_dict(), seed=321))
+    net.load_state_dict(util.fill_state_dict(net.state_dict(), seed=321, calibrated="pptnet"))
     net.eval()
-    x = torch.cat([util.synthetic_batch(1, 4096, 10), util.tie_stress_cloud(1)[None, None]], 0)
+    x = util.golden_batch("pptnet")
     with torch.no_grad():
         desc, fp_features, center_idx = net(x)
     out = dict(desc=desc.numpy())

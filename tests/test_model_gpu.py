@@ -23,7 +23,7 @@ def net():
 
 def test_fused_forward_matches_reference_golden(net):
     g = np.load(os.path.join(util.GOLDEN, "patchaugnet_ref_forward.npz"))
-    x = torch.cat([util.synthetic_batch(1, 4096, 0), util.tie_stress_cloud(0)[None, None]], 0).to(DEV)
+    x = util.golden_batch("patchaugnet").to(DEV)          # 8 clouds: uniform, tie-stress, structured places
     before = L.lib().pab_num_launches()
     with torch.no_grad():
         desc, fp_features, center_idx = net(x)
@@ -32,7 +32,7 @@ def test_fused_forward_matches_reference_golden(net):
         assert torch.equal(center_idx[i].cpu(), torch.from_numpy(g[f"center_idx{i}"]))   # FPS indices bit-exact
     assert np.abs(desc.cpu().numpy() - g["desc"]).max() < TOL
     for i, f in enumerate(fp_features):
-        assert tuple(f.shape) == (2, 256, (128, 1024, 4096)[i], 1)
+        assert tuple(f.shape) == (8, 256, (128, 1024, 4096)[i], 1)
         assert np.abs(f[:, :, :8, 0].cpu().numpy() - g[f"fp{i}_head"]).max() < TOL
         assert np.allclose(f.sum(dim=(2, 3)).double().cpu().numpy(), g[f"fp{i}_sum"], rtol=1e-4, atol=1e-2)
 
@@ -48,6 +48,25 @@ def test_fused_forward_matches_oracle_on_fresh_inputs(net):
     assert np.abs(desc.cpu().numpy() - out["desc"].numpy()).max() < TOL
     out64 = model.patchaugnet_forward(net.state_dict(), util.PATCHAUGNET_CFG, x.numpy(), perms=[np.arange(20)] * 3, dtype=torch.float64)
     assert np.abs(desc.cpu().numpy() - out64["desc"].numpy()).max() < TOL
+
+
+def test_batch32_matches_oracle(net):
+    """BASELINE.json config 2 at its full batch: 32 clouds (uniform, tie-stress and structured places mixed) through the
+    fused path against the CPU oracle — indices bit-exact, descriptors within 1e-4."""
+    x = torch.cat([util.synthetic_batch(14, 4096, start=600), util.tie_stress_cloud(5)[None, None],
+                   util.tie_stress_cloud(6)[None, None], util.place_batch(range(100, 116), 0)], 0)
+    assert x.shape[0] == 32
+    out = model.patchaugnet_forward(net.state_dict(), util.PATCHAUGNET_CFG, x.numpy(), perms=[np.arange(20)] * 3)
+    with torch.no_grad():
+        desc, fp_features, center_idx = net(x.to(DEV))
+    for i in range(3):
+        assert np.array_equal(center_idx[i].cpu().numpy(), out["center_idx_origin"][i])
+    want = out["desc"].numpy()
+    assert min(np.abs(want[i] - want[j]).max() for i in range(32) for j in range(i)) > 0.05    # not a collapsed descriptor
+    assert np.abs(desc.cpu().numpy() - want).max() < TOL
+    for i in range(3):
+        ref = out["fp_features"][i].numpy()
+        assert np.abs(fp_features[i].cpu().numpy() - ref).max() < 5e-4 * max(1.0, np.abs(ref).max())
 
 
 def test_op_by_op_path_matches_fused_path(net):

@@ -187,12 +187,17 @@ def test_state_dict_manifest_matches_reference():
 def test_oracle_model_matches_reference_forward_golden():
     g = np.load(os.path.join(util.GOLDEN, "patchaugnet_ref_forward.npz"))
     net = util.build_network()
-    x = torch.cat([util.synthetic_batch(1, 4096, 0), util.tie_stress_cloud(0)[None, None]], 0)
+    x = util.golden_batch("patchaugnet")
+    d = g["desc"]
+    # the golden is discriminative: descriptors of different clouds differ by O(0.1) per element, so the 1e-4 contract
+    # is 1e-3 of the input-dependent signal (round 1: 5e-3, VERDICT weak #1)
+    assert len(d) == 8 and min(np.abs(d[i] - d[j]).max() for i in range(8) for j in range(i)) > 0.1
     out = model.patchaugnet_forward(net.state_dict(), util.PATCHAUGNET_CFG, x.numpy(), perms=list(g["perms"]))
     for i in range(3):
         assert np.array_equal(out["center_idx_origin"][i], g[f"center_idx{i}"])          # bit-exact indices
-        assert np.allclose(out["fp_features"][i].numpy()[:, :, :8, 0], g[f"fp{i}_head"], atol=1e-5, rtol=1e-5)
-    assert np.abs(out["desc"].numpy() - g["desc"]).max() < 1e-6
+        # activations reach |x| ~ 9 with the calibrated statistics; the restated BatchNorm formula rounds differently
+        assert np.allclose(out["fp_features"][i].numpy()[:, :, :8, 0], g[f"fp{i}_head"], atol=5e-5, rtol=1e-5)
+    assert np.abs(out["desc"].numpy() - g["desc"]).max() < 5e-6
     # float64 dense path agrees with the fp32 reference within the 1e-4 contract of the north star
     out64 = model.patchaugnet_forward(net.state_dict(), util.PATCHAUGNET_CFG, x.numpy(), perms=list(g["perms"]), dtype=torch.float64)
     assert np.abs(out64["desc"].numpy() - g["desc"]).max() < 1e-5
@@ -208,11 +213,13 @@ def test_pptnet_state_dict_and_oracle_match_reference_golden():
     sa = net.backbone.SA_modules[0].sas[0]
     assert sa.q_conv.weight is sa.k_conv.weight                                  # tied projection, pptnet.py:254
     g = np.load(os.path.join(util.GOLDEN, "pptnet_ref_forward.npz"))
-    x = torch.cat([util.synthetic_batch(1, 4096, 10), util.tie_stress_cloud(1)[None, None]], 0)
+    x = util.golden_batch("pptnet")
+    d = g["desc"]
+    assert len(d) == 8 and min(np.abs(d[i] - d[j]).max() for i in range(8) for j in range(i)) > 0.1
     out = model.pptnet_forward(sd, util.PPTNET_CFG, x.numpy())
     for i in range(4):
         assert np.array_equal(out["center_idx_origin"][i], g[f"center_idx{i}"])
-    assert np.abs(out["desc"].numpy() - g["desc"]).max() < 1e-6
+    assert np.abs(out["desc"].numpy() - g["desc"]).max() < 5e-6
 
 
 def test_pointnetvlad_cpu_plumbing_config():
@@ -224,6 +231,41 @@ def test_pointnetvlad_cpu_plumbing_config():
     with torch.no_grad():
         out = net(util.synthetic_batch(1, 4096, 0))
     assert out.shape == (1, 256) and torch.isfinite(out).all()
+
+
+def test_pointnetvlad_matches_reference_module_golden():
+    """Values, not just shapes: tests/golden/pointnetvlad_ref_forward.npz is the output of the reference's own
+    PointNetVlad.py (make_golden.py make_pointnetvlad) for seeded weights with calibrated BatchNorm statistics."""
+    from patchaugnet_b200.pointnet_vlad import PointNetVlad
+    man = json.load(open(os.path.join(util.GOLDEN, "pointnetvlad_state_dict.json")))
+    g = np.load(os.path.join(util.GOLDEN, "pointnetvlad_ref_forward.npz"))
+    net = PointNetVlad(num_points=4096, global_feat=True, feature_transform=True, max_pool=False, output_dim=256)
+    sd = net.state_dict()
+    assert list(sd.keys()) == list(man["state_dict"].keys()) and all(list(sd[k].shape) == man["state_dict"][k] for k in sd)
+    sd = util.fill_state_dict_raw(sd, seed=55)
+    for k in g.files:
+        if k.startswith("bn:"):
+            sd[k[3:]] = torch.from_numpy(g[k])
+    net.load_state_dict(sd)
+    net.eval()
+    with torch.no_grad():
+        desc = net(util.golden_batch("patchaugnet")[[0, 2, 3, 4]]).numpy()
+    d = g["desc"]
+    assert min(np.abs(d[i] - d[j]).max() for i in range(4) for j in range(i)) > 0.1       # a discriminative golden
+    assert np.abs(desc - d).max() < 1e-5
+
+
+def test_pointnet_decoder_matches_reference_module_golden():
+    """PointNetDecoder values (eval and train-mode BatchNorm) against the reference module's outputs."""
+    g = np.load(os.path.join(util.GOLDEN, "decoder_ref.npz"))
+    dec = util.build_network().decoder
+    f = torch.from_numpy(g["feats"])
+    with torch.no_grad():
+        dec.eval()
+        assert np.abs(dec(f).numpy() - g["out_eval"]).max() < 1e-5
+        dec.train()
+        assert np.abs(dec(f).numpy() - g["out_train"]).max() < 1e-5
+        dec.eval()
 
 
 def test_losses_match_plain_restatement():
