@@ -14,8 +14,15 @@ One "step" = one pass of the descriptor-extraction hot path (PatchAugNet eval fo
             timed region; algorithmic FLOPs/bytes per launch from patchaugnet_b200.engine.stage_work.
   cpu_baseline  the CPU oracle (oracle/, a port of the reference path) on a bounded sample, rank 0, N=1 only.
 
+  stock_gpu     the reference's own Python + its own CUDA kernels compiled for sm_100 (oracle/_ref), same batch: the
+                north star's ">= 10x the stock libs/* build" denominator, fp32 and cuDNN-TF32.
+  pointnetvlad_cpu  BASELINE.json configs[0]: the reference's pure-PyTorch PointNetVLAD forward on the host cores.
+  measured_peaks    fp32 / TF32 / bf16 matmul 8192^3 and copy bandwidth measured in this run (the fp32 configs' peaks).
+  configs       sub-records for BASELINE.json configs[2] (PPT-Net batch 64) and configs[3] (10k-submap retrieval).
+
 --impl reference: the reference path's CPU implementation (the oracle port: the reference ships no CPU code for
-pointops, and its CUDA kernels are what this repo replaces) on the host cores, same metric / config.
+pointops, and its CUDA kernels are what this repo replaces) on the host cores, same metric / config / step shape
+(32 clouds per step, scans OpenMP-parallel over all host threads).
 """
 import argparse
 import json
@@ -88,7 +95,7 @@ class ClockSampler:
                     reasons=sorted(reasons), samples=len(sm))
 
 
-def cpu_oracle_throughput(budget_s=15.0, clouds_per_call=4):
+def cpu_oracle_throughput(budget_s=15.0, clouds_per_call=32):
     """The oracle port of the path on the host cores: submaps/s over a bounded sample (about `budget_s` seconds)."""
     import util
     from oracle import model
@@ -101,39 +108,215 @@ def cpu_oracle_throughput(budget_s=15.0, clouds_per_call=4):
         model.patchaugnet_forward(sd, util.PATCHAUGNET_CFG, x)
         done += clouds_per_call
         el = time.perf_counter() - t0
-        if el >= budget_s or done >= 64:
+        if el >= budget_s or done >= 256:
             break
     return done / el, done, el
 
 
 def run_reference(args):
-    """--impl reference: oracle port on the host cores; rank 0 only."""
+    """--impl reference: oracle port on the host cores, same step shape as the GPU arm (args.batch clouds per step);
+    rank 0 only.  Steps are capped so that the whole run stays within a few minutes on a slow host."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    per_step = 4
+    per_step = args.batch
     import util
     from oracle import model
     net = util.build_network("cpu")
     sd = net.state_dict()
     x = util.synthetic_batch(per_step, NPTS, start=0).numpy()
-    for _ in range(max(1, min(args.warmup, 2))):
+    t0 = time.perf_counter()
+    model.patchaugnet_forward(sd, util.PATCHAUGNET_CFG, x)          # warm-up 1 (library load, thread pools)
+    t_first = time.perf_counter() - t0
+    for _ in range(max(0, min(args.warmup, 2) - 1)):
         model.patchaugnet_forward(sd, util.PATCHAUGNET_CFG, x)
-    steps = max(1, min(args.steps, 8))
+    steps = max(1, min(args.steps, int(180.0 / max(t_first, 1e-3))))
     t0 = time.perf_counter()
     for _ in range(steps):
         model.patchaugnet_forward(sd, util.PATCHAUGNET_CFG, x)
     el = time.perf_counter() - t0
     val = steps * per_step / el
-    sample = f"{steps} steps x {per_step} clouds x {NPTS} pts, PatchAugNet eval forward, fp32"
+    sample = (f"{steps} steps x {per_step} clouds x {NPTS} pts, oracle PatchAugNet eval forward, fp32 (C scans OpenMP over "
+              f"{os.cpu_count()} threads, dense layers torch-CPU)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
         "ms_per_step": el / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"PatchAugNet descriptor extraction, {per_step} x {NPTS}-pt clouds per step (bounded sample of batch 32), fp32, host CPU"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "config": {"workload": f"PatchAugNet descriptor extraction, batch {per_step} x {NPTS}-pt synthetic clouds, fp32, eval "
+                               "(BASELINE.json configs[1]) on the host CPU", "global_batch": per_step},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
+
+
+def measure_matmul_peaks(dev):
+    """Same method as MEASURED_PEAKS.json (torch.matmul 8192^3, best of 5, CUDA events) for fp32, TF32 and bf16, plus a
+    1 GiB device copy: the peaks the fp32 configurations can be read against."""
+    n = 8192
+    out = {}
+    a32 = torch.randn(n, n, device=dev)
+    b32 = torch.randn(n, n, device=dev)
+    saved = torch.backends.cuda.matmul.allow_tf32
+
+    def best(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return min(ts) * 1e-3
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        out["fp32_tflops"] = 2 * n ** 3 / best(lambda: torch.matmul(a32, b32), 3) / 1e12
+        torch.backends.cuda.matmul.allow_tf32 = True
+        out["tf32_tflops"] = 2 * n ** 3 / best(lambda: torch.matmul(a32, b32), 5) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = saved
+    a16, b16 = a32.bfloat16(), b32.bfloat16()
+    out["bf16_tflops"] = 2 * n ** 3 / best(lambda: torch.matmul(a16, b16), 5) / 1e12
+    src = torch.empty(1 << 28, device=dev)
+    dst = torch.empty_like(src)
+    out["copy_gbs"] = 2 * src.numel() * 4 / best(lambda: dst.copy_(src), 5) / 1e9
+    out["how"] = "torch.matmul 8192^3 best-of-N with CUDA events (fp32 = allow_tf32 off), 1 GiB fp32 copy_ (read+write)"
+    return out
+
+
+def stock_gpu_throughput(dev, B):
+    """The reference's own nn.Module Python (oracle/_ref/refpy) over the reference's own kernels compiled for sm_100
+    (oracle/_ref/libref_kernels.so) + cuDNN: what the stock libs/* build does on this GPU.  Timed like the reference
+    times itself (synchronise + wall clock around model(x), datasets/scene_dataset.py:672-686), median of 5."""
+    try:
+        from oracle import refgpu, refpy
+        if not (refpy.available() and refgpu.available()):
+            return {"unavailable": "oracle/_ref (reference kernels + refpy) not built"}
+        import util
+        net0 = util.build_network("cpu")
+        x = util.synthetic_batch(B, NPTS, start=0).unsqueeze(1).squeeze(1).to(dev)
+        res = {}
+        saved = torch.backends.cudnn.allow_tf32
+        ref_net = refpy.reference_patchaugnet(net0.state_dict(), dev, "stock")
+        for tf32 in (False, True):
+            torch.backends.cudnn.allow_tf32 = tf32
+            with torch.no_grad():
+                for _ in range(2):
+                    ref_net(x)
+                torch.cuda.synchronize()
+                ts = []
+                for _ in range(5):
+                    t0 = time.perf_counter()
+                    ref_net(x)
+                    torch.cuda.synchronize()
+                    ts.append(time.perf_counter() - t0)
+            med = sorted(ts)[len(ts) // 2]
+            res["cudnn_tf32" if tf32 else "fp32"] = dict(ms_per_batch=med * 1e3, submaps_per_s=B / med)
+        torch.backends.cudnn.allow_tf32 = saved
+        res["what"] = ("reference patch_aug_net.Network + pointops.py (unchanged Python) over the reference's CUDA kernels built "
+                       "for sm_100 + PyTorch/cuDNN conv/BN/matmul; batch %d" % B)
+        return res
+    except Exception as ex:                                    # a baseline leg must never take the bench line down
+        return {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
+
+
+def pointnetvlad_cpu():
+    """BASELINE.json configs[0] / SURVEY 8(d) CPU baseline (i): PointNetVLAD forward on the host cores (pure PyTorch in the
+    reference; the reference's own file when oracle/_ref/refpy travelled, this repo's mirror of it otherwise)."""
+    try:
+        import util
+        torch.set_num_threads(os.cpu_count() or 1)
+        which = "mirror patchaugnet_b200.pointnet_vlad"
+        net = None
+        try:
+            from oracle import refpy
+            if refpy.available():
+                import importlib.util as iu
+                spec = iu.spec_from_file_location("ref_pointnetvlad", os.path.join(refpy.REFPY, "place_recognition", "pointnet_vlad", "PointNetVlad.py"))
+                mod = iu.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                net = mod.PointNetVlad(global_feat=True, feature_transform=True, max_pool=False, output_dim=256, num_points=NPTS)
+                which = "reference place_recognition/pointnet_vlad/PointNetVlad.py"
+        except Exception:
+            net = None
+        if net is None:
+            from patchaugnet_b200.pointnet_vlad import PointNetVlad
+            net = PointNetVlad(num_points=NPTS, global_feat=True, feature_transform=True, max_pool=False, output_dim=256)
+        net.eval()
+        out = {}
+        for b in (1, 8):
+            x = util.synthetic_batch(b, NPTS, start=0)
+            with torch.no_grad():
+                net(x)
+                ts = []
+                for _ in range(5):
+                    t0 = time.perf_counter()
+                    net(x)
+                    ts.append(time.perf_counter() - t0)
+            med = sorted(ts)[2]
+            out[f"batch{b}"] = dict(ms_per_forward=med * 1e3, submaps_per_s=b / med)
+        out.update(cores=os.cpu_count(), torch_threads=torch.get_num_threads(), module=which)
+        return out
+    except Exception as ex:
+        return {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
+
+
+def other_configs(dev, world, rank):
+    """Sub-records for the BASELINE.json configurations that are not the bench line."""
+    import torch.distributed as dist
+    import util
+    from patchaugnet_b200 import retrieval
+    out = {}
+    # configs[2]: PPT-Net, batch 64 x 4096
+    try:
+        ppt = util.build_pptnet(dev)
+        x = torch.cat([util.synthetic_batch(16, NPTS, start=0)] * 4).to(dev)
+        with torch.no_grad():
+            for _ in range(2):
+                ppt(x)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                ppt(x)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        out["cfg3_pptnet_b64"] = dict(ms_per_batch=ms, submaps_per_s_per_gpu=64 / (ms * 1e-3), dtype=getattr(ppt, "compute_dtype", "f32"),
+                                      what="PPT-Net eval, batch 64 x 4096, fused engine, one GPU")
+        del ppt, x
+    except Exception as ex:
+        out["cfg3_pptnet_b64"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
+    # configs[3]: 10k-submap database + 2k queries: sharded extraction, ONE all-gather, sharded top-k, Recall counters
+    try:
+        n_db, n_q = 10000, 2000
+        net = util.build_network(dev)
+        g = torch.Generator(device=dev).manual_seed(4321)         # same clouds on every rank; each rank reads its shard only
+        clouds = (torch.rand(n_db + n_q, NPTS, 3, generator=g, device=dev) * 2 - 1) * 0.57
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        with torch.no_grad():
+            db = retrieval.extract_descriptors(net, clouds[:n_db], batch_size=32, device=dev)
+            qd = retrieval.extract_descriptors(net, clouds[n_db:], batch_size=32, device=dev)
+        e1.record()
+        res = retrieval.evaluate_recall(db, qd, [{i} for i in range(n_q)], top_k=25)
+        e2.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1), e1.elapsed_time(e2)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_ext, t_ret = t.tolist()
+        out["cfg4_retrieval_10k"] = dict(extract_ms=t_ext, retrieval_ms=t_ret, submaps_per_s=(n_db + n_q) / (t_ext * 1e-3),
+                                         queries_per_s=n_q / (t_ret * 1e-3), k=res["k"], n_gpus=world,
+                                         what="10000 db + 2000 query clouds resident in HBM, sharded by rank, one all_gather per "
+                                              "descriptor set, brute-force top-k per query shard, hit counters all_reduced")
+        del clouds, db, qd
+    except Exception as ex:
+        out["cfg4_retrieval_10k"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
+    return out
 
 
 def main():
@@ -144,6 +327,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip stock_gpu / pointnetvlad_cpu / measured_peaks / configs sub-records")
+    ap.add_argument("--repeats", type=int, default=0, help="repetitions of the K-step timed region (0 = enough for >= 200 steps)")
     ap.add_argument("--mode", default="stream", choices=["stream", "graph", "eager"],
                     help="stream: 2-stream pipelined throughput mode (default); graph: one CUDA graph per step; eager")
     ap.add_argument("--dense-streams", type=int, default=2)
@@ -231,34 +416,42 @@ def main():
     gathered = torch.empty(world * K * B, 256, device=dev) if world > 1 else None
     local_desc = torch.empty(K * B, 256, device=dev)
 
-    # ---- timed region: exactly K steps, device-resident inputs ---------------------------------------------------
+    # ---- timed region: exactly K steps, device-resident inputs; the region is repeated R times (each repetition is
+    # bracketed by barrier + synchronise, timed with CUDA events, max over ranks) and the MEDIAN repetition is reported,
+    # so that the measurement spans >= 200 steps / several clock samples even when K is small -------------------------
+    R = args.repeats if args.repeats > 0 else max(1, -(-200 // K))
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    sync_all()
-    lib.pab_reset_launch_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    with torch.no_grad():
-        if mode == "stream":     # throughput mode: batch i+1's geometry overlaps batch i's dense kernels (2 streams)
-            eng.forward_stream([pool[(W + i) % pool_batches] for i in range(K)], out=local_desc)
-        else:
-            for i in range(K):
-                desc = eng(pool[(W + i) % pool_batches], clone=False, return_feat=False)
-                local_desc[i * B:(i + 1) * B].copy_(desc)
-        if world > 1:   # the one collective of the path: all-gather of the 256-D descriptors before retrieval
-            dist.all_gather_into_tensor(gathered, local_desc)
-    e1.record()
-    sync_all()
-    elapsed_ms = e0.elapsed_time(e1)
-    launches = lib.pab_num_launches()
+    region_ms = []
+    launches = 0
+    for rep in range(R):
+        sync_all()
+        lib.pab_reset_launch_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        with torch.no_grad():
+            if mode == "stream":     # throughput mode: batch i+1's geometry overlaps batch i's dense kernels (2 streams)
+                eng.forward_stream([pool[(W + rep * K + i) % pool_batches] for i in range(K)], out=local_desc)
+            else:
+                for i in range(K):
+                    desc = eng(pool[(W + rep * K + i) % pool_batches], clone=False, return_feat=False)
+                    local_desc[i * B:(i + 1) * B].copy_(desc)
+            if world > 1:   # the one collective of the path: all-gather of the 256-D descriptors before retrieval
+                dist.all_gather_into_tensor(gathered, local_desc)
+        e1.record()
+        sync_all()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        region_ms.append(ms)
+        launches = lib.pab_num_launches()
     if mode == "graph":
         launches = K * eng.launches_per_forward()        # graph replays do not pass through the C ABI counter
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([elapsed_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = t.item()
+    elapsed_ms = float(np.median(region_ms))
     value = world * B * K / (elapsed_ms * 1e-3)
 
     # ---- dominant kernel: events around that stage only, K eager steps over the same rotating inputs -----------
@@ -294,9 +487,10 @@ def main():
     tc_stages = {"sa0", "sa1", "sa2", "fp0", "fp1", "vlad0", "vlad1", "vlad2"}
 
     def traffic_of(stage):
-        """DRAM bytes per launch from the committed `ncu --set full` capture (profiles/r01_traffic.json), B=32 only."""
+        """DRAM bytes per launch from the committed `ncu --set full` capture (profiles/r0N_traffic.json), B=32 only."""
         try:
-            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            name = "r02_traffic.json" if os.path.exists(os.path.join(ROOT, "profiles", "r02_traffic.json")) else "r01_traffic.json"
+            with open(os.path.join(ROOT, "profiles", name)) as f:
                 t = json.load(f)["dram_bytes_per_launch"]
             return int(t[stage]) if B == 32 and stage in t else None
         except (OSError, KeyError, ValueError):
@@ -341,8 +535,18 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
         v, done, el = cpu_oracle_throughput()
-        cpu = dict(value=v, unit=UNIT, cores=torch.get_num_threads(), kind="port",
-                   sample=f"{done} clouds x {NPTS} pts in {el:.1f} s, oracle PatchAugNet eval forward fp32 (C scans single-threaded, dense layers torch-CPU)")
+        cpu = dict(value=v, unit=UNIT, cores=os.cpu_count(), kind="port",
+                   sample=f"{done} clouds x {NPTS} pts in {el:.1f} s (32 per call), oracle PatchAugNet eval forward fp32 "
+                          f"(C scans OpenMP over {os.cpu_count()} threads, dense layers torch-CPU)")
+
+    extras = {}
+    if not args.no_extras:
+        if rank == 0 and world == 1:
+            extras["stock_gpu"] = stock_gpu_throughput(dev, B)
+            extras["measured_peaks"] = measure_matmul_peaks(dev)
+            if not args.no_cpu_baseline:
+                extras["pointnetvlad_cpu"] = pointnetvlad_cpu()
+        extras["configs"] = other_configs(dev, world, rank)          # collective at world > 1: every rank takes part
 
     if rank == 0:
         print(json.dumps({
@@ -353,7 +557,9 @@ def main():
                                    "(BASELINE.json configs[1])", "global_batch": world * B, "l2": "inputs_larger_than_l2 (164 MB rotating pool)",
                        "launch": mode, "parallelism": f"dp{world}, shard-by-submap, one all_gather of descriptors"},
             "roofline": roof, "roofline_all": roof_all, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "stage_ms": {k: round(v, 4) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1])}}))
+            "timed_region": {"repeats": R, "steps_per_repeat": K, "ms_per_repeat": [round(v, 4) for v in region_ms],
+                             "reported": "median repetition"},
+            "stage_ms": {k: round(v, 4) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1])}, **extras}))
     if world > 1:
         dist.destroy_process_group()
 

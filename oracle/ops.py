@@ -254,6 +254,26 @@ def chamfer_backward(xyz1, xyz2, idx1, idx2, g1, g2):
     return gx1, gx2
 
 
+def emd_forward(xyz1, xyz2, eps, iters):
+    """emdFunction.forward (emd_module.py:29-70) over emd_oracle.c -> dist (b,n) f32, assignment (b,n) i32,
+    price (b,n) f32, rounds used per cloud, number of GetMax decisions with more than one candidate per cloud."""
+    xyz1, p1 = _f(xyz1)
+    xyz2, p2 = _f(xyz2)
+    b, n, _ = xyz1.shape
+    assert xyz2.shape == xyz1.shape
+    dist = np.zeros((b, n), np.float32)
+    price = np.zeros((b, n), np.float32)
+    asg = np.zeros((b, n), np.int32)
+    rounds = np.zeros(b, np.int32)
+    ties = np.zeros(b, np.int32)
+    ip, fp = C.POINTER(C.c_int), C.POINTER(C.c_float)
+    rc = lib().ora_emd_forward(b, n, p1, p2, C.c_float(eps), int(iters), dist.ctypes.data_as(fp), asg.ctypes.data_as(ip),
+                               price.ctypes.data_as(fp), rounds.ctypes.data_as(ip), ties.ctypes.data_as(ip))
+    if rc != 1:
+        raise ValueError("emd oracle: unsupported shape")
+    return dist, asg, price, rounds, ties
+
+
 def knn_cuda_raw(ref, query, k):
     """ref (dim,nr), query (dim,nq) -> dist (k,nq) f32 (sqrt), ind (k,nq) int64 1-based.  knn.cpp:23-56."""
     ref, pr = _f(ref)

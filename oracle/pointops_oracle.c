@@ -48,9 +48,11 @@ ORA_API int ora_opt_n_threads(int work_size) {
 ORA_API void ora_furthestsampling(int b, int n, int m, const float *xyz, float *temp, int *idx) {
     if (m <= 0) return;
     const int bs = ora_opt_n_threads(n);
-    float *dists = (float *)malloc(sizeof(float) * bs);
-    int *dists_i = (int *)malloc(sizeof(int) * bs);
+    /* clouds are independent (one CUDA block per cloud in the reference): one host thread per cloud */
+#pragma omp parallel for schedule(dynamic, 1)
     for (int bi = 0; bi < b; ++bi) {
+        float *dists = (float *)malloc(sizeof(float) * bs);
+        int *dists_i = (int *)malloc(sizeof(int) * bs);
         const float *p = xyz + (size_t)bi * n * 3;
         float *t = temp + (size_t)bi * n;
         int *out = idx + (size_t)bi * m;
@@ -81,9 +83,9 @@ ORA_API void ora_furthestsampling(int b, int n, int m, const float *xyz, float *
             old = dists_i[0];
             out[j] = old;
         }
+        free(dists);
+        free(dists_i);
     }
-    free(dists);
-    free(dists_i);
 }
 
 /* sampling_cuda_kernel.cu:6-19 */
@@ -107,11 +109,13 @@ ORA_API void ora_gathering_backward(int b, int c, int n, int m, const float *gra
  * dist2[b,m,k] properly so it can be checked. */
 ORA_API int ora_knnquery(int b, int n, int m, int nsample, const float *xyz, const float *new_xyz, int *idx, float *dist2) {
     if (nsample > 200 || nsample < 0) return -1; /* fixed arrays best[200] at :21-22 */
-    double best[200];
-    int besti[200];
+    /* queries are independent (one CUDA thread per query in the reference): host threads over (cloud, query) */
+#pragma omp parallel for collapse(2) schedule(static)
     for (int bi = 0; bi < b; ++bi) {
-        const float *p = xyz + (size_t)bi * n * 3;
         for (int q = 0; q < m; ++q) {
+            double best[200];
+            int besti[200];
+            const float *p = xyz + (size_t)bi * n * 3;
             const float *c = new_xyz + ((size_t)bi * m + q) * 3;
             for (int i = 0; i < nsample; ++i) { best[i] = 1e40; besti[i] = 0; }
             for (int k = 0; k < n; ++k) {
@@ -191,9 +195,10 @@ ORA_API void ora_grouping_int_forward(int b, int c, int n, int m, int nsample, c
 
 /* libs/pointops/src/interpolation/interpolation_cuda_kernel.cu:134-176 (3-NN, _fast) */
 ORA_API void ora_nearestneighbor(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx) {
+#pragma omp parallel for collapse(2) schedule(static)
     for (int bi = 0; bi < b; ++bi) {
-        const float *kn = known + (size_t)bi * m * 3;
         for (int j = 0; j < n; ++j) {
+            const float *kn = known + (size_t)bi * m * 3;
             const float *u = unknown + ((size_t)bi * n + j) * 3;
             double best1 = 1e40, best2 = 1e40, best3 = 1e40;
             int besti1 = 0, besti2 = 0, besti3 = 0;
@@ -221,6 +226,7 @@ ORA_API void ora_nearestneighbor(int b, int n, int m, const float *unknown, cons
 /* interpolation_cuda_kernel.cu:181-195; nvcc contracts w0*p0 + w1*p1 + w2*p2 as
  * fmaf(w2,p2, fmaf(w0,p0, w1*p1)). */
 ORA_API void ora_interpolation_forward(int b, int c, int m, int n, const float *points, const int *idx, const float *weight, float *out) {
+#pragma omp parallel for collapse(2) schedule(static)
     for (int bi = 0; bi < b; ++bi)
         for (int l = 0; l < c; ++l) {
             const float *p = points + ((size_t)bi * c + l) * m;

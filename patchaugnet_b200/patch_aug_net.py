@@ -44,6 +44,7 @@ class Network(nn.Module):
         if self.use_a2a_recon:
             self.decoder = PointNetDecoder(embedding_size=256, num_points=param["KNN"][0])
         self._engine = None
+        self._engine_key = None
         self.use_fused = True
 
     # ---- fused eval path ---------------------------------------------------------------------------------------
@@ -57,31 +58,41 @@ class Network(nn.Module):
             g = mod.groupers[0]
             if not isinstance(g, pointops.QueryAndGroup_Edge) or not g.use_xyz:
                 return False
+            if g.nsample < 2:      # QueryAndGroup_Edge skips the centre subtraction for single-neighbour groups
+                return False       # (pointops.py:562-563); the fused loaders always subtract
         return len(self.backbone.SA_modules) == 3 and len(self.backbone.FP_modules) == 3
 
+    def _weights_key(self):
+        """Changes whenever any parameter / buffer is modified in place, replaced or moved (optimizer.step(), a parent's
+        or a child's load_state_dict, .to(device), frozen-BN fine-tuning in eval mode): tensor identity, device and
+        the autograd version counter of every entry."""
+        return tuple((id(t), t.device, t._version) for t in list(self.parameters()) + list(self.buffers()))
+
     def engine(self, refresh=False):
-        """The fused inference engine bound to this module's parameters (built lazily; refold after weight updates)."""
+        """The fused inference engine bound to this module's parameters.  Built lazily; the folded weights (BatchNorm
+        folded in, bf16 hi/lo planes) are refolded whenever the module's weights changed since they were derived."""
         from .engine import FusedPatchAugNet
-        if self._engine is None or self._engine.device != next(self.parameters()).device:
+        key = self._weights_key()
+        if self._engine is None or self._engine.device != key[0][1]:
             self._engine = FusedPatchAugNet(self)
-        elif refresh:
+        elif refresh or key != self._engine_key:
             self._engine.refold()
+        self._engine_key = key
         return self._engine
 
     def train(self, mode=True):
         if mode and self._engine is not None:
-            self._engine = None        # weights are about to change: drop the folded copy
+            self._engine = None        # weights are about to change: drop the folded copy and its workspaces
         return super().train(mode)
-
-    def load_state_dict(self, *args, **kwargs):
-        self._engine = None
-        return super().load_state_dict(*args, **kwargs)
 
     def forward(self, x, nn_dict=None, return_feat=True):
         """x: B x 1 x N x 3"""
+        # nn.DataParallel replicas (train_place_recognition.py:546-548) are shallow copies rebuilt on every forward whose
+        # parameters() is empty: they take the op-by-op path on the same kernels instead of refolding every call
         if (self.use_fused and not self.training and nn_dict is None and x.is_cuda and not torch.is_grad_enabled()
-                and self.fusable()):
-            return self.engine()(x, return_feat=return_feat)
+                and not getattr(self, "_is_replica", False) and self.fusable()):
+            with torch.cuda.device(x.device):
+                return self.engine()(x, return_feat=return_feat)
         x = x.squeeze(1)
         xyz = x
         res = self.backbone(x)

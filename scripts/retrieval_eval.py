@@ -29,41 +29,12 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
-def base_place(p, n=8192):
-    rng = np.random.default_rng(10_000 + p)
-    pts = []
-    per = int(n * 0.9) // 12
-    for _ in range(8):                                   # planes: random point + two in-plane axes
-        o = rng.uniform(-1, 1, 3)
-        a, b = rng.normal(size=3), rng.normal(size=3)
-        a /= np.linalg.norm(a); b -= a * (a @ b); b /= np.linalg.norm(b)
-        uv = rng.uniform(-0.8, 0.8, (per, 2))
-        pts.append(o + uv[:, :1] * a + uv[:, 1:] * b)
-    for _ in range(4):                                   # vertical-ish cylinders
-        o = rng.uniform(-1, 1, 3)
-        r = rng.uniform(0.05, 0.3)
-        th = rng.uniform(0, 2 * np.pi, per)
-        h = rng.uniform(-0.8, 0.8, per)
-        pts.append(o + np.stack([r * np.cos(th), r * np.sin(th), h], 1))
-    pts = np.concatenate(pts)
-    noise = rng.uniform(-1.5, 1.5, (n - len(pts), 3))
-    return np.concatenate([pts, noise]).astype(np.float32)
+def visit(p, v, npts=4096):
+    import util
+    return util.place_visit(p, v, npts, rotate=ROTATE)
 
 
 ROTATE = False
-
-
-def visit(p, v, npts=4096):
-    rng = np.random.default_rng(1_000_000 * (v + 1) + p)
-    base = base_place(p)
-    ang = rng.uniform(0, 2 * np.pi) if ROTATE else 0.0
-    c, s = np.cos(ang), np.sin(ang)
-    rot = np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]], np.float32)          # rotate_point_cloud: about the up axis
-    pts = base @ rot
-    pts = pts + np.clip(0.005 * rng.normal(size=pts.shape), -0.05, 0.05).astype(np.float32)
-    pts = pts[rng.choice(len(pts), npts, replace=False)]
-    pts = pts - pts.mean(0, keepdims=True)                                    # normalize_point_cloud
-    return (pts / np.max(np.linalg.norm(pts, axis=1))).astype(np.float32)
 
 
 def main():
@@ -73,6 +44,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--top-k", type=int, default=25)
     ap.add_argument("--rotate", action="store_true", help="random yaw per visit (random-init weights are not rotation invariant)")
+    ap.add_argument("--oracle-check", type=int, default=0, metavar="Q",
+                    help="also run the CPU oracle forward on the first 4Q database clouds and Q queries and compare Recall@N")
     args = ap.parse_args()
     global ROTATE
     ROTATE = args.rotate
@@ -146,7 +119,22 @@ def main():
                    kdtree_max_abs_dist_diff=float(np.abs(gd.cpu().numpy() - kd).max()),
                    kdtree_recall_identical=bool(np.array_equal(hits, hits_g) and one_pct == one_g),
                    gathered_db_identical_on_all_ranks=same_everywhere, data_gen_s=t_gen,
-                   weights="random-init (tests/util.fill_state_dict): recall measures pipeline agreement, not a trained model")
+                   weights="random-init + calibrated BatchNorm statistics (tests/util.fill_state_dict): recall measures pipeline "
+                           "agreement, not a trained model")
+        if args.oracle_check and world == 1:      # single-rank only: evaluate_recall is collective, clouds are sharded
+            from oracle import model                     # the checker, on a bounded sub-database (CPU: ~7 clouds/s)
+            nq_o, ndb_o = args.oracle_check, min(args.db, 4 * args.oracle_check)
+            perms = [np.arange(20)] * 3
+            fwd = lambda x: torch.cat([model.patchaugnet_forward(net.state_dict(), util.PATCHAUGNET_CFG, x[i:i + 16].numpy(),
+                                                                 perms=perms)["desc"] for i in range(0, len(x), 16)])
+            o_db, o_q = fwd(db_clouds[:ndb_o]), fwd(q_clouds[:nq_o])
+            r_new = retrieval.evaluate_recall(db[:ndb_o], qd[:nq_o], positives[:nq_o], top_k=args.top_k)
+            r_ref = retrieval.evaluate_recall(o_db.to(dev), o_q.to(dev), positives[:nq_o], top_k=args.top_k)
+            out["oracle_check"] = dict(db=ndb_o, queries=nq_o,
+                                       max_abs_desc_diff=float(max((db[:ndb_o].cpu() - o_db).abs().max(), (qd[:nq_o].cpu() - o_q).abs().max())),
+                                       recall_new=[float(r_new["recall"][i]) for i in (0, 4, 9)],
+                                       recall_oracle=[float(r_ref["recall"][i]) for i in (0, 4, 9)],
+                                       recall_identical=bool(np.array_equal(r_new["recall"], r_ref["recall"])))
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

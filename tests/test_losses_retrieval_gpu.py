@@ -77,6 +77,23 @@ def test_retrieval_topk_matches_kdtree_distances():
     assert (np.diff(d.cpu().numpy(), axis=1) >= 0).all()
 
 
+@pytest.mark.parametrize("n,eps,iters,seed", [(1024, 0.05, 100, 31), (1024, 0.01, 4000, 31), (4096, 0.02, 1024, 41), (2048, 0.05, 60, 42)])
+def test_emd_matches_the_cpu_oracle(n, eps, iters, seed):
+    """North star: chamfer/EMD within 1e-4.  Same auction, same fp32/double arithmetic, same tie rule as
+    oracle/emd_oracle.c => identical assignments; dist and prices compared at 1e-4 (whole-cloud sizes n in {1024, 4096}
+    of losses/pointnetvlad_loss.py:205-221, converged and unconverged runs)."""
+    from oracle import ops
+    rng = np.random.default_rng(seed)
+    a = rng.random((3, n, 3)).astype(np.float32)
+    b = rng.random((3, n, 3)).astype(np.float32)
+    b[2, : n // 8] = a[2, : n // 8]                                   # exact matches: value 3.0 bids
+    want_d, want_a, want_p, rounds, ties = ops.emd_forward(a, b, eps, iters)
+    dist, assignment = emd_module.emdModule()(_g(a), _g(b), eps, iters)
+    assert np.array_equal(assignment.cpu().numpy(), want_a)
+    assert np.abs(dist.cpu().numpy() - want_d).max() < 1e-4
+    assert abs(float(dist.sqrt().mean()) - float(np.sqrt(want_d).mean())) < 1e-6
+
+
 def test_emd_small_runs_match_reference_semantics():
     rng = np.random.default_rng(4)
     a = rng.random((2, 1024, 3)).astype(np.float32)
@@ -232,3 +249,32 @@ def test_patch_feature_contrast_loss_matches_the_per_pair_loop():
     for a, b in zip(g_new, feats):          # clouds outside every used pair get no gradient on either side
         assert (a - (zero if b.grad is None else b.grad)).abs().max().item() < 1e-5
     assert sum(f.grad is not None for f in feats) >= 4
+
+
+def test_recall_of_new_path_descriptors_equals_recall_of_oracle_descriptors():
+    """The metric's second half (BASELINE.json: 'Recall@1 vs reference'): on a structured synthetic database the
+    Recall@N of the CUDA path's descriptors must equal the Recall@N of the oracle forward's descriptors, and both must
+    be far above chance (calibrated test weights, tests/golden/make_calibration.py).  Evaluation rule:
+    scene_dataset.py:1016-1099 (first hit, cumulative)."""
+    import util
+    from oracle import model
+    n_db, n_q = 96, 48
+    db = util.place_batch(range(200, 200 + n_db), 0)
+    qs = util.place_batch(range(200, 200 + n_q), 1)
+    net = util.build_network("cuda")
+    with torch.no_grad():
+        d_db = retrieval.extract_descriptors(net, db.squeeze(1).pin_memory(), batch_size=32, device=torch.device("cuda"))
+        d_q = retrieval.extract_descriptors(net, qs.squeeze(1).pin_memory(), batch_size=32, device=torch.device("cuda"))
+    perms = [np.arange(20)] * 3
+    o_db = torch.cat([model.patchaugnet_forward(net.state_dict(), util.PATCHAUGNET_CFG, db[i:i + 16].numpy(), perms=perms)["desc"]
+                      for i in range(0, n_db, 16)])
+    o_q = torch.cat([model.patchaugnet_forward(net.state_dict(), util.PATCHAUGNET_CFG, qs[i:i + 16].numpy(), perms=perms)["desc"]
+                     for i in range(0, n_q, 16)])
+    assert (d_db.cpu() - o_db).abs().max().item() < 1e-4 and (d_q.cpu() - o_q).abs().max().item() < 1e-4
+    positives = [{i} for i in range(n_q)]
+    new = retrieval.evaluate_recall(d_db, d_q, positives, top_k=25)
+    ref = retrieval.evaluate_recall(o_db.cuda(), o_q.cuda(), positives, top_k=25)
+    assert np.array_equal(new["recall"], ref["recall"]) and new["one_percent_recall"] == ref["one_percent_recall"]
+    chance_at_1 = 100.0 / n_db
+    assert new["recall"][0] > 15 * chance_at_1, new["recall"][:10]          # discriminative, not a collapsed descriptor
+    assert new["recall"][9] > new["recall"][0]

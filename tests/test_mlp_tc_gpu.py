@@ -94,7 +94,7 @@ def test_tensor_core_scheduling_options_do_not_change_results():
 @pytest.mark.parametrize("spec,c,k,n,m", [([259, 256, 256, 512], 256, 20, 128, 16), ([67, 64, 64, 256], 64, 20, 1024, 128),
                                            ([131, 128, 128, 256], 128, 7, 300, 50), ([6, 32, 32, 64], 3, 20, 4096, 1024),
                                            ([6, 32, 64], 3, 9, 500, 77)])
-def test_sa_module_tensor_core_matches_simt(spec, c, k, n, m):
+def test_sa_module_tensor_core_matches_simt_and_fp64(spec, c, k, n, m):
     B = 4
     g = torch.Generator(device="cpu").manual_seed(n + k)
     mlp = _mlp(spec, n + 1)
@@ -119,6 +119,19 @@ def test_sa_module_tensor_core_matches_simt(spec, c, k, n, m):
     scale = simt.abs().max().item()
     assert torch.isfinite(tcore).all()
     assert (simt - tcore).abs().max().item() < 5e-5 * scale
+    # float64 torch evaluation of the reference's own op sequence (QueryAndGroup_Edge pointops.py:559-570 ->
+    # SharedMLP pt_util.py:98-151 -> max over K patch_aug_net.py:236), independent of both kernels
+    li = nbr.long().view(B, m * k)
+    g_xyz = torch.gather(xyz.double(), 1, li[..., None].expand(-1, -1, 3)).view(B, m, k, 3)
+    g_feat = torch.gather(feat.double(), 1, li[..., None].expand(-1, -1, c)).view(B, m, k, c)
+    ctr_xyz = torch.gather(xyz.double(), 1, cidx.long()[..., None].expand(-1, -1, 3))
+    ctr_feat = torch.gather(feat.double(), 1, cidx.long()[..., None].expand(-1, -1, c))
+    x = torch.cat([g_xyz - ctr_xyz[:, :, None], g_feat - ctr_feat[:, :, None]], -1).permute(0, 3, 1, 2)   # (B, 3+c, m, k)
+    with torch.no_grad():
+        want = mlp.double()(x).max(dim=3)[0].permute(0, 2, 1)                                             # (B, m, c_out)
+    mlp.float()
+    assert (tcore.double() - want).abs().max().item() < 5e-5 * want.abs().max().item()
+    assert (simt.double() - want).abs().max().item() < 5e-5 * want.abs().max().item()
 
 
 @pytest.mark.parametrize("n,K", [(4096, 64), (1024, 16), (128, 4), (300, 64)])

@@ -139,6 +139,32 @@ def test_chamfer_first_minimum_and_gradient():
     assert abs(num - gx1[0, 3, 1]) < 5e-2 * max(1.0, abs(num))
 
 
+def test_emd_oracle_is_an_eps_optimal_assignment():
+    """emd_oracle.c (restating emd_cuda.cu:95-226): a converged auction is a permutation whose total Euclidean cost is
+    within n*eps of the optimal assignment (Bertsekas' bound), computed independently by scipy's Hungarian solver."""
+    from scipy.optimize import linear_sum_assignment
+    rng = np.random.default_rng(31)
+    a = rng.random((1, 1024, 3)).astype(np.float32)
+    b = rng.random((1, 1024, 3)).astype(np.float32)
+    eps = 0.01
+    dist, asg, price, rounds, ties = ops.emd_forward(a, b, eps, 4000)
+    assert rounds[0] < 4000 and sorted(asg[0].tolist()) == list(range(1024))          # converged: one-to-one
+    cost = np.sqrt(((a[0][:, None, :] - b[0][None]) ** 2).sum(-1))
+    ri, ci = linear_sum_assignment(cost)
+    opt = cost[ri, ci].sum()
+    got = np.sqrt(dist[0].astype(np.float64)).sum()
+    assert opt - 1e-3 <= got <= opt + 1024 * eps
+    assert np.allclose(dist[0], ((a[0] - b[0][asg[0]]) ** 2).sum(-1), atol=1e-6)          # CalcDist
+    # identical clouds: every point's best object is itself at value 3.0
+    d0, a0, _, r0, _ = ops.emd_forward(a, a, eps, 50)
+    assert np.array_equal(a0[0], np.arange(1024)) and (d0 == 0).all() and r0[0] == 1
+    # unconverged run: the last round lets every remaining bidder take its bid (emd_cuda.cu:203 `last ||`)
+    d1, a1, _, r1, _ = ops.emd_forward(a, b, 0.05, 20)
+    assert r1[0] == 20 and a1.min() >= 0 and len(set(a1[0].tolist())) < 1024
+    with pytest.raises(ValueError):
+        ops.emd_forward(a[:, :1000], b[:, :1000], eps, 10)                                # n % 1024 != 0 (emd_cuda.cu:246-249)
+
+
 def test_knn_cuda_matches_kdtree_known_answer():
     # the reference's own test: distances vs sklearn KDTree(leaf_size=100), decimal=3 (test_knn_cuda.py:32-47)
     from sklearn.neighbors import KDTree

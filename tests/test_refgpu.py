@@ -116,11 +116,19 @@ def test_reference_chamfer_and_emd():
     r = refgpu.chamfer_forward(_g(a2), _g(b2))
     n = chamfer_dist.forward(_g(a2), _g(b2))
     assert all(torch.equal(x, y) for x, y in zip(r, n))
-    # EMD: same auction, same arithmetic -> same matching cost up to tie handling
+    # EMD: reference kernels == C oracle == new kernel.  The auction is deterministic unless a GetMax decision has two
+    # candidates within 1e-6 (the oracle counts them); these inputs have none, so every assignment must be identical.
     from patchaugnet_b200 import emd_module
-    x1 = rng.random((2, 1024, 3)).astype(np.float32); x2 = rng.random((2, 1024, 3)).astype(np.float32)
-    rdist, rasg = refgpu.emd_forward(_g(x1), _g(x2), 0.05, 200)
-    ndist, nasg = emd_module.emdModule()(_g(x1), _g(x2), 0.05, 200)
-    agree = (rasg == nasg).float().mean().item()
-    assert agree > 0.98, agree
-    assert abs(rdist.sqrt().mean().item() - ndist.sqrt().mean().item()) < 2e-3
+    for n, eps, iters, seed in [(1024, 0.05, 200, 31), (1024, 0.01, 4000, 32), (4096, 0.02, 1024, 41)]:
+        r2 = np.random.default_rng(seed)
+        x1 = r2.random((2, n, 3)).astype(np.float32); x2 = r2.random((2, n, 3)).astype(np.float32)
+        odist, oasg, _, _, ties = ops.emd_forward(x1, x2, eps, iters)
+        assert ties.sum() == 0
+        rdist, rasg = refgpu.emd_forward(_g(x1), _g(x2), eps, iters)
+        ndist, nasg = emd_module.emdModule()(_g(x1), _g(x2), eps, iters)
+        assert np.array_equal(nasg.cpu().numpy(), oasg) and np.abs(ndist.cpu().numpy() - odist).max() < 1e-4
+        agree = (rasg.cpu().numpy() == oasg).mean()
+        # unconverged runs end with a racy last round in the reference (several bidders write one assignment_inv slot,
+        # emd_cuda.cu:203-211) but assignment[j] itself is race-free
+        assert agree == 1.0, (n, eps, iters, agree)
+        assert np.abs(rdist.cpu().numpy() - odist).max() < 1e-4
