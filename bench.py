@@ -336,7 +336,8 @@ def main():
     ap.add_argument("--tc-tune", type=int, default=1, help="pab_tune_tensor_core bits (1 on, +4 CTA-pair multicast, +8 static tiles)")
     ap.add_argument("--fp-order", type=int, default=1, help="FP modules walk their points in Morton order (0 = index order)")
     ap.add_argument("--fps-threads", type=int, default=0, help="force the FPS CTA size (0 = automatic)")
-    ap.add_argument("--fps-cpc", type=int, default=1, help="clouds per FPS CTA in stream mode (1 or 2)")
+    ap.add_argument("--fps-cpc", type=int, default=1, help="clouds per FPS CTA in stream mode (1..3)")
+    ap.add_argument("--fps-pruned", type=int, default=0, help="1 = pruned FPS sampler (exact, but slower at these sizes)")
     ap.add_argument("--prio", default="0,0", help="CUDA stream priorities geometry,dense (lower = higher priority)")
     ap.add_argument("--graph", type=int, default=None, help="deprecated alias: 1 -> --mode graph, 0 -> --mode eager")
     args = ap.parse_args()
@@ -368,6 +369,7 @@ def main():
     eng.fps_clouds_per_cta = args.fps_cpc
     L.lib().pab_tune_tensor_core(args.tc_tune)
     L.lib().pab_tune_fps_threads(args.fps_threads)
+    L.lib().pab_tune_fps_pruned(args.fps_pruned)
     eng.dense_streams = max(1, min(3, args.dense_streams))
     eng.fp_row_order = bool(args.fp_order)
     eng.stream_priorities = tuple(int(v) for v in args.prio.split(","))

@@ -257,6 +257,15 @@ void pab_tune_tc_trace(void *device_buffer);
 /* Tuning hook: force the FPS CTA size (power of two, 32..1024; 0 = automatic). */
 void pab_tune_fps_threads(int threads);
 
+/* Tuning hook: 1 = clouds of 2048/4096/8192 points use the pruned sampler (Morton chunks + box bounds, exact,
+ * bit-identical indices); 0 (default) = always the full-scan register-resident sampler, which is faster at these sizes
+ * because a step is bound by its arg-max latency chain, not by the distance updates. */
+void pab_tune_fps_pruned(int on);
+
+/* How many clouds of n points one SM samples concurrently with the current settings (the engine sizes the persistent
+ * dense kernels of the overlapping batch by it). */
+int pab_fps_clouds_per_sm(int n);
+
 /* Tuning hook: 2 = one FPS CTA samples two clouds side by side (independent halves of the CTA; identical results), so the
  * sampler occupies half as many SMs; 1 (default) = one cloud per CTA. */
 void pab_tune_fps_clouds_per_cta(int n);

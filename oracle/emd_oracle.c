@@ -13,9 +13,11 @@
  *   sq    = fmaf(dz,dz, fmaf(dx,dx, dy*dy))  on (p2 - p1)
  *   value = (float)((3.0 - (double)sqrtf(sq)) - (double)price)        -- the literal 3.0 is a double (:146)
  *   inc   = (best - better) + eps                                     -- float
- * The per-thread split of the objects in Bid (thread_per_unass, delta) does not change its result: every partition
- * yields the two largest values (with multiplicity) and the LOWEST index attaining the maximum (strict '>' in scan
- * order and in the ascending merge :163-170).
+ * The per-thread split of the objects in Bid (:106-108 thread_per_unass = 1024 / ceil(unassigned / (n/1024)); :136-138
+ * delta = ceil(tile / thread_per_unass) per 2048-object tile) does not change the two largest VALUES, but it decides which
+ * of several objects with exactly equal value is picked: a thread keeps the first maximum of its own scan order (its
+ * slice of tile 0, then its slice of tile 1, ...), threads merge in ascending order with a strict '>' (:163-170).
+ * The restatement therefore walks the objects in that (thread, tile, position) order.
  *
  * Where the reference is order-dependent — two bidders on one object whose increments both lie within 1e-6 of the
  * maximum (GetMax: last writer wins), several bidders on one object in the last round (Assign: last writer of
@@ -55,15 +57,23 @@ ORA_API int ora_emd_forward(int b, int n, const float *xyz1, const float *xyz2, 
             for (int j = 0; j < n; ++j) if (asg[j] == -1) unass[total++] = j;
             if (total == 0) break;
             ++used;
+            const int block_cnt = n / 1024, upb = (total + block_cnt - 1) / block_cnt, tpu = 1024 / upb;
             for (int u = 0; u < total; ++u) {                              /* Bid */
                 const int j = unass[u];
                 float best = -1e9f, better = -1e9f;
                 int best_i = -1;
-                for (int k = 0; k < n; ++k) {
-                    const float d = (float)((3.0 - (double)sqrtf(sqdist(p2 + 3 * k, p1 + 3 * j))) - (double)pr[k]);
-                    if (d > best) { better = best; best = d; best_i = k; }
-                    else if (d > better) better = d;
-                }
+                for (int sub = 0; sub < tpu; ++sub)                        /* ascending thread merge */
+                    for (int k2 = 0; k2 < n; k2 += 2048) {                 /* tiles in order within a thread */
+                        const int end_k = (n < k2 + 2048 ? n : k2 + 2048) - k2;
+                        const int delta = (end_k + tpu - 1) / tpu;
+                        const int l = sub * delta, r = (sub + 1) * delta < end_k ? (sub + 1) * delta : end_k;
+                        for (int kk = l; kk < r; ++kk) {
+                            const int k = k2 + kk;
+                            const float d = (float)((3.0 - (double)sqrtf(sqdist(p2 + 3 * k, p1 + 3 * j))) - (double)pr[k]);
+                            if (d > best) { better = best; best = d; best_i = k; }
+                            else if (d > better) better = d;
+                        }
+                    }
                 const float inc = (best - better) + eps;
                 bid[j] = best_i;
                 bid_inc[j] = inc;

@@ -36,6 +36,8 @@ SIGNATURES = {
     "pab_tune_tc_trace": (None, [_P]),
     "pab_tune_tc_max_ctas": (None, [_I]),
     "pab_tune_fps_clouds_per_cta": (None, [_I]),
+    "pab_tune_fps_pruned": (None, [_I]),
+    "pab_fps_clouds_per_sm": (_I, [_I]),
     "pab_furthestsampling": (_I, [_I, _I, _I, _P, _P, _P, _P]),
     "pab_gathering_forward": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),
     "pab_gathering_backward": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),

@@ -57,16 +57,23 @@ emd_kernel(int n, const float *__restrict__ xyz1, const float *__restrict__ xyz2
         if (total == 0) break;
 
         // ---- 2. Bid (emd_cuda.cu:95-179)
-        const int passes = (total + EMD_T - 1) / EMD_T;      // bidders handled per thread group
+        // Threads per bidder exactly as the reference splits them (emd_cuda.cu:106-108: its n/1024 blocks take
+        // unass_per_block = ceil(total / block_cnt) bidders each, thread_per_unass = 1024 / unass_per_block).  The split
+        // decides which of several objects with EXACTLY equal value a bidder picks (a thread keeps the first maximum of its
+        // own scan order — tile after tile —, threads merge in ascending order with a strict '>'), so it is part of the
+        // result, not just of the schedule.  One pass = the bidders of one reference block.
+        const int block_cnt = n / EMD_T;
+        const int per_pass = (total + block_cnt - 1) / block_cnt;
+        const int tpu = EMD_T / per_pass;                      // threads per bidder
+        const int passes = (total + per_pass - 1) / per_pass;
         for (int pass = 0; pass < passes; ++pass) {
-            const int cnt = min(EMD_T, total - pass * EMD_T);  // bidders in this pass
-            const int tpu = EMD_T / cnt;                       // threads per bidder
+            const int cnt = min(per_pass, total - pass * per_pass);  // bidders in this pass
             const int slot = t / tpu, sub = t - slot * tpu;
             const bool has = slot < cnt;
             int me = -1;
             float x1 = 0.f, y1 = 0.f, z1 = 0.f;
             if (has) {
-                me = unass_idx[pass * EMD_T + slot];
+                me = unass_idx[pass * per_pass + slot];
                 x1 = xyz1[me * 3]; y1 = xyz1[me * 3 + 1]; z1 = xyz1[me * 3 + 2];
             }
             float best = -1e9f, better = -1e9f;

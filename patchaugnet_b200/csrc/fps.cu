@@ -170,6 +170,256 @@ fps_generic_kernel(int n, int m, int log2bs, const float *__restrict__ xyz, floa
     }
 }
 
+// ---- pruned sampler ---------------------------------------------------------------------------------------------------
+// Exact FPS that touches only the points a new sample can change.  The cloud is sorted along a Morton curve once (in
+// shared memory) and cut into chunks of 32 consecutive points, each with a bounding box and a record
+// (max running distance, rank of the point attaining it).  A step evaluates, per chunk, the reference's own fp32
+// distance expression on the differences clamped to the box — by monotonicity of every rounding step a lower bound of
+// the distance of any point inside — and skips the chunk when that bound is not below the chunk's maximum: then
+// min(d, temp[k]) == temp[k] for all of its points, i.e. the reference would not change them either.  Only the
+// remaining chunks (a handful once a few dozen samples exist) are updated, one point per lane, and re-reduced; the
+// arg-max of the step is taken over the chunk records with the same (value, rank) order as everywhere else in this
+// file, so indices and the final `temp` are bit-identical to the full scan.
+// Four warps per cloud and 18 bytes of shared memory per point: three clouds share an SM (4096 points), so a batch of
+// 32 occupies 11 SMs instead of 32 and leaves the rest to the dense kernels of the previous batch.
+constexpr int FPSP_WARPS = 4;
+constexpr int FPSP_T = FPSP_WARPS * 32;
+
+__device__ __forceinline__ uint32_t fps_rank16(uint32_t k, int log2bs) {       // order-preserving 13-bit form of fps_rank
+    const uint32_t tid = k & ((1u << log2bs) - 1u);
+    return ((__brev(tid) >> (32 - log2bs)) << 3) | (k >> log2bs);
+}
+__device__ __forceinline__ uint32_t fps_unrank16(uint32_t r, int log2bs) {
+    const uint32_t tid = __brev(r >> 3) >> (32 - log2bs);
+    return ((r & 7u) << log2bs) | tid;
+}
+__device__ __forceinline__ uint32_t morton6(uint32_t v) {                      // 6 bits -> every third bit
+    v = (v | (v << 8)) & 0x0000300Fu;
+    v = (v | (v << 4)) & 0x000030C3u;
+    v = (v | (v << 2)) & 0x00009249u;
+    return v;
+}
+__device__ __forceinline__ float fps_box_bound(float qx, float qy, float qz, const float (&lo)[3], const float (&hi)[3]) {
+    const float dx = fmaxf(fmaxf(__fsub_rn(lo[0], qx), __fsub_rn(qx, hi[0])), 0.f);
+    const float dy = fmaxf(fmaxf(__fsub_rn(lo[1], qy), __fsub_rn(qy, hi[1])), 0.f);
+    const float dz = fmaxf(fmaxf(__fsub_rn(lo[2], qz), __fsub_rn(qz, hi[2])), 0.f);
+    return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+
+constexpr int FPSP_MAX_CPC = 3;
+
+#define FPSP_SYNC() asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(FPSP_T) : "memory")
+
+template <int SLOTS>
+__global__ void __launch_bounds__(FPSP_T * (SLOTS == 1 ? FPSP_MAX_CPC : 1), 1)
+fps_pruned_kernel(int b, int n, int m, int log2bs, const float *__restrict__ xyz, float *__restrict__ temp, int *__restrict__ idx) {
+    // n: power of two, 1024 <= n <= 4096 * SLOTS.  A CTA of cpc * 128 threads samples cpc clouds side by side (independent
+    // groups of four warps with their own named barrier): the packing onto SMs is then fixed by the launch, not left to
+    // the block scheduler (which would spread 32 small CTAs over 32 idle SMs and block the next dense kernel's CTAs)
+    extern __shared__ float sm_all[];
+    const int sub = threadIdx.x / FPSP_T, t = threadIdx.x - sub * FPSP_T;
+    const int cloud = blockIdx.x * (blockDim.x / FPSP_T) + sub;
+    if (cloud >= b) return;                                        // the whole group leaves; its barrier is its own
+    const int bar_id = 1 + sub;
+    float *sm = sm_all + (size_t)sub * ((size_t)n * 18 / 4);
+    float *xs = sm, *ys = xs + n, *zs = ys + n, *td = zs + n;
+    uint16_t *rk = reinterpret_cast<uint16_t *>(td + n);
+    uint32_t *keys = reinterpret_cast<uint32_t *>(td);            // sort keys live in the td region until td is initialised
+    __shared__ float red_all[FPSP_MAX_CPC][6][FPSP_WARPS];
+    __shared__ float bb_all[FPSP_MAX_CPC][6];
+    __shared__ int2 cand_all[FPSP_MAX_CPC][2][FPSP_WARPS];
+    __shared__ int s_pos0_all[FPSP_MAX_CPC];
+    float (*red)[FPSP_WARPS] = red_all[sub];
+    float *bb = bb_all[sub];
+    int2 (*cand)[FPSP_WARPS] = cand_all[sub];
+    int &s_pos0 = s_pos0_all[sub];
+
+    const int lane = t & 31, warp = t >> 5;
+    const int nch = n >> 5;
+    const float *p = xyz + (size_t)cloud * n * 3;
+    idx += (size_t)cloud * m;
+    if (temp) temp += (size_t)cloud * n;
+
+    // ---- bounding box (finite values only)
+    {
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int i = t; i < n; i += FPSP_T)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float v = __ldg(p + (size_t)i * 3 + c);
+                if (fabsf(v) < INFINITY) { lo[c] = fminf(lo[c], v); hi[c] = fmaxf(hi[c], v); }
+            }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+                hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+            }
+            if (lane == 0) { red[c][warp] = lo[c]; red[3 + c][warp] = hi[c]; }
+        }
+        FPSP_SYNC();
+        if (t < 6) {
+            float v = red[t][0];
+            for (int w = 1; w < FPSP_WARPS; ++w) v = t < 3 ? fminf(v, red[t][w]) : fmaxf(v, red[t][w]);
+            bb[t] = v;
+        }
+        FPSP_SYNC();
+    }
+    // ---- Morton keys (6 bits per axis) | original index, bitonic sort
+    {
+        float sc[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float ext = bb[3 + c] - bb[c];
+            sc[c] = (ext > 0.f && ext < INFINITY) ? 63.5f / ext : 0.f;
+        }
+        for (int i = t; i < n; i += FPSP_T) {
+            uint32_t code = 0;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float f = (__ldg(p + (size_t)i * 3 + c) - bb[c]) * sc[c];
+                f = f > 0.f ? f : 0.f;                                   // also maps NaN to cell 0
+                const uint32_t cell = f < 63.f ? (uint32_t)f : 63u;
+                code |= morton6(cell) << c;
+            }
+            keys[i] = (code << 13) | (uint32_t)i;
+        }
+        FPSP_SYNC();
+        for (int size = 2; size <= n; size <<= 1)
+            for (int j = size >> 1; j > 0; j >>= 1) {
+                for (int i = t; i < (n >> 1); i += FPSP_T) {
+                    const int a = 2 * i - (i & (j - 1));
+                    const uint32_t ka = keys[a], kb = keys[a + j];
+                    const bool up = (a & size) == 0;
+                    if ((ka > kb) == up) { keys[a] = kb; keys[a + j] = ka; }
+                }
+                FPSP_SYNC();
+            }
+    }
+    // ---- sorted SoA; rk holds the original index until td (which overlays the keys) is written
+    for (int i = t; i < n; i += FPSP_T) {
+        const int oi = (int)(keys[i] & 8191u);
+        xs[i] = __ldg(p + (size_t)oi * 3); ys[i] = __ldg(p + (size_t)oi * 3 + 1); zs[i] = __ldg(p + (size_t)oi * 3 + 2);
+        rk[i] = (uint16_t)oi;
+        if (oi == 0) s_pos0 = i;
+    }
+    FPSP_SYNC();
+    for (int i = t; i < n; i += FPSP_T) {
+        const int oi = rk[i];
+        td[i] = temp ? temp[oi] : 1e10f;
+        rk[i] = (uint16_t)fps_rank16((uint32_t)oi, log2bs);
+    }
+    FPSP_SYNC();
+
+    // ---- chunk records: chunk c belongs to warp c & 3, lane (c >> 2) & 31, slot c >> 7
+    float blo[SLOTS][3], bhi[SLOTS][3];
+    int cmaxb[SLOTS];
+    uint32_t ckey[SLOTS];
+    bool valid[SLOTS];
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+        valid[s] = (((s * 32 + lane) << 2) | warp) < nch;
+        cmaxb[s] = __float_as_int(-1.f);
+        ckey[s] = 0xFFFFFFFFu;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { blo[s][c] = INFINITY; bhi[s][c] = -INFINITY; }
+        for (int r = 0; r < 32; ++r) {
+            const int c = ((s * 32 + r) << 2) | warp;
+            if (c >= nch) break;                                         // warp-uniform
+            const int pos = (c << 5) + lane;
+            float l3[3] = {xs[pos], ys[pos], zs[pos]}, h3[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                if (!(fabsf(l3[d]) < INFINITY)) { h3[d] = -INFINITY; l3[d] = INFINITY; } else h3[d] = l3[d];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    l3[d] = fminf(l3[d], __shfl_xor_sync(0xffffffffu, l3[d], o));
+                    h3[d] = fmaxf(h3[d], __shfl_xor_sync(0xffffffffu, h3[d], o));
+                }
+            }
+            const int bits = __float_as_int(td[pos]);
+            const int wmax = __reduce_max_sync(0xffffffffu, bits);
+            const uint32_t wkey = __reduce_min_sync(0xffffffffu, bits == wmax ? (((uint32_t)rk[pos] << 16) | (uint32_t)pos) : 0xFFFFFFFFu);
+            if (lane == r) {
+#pragma unroll
+                for (int d = 0; d < 3; ++d) { blo[s][d] = l3[d]; bhi[s][d] = h3[d]; }
+                cmaxb[s] = wmax; ckey[s] = wkey;
+            }
+        }
+    }
+
+    int opos = s_pos0;
+    if (t == 0) idx[0] = 0;
+    for (int j = 1; j < m; ++j) {
+        const float x1 = xs[opos], y1 = ys[opos], z1 = zs[opos];
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+            // a chunk whose box is at least its current maximum away cannot change (NaN bounds compare false: never skipped)
+            const float lb = fps_box_bound(x1, y1, z1, blo[s], bhi[s]);
+            const bool act = valid[s] && !(lb >= __int_as_float(cmaxb[s]));
+            uint32_t mask = __ballot_sync(0xffffffffu, act);
+            while (mask) {
+                // up to four chunks per round so that their load -> distance -> reduce chains overlap; missing ones repeat
+                // the first (the update is idempotent)
+                int r[4];
+                r[0] = __ffs(mask) - 1; mask &= mask - 1;
+#pragma unroll
+                for (int u = 1; u < 4; ++u) {
+                    r[u] = mask ? __ffs(mask) - 1 : r[0];
+                    mask &= mask - 1;
+                }
+                int bits[4], pos[4];
+                uint32_t rank[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    pos[u] = (((((s * 32 + r[u]) << 2) | warp)) << 5) + lane;
+                    const float d = ref_sqdist(xs[pos[u]], ys[pos[u]], zs[pos[u]], x1, y1, z1);
+                    const float v = fminf(d, td[pos[u]]);
+                    td[pos[u]] = v;
+                    bits[u] = __float_as_int(v);
+                    rank[u] = rk[pos[u]];
+                }
+                int wmax[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) wmax[u] = __reduce_max_sync(0xffffffffu, bits[u]);
+                uint32_t wkey[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    wkey[u] = __reduce_min_sync(0xffffffffu, bits[u] == wmax[u] ? ((rank[u] << 16) | (uint32_t)pos[u]) : 0xFFFFFFFFu);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (lane == r[u]) { cmaxb[s] = wmax[u]; ckey[s] = wkey[u]; }
+            }
+        }
+        // arg-max over the warp's records, then over the four warps
+        int bbits = cmaxb[0];
+        uint32_t bkey = ckey[0];
+#pragma unroll
+        for (int s = 1; s < SLOTS; ++s)
+            if (cmaxb[s] > bbits || (cmaxb[s] == bbits && ckey[s] < bkey)) { bbits = cmaxb[s]; bkey = ckey[s]; }
+        const int wb = __reduce_max_sync(0xffffffffu, bbits);
+        const uint32_t wk = __reduce_min_sync(0xffffffffu, bbits == wb ? bkey : 0xFFFFFFFFu);
+        if (lane == 0) cand[j & 1][warp] = make_int2(wb, (int)wk);
+        FPSP_SYNC();
+        int gb = cand[j & 1][0].x;
+        uint32_t gk = (uint32_t)cand[j & 1][0].y;
+#pragma unroll
+        for (int w = 1; w < FPSP_WARPS; ++w) {
+            const int2 c = cand[j & 1][w];
+            if (c.x > gb || (c.x == gb && (uint32_t)c.y < gk)) { gb = c.x; gk = (uint32_t)c.y; }
+        }
+        opos = (int)(gk & 0xFFFFu);
+        if (t == 0) idx[j] = (int)fps_unrank16(gk >> 16, log2bs);
+    }
+    if (temp) {
+        FPSP_SYNC();
+        for (int i = t; i < n; i += FPSP_T) temp[fps_unrank16(rk[i], log2bs)] = td[i];
+    }
+}
+
+int g_fps_pruned = 0;   // measured slower than the full scan at n <= 8192: off by default
+
 int ref_log2_block(int n) {  // log2(opt_n_threads(n)), cuda_utils.h:15-18, without libm
     int l = 0;
     while ((2 << l) <= n && l < 10) ++l;
@@ -182,7 +432,7 @@ int g_fps_clouds_per_cta = 1;
 
 template <int PPT, int MAXT>
 int launch_fps(int b, int n, int m, int threads, int log2bs, const float *xyz, float *temp, int *idx, cudaStream_t st) {
-    const int cpc = (g_fps_clouds_per_cta == 2 && 2 * threads <= MAXT && b > 1) ? 2 : 1;
+    const int cpc = (g_fps_clouds_per_cta >= 2 && 2 * threads <= MAXT && b > 1) ? 2 : 1;
     const size_t smem = (size_t)cpc * n * 3 * sizeof(float);
     // static smem (candidate slots) counts against the 48 KB default too: opt in whenever we are near it
     if (smem > 40 * 1024)
@@ -196,7 +446,19 @@ int launch_fps(int b, int n, int m, int threads, int log2bs, const float *xyz, f
 
 PAB_API void pab_tune_fps_threads(int threads) { g_fps_threads_override = threads; }
 
-PAB_API void pab_tune_fps_clouds_per_cta(int n) { g_fps_clouds_per_cta = n == 2 ? 2 : 1; }
+PAB_API void pab_tune_fps_pruned(int on) { g_fps_pruned = on; }
+
+PAB_API int pab_fps_clouds_per_sm(int n) {
+    const bool pow2 = n > 0 && (n & (n - 1)) == 0;
+    if (g_fps_pruned && pow2 && n >= 2048 && n <= 4096) {
+        const int fit = (int)((227 * 1024 - 1024) / ((size_t)n * 18));
+        const int cpc = g_fps_clouds_per_cta < 1 ? 1 : g_fps_clouds_per_cta;
+        return cpc < fit ? (cpc < FPSP_MAX_CPC ? cpc : FPSP_MAX_CPC) : (fit < FPSP_MAX_CPC ? fit : FPSP_MAX_CPC);
+    }
+    return g_fps_clouds_per_cta == 2 ? 2 : 1;
+}
+
+PAB_API void pab_tune_fps_clouds_per_cta(int n) { g_fps_clouds_per_cta = n >= 1 && n <= 3 ? n : 1; }
 
 PAB_API int pab_furthestsampling(int b, int n, int m, const float *xyz, float *temp, int *idx, pab_stream_t s) {
     if (b < 0 || n <= 0 || m < 0 || m > n) return PAB_EINVAL;
@@ -206,6 +468,25 @@ PAB_API int pab_furthestsampling(int b, int n, int m, const float *xyz, float *t
     if (n > 8192) {
         if (!temp) return PAB_EINVAL;
         fps_generic_kernel<<<b, 1024, 0, st>>>(n, m, log2bs, xyz, temp, idx);
+        PAB_LAUNCH_CHECK();
+        return 0;
+    }
+    if (g_fps_pruned && (n & (n - 1)) == 0 && n >= 2048 && n <= 8192 && m > 1) {
+        // pruned sampler: sorted chunks + box bounds (see fps_pruned_kernel)
+        if (n <= 4096) {
+            int cpc = g_fps_clouds_per_cta < 1 ? 1 : g_fps_clouds_per_cta;
+            const int fit = (int)((227 * 1024 - 1024) / ((size_t)n * 18));      // clouds whose 18 B/point fit one SM
+            if (cpc > fit) cpc = fit;
+            if (cpc > FPSP_MAX_CPC) cpc = FPSP_MAX_CPC;
+            if (cpc > b) cpc = b;
+            const size_t smem = (size_t)cpc * n * 18;
+            PAB_CUDA(cudaFuncSetAttribute(fps_pruned_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            fps_pruned_kernel<1><<<pab_divup(b, cpc), cpc * FPSP_T, smem, st>>>(b, n, m, log2bs, xyz, temp, idx);
+        } else {
+            const size_t smem = (size_t)n * 18;
+            PAB_CUDA(cudaFuncSetAttribute(fps_pruned_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            fps_pruned_kernel<2><<<b, FPSP_T, smem, st>>>(b, n, m, log2bs, xyz, temp, idx);
+        }
         PAB_LAUNCH_CHECK();
         return 0;
     }

@@ -119,7 +119,7 @@ class FusedPatchAugNet:
         self.dense_streams = 2          # dense kernels of consecutive batches alternate between two streams
         self.stream_priorities = (0, 0)
         self.reserve_fps_sms = True     # forward_stream: persistent tensor-core kernels leave the FPS CTAs' SMs alone
-        self.fps_clouds_per_cta = 1     # forward_stream: 2 = two clouds share one FPS CTA (half the SMs held by the sampler)
+        self.fps_clouds_per_cta = 1     # forward_stream: clouds sharing one FPS CTA (2 = half the SMs held by the sampler)
         self.refold()
 
     # ---- weights -------------------------------------------------------------------------------------------------
@@ -354,8 +354,8 @@ class FusedPatchAugNet:
         # (measured: 28.3 k -> 31.2 k submaps/s at B = 32 with the cap; 120 instead of 116 CTAs is already slower than no cap).
         n_sm = torch.cuda.get_device_properties(self.device).multi_processor_count
         if self.reserve_fps_sms:
-            cpc = 2 if self.fps_clouds_per_cta == 2 else 1
-            L.lib().pab_tune_fps_clouds_per_cta(cpc)
+            L.lib().pab_tune_fps_clouds_per_cta(self.fps_clouds_per_cta)
+            cpc = max(1, L.lib().pab_fps_clouds_per_sm(N))          # what the sampler will really pack for this cloud size
             L.lib().pab_tune_tc_max_ctas(n_sm - (B + cpc - 1) // cpc if 0 < B <= n_sm // 2 else 0)
         geo_done = [None, None]
         dense_done = [None, None]

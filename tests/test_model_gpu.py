@@ -36,7 +36,9 @@ def test_fused_forward_matches_reference_golden(net):
         # features reach |x| ~ 9 with the calibrated statistics: 2e-4 of the largest magnitude (the reference's own fp32
         # features sit 3e-5 from a float64 evaluation); the contract quantity is the descriptor above
         assert np.abs(f[:, :, :8, 0].cpu().numpy() - g[f"fp{i}_head"]).max() < 2e-4 * max(1.0, np.abs(g[f"fp{i}_head"]).max())
-        assert np.allclose(f.sum(dim=(2, 3)).double().cpu().numpy(), g[f"fp{i}_sum"], rtol=1e-4, atol=1e-2)
+        # per-channel sums over all points: mean absolute error below 2e-5 of the largest magnitude
+        n_pts = f.shape[2]
+        assert np.abs(f.sum(dim=(2, 3)).double().cpu().numpy() - g[f"fp{i}_sum"]).max() < 2e-5 * n_pts * max(1.0, np.abs(g[f"fp{i}_head"]).max())
 
 
 def test_fused_forward_matches_oracle_on_fresh_inputs(net):

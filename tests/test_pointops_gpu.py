@@ -49,6 +49,55 @@ def test_fps_thread_layout_does_not_change_result():
         assert torch.equal(got.cpu(), torch.from_numpy(want)), threads
 
 
+@pytest.mark.parametrize("n,m,b", [(4096, 1024, 7), (2048, 300, 4), (8192, 200, 2), (4096, 4096, 2), (4096, 2, 3)])
+def test_fps_pruned_sampler_is_bit_exact(n, m, b):
+    """The pruned sampler (Morton chunks + box bounds, fps.cu) must give the full scan's indices and `temp` bit for
+    bit: against the C oracle, against the full-scan kernel, for every packing of clouds per CTA, on uniform,
+    duplicate-heavy, zero-padded and structured (planes / cylinders) clouds."""
+    import util
+    from patchaugnet_b200 import pointops_cuda as K
+    clouds = [_clouds(b, n, seed=n + m), _clouds(b, n, seed=n + m + 1, dup=True), _clouds(b, n, seed=n + m + 2, zero_tail=n // 50),
+              np.stack([util.place_visit(40 + i, 0, n) for i in range(b)])]
+    for xyz in clouds:
+        temp_want = np.full((b, n), 1e10, np.float32)
+        want = ops.furthestsampling(xyz, m, temp_want)
+        L.lib().pab_tune_fps_pruned(1)
+        try:
+            for cpc in (1, 2, 3):
+                L.lib().pab_tune_fps_clouds_per_cta(cpc)
+                t = torch.full((b, n), 1e10, device=DEV)
+                idx = torch.zeros(b, m, dtype=torch.int32, device=DEV)
+                K.furthestsampling_cuda(b, n, m, _g(xyz), t, idx)
+                assert torch.equal(idx.cpu(), torch.from_numpy(want)), (n, m, cpc)
+                assert torch.equal(t.cpu(), torch.from_numpy(temp_want)), (n, m, cpc)
+        finally:
+            L.lib().pab_tune_fps_pruned(0)
+            L.lib().pab_tune_fps_clouds_per_cta(1)
+        full = pointops.furthestsampling(_g(xyz), m)              # the default full-scan sampler
+        assert torch.equal(full.cpu(), torch.from_numpy(want))
+
+
+def test_fps_pruned_sampler_continues_from_a_given_temp():
+    """`temp` is an input too (pointops.py:21 fills it with 1e10, the ABI takes any state): sampling on from the
+    distances an earlier call left behind must match the oracle doing the same."""
+    from patchaugnet_b200 import pointops_cuda as K
+    xyz = _clouds(2, 4096, 77)
+    temp = np.full((2, 4096), 1e10, np.float32)
+    ops.furthestsampling(xyz, 50, temp)
+    want = ops.furthestsampling(xyz, 40, temp.copy())
+    for pruned in (1, 0):
+        t = torch.from_numpy(temp.copy()).to(DEV)
+        final = temp.copy()
+        ops.furthestsampling(xyz, 40, final)
+        idx = torch.zeros(2, 40, dtype=torch.int32, device=DEV)
+        L.lib().pab_tune_fps_pruned(pruned)
+        try:
+            K.furthestsampling_cuda(2, 4096, 40, _g(xyz), t, idx)
+        finally:
+            L.lib().pab_tune_fps_pruned(0)
+        assert torch.equal(idx.cpu(), torch.from_numpy(want)) and torch.equal(t.cpu(), torch.from_numpy(final))
+
+
 def test_fps_temp_is_updated_like_the_reference():
     from patchaugnet_b200 import pointops_cuda as K
     xyz = _clouds(2, 300, 6)

@@ -117,18 +117,20 @@ def test_reference_chamfer_and_emd():
     n = chamfer_dist.forward(_g(a2), _g(b2))
     assert all(torch.equal(x, y) for x, y in zip(r, n))
     # EMD: reference kernels == C oracle == new kernel.  The auction is deterministic unless a GetMax decision has two
-    # candidates within 1e-6 (the oracle counts them); these inputs have none, so every assignment must be identical.
+    # candidates within 1e-6 (the reference then keeps the last writer; the oracle counts such decisions per cloud):
+    # every cloud without one must give identical assignments, and at least one such cloud is required per size.
     from patchaugnet_b200 import emd_module
-    for n, eps, iters, seed in [(1024, 0.05, 200, 31), (1024, 0.01, 4000, 32), (4096, 0.02, 1024, 41)]:
+    for n, eps, iters, seed in [(1024, 0.05, 200, 31), (1024, 0.01, 4000, 32), (4096, 0.02, 1024, 41), (4096, 0.05, 300, 43)]:
         r2 = np.random.default_rng(seed)
-        x1 = r2.random((2, n, 3)).astype(np.float32); x2 = r2.random((2, n, 3)).astype(np.float32)
+        x1 = r2.random((3, n, 3)).astype(np.float32); x2 = r2.random((3, n, 3)).astype(np.float32)
         odist, oasg, _, _, ties = ops.emd_forward(x1, x2, eps, iters)
-        assert ties.sum() == 0
         rdist, rasg = refgpu.emd_forward(_g(x1), _g(x2), eps, iters)
         ndist, nasg = emd_module.emdModule()(_g(x1), _g(x2), eps, iters)
         assert np.array_equal(nasg.cpu().numpy(), oasg) and np.abs(ndist.cpu().numpy() - odist).max() < 1e-4
-        agree = (rasg.cpu().numpy() == oasg).mean()
-        # unconverged runs end with a racy last round in the reference (several bidders write one assignment_inv slot,
-        # emd_cuda.cu:203-211) but assignment[j] itself is race-free
-        assert agree == 1.0, (n, eps, iters, agree)
-        assert np.abs(rdist.cpu().numpy() - odist).max() < 1e-4
+        clean = ties == 0
+        assert clean.any(), (n, eps, iters, ties)
+        agree = (rasg.cpu().numpy() == oasg).mean(axis=1)
+        assert (agree[clean] == 1.0).all(), (n, eps, iters, ties, agree)
+        assert np.abs(rdist.cpu().numpy() - odist)[clean].max() < 1e-4
+        # a cloud that met a tie follows a different (equally valid) auction path from there on: only its cost is comparable
+        assert np.abs(np.sqrt(rdist.cpu().numpy()).mean(axis=1) - np.sqrt(odist).mean(axis=1)).max() < 5e-3
