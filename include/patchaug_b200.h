@@ -185,6 +185,12 @@ int pab_pointwise_mlp_forward(int rows, const float *x, const pab_layer_t *layer
 size_t pab_sa_layer_workspace_bytes(int b, int n, int c);
 int pab_sa_layer_forward(int b, int n, int c, const float *x, const pab_layer_t *q_layer, const pab_layer_t *v_layer,
                          const pab_layer_t *trans_layer, float *out, void *workspace, pab_stream_t s);
+/* Same layer with the arithmetic of the two N x N passes chosen by the caller: precision 2 (what pab_sa_layer_forward
+ * uses) = tcgen05 tensor cores on bf16 hi/lo operand planes, three MMAs per product — the fp32 contract; 1 = tensor cores on
+ * plain bf16 operands (BASELINE.json configs[2]); 0 = the fp32 SIMT kernels.  Shapes the tensor-core kernel does not take
+ * (c not in {64, 128}, n < 64) run on the SIMT kernels whatever the precision. */
+int pab_sa_layer_forward_p(int b, int n, int c, const float *x, const pab_layer_t *q_layer, const pab_layer_t *v_layer,
+                           const pab_layer_t *trans_layer, float *out, void *workspace, int precision, pab_stream_t s);
 
 /* NetVLADBase.forward (patch_aug_net/models/loupe.py:191-222), eval: x (b,n,c) point-major, wc (c,K) with the
  * bn1 scale folded in, shift (K), w2 (c,K) = cluster_weights2; out written at out[b*out_bstride + ch*out_cstride + k]

@@ -74,6 +74,7 @@ SIGNATURES = {
     "pab_pointwise_mlp_forward": (_I, [_I, _P, C.POINTER(PabLayer), _I, _P, _P]),
     "pab_sa_layer_workspace_bytes": (_SZ, [_I, _I, _I]),
     "pab_sa_layer_forward": (_I, [_I, _I, _I, _P, C.POINTER(PabLayer), C.POINTER(PabLayer), C.POINTER(PabLayer), _P, _P, _P]),
+    "pab_sa_layer_forward_p": (_I, [_I, _I, _I, _P, C.POINTER(PabLayer), C.POINTER(PabLayer), C.POINTER(PabLayer), _P, _P, _I, _P]),
     "pab_netvlad_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
     "pab_netvlad_forward": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P, _L, _L, _P, _P]),
     "pab_netvlad_forward_tc": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _L, _L, _P, _P]),

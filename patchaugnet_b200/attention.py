@@ -39,8 +39,9 @@ def _versions(layer):
     return tuple(p._version for p in layer.parameters()) + tuple(b._version for b in layer.buffers())
 
 
-def sa_layer_forward(layer, x):
-    """x (B, C, N) float32 CUDA -> (B, C, N), eval-mode SA_Layer (pptnet.py:261-282)."""
+def sa_layer_forward(layer, x, precision=2):
+    """x (B, C, N) float32 CUDA -> (B, C, N), eval-mode SA_Layer (pptnet.py:261-282).
+    precision: 2 tensor cores with bf16 hi/lo operands (fp32 contract), 1 tensor cores with plain bf16, 0 fp32 SIMT."""
     L.require_cuda(x)
     B, C, N = x.shape
     cache = getattr(layer, "_pab_fold", None)
@@ -53,8 +54,8 @@ def sa_layer_forward(layer, x):
     out = torch.empty_like(xp)
     ws = torch.empty(L.lib().pab_sa_layer_workspace_bytes(B, N, C), dtype=torch.uint8, device=x.device)
     arr = cache["arr"]
-    L.check(L.lib().pab_sa_layer_forward(B, N, C, L.ptr(xp), arr, C_ptr_offset(arr, 1), C_ptr_offset(arr, 2), L.ptr(out),
-                                         L.ptr(ws), L.stream_ptr()), "sa_layer_forward")
+    L.check(L.lib().pab_sa_layer_forward_p(B, N, C, L.ptr(xp), arr, C_ptr_offset(arr, 1), C_ptr_offset(arr, 2), L.ptr(out),
+                                           L.ptr(ws), int(precision), L.stream_ptr()), "sa_layer_forward")
     return out.transpose(1, 2).contiguous()
 
 

@@ -20,6 +20,9 @@
 int pab_pointwise_mlp_residual(int rows, const float *x, const pab_layer_t *layers, int n_layers, const float *residual,
                                float *out, long out_ld, cudaStream_t st);   // mlp.cu
 
+int pab_attention_tc(int b, int n, int c, const float *q, const float *v, long ld, const float *x, float *rowmax, float *rowsum,
+                     float *d, int precision, cudaStream_t st);   // attention_tc.cu
+
 namespace {
 
 constexpr int AT_R = 64;       // rows per CTA tile
@@ -169,6 +172,11 @@ PAB_API size_t pab_sa_layer_workspace_bytes(int b, int n, int c) {
 
 PAB_API int pab_sa_layer_forward(int b, int n, int c, const float *x, const pab_layer_t *q_layer, const pab_layer_t *v_layer,
                                  const pab_layer_t *trans_layer, float *out, void *workspace, pab_stream_t s) {
+    return pab_sa_layer_forward_p(b, n, c, x, q_layer, v_layer, trans_layer, out, workspace, 2, s);
+}
+
+PAB_API int pab_sa_layer_forward_p(int b, int n, int c, const float *x, const pab_layer_t *q_layer, const pab_layer_t *v_layer,
+                                   const pab_layer_t *trans_layer, float *out, void *workspace, int precision, pab_stream_t s) {
     if (b < 0 || b > 65535 || n <= 0 || c <= 0 || c % 64 || !q_layer || !v_layer || !trans_layer || !workspace) return PAB_EINVAL;
     if (q_layer->c_in != c || q_layer->c_out != c || v_layer->c_in != c || v_layer->c_out != c || trans_layer->c_in != c ||
         trans_layer->c_out != c) return PAB_EINVAL;
@@ -184,6 +192,8 @@ PAB_API int pab_sa_layer_forward(int b, int n, int c, const float *x, const pab_
     if (rc) return rc;
     rc = pab_pointwise_mlp_residual(b * n, x, v_layer, 1, nullptr, qv + c, ld, st);
     if (rc) return rc;
+    if (precision > 0 && pab_attention_tc(b, n, c, qv, qv + c, ld, x, rmax, rsum, d, precision, st) == 0)
+        return pab_pointwise_mlp_residual(b * n, d, trans_layer, 1, x, out, 0, st);
     const dim3 grid(pab_divup(n, AT_R), b);
     const size_t smem_a = sizeof(float) * (AT_R * SXQ + AT_KC * AT_C + AT_R * SPT);
     const size_t smem_b = sizeof(float) * (AT_R * SXQ + AT_C * AT_C + AT_R * SPT + 2 * AT_C + AT_R);

@@ -52,6 +52,7 @@ struct alignas(64) TcArgs {
     int K[MAX_LAYERS], N[MAX_LAYERS], relu[MAX_LAYERS];
     int ksteps[MAX_LAYERS];                    // 16-wide k-steps that carry data (the rest of the last 64-chunk is zero padding)
     int n_layers, n_stages, mode;
+    int planes;                                // 2: bf16 hi/lo split, 3 MMAs per product (fp32 contract); 1: plain bf16 operands, 1 MMA
     int csize, iters;                          // CTAs per cluster sharing the weight stream (1 or 2); tile-loop trips (equal for all CTAs)
     int dynamic;                               // 1: CTAs draw tiles from *counter (atomic) instead of the static blockIdx + i*grid sequence
     unsigned int *counter;                     // zeroed by the host before the launch
@@ -113,7 +114,7 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_constant__ TcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *a1 = smem;                                            // layer-0 operand, hi plane
-    uint8_t *a2 = a1 + (size_t)(a.a_region >> 1);                  //                  lo plane
+    uint8_t *a2 = a.planes == 2 ? a1 + (size_t)(a.a_region >> 1) : nullptr;   //            lo plane (bf16 hi/lo mode only)
     uint8_t *stages = a1 + (size_t)a.a_region;
     uint8_t *stg = stages + (size_t)a.n_stages * (NBLK_MAX * 128);
     uint8_t *misc = stg + (a.mode == TC_SA ? STG_BYTES : STG_BYTES_FP);
@@ -210,13 +211,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                     for (int g = 0; g < ngroups; ++g)
                       for (int nb = 0; nb < nnb; ++nb)
                         for (int kc = g * gc; kc < (g == ngroups - 1 ? nkc : (g + 1) * gc); ++kc)
-                            for (int pl = 0; pl < 2; ++pl) {
+                            for (int pl = 0; pl < a.planes; ++pl) {
                                 // narrow layers (<= 64 output channels): both planes share one slot and one barrier round trip
                                 const bool first = pl == 0 || nbr > 64;
                                 uint8_t *dst = stages + (size_t)s * (NBLK_MAX * 128) + (first ? 0 : nbr * 128);
                                 if (first) {
                                     mbar_wait(empty + s, ph ^ 1);                // released by every CTA of the cluster
-                                    mbar_expect_tx(full + s, (uint32_t)nbr * 128u * (nbr > 64 ? 1u : 2u));
+                                    mbar_expect_tx(full + s, (uint32_t)nbr * 128u * (nbr > 64 ? 1u : (uint32_t)a.planes));
                                 }
                                 if (a.csize == 1) {
                                     tma_load_2d(dst, &a.tm[l][pl], kc * KCH, nb * nbr, full + s);
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                                     tma_load_2d_mc(dst + (size_t)crank * share * 128, &a.tm[l][pl], kc * KCH, nb * nbr + (int)crank * share,
                                                    full + s, cmask_all);
                                 }
-                                if (nbr > 64 || pl == 1) {
+                                if (nbr > 64 || pl == a.planes - 1) {
                                     if (++s == (uint32_t)a.n_stages) { s = 0; ph ^= 1; }
                                 }
                             }
@@ -236,11 +237,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     } else if (warp == 1) {
         // ================= MMA issuer: all lanes run the loops, one elected lane issues ===========================
         const uint32_t leader = elect_one();
-        const uint32_t a1_lo = umma_desc_lo(smem_u32(a1)), a2_lo = umma_desc_lo(smem_u32(a2));
+        const uint32_t a1_lo = umma_desc_lo(smem_u32(a1)), a2_lo = umma_desc_lo(smem_u32(a1) + (uint32_t)(a.a_region >> 1));
         const uint32_t st_lo = umma_desc_lo(smem_u32(stages));
         constexpr uint32_t st_step = (NBLK_MAX * 128) >> 4;
         uint32_t s = 0, ph = 0, pcount = 0, tcount = 0, gcount = 0;
         bool t1_pending = false;
+        const bool two = a.planes == 2;
         for (int it = 0; tile_at((uint32_t)it) >= 0; ++it, ++tcount) {
             for (int l = 0; l < a.n_layers; ++l) {
                 const int ksteps = a.ksteps[l], nkc_main = (ksteps + 3) >> 2;
@@ -287,13 +289,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                             if (ks < kn) {
                                 if (from_smem) {
                                     umma_f16_if(leader, d, a1_lo + ka + 2 * ks, UMMA_DESC_HI, sb + 2 * ks, UMMA_DESC_HI, idesc, (kc | ks) != 0);
-                                    umma_f16_if(leader, d, a2_lo + ka + 2 * ks, UMMA_DESC_HI, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
+                                    if (two) umma_f16_if(leader, d, a2_lo + ka + 2 * ks, UMMA_DESC_HI, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
                                 } else {
                                     umma_f16_ts_if(leader, d, tmem + AH_COL + ta + ks * 8, sb + 2 * ks, UMMA_DESC_HI, idesc, (kc | ks) != 0);
-                                    umma_f16_ts_if(leader, d, tmem + AL_COL + ta + ks * 8, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
+                                    if (two) umma_f16_ts_if(leader, d, tmem + AL_COL + ta + ks * 8, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
                                 }
                             }
                         }
+                        if (two) {
                         if (nbr > 64) {                          // wide block: the lo plane sits in the next slot
                             if (a.csize == 1) umma_commit_if(leader, empty + s);
                             else umma_commit_mc_if(leader, empty + s, cmask_all);
@@ -310,6 +313,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                                 if (from_smem) umma_f16_if(leader, d, a1_lo + ka + 2 * ks, UMMA_DESC_HI, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
                                 else umma_f16_ts_if(leader, d, tmem + AH_COL + ta + ks * 8, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
                             }
+                        }
                         }
                         if (a.csize == 1) umma_commit_if(leader, empty + s);
                         else umma_commit_mc_if(leader, empty + s, cmask_all);
@@ -386,7 +390,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             split_pack(xe[0], xe[1], hi[0], lo[0]);
             split_pack(xe[2], 0.f, hi[1], lo[1]);
             tmem_st16(trow + AH_COL + XTRA_COL, hi);
-            tmem_st16(trow + AL_COL + XTRA_COL, lo);
+            if (a.planes == 2) tmem_st16(trow + AL_COL + XTRA_COL, lo);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         };
         const bool xwriter = a.n_extra > 0 && half == 0;
@@ -459,7 +463,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                             }
                             if (active) {                       // next layer's operand: bf16 pairs into the TMEM planes
                                 tmem_st16(trow + AH_COL + (uint32_t)(dcol >> 1), hi);
-                                tmem_st16(trow + AL_COL + (uint32_t)(dcol >> 1), lo);
+                                if (a.planes == 2) tmem_st16(trow + AL_COL + (uint32_t)(dcol >> 1), lo);
                             }
                         } else {
                             const bool final_batch = cb + 32 >= per;
@@ -850,6 +854,7 @@ int g_tc_cluster = 0;      // weight multicast across CTA pairs (pab_tune_tensor
 struct TcPlan { int a_region, gchunks, n_stages, coff[MAX_LAYERS], pre_off; size_t misc, smem; };
 
 bool tc_plan(const pab_layer_t *layers, int n_layers, const pab_layer_t *pre, int mode, TcPlan *p) {
+    const int planes = layers[0].w_lo ? 2 : 1;
     const long stg_bytes = mode == TC_SA ? STG_BYTES : STG_BYTES_FP;
     int ctab = 0;
     for (int l = 0; l < n_layers; ++l) {
@@ -865,7 +870,7 @@ bool tc_plan(const pab_layer_t *layers, int n_layers, const pab_layer_t *pre, in
         if (pre || layers[0].c_out > D_COLS) return false;
         p->gchunks = 4;
     }
-    p->a_region = 2 * p->gchunks * A_CHUNK;
+    p->a_region = planes * p->gchunks * A_CHUNK;
     p->misc = 384 + (size_t)ctab * 4 + 64;
     const long budget = 227L * 1024 - p->a_region - stg_bytes - (long)p->misc;
     p->n_stages = (int)(budget / (NBLK_MAX * 128));
@@ -878,7 +883,8 @@ bool tc_layers_ok(const pab_layer_t *layers, int n_layers, bool first_is_module_
     if (n_layers < 1 || n_layers > MAX_LAYERS) return false;
     for (int l = 0; l < n_layers; ++l) {
         const pab_layer_t &L = layers[l];
-        if (!L.w_hi || !L.w_lo || L.tc_k <= 0 || L.tc_k % KCH) return false;
+        if (!L.w_hi || L.tc_k <= 0 || L.tc_k % KCH) return false;
+        if ((L.w_lo != nullptr) != (layers[0].w_lo != nullptr)) return false;     // one precision mode per module
         if (!(L.c_out == 32 || L.c_out == 64 || L.c_out % NBLK_MAX == 0) || L.c_out > 512) return false;
         if (l < n_layers - 1 && L.c_out > D_COLS) return false;       // the next operand must fit the TMEM planes
         const bool module_input = l == 0 && first_is_module_input;
@@ -938,13 +944,14 @@ int pab_tc_launch(int mode, long rows, int k_group, const pab_layer_t *all_layer
         // layer 0 of a module with extra (xyz) channels: the planes carry one more 64-column chunk with their weights
         const int kcols = L.tc_k + ((l == 0 && !pre && L.c_in > L.tc_k) ? KCH : 0);
         if (make_weight_map(&a.tm[l][0], L.w_hi, L.c_out, kcols, nbr / a.csize)) return PAB_EINVAL;
-        if (make_weight_map(&a.tm[l][1], L.w_lo, L.c_out, kcols, nbr / a.csize)) return PAB_EINVAL;
+        if (L.w_lo && make_weight_map(&a.tm[l][1], L.w_lo, L.c_out, kcols, nbr / a.csize)) return PAB_EINVAL;
         a.shift[l] = L.shift; a.K[l] = L.tc_k; a.N[l] = L.c_out; a.relu[l] = L.relu; a.coff[l] = p.coff[l];
         // k-steps that carry data: the staged layer-0 operand spans whole 64-chunks (only the pre-layer's output is
         // narrower), the TMEM operand of later layers exactly c_in channels
         a.ksteps[l] = l == 0 ? (pre ? (pre->c_out + 15) / 16 : L.tc_k / 16) : L.c_in / 16;
     }
     a.n_layers = n_layers; a.mode = mode; a.rows = rows; a.trace = g_tc_trace;
+    a.planes = layers[0].w_lo ? 2 : 1;
     if (pre) {
         a.n_extra = 0; a.w_extra = nullptr;
         a.pre_cin = pre->c_in; a.pre_cout = pre->c_out; a.pre_relu = pre->relu; a.pre_wt = pre->wt; a.pre_shift = pre->shift;

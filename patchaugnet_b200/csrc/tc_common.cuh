@@ -148,6 +148,7 @@ __device__ __forceinline__ void split_pack(float a, float b, uint32_t &hi, uint3
 __device__ __forceinline__ uint32_t a_unit_offset(int r, int j) {
     return (uint32_t)((j >> 3) * A_CHUNK + r * 128 + (((j & 7) ^ (r & 7)) << 4));
 }
+// a2 == nullptr: single-plane (plain bf16) operands, only the rounded values are stored
 __device__ __forceinline__ void store_units(uint8_t *a1, uint8_t *a2, int r, int j, const float (&v)[8]) {
     uint4 h, l;
     split_pack(v[0], v[1], h.x, l.x);
@@ -156,7 +157,7 @@ __device__ __forceinline__ void store_units(uint8_t *a1, uint8_t *a2, int r, int
     split_pack(v[6], v[7], h.w, l.w);
     const uint32_t off = a_unit_offset(r, j);
     *reinterpret_cast<uint4 *>(a1 + off) = h;
-    *reinterpret_cast<uint4 *>(a2 + off) = l;
+    if (a2) *reinterpret_cast<uint4 *>(a2 + off) = l;
 }
 
 

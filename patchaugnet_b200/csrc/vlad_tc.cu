@@ -36,6 +36,7 @@ constexpr int VT_C = 256;                     // channels (4 chunks of 64)
 
 struct VtArgs {
     int n, K, Kp, nchunk, nitems, rows_per_item;
+    int planes;                               // 2: bf16 hi/lo operands (three MMAs per product); 1: plain bf16 (one MMA)
     const float *x, *shift;
     const __nv_bfloat16 *wc_hi, *wc_lo;       // (Kp, 256) K-major, bn1 scale folded, rows >= K zero
     float *part, *asum;
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vlad_tc_kernel(const VtArgs a) 
         const int k = u >> 5, j = u & 31;
         const uint32_t off = (uint32_t)((j >> 3) * wchunk + k * 128 + (((j & 7) ^ (k & 7)) << 4));
         *reinterpret_cast<uint4 *>(w1 + off) = __ldg(reinterpret_cast<const uint4 *>(a.wc_hi + (size_t)k * VT_C) + j);
-        *reinterpret_cast<uint4 *>(w2 + off) = __ldg(reinterpret_cast<const uint4 *>(a.wc_lo + (size_t)k * VT_C) + j);
+        if (a.planes == 2) *reinterpret_cast<uint4 *>(w2 + off) = __ldg(reinterpret_cast<const uint4 *>(a.wc_lo + (size_t)k * VT_C) + j);
     }
     if (tid < 64) shift_s[tid] = tid < a.K ? __ldg(a.shift + tid) : 0.f;
     fence_proxy_async();
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vlad_tc_kernel(const VtArgs a) 
     if (warp == 1) {
         // all lanes run the loops, one elected lane issues (tc_common.cuh: warp-uniform issue path)
         const uint32_t leader = elect_one();
+        const bool two = a.planes == 2;
         uint32_t tcount = 0;
         const uint32_t id1 = umma_idesc(a.Kp), id2 = umma_idesc_amn(a.Kp) | (1u << 16);   // GEMM2: A and B MN-major
         const uint32_t x1_lo = umma_desc_lo(smem_u32(x1)), x2_lo = umma_desc_lo(smem_u32(x2));
@@ -128,8 +130,10 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vlad_tc_kernel(const VtArgs a) 
                     for (int ks = 0; ks < 4; ++ks) {
                         const uint32_t xa = (uint32_t)kc * (A_CHUNK >> 4) + 2 * ks, wb = (uint32_t)kc * wstep + 2 * ks;
                         umma_f16_if(leader, d1, x1_lo + xa, UMMA_DESC_HI, w1_lo + wb, UMMA_DESC_HI, id1, (kc | ks) != 0);
-                        umma_f16_if(leader, d1, x2_lo + xa, UMMA_DESC_HI, w1_lo + wb, UMMA_DESC_HI, id1, 1);
-                        umma_f16_if(leader, d1, x1_lo + xa, UMMA_DESC_HI, w2_lo + wb, UMMA_DESC_HI, id1, 1);
+                        if (two) {
+                            umma_f16_if(leader, d1, x2_lo + xa, UMMA_DESC_HI, w1_lo + wb, UMMA_DESC_HI, id1, 1);
+                            umma_f16_if(leader, d1, x1_lo + xa, UMMA_DESC_HI, w2_lo + wb, UMMA_DESC_HI, id1, 1);
+                        }
                     }
                 }
                 umma_commit_if(leader, d1_ready);
@@ -142,8 +146,10 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vlad_tc_kernel(const VtArgs a) 
                         const uint32_t xa = (uint32_t)(2 * cb) * (A_CHUNK >> 4) + (uint32_t)ks * (2048 >> 4);
                         const uint32_t pb = (uint32_t)ks * (2048 >> 4);   // 16 points = two 8-row swizzle atoms
                         umma_f16_if(leader, d2 + cb * 64, xm1_lo + xa, UMMA_DESC_MN_HI, p1_lo + pb, UMMA_DESC_MN_HI, id2, (t_in_item | ks) != 0);
-                        umma_f16_if(leader, d2 + cb * 64, xm2_lo + xa, UMMA_DESC_MN_HI, p1_lo + pb, UMMA_DESC_MN_HI, id2, 1);
-                        umma_f16_if(leader, d2 + cb * 64, xm1_lo + xa, UMMA_DESC_MN_HI, p2_lo + pb, UMMA_DESC_MN_HI, id2, 1);
+                        if (two) {
+                            umma_f16_if(leader, d2 + cb * 64, xm2_lo + xa, UMMA_DESC_MN_HI, p1_lo + pb, UMMA_DESC_MN_HI, id2, 1);
+                            umma_f16_if(leader, d2 + cb * 64, xm1_lo + xa, UMMA_DESC_MN_HI, p2_lo + pb, UMMA_DESC_MN_HI, id2, 1);
+                        }
                     }
                     if (cb == 0) umma_commit_if(leader, g2_half);      // channels 0..127 = chunks 0,1 of the x planes are free
                 }
@@ -212,7 +218,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vlad_tc_kernel(const VtArgs a) 
 #pragma unroll
                     for (int st4 = 0; st4 < 4; ++st4) {
                         const float v[8] = {a0[st4].x, a0[st4].y, a0[st4].z, a0[st4].w, a1[st4].x, a1[st4].y, a1[st4].z, a1[st4].w};
-                        store_units(x1, x2, wwarp * 16 + st4 * 4 + lr, c * 8 + lu, v);
+                        store_units(x1, a.planes == 2 ? x2 : nullptr, wwarp * 16 + st4 * 4 + lr, c * 8 + lu, v);
                     }
                     fence_proxy_async();
                     mbar_arrive(c == 0 ? a_ready : a_ready_c + c);
@@ -276,11 +282,12 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vlad_tc_kernel(const VtArgs a) 
                                 const float2 lf = __bfloat1622float2(ll);
                                 hw[i] = *reinterpret_cast<const uint32_t *>(&hh);
                                 lw[i] = *reinterpret_cast<const uint32_t *>(&ll);
-                                lg[k0] = hf.x + lf.x; lg[k0 + 1] = hf.y + lf.y;
+                                if (a.planes == 2) { lg[k0] = hf.x + lf.x; lg[k0 + 1] = hf.y + lf.y; }
+                                else { lg[k0] = hf.x; lg[k0 + 1] = hf.y; }
                             }
                             const uint32_t off = (uint32_t)(row * 128 + ((((kb >> 3) + u) ^ (row & 7)) << 4));
                             *reinterpret_cast<uint4 *>(p1 + off) = h;
-                            *reinterpret_cast<uint4 *>(p2 + off) = l;
+                            if (a.planes == 2) *reinterpret_cast<uint4 *>(p2 + off) = l;
                         } else {
 #pragma unroll
                             for (int i = 0; i < 8; ++i) lg[8 * u + i] = 0.f;
@@ -346,7 +353,7 @@ __global__ void __launch_bounds__(VT_THREADS, 1) vlad_tc_kernel(const VtArgs a) 
 // host entry used by vlad.cu: returns 0 on success, PAB_EINVAL if the shape is not supported (caller falls back to SIMT)
 int pab_vlad_tc_partial(int b, int n, int c, int K, const float *x, const void *wc_hi, const void *wc_lo, const float *shift,
                         float *part, float *asum, int *nchunk_out, cudaStream_t st) {
-    if (c != VT_C || K <= 0 || K > 64 || !wc_hi || !wc_lo) return PAB_EINVAL;
+    if (c != VT_C || K <= 0 || K > 64 || !wc_hi) return PAB_EINVAL;
     VtArgs a;
     static int n_sm = 0;
     if (!n_sm) {
@@ -362,6 +369,7 @@ int pab_vlad_tc_partial(int b, int n, int c, int K, const float *x, const void *
     a.rows_per_item = rpi;
     a.n = n; a.K = K; a.Kp = (K + 15) / 16 * 16; a.nchunk = (n + rpi - 1) / rpi; a.nitems = b * a.nchunk;
     a.trace = g_tc_trace;
+    a.planes = wc_lo ? 2 : 1;
     a.x = x; a.shift = shift; a.wc_hi = (const __nv_bfloat16 *)wc_hi; a.wc_lo = (const __nv_bfloat16 *)wc_lo; a.part = part; a.asum = asum;
     *nchunk_out = a.nchunk;
     const size_t smem = 10 * (size_t)A_CHUNK + 8 * (size_t)a.Kp * 128 + 64 + 64 * 4 + 4 * TM * 4 + 64;

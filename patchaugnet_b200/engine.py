@@ -44,7 +44,10 @@ class _Layers:
     64 the bf16 hi/lo weight planes are attached (pab_layer_t.w_hi / w_lo) and the C side picks the tcgen05 kernel.
     """
 
-    def __init__(self, shared_mlp, device, extra_first=0, extra_last=0):
+    def __init__(self, shared_mlp, device, extra_first=0, extra_last=0, precision="f32"):
+        # precision "f32": bf16 hi/lo operand planes, three MMAs per product (the 1e-4 fp32 contract);
+        #           "bf16": the rounded plane only (w_lo = NULL -> the kernels issue one MMA per product)
+        self.precision = precision
         self.tensors = []
         blocks = list(shared_mlp.children())
         self.arr = (L.PabLayer * len(blocks))()
@@ -94,7 +97,7 @@ class _Layers:
                     wk[:, kpad:kpad + n_extra] = wf[:, ex0:ex0 + n_extra]
                 hi, lo = _split_bf16(wk)
                 self.tensors += [hi, lo]
-                hi_p, lo_p = hi.data_ptr(), lo.data_ptr()
+                hi_p, lo_p = hi.data_ptr(), (lo.data_ptr() if precision == "f32" else 0)
             self.arr[i] = L.PabLayer(wt.data_ptr(), sh.data_ptr(), c_in, c_in_pad, c_out, 1 if act else 0, hi_p, lo_p, k0, kpad)
             self.spec.append((c_in, c_out))
         self.n = len(blocks)

@@ -25,8 +25,13 @@ from .engine import _Layers, _fold_bn, _split_bf16
 
 
 class FusedPPTNet:
-    def __init__(self, net):
+    def __init__(self, net, precision="f32"):
+        """precision "f32": the reference's fp32 contract (bf16 hi/lo tensor-core operands, descriptors within 1e-4);
+        "bf16": BASELINE.json configs[2] — every tensor-core operand rounded to bf16 once, fp32 accumulation, geometry
+        (FPS / kNN / 3-NN indices and weights) unchanged and still bit-exact."""
         self.net = net
+        self.precision = precision
+        self.attention_precision = 2 if precision == "f32" else 1     # tensor-core attention: hi/lo planes or plain bf16 (0 = SIMT)
         self.device = next(net.parameters()).device
         if self.device.type != "cuda":
             raise L.PabError("FusedPPTNet needs the network on a CUDA device (there is no CPU fallback)")
@@ -40,10 +45,10 @@ class FusedPPTNet:
         self.sa = []
         for mod in bb.SA_modules:
             g = mod.groupers[0]
-            self.sa.append(dict(npoint=mod.npoint, k=g.nsample, layers=_Layers(mod.mlps[0], dev, extra_first=3),
+            self.sa.append(dict(npoint=mod.npoint, k=g.nsample, layers=_Layers(mod.mlps[0], dev, extra_first=3, precision=self.precision),
                                 att=attention._fold(mod.sas[0], dev)))
         # FP_modules[0] takes the raw xyz (3 channels) as its skip input (pptnet.py:83-90: l_features[0] = xyz^T)
-        self.fp = [_Layers(mod.mlp, dev, extra_last=3 if i == 0 else 0) for i, mod in enumerate(bb.FP_modules)]
+        self.fp = [_Layers(mod.mlp, dev, extra_last=3 if i == 0 else 0, precision=self.precision) for i, mod in enumerate(bb.FP_modules)]
         agg = net.aggregation
         self.vlad = []
         for i in range(4):
@@ -147,8 +152,9 @@ class FusedPPTNet:
             chk(lib.pab_sa_module_forward(B, n, m, k, k, c, p(xyz), p(feat), p(lv["cidx"]), p(lv["nbr"]), sa["layers"].arr,
                                           sa["layers"].n, p(lv["pooled"]), p(None), st), "sa")
             arr = sa["att"]["arr"]
-            chk(lib.pab_sa_layer_forward(B, m, sa["att"]["C"], p(lv["pooled"]), arr, attention.C_ptr_offset(arr, 1),
-                                         attention.C_ptr_offset(arr, 2), p(lv["feat"]), p(ws["scratch"]), st), "sa_layer")
+            chk(lib.pab_sa_layer_forward_p(B, m, sa["att"]["C"], p(lv["pooled"]), arr, attention.C_ptr_offset(arr, 1),
+                                           attention.C_ptr_offset(arr, 2), p(lv["feat"]), p(ws["scratch"]),
+                                           self.attention_precision, st), "sa_layer")
             xyz, feat, c = lv["new_xyz"], lv["feat"], sa["layers"].c_out
 
         xyzs = [xyz0] + [lv["new_xyz"] for lv in ws["levels"]]
@@ -177,7 +183,8 @@ class FusedPPTNet:
             if K % 4 == 0:
                 dst = C.c_void_p(flat.data_ptr() + 4 * off)       # element (c, k) of this level sits at off + c*K + k
                 if Cf == 256:
-                    chk(lib.pab_netvlad_forward_tc(B, x_l.shape[1], Cf, K, p(x_l), p(lvl["wc_hi"]), p(lvl["wc_lo"]), p(lvl["shift"]),
+                    chk(lib.pab_netvlad_forward_tc(B, x_l.shape[1], Cf, K, p(x_l), p(lvl["wc_hi"]),
+                                                   p(lvl["wc_lo"] if self.precision == "f32" else None), p(lvl["shift"]),
                                                    p(lvl["w2"]), dst, flat.stride(0), K, p(ws["scratch"]), st), "vlad")
                 else:
                     chk(lib.pab_netvlad_forward(B, x_l.shape[1], Cf, K, p(x_l), p(lvl["wc"]), p(lvl["shift"]), p(lvl["w2"]), dst,

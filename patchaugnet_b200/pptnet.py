@@ -35,15 +35,16 @@ class Network(nn.Module):
             print("No aggregation algorithm: ", aggregation)
         self.use_normalize = use_normalize
         self.use_fused = True          # eval-mode CUDA forward on the fused engine (engine_ppt.FusedPPTNet)
+        self.compute_dtype = "f32"     # "bf16": single-rounding bf16 tensor-core operands in the fused engine (configs[2])
         self._engine = None
         self._engine_key = None
 
     def engine(self, refresh=False):
         """The fused eval engine; rebuilt when parameters / buffers changed (state_dict load, in-place updates)."""
-        key = tuple(p._version for p in self.parameters()) + tuple(b._version for b in self.buffers())
+        key = (self.compute_dtype,) + tuple(p._version for p in self.parameters()) + tuple(b._version for b in self.buffers())
         if self._engine is None or refresh or key != self._engine_key:
             from .engine_ppt import FusedPPTNet
-            self._engine = FusedPPTNet(self)
+            self._engine = FusedPPTNet(self, precision=self.compute_dtype)
             self._engine_key = key
         return self._engine
 
@@ -185,7 +186,7 @@ class SA_Layer(nn.Module):
         """x: B x C x N"""
         if self.use_fused and not self.training and x.is_cuda and not torch.is_grad_enabled():
             from . import attention
-            return attention.sa_layer_forward(self, x)
+            return attention.sa_layer_forward(self, x, getattr(self, "attention_precision", 2))
         bs, ch, nums = x.size()
         x_q = self.q_conv(x).reshape(bs, self.gp, ch // self.gp, nums).permute(0, 1, 3, 2)
         x_k = self.k_conv(x).reshape(bs, self.gp, ch // self.gp, nums)
