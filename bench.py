@@ -316,6 +316,55 @@ def other_configs(dev, world, rank):
         del clouds, db, qd
     except Exception as ex:
         out["cfg4_retrieval_10k"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
+    # configs[4]: training step, 16 anchors x 18 clouds x 4096 points per GPU (128 anchors over 8 GPUs), quadruplet + patch chamfer
+    try:
+        from patchaugnet_b200 import training
+        torch.cuda.empty_cache()
+        anchors = 16
+        net = util.build_network(dev).train()
+        model = training.build_ddp(net, dev)
+        opt = torch.optim.Adam(model.parameters(), lr=5e-4)
+        step = training.TrainStep(model, opt, n_anchors=anchors)
+        g = torch.Generator(device=dev).manual_seed(77 + rank)
+        feed = ((torch.rand(anchors * training.CLOUDS_PER_ANCHOR, 1, NPTS, 3, generator=g, device=dev) * 2 - 1) * 0.57)
+        for _ in range(2):
+            step(feed)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        n_steps = 3
+        for _ in range(n_steps):
+            loss, _terms = step(feed)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / n_steps], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+        rec = dict(ms_per_step=ms, anchors_per_gpu=anchors, clouds_per_gpu=anchors * training.CLOUDS_PER_ANCHOR, n_gpus=world,
+                   clouds_per_s=world * anchors * training.CLOUDS_PER_ANCHOR / (ms * 1e-3), loss=float(loss),
+                   grad_allreduce_bytes=training.grad_bytes(net), peak_mem_gb=torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+                   what="train-mode forward (batch statistics, PyTorch/cuDNN dense layers, this repo's pointops / chamfer kernels with "
+                        "deterministic backward) + quadruplet + patch-chamfer loss + backward + Adam; DistributedDataParallel over anchors")
+        if world > 1:      # the one collective of the step, timed alone: a flat all-reduce of the gradient bytes
+            flat = torch.empty(rec["grad_allreduce_bytes"] // 4, device=dev)
+            dist.all_reduce(flat)
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(5):
+                dist.all_reduce(flat)
+            a1.record()
+            torch.cuda.synchronize()
+            rec["allreduce_alone_ms"] = a0.elapsed_time(a1) / 5
+            rec["allreduce_share_of_step"] = rec["allreduce_alone_ms"] / ms
+        out["cfg5_train_step"] = rec
+        del net, model, opt, step, feed
+        torch.cuda.empty_cache()
+    except Exception as ex:
+        out["cfg5_train_step"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
     return out
 
 

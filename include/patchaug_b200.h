@@ -174,6 +174,15 @@ int pab_fp_module_forward_ordered(int b, int n, int m, int c_known, int c_skip, 
 const int *pab_knn_index_order(int n, const void *index, long *stride_ints);
 
 
+/* Deterministic backward of the index-driven ops (replaces the fp32 atomicAdd scatters of sampling_cuda_kernel.cu:23-36,
+ * grouping_cuda_kernel.cu:28-46, interpolation_cuda_kernel.cu:90-114): grad_points[b,ch,idx[b,e]] += grad_out[b,ch,e] *
+ * (weight ? weight[b,e] : 1) for e in [0,L), summed per target in ascending e — bit-identical from run to run.
+ * grad_out (b,c,L), idx (b,L), weight (b,L) or NULL, grad_points (b,c,n); workspace >= pab_scatter_workspace_bytes(b,n,L).
+ * L <= 32768 per cloud (PAB_EINVAL beyond: use the atomic entry points). */
+size_t pab_scatter_workspace_bytes(int b, int n, int L);
+int pab_scatter_add_deterministic(int b, int c, int n, int L, int gdiv, const float *grad_out, const int *idx, const float *weight,
+                                  float *grad_points, void *workspace, pab_stream_t s);
+
 /* Plain point-wise SharedMLP over rows: x (rows, c_in) -> out (rows, c_out_last). */
 int pab_pointwise_mlp_forward(int rows, const float *x, const pab_layer_t *layers, int n_layers, float *out, pab_stream_t s);
 

@@ -37,6 +37,8 @@ SIGNATURES = {
     "pab_tune_tc_max_ctas": (None, [_I]),
     "pab_tune_fps_clouds_per_cta": (None, [_I]),
     "pab_tune_fps_pruned": (None, [_I]),
+    "pab_scatter_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
+    "pab_scatter_add_deterministic": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "pab_fps_clouds_per_sm": (_I, [_I]),
     "pab_furthestsampling": (_I, [_I, _I, _I, _P, _P, _P, _P]),
     "pab_gathering_forward": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),

@@ -31,6 +31,12 @@ class FusedPPTNet:
         (FPS / kNN / 3-NN indices and weights) unchanged and still bit-exact."""
         self.net = net
         self.precision = precision
+        # per-part arithmetic.  "bf16" mode: FP modules, NetVLAD and the attention passes use plain bf16 operands (one MMA per
+        # product); the SA modules keep the hi/lo planes — their inputs are coordinate / feature DIFFERENCES of neighbouring
+        # points, and rounding those to 8 mantissa bits alone costs the descriptor 4e-3 of cosine (measured, profiles/r02_results.md),
+        # which would break the configuration's parity definition (cosine >= 0.999 against the fp32 forward)
+        self.fp_precision = self.vlad_precision = precision
+        self.sa_precision = "f32"
         self.attention_precision = 2 if precision == "f32" else 1     # tensor-core attention: hi/lo planes or plain bf16 (0 = SIMT)
         self.device = next(net.parameters()).device
         if self.device.type != "cuda":
@@ -45,10 +51,10 @@ class FusedPPTNet:
         self.sa = []
         for mod in bb.SA_modules:
             g = mod.groupers[0]
-            self.sa.append(dict(npoint=mod.npoint, k=g.nsample, layers=_Layers(mod.mlps[0], dev, extra_first=3, precision=self.precision),
+            self.sa.append(dict(npoint=mod.npoint, k=g.nsample, layers=_Layers(mod.mlps[0], dev, extra_first=3, precision=self.sa_precision),
                                 att=attention._fold(mod.sas[0], dev)))
         # FP_modules[0] takes the raw xyz (3 channels) as its skip input (pptnet.py:83-90: l_features[0] = xyz^T)
-        self.fp = [_Layers(mod.mlp, dev, extra_last=3 if i == 0 else 0, precision=self.precision) for i, mod in enumerate(bb.FP_modules)]
+        self.fp = [_Layers(mod.mlp, dev, extra_last=3 if i == 0 else 0, precision=self.fp_precision) for i, mod in enumerate(bb.FP_modules)]
         agg = net.aggregation
         self.vlad = []
         for i in range(4):
@@ -184,7 +190,7 @@ class FusedPPTNet:
                 dst = C.c_void_p(flat.data_ptr() + 4 * off)       # element (c, k) of this level sits at off + c*K + k
                 if Cf == 256:
                     chk(lib.pab_netvlad_forward_tc(B, x_l.shape[1], Cf, K, p(x_l), p(lvl["wc_hi"]),
-                                                   p(lvl["wc_lo"] if self.precision == "f32" else None), p(lvl["shift"]),
+                                                   p(lvl["wc_lo"] if self.vlad_precision == "f32" else None), p(lvl["shift"]),
                                                    p(lvl["w2"]), dst, flat.stride(0), K, p(ws["scratch"]), st), "vlad")
                 else:
                     chk(lib.pab_netvlad_forward(B, x_l.shape[1], Cf, K, p(x_l), p(lvl["wc"]), p(lvl["shift"]), p(lvl["w2"]), dst,

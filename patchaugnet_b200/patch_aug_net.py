@@ -111,12 +111,13 @@ class Network(nn.Module):
             centers, origin_out, feats, recon_out = [], [], [], []
             origin_patches = pointops.grouping(xyz.transpose(1, 2).contiguous(), sample_idx[0])   # B x 3 x M x K
             for ci in related:
-                sel = torch.tensor([ci]).to(out.device)
-                f = torch.index_select(fp_features[1], dim=0, index=sel).squeeze().transpose(1, 0)   # M x 256
+                # the reference builds a one-element index tensor on the host and copies it to the device for every related
+                # cloud (patch_aug_net.py:84): slicing selects the same rows without the per-cloud host-to-device copy
+                f = fp_features[1][ci:ci + 1].squeeze().transpose(1, 0)                              # M x 256
                 if self.use_l2_norm:
                     f = F.normalize(f)
-                patches = torch.index_select(origin_patches, dim=0, index=sel).squeeze().transpose(2, 0).transpose(1, 0)
-                centers.append(torch.index_select(center_idx[0], dim=0, index=sel))
+                patches = origin_patches[ci:ci + 1].squeeze().transpose(2, 0).transpose(1, 0)
+                centers.append(center_idx[0][ci:ci + 1])
                 origin_out.append(patches)
                 feats.append(f)
                 if self.use_a2a_recon:

@@ -48,7 +48,24 @@ def grouping_forward_cuda(b, c, n, m, nsample, points, idx, out):
                                          L.stream_ptr()), "grouping_forward_cuda")
 
 
+DETERMINISTIC_BACKWARD = True      # scatter-adds as ordered gathers over an inverted index (scatter.cu); False: fp32 atomics like the reference
+_MAX_L = 32768
+
+
+def _scatter(b, c, n, Lc, grad_out, idx, weight, grad_points, what, gdiv=1):
+    """grad_points[b,ch,idx[b,e]] += grad_out[b,ch,e] * weight[b,e], deterministic.  Returns False when the shape is out of range."""
+    if not DETERMINISTIC_BACKWARD or Lc > _MAX_L or Lc == 0 or b == 0 or c == 0:
+        return False
+    ws = torch.empty(L.lib().pab_scatter_workspace_bytes(b, n, Lc), dtype=torch.uint8, device=grad_out.device)
+    L.check(L.lib().pab_scatter_add_deterministic(b, c, n, Lc, gdiv, _f(grad_out, "grad_out"), _i(idx, "idx"),
+                                                  _f(weight, "weight") if weight is not None else L.ptr(None),
+                                                  _f(grad_points, "grad_points"), L.ptr(ws), L.stream_ptr()), what)
+    return True
+
+
 def grouping_backward_cuda(b, c, n, m, nsample, grad_out, idx, grad_points):
+    if _scatter(b, c, n, m * nsample, grad_out, idx, None, grad_points, "grouping_backward_cuda"):
+        return
     L.check(L.lib().pab_grouping_backward(b, c, n, m, nsample, _f(grad_out, "grad_out"), _i(idx, "idx"),
                                           _f(grad_points, "grad_points"), L.stream_ptr()), "grouping_backward_cuda")
 
@@ -64,6 +81,8 @@ def gathering_forward_cuda(b, c, n, m, points, idx, out):
 
 
 def gathering_backward_cuda(b, c, n, m, grad_out, idx, grad_points):
+    if _scatter(b, c, n, m, grad_out, idx, None, grad_points, "gathering_backward_cuda"):
+        return
     L.check(L.lib().pab_gathering_backward(b, c, n, m, _f(grad_out, "grad_out"), _i(idx, "idx"),
                                            _f(grad_points, "grad_points"), L.stream_ptr()), "gathering_backward_cuda")
 
@@ -84,6 +103,9 @@ def interpolation_forward_cuda(b, c, m, n, points, idx, weight, out):
 
 
 def interpolation_backward_cuda(b, c, n, m, grad_out, idx, weight, grad_points):
+    # entry e = 3 j + t scatters grad_out[b, ch, j] * weight[b, j, t] to known point idx[b, j, t]
+    if _scatter(b, c, m, 3 * n, grad_out, idx, weight, grad_points, "interpolation_backward_cuda", gdiv=3):
+        return
     L.check(L.lib().pab_interpolation_backward(b, c, n, m, _f(grad_out, "grad_out"), _i(idx, "idx"), _f(weight, "weight"),
                                                _f(grad_points, "grad_points"), L.stream_ptr()), "interpolation_backward_cuda")
 

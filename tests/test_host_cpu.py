@@ -234,3 +234,66 @@ def test_triplet_batch_flattening_matches_the_per_pair_entry_lists():
     a = patch_pairs.select_pair(centers, centers, [(3, [3, 6, 9], [12, 15]), (5, [3], [12])], seed=7, pair=2)
     assert a == patch_pairs.select_pair(centers, centers, [(3, [3, 6, 9], [12, 15]), (5, [3], [12])], seed=7, pair=2)
     assert a[0] == [1, 1, 1] and a[1] == [1, 2, 3] and set(a[2]) <= {4, 5}
+
+
+# ---- training step host logic (BASELINE.json configs[4]) -----------------------------------------------------------------
+class _StubNet(torch.nn.Module):
+    """Stands in for patch_aug_net.Network on the CPU (the real model has no CPU path): (A*18,1,N,3) -> (A*18, 8) descriptors."""
+
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(3)
+        self.fc = torch.nn.Linear(6, 8)
+
+    def forward(self, x, nn_dict=None, return_feat=True):
+        x = x.squeeze(1)
+        return torch.nn.functional.normalize(self.fc(torch.cat([x.mean(1), x.std(1)], 1)))
+
+
+def _train_world(rank, world, port, feed, out):
+    import torch.distributed as dist
+    from patchaugnet_b200 import training
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        net = _StubNet()
+        model = training.build_ddp(net, torch.device("cpu"))
+        assert isinstance(model, torch.nn.parallel.DistributedDataParallel)
+        per = feed.shape[0] // world
+        step = training.TrainStep(model, torch.optim.SGD(model.parameters(), lr=0.1), n_anchors=per // training.CLOUDS_PER_ANCHOR,
+                                  use_patch_recon=False)
+        step(feed[rank * per:(rank + 1) * per])
+        if rank == 0:
+            out.put({k: v.detach().numpy() for k, v in net.state_dict().items()})
+    finally:
+        dist.destroy_process_group()
+
+
+def test_training_step_host_logic_and_two_rank_ddp_equals_single_rank():
+    from patchaugnet_b200 import training
+    d = training.make_nn_dict(2)
+    assert list(d) == [(0, 1), (0, 2), (18, 19), (18, 20)]                       # scene_dataset.py:293-296 key layout
+    q, pos, neg, other = training.split_descriptors(torch.arange(2 * 18 * 4.0).view(36, 4), 2)
+    assert q.shape == (2, 1, 4) and pos.shape == (2, 2, 4) and neg.shape == (2, 14, 4) and other.shape == (2, 1, 4)
+    assert torch.equal(other[1, 0], torch.arange(2 * 18 * 4.0).view(36, 4)[35])
+    g = torch.Generator().manual_seed(1)
+    feed = torch.rand(4 * 18, 1, 32, 3, generator=g)
+    # single rank, 4 anchors
+    net = _StubNet()
+    step = training.TrainStep(net, torch.optim.SGD(net.parameters(), lr=0.1), n_anchors=4, use_patch_recon=False)
+    loss, terms = step(feed)
+    assert torch.isfinite(loss) and set(terms) == {"place_recognition"}
+    want = {k: v.detach().numpy() for k, v in net.state_dict().items()}
+    # two ranks, 2 anchors each: DDP's gradient average of per-rank means == gradient of the global mean
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_train_world, args=(r, 2, port, feed, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = out.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for k in want:
+        assert np.allclose(got[k], want[k], atol=1e-6), k

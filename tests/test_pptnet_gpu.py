@@ -99,7 +99,7 @@ def test_pptnet_bf16_mode_meets_the_config3_parity_definition():
         assert torch.equal(a, b)
     cos = torch.nn.functional.cosine_similarity(d16, torch.from_numpy(g["desc"]).to(DEV)).min().item()
     assert cos >= 0.999, cos
-    assert not torch.equal(d16, d32)                                     # the bf16 path really is a different arithmetic
+    assert not torch.equal(d16, d32) and (d16 - d32).abs().max().item() > 1e-4      # the bf16 path really is a different arithmetic
     # Recall@1 on a small structured database: bf16 descriptors must retrieve what fp32 descriptors retrieve
     n_db, n_q = 64, 32
     db = util.place_batch(range(400, 400 + n_db), 0).to(DEV)
