@@ -327,14 +327,14 @@ def other_configs(dev, world, rank):
         step = training.TrainStep(model, opt, n_anchors=anchors)
         g = torch.Generator(device=dev).manual_seed(77 + rank)
         feed = ((torch.rand(anchors * training.CLOUDS_PER_ANCHOR, 1, NPTS, 3, generator=g, device=dev) * 2 - 1) * 0.57)
-        for _ in range(2):
+        for _ in range(3):                                         # allocator growth, cuDNN algorithm choice, Adam state
             step(feed)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        n_steps = 3
+        n_steps = 5
         for _ in range(n_steps):
             loss, _terms = step(feed)
         e1.record()
@@ -346,8 +346,9 @@ def other_configs(dev, world, rank):
         rec = dict(ms_per_step=ms, anchors_per_gpu=anchors, clouds_per_gpu=anchors * training.CLOUDS_PER_ANCHOR, n_gpus=world,
                    clouds_per_s=world * anchors * training.CLOUDS_PER_ANCHOR / (ms * 1e-3), loss=float(loss),
                    grad_allreduce_bytes=training.grad_bytes(net), peak_mem_gb=torch.cuda.max_memory_allocated(dev) / 2 ** 30,
-                   what="train-mode forward (batch statistics, PyTorch/cuDNN dense layers, this repo's pointops / chamfer kernels with "
-                        "deterministic backward) + quadruplet + patch-chamfer loss + backward + Adam; DistributedDataParallel over anchors")
+                   what="train-mode forward (batch statistics: cuDNN 1x1 convolutions + this repo's fused BatchNorm+ReLU kernels, pointops / "
+                        "chamfer kernels with deterministic backward) + quadruplet + patch-chamfer loss + backward + Adam; "
+                        "DistributedDataParallel over anchors")
         if world > 1:      # the one collective of the step, timed alone: a flat all-reduce of the gradient bytes
             flat = torch.empty(rec["grad_allreduce_bytes"] // 4, device=dev)
             dist.all_reduce(flat)

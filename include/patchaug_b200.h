@@ -183,6 +183,20 @@ size_t pab_scatter_workspace_bytes(int b, int n, int L);
 int pab_scatter_add_deterministic(int b, int c, int n, int L, int gdiv, const float *grad_out, const int *idx, const float *weight,
                                   float *grad_points, void *workspace, pab_stream_t s);
 
+/* Train-mode BatchNorm + ReLU of a SharedMLP block (utils/model_util/pt_util.py:98-151: conv -> BatchNorm (batch statistics)
+ * -> ReLU), fused: x, y, dy, dx are (B, C, S) contiguous, S = product of the trailing dimensions.  forward: batch mean / biased
+ * variance per channel, y = relu((x - mean) * invstd * gamma + beta), saved mean / invstd for the backward, running statistics
+ * updated like nn.BatchNorm (momentum, unbiased variance) when the pointers are not NULL.  backward: dz = dy * (y > 0),
+ * dbeta = sum dz, dgamma = sum dz * xhat, dx = gamma * invstd * (dz - dbeta/N - xhat * dgamma/N).  Deterministic reductions.
+ * workspace >= pab_bn_train_workspace_bytes(C). */
+size_t pab_bn_train_workspace_bytes(int C);
+int pab_bn_relu_train_forward(int B, int C, long S, const float *x, const float *gamma, const float *beta, float eps, float momentum,
+                              float *running_mean, float *running_var, float *mean, float *invstd, float *y, void *workspace,
+                              pab_stream_t s);
+int pab_bn_relu_train_backward(int B, int C, long S, const float *dy, const float *y, const float *x, const float *gamma,
+                               const float *mean, const float *invstd, float *dx, float *dgamma, float *dbeta, void *workspace,
+                               pab_stream_t s);
+
 /* Plain point-wise SharedMLP over rows: x (rows, c_in) -> out (rows, c_out_last). */
 int pab_pointwise_mlp_forward(int rows, const float *x, const pab_layer_t *layers, int n_layers, float *out, pab_stream_t s);
 

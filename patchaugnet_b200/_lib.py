@@ -37,6 +37,9 @@ SIGNATURES = {
     "pab_tune_tc_max_ctas": (None, [_I]),
     "pab_tune_fps_clouds_per_cta": (None, [_I]),
     "pab_tune_fps_pruned": (None, [_I]),
+    "pab_bn_train_workspace_bytes": (C.c_size_t, [_I]),
+    "pab_bn_relu_train_forward": (_I, [_I, _I, C.c_long, _P, _P, _P, C.c_float, C.c_float, _P, _P, _P, _P, _P, _P, _P]),
+    "pab_bn_relu_train_backward": (_I, [_I, _I, C.c_long, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "pab_scatter_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
     "pab_scatter_add_deterministic": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "pab_fps_clouds_per_sm": (_I, [_I]),
