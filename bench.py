@@ -293,6 +293,9 @@ def other_configs(dev, world, rank):
         net = util.build_network(dev)
         g = torch.Generator(device=dev).manual_seed(4321)         # same clouds on every rank; each rank reads its shard only
         clouds = (torch.rand(n_db + n_q, NPTS, 3, generator=g, device=dev) * 2 - 1) * 0.57
+        with torch.no_grad():                                        # warm-up: kernels / lazily loaded modules of the retrieval ops
+            wd = retrieval.extract_descriptors(net, clouds[:64 * world], batch_size=32, device=dev)
+        retrieval.evaluate_recall(wd, wd[: 8 * world], [{i} for i in range(8 * world)], top_k=25)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()

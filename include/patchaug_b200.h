@@ -107,6 +107,11 @@ int pab_knn(const float *ref, int nr, const float *query, int nq, int dim, int k
  * datasets/place_recognition_dataset.py:60, scene_dataset.py:1052): db (ndb,dim), q (nq,dim) ->
  * dist (nq,k) f32 Euclidean ascending, ind (nq,k) i32 0-based, ties to the lower index. k <= 1024. */
 int pab_retrieval_topk(const float *db, int ndb, const float *q, int nq, int dim, int k, float *dist, int *ind, pab_stream_t s);
+/* The same search with a per-query candidate set: mask has nq rows of ceil(ndb/32) 32-bit words, bit p of row q set = query q
+ * may retrieve database entry p.  One launch for a whole batch of ragged sets (hard-negative mining,
+ * datasets/scene_dataset.py:1101-1113).  Unused slots of a query with fewer than k candidates hold +inf / index 0. */
+int pab_retrieval_topk_masked(const float *db, int ndb, const float *q, int nq, int dim, int k, const unsigned *mask,
+                              float *dist, int *ind, pab_stream_t s);
 
 /* ---- libs/emd_module ----------------------------------------------------------------------------- */
 /* emd_cuda_forward  emd.cpp:14-22, emd_cuda.cu:228-282.  Same buffers, same return convention
@@ -290,6 +295,10 @@ void pab_tune_fps_threads(int threads);
  * bit-identical indices); 0 (default) = always the full-scan register-resident sampler, which is faster at these sizes
  * because a step is bound by its arg-max latency chain, not by the distance updates. */
 void pab_tune_fps_pruned(int on);
+
+/* Tuning hook: 1 = a full-scan sampler CTA claims more than half an SM's shared memory, so no two of them can share an SM;
+ * 0 (default) = only the memory it needs (measured identical: 0.40 ms for 1..128 clouds of 4096 points). */
+void pab_tune_fps_exclusive(int on);
 
 /* How many clouds of n points one SM samples concurrently with the current settings (the engine sizes the persistent
  * dense kernels of the overlapping batch by it). */

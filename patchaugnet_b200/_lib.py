@@ -37,6 +37,7 @@ SIGNATURES = {
     "pab_tune_tc_max_ctas": (None, [_I]),
     "pab_tune_fps_clouds_per_cta": (None, [_I]),
     "pab_tune_fps_pruned": (None, [_I]),
+    "pab_tune_fps_exclusive": (None, [_I]),
     "pab_bn_train_workspace_bytes": (C.c_size_t, [_I]),
     "pab_bn_relu_train_forward": (_I, [_I, _I, C.c_long, _P, _P, _P, C.c_float, C.c_float, _P, _P, _P, _P, _P, _P, _P]),
     "pab_bn_relu_train_backward": (_I, [_I, _I, C.c_long, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
@@ -68,6 +69,7 @@ SIGNATURES = {
     "pab_chamfer_backward": (_I, [_I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "pab_knn": (_I, [_P, _I, _P, _I, _I, _I, _P, _P, _P]),
     "pab_retrieval_topk": (_I, [_P, _I, _P, _I, _I, _I, _P, _P, _P]),
+    "pab_retrieval_topk_masked": (_I, [_P, _I, _P, _I, _I, _I, _P, _P, _P, _P]),
     "pab_emd_forward": (_I, [_I, _I] + [_P] * 14 + [_F, _I, _P]),
     "pab_emd_backward": (_I, [_I, _I, _P, _P, _P, _P, _P, _P]),
     "pab_gather_rows": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),

@@ -430,10 +430,14 @@ int g_fps_threads_override = 0;
 
 int g_fps_clouds_per_cta = 1;
 
+int g_fps_exclusive = 0;   // (measured: no effect — the scheduler already spreads the sampler CTAs; kept as a hook) pad the sampler's dynamic shared memory beyond half an SM so that two sampler CTAs never share one:
+                           // the block scheduler otherwise pairs them up on some SMs and both run their latency chain slower
+
 template <int PPT, int MAXT>
 int launch_fps(int b, int n, int m, int threads, int log2bs, const float *xyz, float *temp, int *idx, cudaStream_t st) {
     const int cpc = (g_fps_clouds_per_cta >= 2 && 2 * threads <= MAXT && b > 1) ? 2 : 1;
-    const size_t smem = (size_t)cpc * n * 3 * sizeof(float);
+    size_t smem = (size_t)cpc * n * 3 * sizeof(float);
+    if (g_fps_exclusive && smem < 116 * 1024) smem = 116 * 1024;
     // static smem (candidate slots) counts against the 48 KB default too: opt in whenever we are near it
     if (smem > 40 * 1024)
         PAB_CUDA(cudaFuncSetAttribute(fps_kernel<PPT, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -447,6 +451,8 @@ int launch_fps(int b, int n, int m, int threads, int log2bs, const float *xyz, f
 PAB_API void pab_tune_fps_threads(int threads) { g_fps_threads_override = threads; }
 
 PAB_API void pab_tune_fps_pruned(int on) { g_fps_pruned = on; }
+
+PAB_API void pab_tune_fps_exclusive(int on) { g_fps_exclusive = on; }
 
 PAB_API int pab_fps_clouds_per_sm(int n) {
     const bool pow2 = n > 0 && (n & (n - 1)) == 0;

@@ -27,6 +27,8 @@ struct TopkArgs {
     long d_sq, d_sk;
     void *ind;
     int ind64, ind_base;               // int64 (1-based for KNN_CUDA) or int32
+    const unsigned *mask;              // optional (nq, mask_words) bit mask of the reference points each query may retrieve
+    long mask_words;
 };
 
 template <int QPW, int KPL>
@@ -84,7 +86,12 @@ __global__ void __launch_bounds__(TK_WARPS * 32) topk_kernel(const TopkArgs a) {
         const bool pvalid = p0 + lane < a.nr;
 #pragma unroll
         for (int qi = 0; qi < QPW; ++qi) {
-            const float d = pvalid ? ssd[qi] : INFINITY;
+            float d = pvalid ? ssd[qi] : INFINITY;
+            if (a.mask) {                // ragged candidate sets (hard-negative mining): bit p of the query's row = allowed
+                const int q = q0 + warp * QPW + qi;
+                const unsigned w = q < a.nq ? __ldg(a.mask + (size_t)q * a.mask_words + (p0 >> 5)) : 0u;
+                if (!((w >> lane) & 1u)) d = INFINITY;
+            }
             unsigned hit = __ballot_sync(0xffffffffu, d < tau[qi]);
             while (hit) {
                 const int src = __ffs(hit) - 1;
@@ -159,6 +166,20 @@ PAB_API int pab_knn(const float *ref, int nr, const float *query, int nq, int di
     a.ref = ref; a.query = query; a.ref_sd = nr; a.ref_sp = 1; a.q_sd = nq; a.q_sp = 1;
     a.nr = nr; a.nq = nq; a.dim = dim; a.k = k;
     a.dist = dist; a.d_sq = 1; a.d_sk = nq; a.ind = ind; a.ind64 = 1; a.ind_base = 1;
+    return run_topk(a, (cudaStream_t)s);
+}
+
+// Same search restricted, per query, to the reference points whose bit is set in mask (nq rows of ceil(ndb/32) words): one
+// launch ranks every query against its own ragged candidate set.  A query with fewer than k candidates gets +inf distances
+// (and index 0) in the unused slots.
+PAB_API int pab_retrieval_topk_masked(const float *db, int ndb, const float *q, int nq, int dim, int k, const unsigned *mask,
+                                      float *dist, int *ind, pab_stream_t s) {
+    if (!mask) return PAB_EINVAL;
+    TopkArgs a{};
+    a.ref = db; a.query = q; a.ref_sd = 1; a.ref_sp = dim; a.q_sd = 1; a.q_sp = dim;
+    a.nr = ndb; a.nq = nq; a.dim = dim; a.k = k;
+    a.dist = dist; a.d_sq = k; a.d_sk = 1; a.ind = ind; a.ind64 = 0; a.ind_base = 0;
+    a.mask = mask; a.mask_words = (ndb + 31) / 32;
     return run_topk(a, (cudaStream_t)s);
 }
 

@@ -167,6 +167,35 @@ def recall_counts(ind, positives, top_k, threshold, query_db_index=None):
     return hits, one_pct, evaluated
 
 
+def pad_positives(positives, device=None):
+    """list of sets -> (Nq, Pmax) int64 tensor padded with -1 (the device-side form of the reference's per-query lists)."""
+    pmax = max((len(p) for p in positives), default=0)
+    out = np.full((len(positives), max(pmax, 1)), -1, dtype=np.int64)
+    for i, p in enumerate(positives):
+        if p:
+            out[i, : len(p)] = sorted(p)
+    t = torch.from_numpy(out)
+    return t.to(device) if device is not None else t
+
+
+def recall_counts_device(ind, pos_padded, top_k, threshold):
+    """``recall_counts`` (scene_dataset.py:1056-1081, query set disjoint from the database) for all queries at once on the
+    tensor's device: ind (Nq,K) retrieved indices, pos_padded (Nq,Pmax) int64 with -1 padding.
+    Returns an int64 tensor [hits_at_rank_0 .. hits_at_rank_{top_k-1}, one_percent_hits, evaluated]."""
+    ind = ind.long()
+    has_pos = (pos_padded >= 0).any(1)                                              # :1044-1045 queries without positives are skipped
+    kk = min(top_k, ind.shape[1])
+    hit = (ind[:, :kk, None] == pos_padded[:, None, :]).any(2) & has_pos[:, None]     # (Nq, kk)
+    any_hit = hit.any(1)
+    first = torch.where(any_hit, hit.float().argmax(1), torch.full_like(any_hit, kk, dtype=torch.long))
+    hits = torch.bincount(first, minlength=kk + 1)[:kk]
+    if kk < top_k:
+        hits = torch.cat([hits, hits.new_zeros(top_k - kk)])
+    th = min(threshold, ind.shape[1])
+    one_pct = ((ind[:, :th, None] == pos_padded[:, None, :]).any(2).any(1) & has_pos).sum()
+    return torch.cat([hits, one_pct.view(1), has_pos.sum().view(1)])
+
+
 def evaluate_recall(db_desc, query_desc, positives, top_k=25, group=None, topk_fn=None):
     """Recall@1..top_k (%) and top-1 % recall (%) of ``query_desc`` against ``db_desc`` with queries sharded over ranks.
 
@@ -181,10 +210,12 @@ def evaluate_recall(db_desc, query_desc, positives, top_k=25, group=None, topk_f
     lo, hi = shard_range(query_desc.shape[0], rank, world)
     if hi > lo:
         _, ind = (topk_fn or retrieval_topk)(db_desc, query_desc[lo:hi], k)
-        hits, one_pct, evaluated = recall_counts(ind.cpu().numpy(), positives[lo:hi], top_k, threshold)
+        # first-hit counters for the whole query shard in a handful of tensor ops on the descriptors' device (the reference walks
+        # the queries one by one on the host, scene_dataset.py:1040-1081)
+        pos = positives[lo:hi] if torch.is_tensor(positives) else pad_positives(positives[lo:hi])
+        counters = recall_counts_device(ind, pos.to(ind.device), top_k, threshold).to(db_desc.device)
     else:
-        hits, one_pct, evaluated = np.zeros(top_k, dtype=np.int64), 0, 0
-    counters = torch.tensor(list(hits) + [one_pct, evaluated], dtype=torch.int64, device=db_desc.device)
+        counters = torch.zeros(top_k + 2, dtype=torch.int64, device=db_desc.device)
     if world > 1:
         dist.all_reduce(counters, group=group)
     counters = counters.cpu().numpy()
@@ -200,19 +231,31 @@ def hard_negatives(query_desc, ref_desc, negative_indices, num_hard_neg=10):
     query_desc (Q,D), ref_desc (N,D) float32 CUDA; negative_indices: per query, the reference indices that are negatives.
     Returns, per query, the ``num_hard_neg`` negatives nearest in descriptor space (ascending distance, as the KDTree query
     of the reference returns them) or ``[]`` when the query has fewer than ``num_hard_neg`` negatives.
-    The negative sets are ragged, so each query's negatives are gathered (one index_select) and ranked by one launch of the
-    exact top-k kernel; ties go to the lower position in ``negative_indices``.
+    The negative sets are ragged: they become one (Q, N/32) bit mask and ONE launch of the masked top-k kernel ranks every
+    query against its own set (the reference builds a KDTree per query).  Ties go to the lower reference index.
     """
     L.require_cuda(query_desc, ref_desc)
-    out = []
+    Q, N = query_desc.shape[0], ref_desc.shape[0]
+    if Q == 0:
+        return []
+    words = (N + 31) // 32
+    bits = np.zeros((Q, words * 32), dtype=bool)
+    enough = np.zeros(Q, dtype=bool)
     for qi, neg in enumerate(negative_indices):
-        if len(neg) < num_hard_neg:
-            out.append([])
-            continue
-        neg_t = torch.as_tensor(np.asarray(neg, dtype=np.int64), device=ref_desc.device)
-        _, ind = retrieval_topk(ref_desc.index_select(0, neg_t), query_desc[qi:qi + 1], num_hard_neg)
-        out.append(neg_t[ind[0].long()].tolist())
-    return out
+        neg = np.asarray(neg, dtype=np.int64)
+        enough[qi] = len(np.unique(neg)) >= num_hard_neg and len(neg) >= num_hard_neg
+        if len(neg):
+            bits[qi, neg] = True
+    mask = np.packbits(bits.reshape(Q, words, 32), axis=-1, bitorder="little").view(np.uint32).reshape(Q, words)
+    mask_t = torch.from_numpy(mask.view(np.int32).copy()).to(ref_desc.device)
+    k = min(num_hard_neg, N)
+    out_d = torch.empty(Q, k, dtype=torch.float32, device=ref_desc.device)
+    out_i = torch.empty(Q, k, dtype=torch.int32, device=ref_desc.device)
+    L.check(L.lib().pab_retrieval_topk_masked(L.ptr(ref_desc.contiguous().float()), N, L.ptr(query_desc.contiguous().float()), Q,
+                                              ref_desc.shape[1], k, L.ptr(mask_t), L.ptr(out_d), L.ptr(out_i), L.stream_ptr()),
+            "retrieval_topk_masked")
+    ind = out_i.cpu().numpy()
+    return [ind[qi].tolist() if enough[qi] else [] for qi in range(Q)]
 
 
 def top_k_in_feature_space(desc, positions, r_pos, r_neg, top_k=300, k_search=1000):

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""FPS timing: full-scan vs pruned sampler, clouds per CTA, uniform vs structured clouds (B=32)."""
+"""FPS timing vs batch size, with and without the exclusive-SM shared-memory pad."""
 import json, os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -16,17 +16,13 @@ def timed(fn, reps=20):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
 
-dev = "cuda"
-B = 32
-sets = {"uniform": util.synthetic_batch(B, 4096, 0).squeeze(1).to(dev),
-        "places": torch.from_numpy(np.stack([util.place_visit(i, 0) for i in range(B)])).to(dev)}
+x = torch.cat([util.synthetic_batch(16, 4096, 0)] * 8).squeeze(1).cuda()
 out = {}
-for name, x in sets.items():
-    for (n, m) in [(4096, 1024), (2048, 512)]:
-        xx = x[:, :n].contiguous()
-        for pruned in (0, 1):
-            for cpc in ((1,) if not pruned else (1, 2, 3)):
-                L.lib().pab_tune_fps_pruned(pruned); L.lib().pab_tune_fps_clouds_per_cta(cpc)
-                out[f"{name}_n{n}_m{m}_pruned{pruned}_cpc{cpc}"] = round(timed(lambda: pointops.furthestsampling(xx, m)), 4)
-L.lib().pab_tune_fps_pruned(1); L.lib().pab_tune_fps_clouds_per_cta(1)
+for excl in (0, 1):
+    L.lib().pab_tune_fps_exclusive(excl)
+    for B in (1, 16, 32, 64, 128):
+        for (n, m) in [(4096, 1024), (1024, 256)]:
+            xx = x[:B, :n].contiguous()
+            out[f"excl{excl}_B{B}_n{n}_m{m}"] = round(timed(lambda: pointops.furthestsampling(xx, m)), 4)
+L.lib().pab_tune_fps_exclusive(1)
 print(json.dumps(out, indent=1))

@@ -86,6 +86,25 @@ def _world(rank, world, port, clouds, queries, positives, out):
         dist.destroy_process_group()
 
 
+def test_device_recall_counters_equal_the_per_query_loop():
+    """retrieval.recall_counts_device (tensor ops, all queries at once) against the restated per-query loop of
+    scene_dataset.py:1056-1081 on random rankings: empty positive sets, several positives, hits beyond top_k."""
+    rng = np.random.default_rng(11)
+    nq, ndb, K, top_k, thr = 300, 500, 40, 25, 5
+    ind = np.stack([rng.permutation(ndb)[:K] for _ in range(nq)]).astype(np.int32)
+    positives = []
+    for q in range(nq):
+        r = rng.random()
+        positives.append(set() if r < 0.1 else set(rng.choice(ndb, size=int(rng.integers(1, 6)), replace=False).tolist()))
+    hits, one_pct, ev = retrieval.recall_counts(ind, positives, top_k, thr)
+    got = retrieval.recall_counts_device(torch.from_numpy(ind), retrieval.pad_positives(positives), top_k, thr).numpy()
+    assert np.array_equal(got[:top_k], hits) and got[top_k] == one_pct and got[top_k + 1] == ev
+    # fewer retrieved neighbours than top_k
+    hits2, one2, ev2 = retrieval.recall_counts(ind[:, :10], positives, top_k, thr)
+    got2 = retrieval.recall_counts_device(torch.from_numpy(ind[:, :10]), retrieval.pad_positives(positives), top_k, thr).numpy()
+    assert np.array_equal(got2[:top_k], hits2) and got2[top_k] == one2 and got2[top_k + 1] == ev2
+
+
 def test_two_rank_gloo_matches_single_rank():
     g = torch.Generator().manual_seed(0)
     clouds = torch.rand(11, 64, 3, generator=g)                       # 11 places: uneven shards on 2 ranks
