@@ -267,24 +267,36 @@ def other_configs(dev, world, rank):
     import util
     from patchaugnet_b200 import retrieval
     out = {}
-    # configs[2]: PPT-Net, batch 64 x 4096
+    # configs[2]: PPT-Net, batch 64 x 4096: fp32 contract (bf16 hi/lo operands) and the bf16 mode, single forwards and throughput mode
     try:
         ppt = util.build_pptnet(dev)
-        x = torch.cat([util.synthetic_batch(16, NPTS, start=0)] * 4).to(dev)
-        with torch.no_grad():
-            for _ in range(2):
-                ppt(x)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(5):
-                ppt(x)
-            e1.record()
-            torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 5
-        out["cfg3_pptnet_b64"] = dict(ms_per_batch=ms, submaps_per_s_per_gpu=64 / (ms * 1e-3), dtype=getattr(ppt, "compute_dtype", "f32"),
-                                      what="PPT-Net eval, batch 64 x 4096, fused engine, one GPU")
-        del ppt, x
+        xs = [torch.cat([util.synthetic_batch(16, NPTS, start=16 * j)] * 4).to(dev) for j in range(2)]
+        rec = {}
+        for mode in ("f32", "bf16"):
+            ppt.compute_dtype = mode
+            eng = ppt.engine()
+            seq = [xs[i & 1] for i in range(8)]
+            with torch.no_grad():
+                for _ in range(2):
+                    ppt(xs[0], return_feat=False)
+                eng.forward_stream(seq[:2])
+                torch.cuda.synchronize()
+                e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                e0.record()
+                for _ in range(5):
+                    ppt(xs[0], return_feat=False)
+                e1.record()
+                eng.forward_stream(seq)
+                e2.record()
+                torch.cuda.synchronize()
+            ms, ms_stream = e0.elapsed_time(e1) / 5, e1.elapsed_time(e2) / len(seq)
+            rec[mode] = dict(ms_per_batch=ms, submaps_per_s_per_gpu=64 / (ms * 1e-3), ms_per_batch_stream=ms_stream,
+                             submaps_per_s_per_gpu_stream=64 / (ms_stream * 1e-3))
+        rec["what"] = ("PPT-Net eval, batch 64 x 4096, fused engine, one GPU; f32 = the reference's fp32 contract (bf16 hi/lo tensor-core "
+                       "operands), bf16 = plain bf16 operands for FP modules / NetVLAD / attention (SA modules keep hi/lo); stream = "
+                       "geometry of batch i+1 under the dense kernels of batch i")
+        out["cfg3_pptnet_b64"] = rec
+        del ppt, xs
     except Exception as ex:
         out["cfg3_pptnet_b64"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
     # configs[3]: 10k-submap database + 2k queries: sharded extraction, ONE all-gather, sharded top-k, Recall counters

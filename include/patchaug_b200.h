@@ -107,6 +107,11 @@ int pab_knn(const float *ref, int nr, const float *query, int nq, int dim, int k
  * datasets/place_recognition_dataset.py:60, scene_dataset.py:1052): db (ndb,dim), q (nq,dim) ->
  * dist (nq,k) f32 Euclidean ascending, ind (nq,k) i32 0-based, ties to the lower index. k <= 1024. */
 int pab_retrieval_topk(const float *db, int ndb, const float *q, int nq, int dim, int k, float *dist, int *ind, pab_stream_t s);
+/* The same search with the database ALSO split over the grid (partial top-k per slice + a merge kernel): identical results, and a
+ * small query set (a rank's shard) still fills the machine.  k <= 128; workspace >= pab_retrieval_topk_workspace_bytes(nq, k). */
+size_t pab_retrieval_topk_workspace_bytes(int nq, int k);
+int pab_retrieval_topk_split(const float *db, int ndb, const float *q, int nq, int dim, int k, float *dist, int *ind,
+                             void *workspace, pab_stream_t s);
 /* The same search with a per-query candidate set: mask has nq rows of ceil(ndb/32) 32-bit words, bit p of row q set = query q
  * may retrieve database entry p.  One launch for a whole batch of ragged sets (hard-negative mining,
  * datasets/scene_dataset.py:1101-1113).  Unused slots of a query with fewer than k candidates hold +inf / index 0. */

@@ -70,6 +70,8 @@ SIGNATURES = {
     "pab_knn": (_I, [_P, _I, _P, _I, _I, _I, _P, _P, _P]),
     "pab_retrieval_topk": (_I, [_P, _I, _P, _I, _I, _I, _P, _P, _P]),
     "pab_retrieval_topk_masked": (_I, [_P, _I, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "pab_retrieval_topk_workspace_bytes": (C.c_size_t, [_I, _I]),
+    "pab_retrieval_topk_split": (_I, [_P, _I, _P, _I, _I, _I, _P, _P, _P, _P]),
     "pab_emd_forward": (_I, [_I, _I] + [_P] * 14 + [_F, _I, _P]),
     "pab_emd_backward": (_I, [_I, _I, _P, _P, _P, _P, _P, _P]),
     "pab_gather_rows": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),

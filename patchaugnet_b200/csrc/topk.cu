@@ -29,6 +29,8 @@ struct TopkArgs {
     int ind64, ind_base;               // int64 (1-based for KNN_CUDA) or int32
     const unsigned *mask;              // optional (nq, mask_words) bit mask of the reference points each query may retrieve
     long mask_words;
+    int nsplit, slice;                 // the reference set is cut into nsplit slices of `slice` points (multiple of 32), one per blockIdx.y:
+    int raw;                           // split runs write SQUARED distances of their partial lists at (q, split, j); a merge kernel finishes
 };
 
 template <int QPW, int KPL>
@@ -58,7 +60,8 @@ __global__ void __launch_bounds__(TK_WARPS * 32) topk_kernel(const TopkArgs a) {
     }
     const int ks = (a.k - 1) >> 5, kl = (a.k - 1) & 31;
 
-    for (int p0 = 0; p0 < a.nr; p0 += TK_PTS) {
+    const int p_begin = blockIdx.y * a.slice, p_end = min(a.nr, p_begin + a.slice);
+    for (int p0 = p_begin; p0 < p_end; p0 += TK_PTS) {
         float ssd[QPW];
 #pragma unroll
         for (int qi = 0; qi < QPW; ++qi) ssd[qi] = 0.f;
@@ -129,9 +132,10 @@ __global__ void __launch_bounds__(TK_WARPS * 32) topk_kernel(const TopkArgs a) {
         for (int s = 0; s < KPL; ++s) {
             const int j = s * 32 + lane;
             if (j < a.k) {
-                a.dist[q * a.d_sq + j * a.d_sk] = __fsqrt_rn(ld[qi][s]);
-                if (a.ind64) ((long long *)a.ind)[q * a.d_sq + j * a.d_sk] = (long long)li[qi][s] + a.ind_base;
-                else ((int *)a.ind)[q * a.d_sq + j * a.d_sk] = li[qi][s] + a.ind_base;
+                const long o = q * a.d_sq + (long)blockIdx.y * a.k * a.d_sk + j * a.d_sk;
+                a.dist[o] = a.raw ? ld[qi][s] : __fsqrt_rn(ld[qi][s]);
+                if (a.ind64) ((long long *)a.ind)[o] = (long long)li[qi][s] + a.ind_base;
+                else ((int *)a.ind)[o] = li[qi][s] + a.ind_base;
             }
         }
     }
@@ -143,12 +147,13 @@ int launch_topk(const TopkArgs &a, cudaStream_t st) {
     const size_t smem = sizeof(float) * ((size_t)a.dim * QB + TK_DCH * TK_RS);
     if (smem > 200 * 1024) return PAB_EINVAL;
     if (smem > 48 * 1024) PAB_CUDA(cudaFuncSetAttribute(topk_kernel<QPW, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    topk_kernel<QPW, KPL><<<pab_divup(a.nq, QB), TK_WARPS * 32, smem, st>>>(a);
+    topk_kernel<QPW, KPL><<<dim3(pab_divup(a.nq, QB), a.nsplit), TK_WARPS * 32, smem, st>>>(a);
     PAB_LAUNCH_CHECK();
     return 0;
 }
 
-int run_topk(const TopkArgs &a, cudaStream_t st) {
+int run_topk(TopkArgs a, cudaStream_t st) {
+    if (a.nsplit < 1) { a.nsplit = 1; a.slice = (a.nr + 31) / 32 * 32; a.raw = 0; }
     if (a.nr <= 0 || a.nq < 0 || a.dim <= 0 || a.k <= 0 || a.k > 1024 || a.k > a.nr) return PAB_EINVAL;
     if (a.nq == 0) return 0;
     if (a.k <= 32) return launch_topk<4, 1>(a, st);
@@ -159,7 +164,70 @@ int run_topk(const TopkArgs &a, cudaStream_t st) {
     return launch_topk<1, 32>(a, st);
 }
 
+// partial lists (nq, nsplit, k) of (squared distance, index), each ascending -> the k best of their union, ascending distance,
+// ties to the lower index; one CTA per query sorts the nsplit*k candidates as 64-bit (distance bits, index) keys in shared memory
+__global__ void __launch_bounds__(256) topk_merge_kernel(int k, int total, int P, const float *__restrict__ pd, const int *__restrict__ pi,
+                                                         float *__restrict__ dist, int *__restrict__ ind) {
+    extern __shared__ unsigned long long mkeys[];
+    const int q = blockIdx.x, t = threadIdx.x;
+    for (int i = t; i < P; i += 256) {
+        unsigned long long key = ~0ull;
+        if (i < total) key = ((unsigned long long)__float_as_uint(pd[(size_t)q * total + i]) << 32) | (unsigned)pi[(size_t)q * total + i];
+        mkeys[i] = key;                                   // squared distances are >= 0 (or +inf): their bit patterns order like the values
+    }
+    __syncthreads();
+    for (int size = 2; size <= P; size <<= 1)
+        for (int j = size >> 1; j > 0; j >>= 1) {
+            for (int i = t; i < (P >> 1); i += 256) {
+                const int a0 = 2 * i - (i & (j - 1));
+                const unsigned long long ka = mkeys[a0], kb = mkeys[a0 + j];
+                const bool up = (a0 & size) == 0;
+                if ((ka > kb) == up) { mkeys[a0] = kb; mkeys[a0 + j] = ka; }
+            }
+            __syncthreads();
+        }
+    for (int j = t; j < k; j += 256) {
+        dist[(size_t)q * k + j] = __fsqrt_rn(__uint_as_float((unsigned)(mkeys[j] >> 32)));
+        ind[(size_t)q * k + j] = (int)(mkeys[j] & 0xFFFFFFFFu);
+    }
+}
+
 }  // namespace
+
+PAB_API int pab_retrieval_topk(const float *db, int ndb, const float *q, int nq, int dim, int k, float *dist, int *ind, pab_stream_t s);
+
+// Retrieval top-k with the DATABASE split over the grid as well: with few queries (a rank's 250-query shard of configs[3] is 16
+// query blocks) a grid over queries alone leaves most SMs idle, so the database is cut into slices, every (query block, slice)
+// CTA keeps a partial top-k, and a merge kernel takes the k best of each query's partial lists.  Same results as
+// pab_retrieval_topk (exact, ascending distance, ties to the lower index).  workspace >= pab_retrieval_topk_workspace_bytes(nq, k).
+PAB_API size_t pab_retrieval_topk_workspace_bytes(int nq, int k) { return (size_t)nq * 32 * (size_t)k * 8; }
+
+PAB_API int pab_retrieval_topk_split(const float *db, int ndb, const float *q, int nq, int dim, int k, float *dist, int *ind,
+                                     void *workspace, pab_stream_t s) {
+    if (ndb <= 0 || nq < 0 || k <= 0 || k > 128 || k > ndb || !workspace) return PAB_EINVAL;
+    if (nq == 0) return 0;
+    cudaStream_t st = (cudaStream_t)s;
+    const int qblocks = pab_divup(nq, TK_WARPS * 4);
+    int nsplit = (2 * 148 + qblocks - 1) / qblocks;                     // about two CTAs per SM
+    if (nsplit > 32) nsplit = 32;
+    while (nsplit > 1 && ndb / nsplit < 4 * k) --nsplit;                // slices much longer than the lists they feed
+    if (nsplit <= 1) return pab_retrieval_topk(db, ndb, q, nq, dim, k, dist, ind, s);
+    TopkArgs a{};
+    a.ref = db; a.query = q; a.ref_sd = 1; a.ref_sp = dim; a.q_sd = 1; a.q_sp = dim;
+    a.nr = ndb; a.nq = nq; a.dim = dim; a.k = k;
+    float *pd = (float *)workspace;
+    int *pi = (int *)(pd + (size_t)nq * nsplit * k);
+    a.dist = pd; a.ind = pi; a.d_sq = (long)nsplit * k; a.d_sk = 1; a.ind64 = 0; a.ind_base = 0;
+    a.nsplit = nsplit; a.slice = ((ndb + nsplit - 1) / nsplit + 31) / 32 * 32; a.raw = 1;
+    const int rc = run_topk(a, st);
+    if (rc) return rc;
+    const int total = nsplit * k;
+    int P = 2;
+    while (P < total) P <<= 1;
+    topk_merge_kernel<<<nq, 256, (size_t)P * 8, st>>>(k, total, P, pd, pi, dist, ind);
+    PAB_LAUNCH_CHECK();
+    return 0;
+}
 
 PAB_API int pab_knn(const float *ref, int nr, const float *query, int nq, int dim, int k, float *dist, int64_t *ind, pab_stream_t s) {
     TopkArgs a{};

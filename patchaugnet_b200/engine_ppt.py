@@ -95,8 +95,8 @@ class FusedPPTNet:
         self._ws.clear()
 
     # ---- workspace -----------------------------------------------------------------------------------------------
-    def _workspace(self, B, N):
-        key = (B, N)
+    def _workspace(self, B, N, slot=0):
+        key = (B, N, slot)
         ws = self._ws.get(key)
         if ws is not None:
             return ws
@@ -130,19 +130,12 @@ class FusedPPTNet:
         return ws
 
     # ---- forward -------------------------------------------------------------------------------------------------
-    @torch.no_grad()
-    def forward(self, x, return_feat=True):
-        """x: (B,1,N,3) or (B,N,3) float32 CUDA -> (desc (B,256), fp_features [4 x (B,256,n,1)], center_idx_origin [4])."""
-        L.require_cuda(x)
-        net = self.net
-        xyz0 = (x.squeeze(1) if x.dim() == 4 else x).contiguous().float()
-        B, N, _ = xyz0.shape
-        ws = self._workspace(B, N)
-        lib, st, p = L.lib(), L.stream_ptr(), L.ptr
-        chk = L.check
-
-        xyz, feat, c = xyz0, xyz0, 3
-        for i, (sa, lv) in enumerate(zip(self.sa, ws["levels"])):
+    def _launch_geo(self, xyz0, ws):
+        """Geometry of every level — FPS, centre gather, spatial index, kNN, 3-NN weights.  Depends on xyz only."""
+        lib, st, p, chk = L.lib(), L.stream_ptr(), L.ptr, L.check
+        B = xyz0.shape[0]
+        xyz = xyz0
+        for sa, lv in zip(self.sa, ws["levels"]):
             n, m, k = lv["n"], lv["m"], sa["k"]
             temp = None
             if n > 8192:
@@ -155,18 +148,9 @@ class FusedPPTNet:
                 chk(lib.pab_knnquery_indexed(B, n, m, k, p(lv["index"]), p(lv["new_xyz"]), p(lv["nbr"]), p(None), st), "knn")
             else:
                 chk(lib.pab_knnquery(B, n, m, k, p(xyz), p(lv["new_xyz"]), p(lv["nbr"]), p(None), st), "knn")
-            chk(lib.pab_sa_module_forward(B, n, m, k, k, c, p(xyz), p(feat), p(lv["cidx"]), p(lv["nbr"]), sa["layers"].arr,
-                                          sa["layers"].n, p(lv["pooled"]), p(None), st), "sa")
-            arr = sa["att"]["arr"]
-            chk(lib.pab_sa_layer_forward_p(B, m, sa["att"]["C"], p(lv["pooled"]), arr, attention.C_ptr_offset(arr, 1),
-                                           attention.C_ptr_offset(arr, 2), p(lv["feat"]), p(ws["scratch"]),
-                                           self.attention_precision, st), "sa_layer")
-            xyz, feat, c = lv["new_xyz"], lv["feat"], sa["layers"].c_out
-
+            xyz = lv["new_xyz"]
         xyzs = [xyz0] + [lv["new_xyz"] for lv in ws["levels"]]
-        feats = [xyz0] + [lv["feat"] for lv in ws["levels"]]
-        ns = [N] + [lv["m"] for lv in ws["levels"]]
-        known_feat = feats[-1]
+        ns = [xyz0.shape[1]] + [lv["m"] for lv in ws["levels"]]
         for li in range(len(self.fp) - 1, -1, -1):
             f = ws["fp"][li]
             n, m = ns[li], ns[li + 1]
@@ -176,6 +160,29 @@ class FusedPPTNet:
                 chk(lib.pab_three_nn_weights_indexed(B, n, m, p(xyzs[li]), p(uidx), p(kidx), p(f["idx"]), p(f["w"]), st), "3nn")
             else:
                 chk(lib.pab_three_nn_weights(B, n, m, p(xyzs[li]), p(xyzs[li + 1]), p(f["idx"]), p(f["w"]), st), "3nn")
+
+    def _launch_dense(self, xyz0, ws):
+        """Feature path — fused SA modules + SA_Layer attention, FP modules, NetVLAD levels, gated fc head."""
+        net = self.net
+        B, N, _ = xyz0.shape
+        lib, st, p, chk = L.lib(), L.stream_ptr(), L.ptr, L.check
+        xyz, feat, c = xyz0, xyz0, 3
+        for sa, lv in zip(self.sa, ws["levels"]):
+            n, m, k = lv["n"], lv["m"], sa["k"]
+            chk(lib.pab_sa_module_forward(B, n, m, k, k, c, p(xyz), p(feat), p(lv["cidx"]), p(lv["nbr"]), sa["layers"].arr,
+                                          sa["layers"].n, p(lv["pooled"]), p(None), st), "sa")
+            arr = sa["att"]["arr"]
+            chk(lib.pab_sa_layer_forward_p(B, m, sa["att"]["C"], p(lv["pooled"]), arr, attention.C_ptr_offset(arr, 1),
+                                           attention.C_ptr_offset(arr, 2), p(lv["feat"]), p(ws["scratch"]),
+                                           self.attention_precision, st), "sa_layer")
+            xyz, feat, c = lv["new_xyz"], lv["feat"], sa["layers"].c_out
+
+        feats = [xyz0] + [lv["feat"] for lv in ws["levels"]]
+        ns = [N] + [lv["m"] for lv in ws["levels"]]
+        known_feat = feats[-1]
+        for li in range(len(self.fp) - 1, -1, -1):
+            f = ws["fp"][li]
+            n, m = ns[li], ns[li + 1]
             skip = feats[li]
             chk(lib.pab_fp_module_forward(B, n, m, known_feat.shape[2], skip.shape[2], p(known_feat), p(skip), p(f["idx"]), p(f["w"]),
                                           self.fp[li].arr, self.fp[li].n, p(f["out"]), st), "fp")
@@ -205,6 +212,18 @@ class FusedPPTNet:
         gw, gs, gb = self.gate if self.gate is not None else (None, None, None)
         chk(lib.pab_gated_fc_forward(B, self.flat, self.c_out, p(flat), p(self.fc_wt), p(self.fc_scale), p(self.fc_shift), p(gw), p(gs),
                                      p(gb), 1 if net.use_normalize else 0, p(ws["desc"]), p(ws["scratch"]), st), "head")
+        return fp_out
+
+    # ---- forward -------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x, return_feat=True):
+        """x: (B,1,N,3) or (B,N,3) float32 CUDA -> (desc (B,256), fp_features [4 x (B,256,n,1)], center_idx_origin [4])."""
+        L.require_cuda(x)
+        xyz0 = (x.squeeze(1) if x.dim() == 4 else x).contiguous().float()
+        B, N, _ = xyz0.shape
+        ws = self._workspace(B, N)
+        self._launch_geo(xyz0, ws)
+        fp_out = self._launch_dense(xyz0, ws)
         out = ws["desc"].clone()
         if not return_feat:
             return out
@@ -214,5 +233,48 @@ class FusedPPTNet:
             origin.append(torch.gather(origin[-1], -1, ci.long()))                    # pptnet.py:109-118
         fp_features = [f.transpose(1, 2).unsqueeze(-1).clone() for f in fp_out]
         return out, fp_features, origin
+
+    @torch.no_grad()
+    def forward_stream(self, batches, out=None):
+        """Throughput mode (as engine.FusedPatchAugNet.forward_stream): descriptors of a sequence of equally shaped batches, the
+        geometry of batch i+1 (FPS is a serial chain on B of the 148 SMs) on a second stream under the dense kernels of batch i;
+        two workspaces ping-pong, events order their reuse.  Returns (len(batches)*B, c_out) on the device."""
+        batches = list(batches)
+        if not batches:
+            return torch.empty(0, self.c_out, device=self.device)
+        x0 = batches[0].squeeze(1) if batches[0].dim() == 4 else batches[0]
+        B, N, _ = x0.shape
+        if out is None:
+            out = torch.empty(len(batches) * B, self.c_out, dtype=torch.float32, device=self.device)
+        cur = torch.cuda.current_stream()
+        if getattr(self, "_streams", None) is None:
+            self._streams = (torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device))
+        s_geo, s_dense = self._streams
+        s_geo.wait_stream(cur)
+        s_dense.wait_stream(cur)
+        slots = [self._workspace(B, N, slot) for slot in (0, 1)]
+        geo_done, dense_done = [None, None], [None, None]
+        for i, x in enumerate(batches):
+            L.require_cuda(x)
+            xyz0 = (x.squeeze(1) if x.dim() == 4 else x).contiguous().float()
+            slot = i & 1
+            ws = slots[slot]
+            with torch.cuda.stream(s_geo):
+                if dense_done[slot] is not None:
+                    s_geo.wait_event(dense_done[slot])             # workspace free again
+                self._launch_geo(xyz0, ws)
+                geo_done[slot] = torch.cuda.Event()
+                geo_done[slot].record()
+            with torch.cuda.stream(s_dense):
+                s_dense.wait_event(geo_done[slot])
+                self._launch_dense(xyz0, ws)
+                out[i * B:(i + 1) * B].copy_(ws["desc"], non_blocking=True)
+                dense_done[slot] = torch.cuda.Event()
+                dense_done[slot].record()
+            xyz0.record_stream(s_geo)
+            xyz0.record_stream(s_dense)
+        cur.wait_stream(s_dense)
+        cur.wait_stream(s_geo)
+        return out
 
     __call__ = forward

@@ -126,8 +126,14 @@ def retrieval_topk(db, queries, k):
     nq = queries.shape[0]
     out_d = torch.empty(nq, k, dtype=torch.float32, device=db.device)
     out_i = torch.empty(nq, k, dtype=torch.int32, device=db.device)
-    L.check(L.lib().pab_retrieval_topk(L.ptr(db), ndb, L.ptr(queries), nq, d, k, L.ptr(out_d), L.ptr(out_i), L.stream_ptr()),
-            "retrieval_topk")
+    if k <= 128 and nq > 0:
+        # database split over the grid + merge: the same exact result, and a small query shard still fills the machine
+        ws = torch.empty(L.lib().pab_retrieval_topk_workspace_bytes(nq, k), dtype=torch.uint8, device=db.device)
+        L.check(L.lib().pab_retrieval_topk_split(L.ptr(db), ndb, L.ptr(queries), nq, d, k, L.ptr(out_d), L.ptr(out_i), L.ptr(ws),
+                                                 L.stream_ptr()), "retrieval_topk_split")
+    else:
+        L.check(L.lib().pab_retrieval_topk(L.ptr(db), ndb, L.ptr(queries), nq, d, k, L.ptr(out_d), L.ptr(out_i), L.stream_ptr()),
+                "retrieval_topk")
     return out_d, out_i
 
 

@@ -278,3 +278,20 @@ def test_recall_of_new_path_descriptors_equals_recall_of_oracle_descriptors():
     chance_at_1 = 100.0 / n_db
     assert new["recall"][0] > 15 * chance_at_1, new["recall"][:10]          # discriminative, not a collapsed descriptor
     assert new["recall"][9] > new["recall"][0]
+
+
+@pytest.mark.parametrize("nq,ndb,k", [(7, 1000, 10), (250, 10000, 101), (2000, 10000, 101), (33, 700, 128), (5, 300, 101)])
+def test_split_topk_equals_single_pass_topk(nq, ndb, k):
+    """pab_retrieval_topk_split (database sliced over the grid + merge kernel) must return exactly what the single-pass kernel
+    returns — same neighbours in the same order, including ties (duplicated database rows) — for query counts from a
+    handful to the 2000 of BASELINE.json configs[3]."""
+    from patchaugnet_b200 import _lib as L
+    g = torch.Generator().manual_seed(nq + ndb)
+    db = torch.nn.functional.normalize(torch.randn(ndb, 256, generator=g)).cuda()
+    db[ndb // 2: ndb // 2 + 50] = db[:50]                                   # exact duplicates: ties by index
+    q = torch.nn.functional.normalize(db[torch.randint(0, ndb, (nq,), generator=g)] + 0.05 * torch.randn(nq, 256, generator=g).cuda())
+    d1 = torch.empty(nq, k, device="cuda"); i1 = torch.empty(nq, k, dtype=torch.int32, device="cuda")
+    L.check(L.lib().pab_retrieval_topk(L.ptr(db), ndb, L.ptr(q), nq, 256, k, L.ptr(d1), L.ptr(i1), L.stream_ptr()), "topk")
+    d2, i2 = retrieval.retrieval_topk(db, q, k)                              # split path (k <= 128)
+    assert torch.equal(i1, i2) and torch.equal(d1, d2)
+    assert (d2[:, 1:] >= d2[:, :-1]).all()

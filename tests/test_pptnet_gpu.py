@@ -112,3 +112,13 @@ def test_pptnet_bf16_mode_meets_the_config3_parity_definition():
             dq = net(qs, return_feat=False)
             res[mode] = retrieval.evaluate_recall(ddb, dq, [{i} for i in range(n_q)], top_k=25)["recall"]
     assert res["f32"][0] == res["bf16"][0] and res["f32"][0] > 10.0, (res["f32"][:5], res["bf16"][:5])
+
+
+def test_pptnet_pipelined_forward_stream_matches_per_batch_forward():
+    net = util.build_pptnet(DEV)
+    batches = [util.synthetic_batch(3, 4096, start=900 + 3 * i).to(DEV) for i in range(4)]
+    with torch.no_grad():
+        want = torch.cat([net(b, return_feat=False) for b in batches])
+        got = net.engine().forward_stream(batches)
+        torch.cuda.synchronize()
+    assert torch.equal(got, want)
