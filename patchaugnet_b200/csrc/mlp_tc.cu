@@ -52,6 +52,8 @@ struct alignas(64) TcArgs {
     int K[MAX_LAYERS], N[MAX_LAYERS], relu[MAX_LAYERS];
     int ksteps[MAX_LAYERS];                    // 16-wide k-steps that carry data (the rest of the last 64-chunk is zero padding)
     int n_layers, n_stages, mode;
+    int stage_bytes;                           // bytes of one weight stage: 16 KB (one plane of a <=128-channel block) or, with `pair`,
+    int pair;                                  // 32 KB: hi AND lo plane of a wide block behind ONE barrier round trip
     int planes;                                // 2: bf16 hi/lo split, 3 MMAs per product (fp32 contract); 1: plain bf16 operands, 1 MMA
     int csize, iters;                          // CTAs per cluster sharing the weight stream (1 or 2); tile-loop trips (equal for all CTAs)
     int dynamic;                               // 1: CTAs draw tiles from *counter (atomic) instead of the static blockIdx + i*grid sequence
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     uint8_t *a1 = smem;                                            // layer-0 operand, hi plane
     uint8_t *a2 = a.planes == 2 ? a1 + (size_t)(a.a_region >> 1) : nullptr;   //            lo plane (bf16 hi/lo mode only)
     uint8_t *stages = a1 + (size_t)a.a_region;
-    uint8_t *stg = stages + (size_t)a.n_stages * (NBLK_MAX * 128);
+    uint8_t *stg = stages + (size_t)a.n_stages * a.stage_bytes;
     uint8_t *misc = stg + (a.mode == TC_SA ? STG_BYTES : STG_BYTES_FP);
     uint64_t *full = reinterpret_cast<uint64_t *>(misc);
     uint64_t *empty = full + MAX_STAGES;
@@ -213,11 +215,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                         for (int kc = g * gc; kc < (g == ngroups - 1 ? nkc : (g + 1) * gc); ++kc)
                             for (int pl = 0; pl < a.planes; ++pl) {
                                 // narrow layers (<= 64 output channels): both planes share one slot and one barrier round trip
-                                const bool first = pl == 0 || nbr > 64;
-                                uint8_t *dst = stages + (size_t)s * (NBLK_MAX * 128) + (first ? 0 : nbr * 128);
+                                const bool separate = nbr > 64 && !a.pair;      // each plane of a wide block in its own stage
+                                const bool first = pl == 0 || separate;
+                                uint8_t *dst = stages + (size_t)s * a.stage_bytes + (first ? 0 : nbr * 128);
                                 if (first) {
                                     mbar_wait(empty + s, ph ^ 1);                // released by every CTA of the cluster
-                                    mbar_expect_tx(full + s, (uint32_t)nbr * 128u * (nbr > 64 ? 1u : (uint32_t)a.planes));
+                                    mbar_expect_tx(full + s, (uint32_t)nbr * 128u * (separate ? 1u : (uint32_t)a.planes));
                                 }
                                 if (a.csize == 1) {
                                     tma_load_2d(dst, &a.tm[l][pl], kc * KCH, nb * nbr, full + s);
@@ -226,7 +229,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                                     tma_load_2d_mc(dst + (size_t)crank * share * 128, &a.tm[l][pl], kc * KCH, nb * nbr + (int)crank * share,
                                                    full + s, cmask_all);
                                 }
-                                if (nbr > 64 || pl == a.planes - 1) {
+                                if (separate || pl == a.planes - 1) {
                                     if (++s == (uint32_t)a.n_stages) { s = 0; ph ^= 1; }
                                 }
                             }
@@ -239,7 +242,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         const uint32_t leader = elect_one();
         const uint32_t a1_lo = umma_desc_lo(smem_u32(a1)), a2_lo = umma_desc_lo(smem_u32(a1) + (uint32_t)(a.a_region >> 1));
         const uint32_t st_lo = umma_desc_lo(smem_u32(stages));
-        constexpr uint32_t st_step = (NBLK_MAX * 128) >> 4;
+        const uint32_t st_step = (uint32_t)a.stage_bytes >> 4;
         uint32_t s = 0, ph = 0, pcount = 0, tcount = 0, gcount = 0;
         bool t1_pending = false;
         const bool two = a.planes == 2;
@@ -297,7 +300,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                             }
                         }
                         if (two) {
-                        if (nbr > 64) {                          // wide block: the lo plane sits in the next slot
+                        if (nbr > 64 && !a.pair) {               // wide block, separate stages: the lo plane sits in the next slot
                             if (a.csize == 1) umma_commit_if(leader, empty + s);
                             else umma_commit_mc_if(leader, empty + s, cmask_all);
                             if (++s == (uint32_t)a.n_stages) { s = 0; ph ^= 1; }
@@ -851,7 +854,9 @@ int g_tc_cluster = 0;      // weight multicast across CTA pairs (pab_tune_tensor
 
 // Shared-memory plan of one launch: layer-0 operand region, staging, weight stages, constant table.
 // `layers` are the TENSOR-CORE layers only (the optional pre-layer is passed separately).
-struct TcPlan { int a_region, gchunks, n_stages, coff[MAX_LAYERS], pre_off; size_t misc, smem; };
+struct TcPlan { int a_region, gchunks, n_stages, stage_bytes, pair, coff[MAX_LAYERS], pre_off; size_t misc, smem; };
+
+int g_tc_pair = 1;         // wide weight blocks: hi + lo plane in one 32-KB stage (pab_tune_tensor_core bit 4 = 16 clears it)
 
 bool tc_plan(const pab_layer_t *layers, int n_layers, const pab_layer_t *pre, int mode, TcPlan *p) {
     const int planes = layers[0].w_lo ? 2 : 1;
@@ -873,9 +878,13 @@ bool tc_plan(const pab_layer_t *layers, int n_layers, const pab_layer_t *pre, in
     p->a_region = planes * p->gchunks * A_CHUNK;
     p->misc = 384 + (size_t)ctab * 4 + 64;
     const long budget = 227L * 1024 - p->a_region - stg_bytes - (long)p->misc;
-    p->n_stages = (int)(budget / (NBLK_MAX * 128));
+    bool wide = false;
+    for (int l = 0; l < n_layers; ++l) wide = wide || layers[l].c_out > 64;
+    p->pair = (g_tc_pair && wide && planes == 2 && budget / (2 * NBLK_MAX * 128) >= 2) ? 1 : 0;
+    p->stage_bytes = p->pair ? 2 * NBLK_MAX * 128 : NBLK_MAX * 128;
+    p->n_stages = (int)(budget / p->stage_bytes);
     if (p->n_stages > MAX_STAGES) p->n_stages = MAX_STAGES;
-    p->smem = (size_t)p->a_region + (size_t)p->n_stages * (NBLK_MAX * 128) + stg_bytes + p->misc;
+    p->smem = (size_t)p->a_region + (size_t)p->n_stages * p->stage_bytes + stg_bytes + p->misc;
     return p->n_stages >= 2;
 }
 
@@ -920,7 +929,7 @@ int pab_tc_launch(int mode, long rows, int k_group, const pab_layer_t *all_layer
     const int n_layers = kind == 2 ? n_all - 1 : n_all;
     TcPlan p;
     if (!tc_plan(layers, n_layers, pre, mode, &p)) return PAB_EINVAL;
-    a.a_region = p.a_region; a.gchunks = p.gchunks; a.n_stages = p.n_stages;
+    a.a_region = p.a_region; a.gchunks = p.gchunks; a.n_stages = p.n_stages; a.stage_bytes = p.stage_bytes; a.pair = p.pair;
     const long per_tile = mode == TC_SA ? (TM / k_group) : TM;
     if (rows >= (1L << 31)) return PAB_EINVAL;
     a.ntiles = (int)((rows + per_tile - 1) / per_tile);
@@ -995,6 +1004,7 @@ PAB_API void pab_tune_tensor_core(int enable) {
     g_tc_enabled = enable & 1;
     g_tc_cluster = (enable & 4) != 0;
     g_tc_dynamic = (enable & 8) != 0;
+    g_tc_pair = (enable & 16) == 0;
 }
 
 int pab_tc_sa(int kind, int b, int n, int m, int k, int nbr_stride, int c, const float *xyz, const float *feat, const int *center_idx,

@@ -1,78 +1,97 @@
 #!/usr/bin/env python
-"""Turn the ncu outputs of scripts/gpu_round.sh (gpurun_out/r01_top.ncu-rep, gpurun_out/r01_launches.csv) into the tracked
-summaries under profiles/: r01_top_kernels.csv (per-kernel metrics), r01_traffic.json (DRAM bytes per launch, read by bench.py),
-r01_launches_tc.csv (the launch list) and a share-of-step table on stdout."""
-import csv, io, json, os, subprocess, sys, collections
+"""Turn the ncu outputs of scripts/gpu_profile.sh (gpurun_out/r02_step_metrics.csv = one whole eager forward with a metric set,
+r02_top.ncu-rep = `--set full` of the top kernels, r02_extra_metrics.csv = kernels outside the bench step) into the tracked
+summaries under profiles/: r02_top_kernels.csv, r02_extra_kernels.csv, r02_traffic.json (read by bench.py) and a share-of-step
+table (profiles/r02_share_of_step.md)."""
+import collections, csv, io, json, os, subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT, PROF = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
-METRICS = ["gpu__time_duration.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
-           "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
-           "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum", "l1tex__t_sector_hit_rate.pct",
-           "lts__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum", "launch__registers_per_thread",
-           "launch__shared_mem_per_block_dynamic"]
-# eager forward order of the kernels matched by the capture's -k regex (batch 32 x 4096)
-STAGES = ["fps0", "knn0", "fps1", "knn1", "fps2", "three_nn0", "sa0", "sa1", "sa2", "fp2", "fp1", "fp0", "vlad0", "vlad1", "vlad2"]
+COLS = ["gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
+        "l1tex__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum", "launch__registers_per_thread",
+        "launch__shared_mem_per_block_dynamic"]
+ORDER = {"fps_kernel": ["fps0", "fps1", "fps2"], "gather_rows_kernel": ["gather0", "gather1", "gather2"],
+         "knn_index_kernel": ["index0", "index1"], "knn_pruned32_kernel": ["knn0", "knn1"], "knn_kernel": ["knn2"],
+         "three_nn_kernel": ["three_nn2", "three_nn1"], "three_nn_pruned_kernel": ["three_nn0"],
+         "mlp_tc_kernel": ["sa0", "sa1", "sa2", "fp2", "fp1", "fp0"], "vlad_tc_kernel": ["vlad0", "vlad1", "vlad2"],
+         "vlad_finalize_kernel": ["vlad0_fin", "vlad1_fin", "vlad2_fin"], "afa_att_kernel": ["afa_att"],
+         "afa_softmax_kernel": ["afa_softmax"], "afa_fc_kernel": ["afa_fc"], "afa_finalize_kernel": ["afa_finalize"]}
+UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "us": 1, "ms": 1e3, "ns": 1e-3, "s": 1e6}
 
 
-def raw_page(rep):
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--metrics", ",".join(METRICS)], capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(txt)))
+def launches(path):
+    rows = list(csv.reader(open(path)))
     h = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
-    return rows[h], rows[h + 1], rows[h + 2:]
+    col = {n: i for i, n in enumerate(rows[h])}
+    out = collections.OrderedDict()
+    for r in rows[h + 1:]:
+        if not r or not r[0].isdigit():
+            continue
+        d = out.setdefault(int(r[0]), {"kernel": r[col["Kernel Name"]], "grid": r[col["Grid Size"]], "block": r[col["Block Size"]]})
+        try:
+            d[r[col["Metric Name"]]] = float(r[col["Metric Value"]].replace(",", "")) * UNIT.get(r[col["Metric Unit"]], 1)
+        except ValueError:
+            pass
+    return list(out.values())
 
 
-def to_bytes(v, unit):
-    mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
-    return float(v) * mult
+def short(name):
+    n = name.replace("void ", "").replace("<unnamed>::", "").split("(")[0]
+    return n.split("<")[0], n
+
+
+def write_table(rows, path, stage_of=None):
+    with open(path, "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["stage", "kernel", "grid", "block"] + COLS)
+        for i, r in enumerate(rows):
+            w.writerow([stage_of(i, r) if stage_of else "", short(r["kernel"])[1], r["grid"], r["block"]] + [r.get(c, "") for c in COLS])
 
 
 def main():
-    rep = os.path.join(OUT, "r01_top.ncu-rep")
-    head, units, rows = raw_page(rep)
-    col = {name: i for i, name in enumerate(head)}
+    step = launches(os.path.join(OUT, "r02_step_metrics.csv"))
+    counters = collections.Counter()
+    stages = []
+    for r in step:
+        base = short(r["kernel"])[0]
+        names = ORDER.get(base, [base])
+        stages.append(names[min(counters[base], len(names) - 1)])
+        counters[base] += 1
+    write_table(step, os.path.join(PROF, "r02_top_kernels.csv"), lambda i, r: stages[i])
+    total = sum(r["gpu__time_duration.sum"] for r in step)
     traffic = {}
-    with open(os.path.join(PROF, "r01_top_kernels.csv"), "w", newline="") as f:
-        w = csv.writer(f)
-        w.writerow(["stage", "Kernel Name", "Grid Size", "Block Size"] + [f"{m} [{units[col[m]]}]" for m in METRICS if m in col])
-        for stage, r in zip(STAGES, rows):
-            name = r[col["Kernel Name"]].replace("<unnamed>::", "").split("(")[0]
-            w.writerow([stage, name, r[col["Grid Size"]], r[col["Block Size"]]] + [r[col[m]] for m in METRICS if m in col])
-            rd = to_bytes(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]])
-            wr = to_bytes(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
-            traffic[stage] = int(rd + wr)
-    old = {}
-    try:
-        old = json.load(open(os.path.join(PROF, "r01_traffic.json")))["dram_bytes_per_launch"]
-    except Exception:
-        pass
-    kept = [k for k in old if k not in traffic]
-    for k in kept:
-        traffic[k] = old[k]
-    json.dump({"source": "profiles/r01_top_kernels.csv (ncu --set full --clock-control none, one launch each, batch 32 x 4096"
-                         + (f"; {', '.join(kept)} from the previous capture of the same kernel)" if kept else ")"),
-               "dram_bytes_per_launch": traffic}, open(os.path.join(PROF, "r01_traffic.json"), "w"), indent=1)
-    # launch list -> share of the step
-    src = os.path.join(OUT, "r01_launches.csv")
-    rows = list(csv.reader(open(src)))
-    h = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
-    head = rows[h]
-    kn, mv = head.index("Kernel Name"), head.index("Metric Value")
-    with open(os.path.join(PROF, "r01_launches_tc.csv"), "w", newline="") as f:
-        csv.writer(f).writerows(rows[h:])
-    per = collections.OrderedDict()
-    data = rows[h + 1:]
-    # the last forward of the run: launches after the last occurrence of the first fps kernel
-    starts = [i for i, r in enumerate(data) if "fps_kernel<8" in r[kn]]
-    fwd = data[starts[-2]:starts[-1]] if len(starts) >= 2 else data     # the last COMPLETE forward (-c may cut the final one)
-    for r in fwd:
-        name = r[kn].replace("<unnamed>::", "").replace("void ", "")[:70]
-        per[name] = per.get(name, 0.0) + float(r[mv].replace(",", "")) / 1000.0
-    tot = sum(per.values())
-    print("| kernel | µs per forward | share |\n|---|---|---|")
-    for k, v in sorted(per.items(), key=lambda kv: -kv[1]):
-        print(f"| `{k}` | {v:.1f} | {100 * v / tot:.1f} % |")
-    print(f"| total ({len(fwd)} launches) | {tot:.1f} | 100 % |")
+    lines = ["# One eager forward (batch 32 x 4096) under ncu: share of the step per kernel, tensor-pipe activity, DRAM and L2 traffic", "",
+             "`ncu --metrics ... --clock-control none -k regex:<all hand-written kernels> -s 60 -c 30 python bench.py --mode eager` "
+             "(scripts/gpu_profile.sh).  Times under ncu are serialised and cold-cache: the SHARE column is what compares with the "
+             "live per-stage events of bench.py (`stage_ms`).", "",
+             "| stage | kernel | grid | us | share | tensor pipe active % | issue active % | DRAM MB | L2 MB | regs |", "|---|---|---|---|---|---|---|---|---|---|"]
+    merged = collections.OrderedDict()
+    for st, r in zip(stages, step):
+        key = "afa" if st.startswith("afa_") else st.replace("_fin", "")
+        traffic[key] = traffic.get(key, 0) + int(r.get("dram__bytes_read.sum", 0) + r.get("dram__bytes_write.sum", 0))
+        lines.append("| %s | %s | %s | %.1f | %.1f %% | %.1f | %.1f | %.1f | %.1f | %d |" % (
+            st, short(r["kernel"])[1][:34], r["grid"], r["gpu__time_duration.sum"], 100 * r["gpu__time_duration.sum"] / total,
+            r.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", 0), r.get("smsp__issue_active.avg.pct_of_peak_sustained_active", 0),
+            (r.get("dram__bytes_read.sum", 0) + r.get("dram__bytes_write.sum", 0)) / 1e6, r.get("lts__t_bytes.sum", 0) / 1e6,
+            int(r.get("launch__registers_per_thread", 0))))
+    lines.append("")
+    lines.append("Sum of kernel times under ncu: %.1f us." % total)
+    open(os.path.join(PROF, "r02_share_of_step.md"), "w").write("\n".join(lines) + "\n")
+    json.dump({"source": "profiles/r02_top_kernels.csv (ncu metric capture of one eager forward, --clock-control none, batch 32 x 4096): "
+                         "dram__bytes_read.sum + dram__bytes_write.sum per launch (afa = its four launches)",
+               "dram_bytes_per_launch": traffic}, open(os.path.join(PROF, "r02_traffic.json"), "w"), indent=1)
+    extra = os.path.join(OUT, "r02_extra_metrics.csv")
+    if os.path.exists(extra):
+        write_table(launches(extra), os.path.join(PROF, "r02_extra_kernels.csv"))
+    rep = os.path.join(OUT, "r02_top.ncu-rep")
+    if os.path.exists(rep):
+        keys = "gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio,smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio,smsp__average_warp_latency_issue_stalled_wait.ratio"
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--metrics", keys], capture_output=True, text=True).stdout
+        open(os.path.join(PROF, "r02_top_full_set_raw.csv"), "w").write(txt)
+    print("\n".join(lines))
 
 
 if __name__ == "__main__":

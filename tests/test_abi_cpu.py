@@ -85,3 +85,27 @@ def test_dropin_shims_expose_reference_module_names():
         sys.path.remove(os.path.join(util.ROOT, "dropin"))
         for name in ("pointops_cuda", "chamfer", "emd", "knn_cuda"):
             sys.modules.pop(name, None)
+
+
+def test_setup_py_installs_the_four_reference_import_names(tmp_path):
+    """setup.py (the replacement of libs/pointops/setup.py:1-32 and of the three other extension installs): the built tree
+    holds the package + the library and resolves `pointops_cuda`, `chamfer`, `emd`, `knn_cuda` without the repo on sys.path."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "lib")
+    subprocess.check_call([sys.executable, "setup.py", "-q", "build", "--build-lib", out, "--build-temp", str(tmp_path / "tmp")],
+                          cwd=root, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    assert os.path.exists(os.path.join(out, "patchaugnet_b200", "libpatchaug_b200.so"))
+    code = ("import pointops_cuda, chamfer, emd, knn_cuda, patchaugnet_b200, os;"
+            "assert os.path.dirname(patchaugnet_b200.__file__).startswith(%r);"
+            "names = [n for n in dir(pointops_cuda) if n.endswith('_cuda')]; assert len(names) == 17, names;"
+            "assert callable(chamfer.forward) and callable(emd.backward) and knn_cuda.KNN(3).k == 3" % out)
+    env = dict(os.environ, PYTHONPATH=out)
+    subprocess.check_call([sys.executable, "-c", code], cwd=str(tmp_path), env=env)
+    import shutil
+    shutil.rmtree(os.path.join(root, "build"), ignore_errors=True)
+    for d in (root, os.path.join(root, "dropin")):
+        for e in os.listdir(d):
+            if e.endswith(".egg-info"):
+                shutil.rmtree(os.path.join(d, e), ignore_errors=True)
