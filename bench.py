@@ -311,21 +311,22 @@ def other_configs(dev, world, rank):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0, em, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
         e0.record()
         with torch.no_grad():
             db = retrieval.extract_descriptors(net, clouds[:n_db], batch_size=32, device=dev)
+            em.record()
             qd = retrieval.extract_descriptors(net, clouds[n_db:], batch_size=32, device=dev)
         e1.record()
         res = retrieval.evaluate_recall(db, qd, [{i} for i in range(n_q)], top_k=25)
         e2.record()
         torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1), e1.elapsed_time(e2)], device=dev)
+        t = torch.tensor([e0.elapsed_time(e1), e1.elapsed_time(e2), e0.elapsed_time(em)], device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_ext, t_ret = t.tolist()
+        t_ext, t_ret, t_db = t.tolist()
         out["cfg4_retrieval_10k"] = dict(extract_ms=t_ext, retrieval_ms=t_ret, submaps_per_s=(n_db + n_q) / (t_ext * 1e-3),
-                                         queries_per_s=n_q / (t_ret * 1e-3), k=res["k"], n_gpus=world,
+                                         queries_per_s=n_q / (t_ret * 1e-3), k=res["k"], n_gpus=world, extract_db_ms=t_db,
                                          what="10000 db + 2000 query clouds resident in HBM, sharded by rank, one all_gather per "
                                               "descriptor set, brute-force top-k per query shard, hit counters all_reduced")
         del clouds, db, qd
@@ -397,6 +398,7 @@ def main():
     ap.add_argument("--mode", default="stream", choices=["stream", "graph", "eager"],
                     help="stream: 2-stream pipelined throughput mode (default); graph: one CUDA graph per step; eager")
     ap.add_argument("--dense-streams", type=int, default=2)
+    ap.add_argument("--stream-graphs", type=int, default=1, help="stream mode: replay the geometry / dense launch sequences as CUDA graphs")
     ap.add_argument("--tc-ctas", type=int, default=0, help="cap on persistent tensor-core CTAs (0 = one per SM)")
     ap.add_argument("--tc-tune", type=int, default=1, help="pab_tune_tensor_core bits (1 on, +4 CTA-pair multicast, +8 static tiles)")
     ap.add_argument("--fp-order", type=int, default=1, help="FP modules walk their points in Morton order (0 = index order)")
@@ -436,6 +438,7 @@ def main():
     L.lib().pab_tune_fps_threads(args.fps_threads)
     L.lib().pab_tune_fps_pruned(args.fps_pruned)
     eng.dense_streams = max(1, min(3, args.dense_streams))
+    eng.stream_graphs = bool(args.stream_graphs)
     eng.fp_row_order = bool(args.fp_order)
     eng.stream_priorities = tuple(int(v) for v in args.prio.split(","))
     lib = L.lib()
@@ -515,7 +518,7 @@ def main():
             ms = t.item()
         region_ms.append(ms)
         launches = lib.pab_num_launches()
-    if mode == "graph":
+    if mode == "graph" or (mode == "stream" and getattr(eng, "last_stream_used_graphs", False)):
         launches = K * eng.launches_per_forward()        # graph replays do not pass through the C ABI counter
     clocks = sampler.stop() if rank == 0 else None
     elapsed_ms = float(np.median(region_ms))

@@ -192,6 +192,9 @@ const int *pab_knn_index_order(int n, const void *index, long *stride_ints);
 size_t pab_scatter_workspace_bytes(int b, int n, int L);
 int pab_scatter_add_deterministic(int b, int c, int n, int L, int gdiv, const float *grad_out, const int *idx, const float *weight,
                                   float *grad_points, void *workspace, pab_stream_t s);
+/* build_index = 0: workspace already holds the inverse of this idx from an earlier call with the same b, n, L, idx. */
+int pab_scatter_add_deterministic_ex(int b, int c, int n, int L, int gdiv, const float *grad_out, const int *idx, const float *weight,
+                                     float *grad_points, void *workspace, int build_index, pab_stream_t s);
 
 /* Train-mode BatchNorm + ReLU of a SharedMLP block (utils/model_util/pt_util.py:98-151: conv -> BatchNorm (batch statistics)
  * -> ReLU), fused: x, y, dy, dx are (B, C, S) contiguous, S = product of the trailing dimensions.  forward: batch mean / biased

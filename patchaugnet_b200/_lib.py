@@ -43,6 +43,7 @@ SIGNATURES = {
     "pab_bn_relu_train_backward": (_I, [_I, _I, C.c_long, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "pab_scatter_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
     "pab_scatter_add_deterministic": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "pab_scatter_add_deterministic_ex": (_I, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P]),
     "pab_fps_clouds_per_sm": (_I, [_I]),
     "pab_furthestsampling": (_I, [_I, _I, _I, _P, _P, _P, _P]),
     "pab_gathering_forward": (_I, [_I, _I, _I, _I, _P, _P, _P, _P]),

@@ -79,6 +79,13 @@ PAB_API size_t pab_scatter_workspace_bytes(int b, int n, int L) { return sizeof(
 // Returns PAB_EINVAL when L exceeds what one CTA sorts in shared memory (the caller then uses the atomic kernels).
 PAB_API int pab_scatter_add_deterministic(int b, int c, int n, int L, int gdiv, const float *grad_out, const int *idx, const float *weight,
                                           float *grad_points, void *workspace, pab_stream_t s) {
+    return pab_scatter_add_deterministic_ex(b, c, n, L, gdiv, grad_out, idx, weight, grad_points, workspace, 1, s);
+}
+
+// build_index = 0: `workspace` already holds the inverse of this idx (an earlier call with the same b, n, L, idx) — the two
+// grouping backward passes of an SA module (coordinates and features) share one index tensor, hence one inversion
+PAB_API int pab_scatter_add_deterministic_ex(int b, int c, int n, int L, int gdiv, const float *grad_out, const int *idx,
+                                             const float *weight, float *grad_points, void *workspace, int build_index, pab_stream_t s) {
     if (gdiv < 1 || L % gdiv) return PAB_EINVAL;
     if (b < 0 || c < 0 || b > 65535 || c > 65535 || n <= 0 || n > (1 << 17) || L < 0 || L > INV_MAX_L || !workspace) return PAB_EINVAL;
     if (!b || !c || !L) return 0;
@@ -87,8 +94,10 @@ PAB_API int pab_scatter_add_deterministic(int b, int c, int n, int L, int gdiv, 
     while (P < L) P <<= 1;
     const size_t smem = (size_t)P * sizeof(unsigned);
     PAB_CUDA(cudaFuncSetAttribute(inverse_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    inverse_index_kernel<<<b, INV_T, smem, st>>>(n, L, P, idx, (int *)workspace);
-    PAB_LAUNCH_CHECK();
+    if (build_index) {
+        inverse_index_kernel<<<b, INV_T, smem, st>>>(n, L, P, idx, (int *)workspace);
+        PAB_LAUNCH_CHECK();
+    }
     scatter_add_csr_kernel<<<dim3(pab_divup(n, 256), c, b), 256, 0, st>>>(c, n, L, gdiv, grad_out, weight, (const int *)workspace, grad_points);
     PAB_LAUNCH_CHECK();
     return 0;

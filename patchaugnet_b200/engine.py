@@ -121,6 +121,8 @@ class FusedPatchAugNet:
         self.fp_row_order = True        # FP modules walk their points in the Morton order of the level's spatial index
         self.dense_streams = 2          # dense kernels of consecutive batches alternate between two streams
         self.stream_priorities = (0, 0)
+        self.stream_graphs = True       # forward_stream: geometry / dense launch sequences replayed as CUDA graphs (2 launches per batch)
+        self._sgraphs = {}
         self.reserve_fps_sms = True     # forward_stream: persistent tensor-core kernels leave the FPS CTAs' SMs alone
         self.fps_clouds_per_cta = 1     # forward_stream: clouds sharing one FPS CTA (2 = half the SMs held by the sampler)
         self.refold()
@@ -159,6 +161,7 @@ class FusedPatchAugNet:
         self.fused_tail = agg.aggregation_type == 2 and not agg.gating
         self._ws.clear()
         self._graphs.clear()
+        self._sgraphs.clear()
         if not self.fused_tail:
             return
         afa = agg.afa
@@ -362,6 +365,13 @@ class FusedPatchAugNet:
             L.lib().pab_tune_tc_max_ctas(n_sm - (B + cpc - 1) // cpc if 0 < B <= n_sm // 2 else 0)
         geo_done = [None, None]
         dense_done = [None, None]
+        # The 30 launches of a batch are replayed as TWO CUDA graphs (geometry, dense) per workspace slot: the host then issues
+        # a copy + two graph launches + a few event operations per batch instead of ~30 ctypes calls, so the pipeline stays
+        # GPU-bound when the host cores are contended (8 ranks on one box) — measured host time per batch 0.57 ms -> 0.1 ms.
+        graphs = None
+        if self.stream_graphs and self.fused_tail and self._events is None and len(batches) >= 4:
+            graphs = self._capture_stream_graphs(B, N, slots)
+        self.last_stream_used_graphs = graphs is not None
         for i, x in enumerate(batches):
             L.require_cuda(x)
             xyz0 = (x.squeeze(1) if x.dim() == 4 else x).contiguous().float()
@@ -374,14 +384,21 @@ class FusedPatchAugNet:
                 if ready_events is not None and ready_events[i] is not None:
                     s_geo.wait_event(ready_events[i])
                 if dense_done[slot] is not None:
-                    s_geo.wait_event(dense_done[slot])          # workspace free again
-                self._launch_geo(xyz0, ws)
+                    s_geo.wait_event(dense_done[slot])          # workspace (and the slot's static input) free again
+                if graphs is not None:
+                    graphs[slot]["x"].copy_(xyz0, non_blocking=True)
+                    graphs[slot]["geo"].replay()
+                else:
+                    self._launch_geo(xyz0, ws)
                 geo_done[slot] = torch.cuda.Event()
                 geo_done[slot].record()
             s_dense = dense_streams[i % len(dense_streams)]   # alternate: the tail of one batch's kernels overlaps the next's
             with torch.cuda.stream(s_dense):
                 s_dense.wait_event(geo_done[slot])
-                self._launch_dense(xyz0, ws)
+                if graphs is not None:
+                    graphs[slot]["dense"].replay()
+                else:
+                    self._launch_dense(xyz0, ws)
                 out[i * B:(i + 1) * B].copy_(ws["desc"], non_blocking=True)
                 dense_done[slot] = torch.cuda.Event()
                 dense_done[slot].record()
@@ -394,6 +411,34 @@ class FusedPatchAugNet:
             L.lib().pab_tune_tc_max_ctas(0)
             L.lib().pab_tune_fps_clouds_per_cta(1)
         return out
+
+    def _capture_stream_graphs(self, B, N, slots):
+        """Geometry and dense launch sequences of both workspace slots as CUDA graphs over a static per-slot input buffer.
+        Captured with the current tuning state (CTA cap of the persistent kernels, FPS packing): the key holds it."""
+        key = (B, N, L.lib().pab_fps_clouds_per_sm(N), self.reserve_fps_sms, self.fp_row_order, self.vlad_tensor_core,
+               torch.cuda.get_device_properties(self.device).multi_processor_count)
+        got = self._sgraphs.get(key)
+        if got is not None:
+            return got
+        got = []
+        cur = torch.cuda.current_stream()
+        for ws in slots:
+            x = torch.zeros(B, N, 3, dtype=torch.float32, device=self.device)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):                     # warm-up outside capture (function attributes, lazy state)
+                self._launch_geo(x, ws)
+                self._launch_dense(x, ws)
+            cur.wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            g_geo, g_dense = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_geo):
+                self._launch_geo(x, ws)
+            with torch.cuda.graph(g_dense):
+                self._launch_dense(x, ws)
+            got.append(dict(x=x, geo=g_geo, dense=g_dense))
+        self._sgraphs[key] = got
+        return got
 
     # ---- per-stage timing and algorithmic work (bench.py roofline) ---------------------------------------------
     def enable_stage_timing(self, stages=None):

@@ -52,14 +52,29 @@ DETERMINISTIC_BACKWARD = True      # scatter-adds as ordered gathers over an inv
 _MAX_L = 32768
 
 
+_INVERSE_CACHE = {}      # id(idx) -> (weakref(idx), idx._version, (b, n, L), stream, workspace): the inverse index of a live index tensor
+
+
 def _scatter(b, c, n, Lc, grad_out, idx, weight, grad_points, what, gdiv=1):
-    """grad_points[b,ch,idx[b,e]] += grad_out[b,ch,e] * weight[b,e], deterministic.  Returns False when the shape is out of range."""
+    """grad_points[b,ch,idx[b,e]] += grad_out[b,ch,e/gdiv] * weight[b,e], deterministic.  Returns False when the shape is out of
+    range.  The inverse index is cached per index TENSOR OBJECT (weak reference + version counter): the coordinate and the
+    feature grouping of an SA module share one idx, so their backward passes share one inversion."""
+    import weakref
     if not DETERMINISTIC_BACKWARD or Lc > _MAX_L or Lc == 0 or b == 0 or c == 0:
         return False
-    ws = torch.empty(L.lib().pab_scatter_workspace_bytes(b, n, Lc), dtype=torch.uint8, device=grad_out.device)
-    L.check(L.lib().pab_scatter_add_deterministic(b, c, n, Lc, gdiv, _f(grad_out, "grad_out"), _i(idx, "idx"),
-                                                  _f(weight, "weight") if weight is not None else L.ptr(None),
-                                                  _f(grad_points, "grad_points"), L.ptr(ws), L.stream_ptr()), what)
+    st = L.stream_ptr()
+    key, build, ws = id(idx), 1, None
+    hit = _INVERSE_CACHE.get(key)
+    if hit is not None and hit[0]() is idx and hit[1] == idx._version and hit[2] == (b, n, Lc) and hit[3] == st.value:
+        ws, build = hit[4], 0
+    if ws is None:
+        for k in [k for k, v in _INVERSE_CACHE.items() if v[0]() is None]:        # entries of dead tensors
+            del _INVERSE_CACHE[k]
+        ws = torch.empty(L.lib().pab_scatter_workspace_bytes(b, n, Lc), dtype=torch.uint8, device=grad_out.device)
+        _INVERSE_CACHE[key] = (weakref.ref(idx), idx._version, (b, n, Lc), st.value, ws)
+    L.check(L.lib().pab_scatter_add_deterministic_ex(b, c, n, Lc, gdiv, _f(grad_out, "grad_out"), _i(idx, "idx"),
+                                                     _f(weight, "weight") if weight is not None else L.ptr(None),
+                                                     _f(grad_points, "grad_points"), L.ptr(ws), build, st), what)
     return True
 
 
