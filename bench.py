@@ -343,22 +343,23 @@ def other_configs(dev, world, rank):
         step = training.TrainStep(model, opt, n_anchors=anchors)
         g = torch.Generator(device=dev).manual_seed(77 + rank)
         feed = ((torch.rand(anchors * training.CLOUDS_PER_ANCHOR, 1, NPTS, 3, generator=g, device=dev) * 2 - 1) * 0.57)
-        for _ in range(3):                                         # allocator growth, cuDNN algorithm choice, Adam state
+        for _ in range(5):                                         # allocator growth, cuDNN algorithm choice, Adam state, DDP buckets
             step(feed)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        n_steps = 5
-        for _ in range(n_steps):
+        per_step = []
+        for _ in range(7):                                         # median of 7 individually timed steps (max over ranks each)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             loss, _terms = step(feed)
-        e1.record()
-        torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1) / n_steps], device=dev)
+            e1.record()
+            torch.cuda.synchronize()
+            per_step.append(e0.elapsed_time(e1))
+        t = torch.tensor(per_step, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = t.item()
+        ms = float(t.median())
         rec = dict(ms_per_step=ms, anchors_per_gpu=anchors, clouds_per_gpu=anchors * training.CLOUDS_PER_ANCHOR, n_gpus=world,
                    clouds_per_s=world * anchors * training.CLOUDS_PER_ANCHOR / (ms * 1e-3), loss=float(loss),
                    grad_allreduce_bytes=training.grad_bytes(net), peak_mem_gb=torch.cuda.max_memory_allocated(dev) / 2 ** 30,
