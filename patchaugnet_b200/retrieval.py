@@ -52,68 +52,90 @@ def extract_descriptors(extract_fn, clouds, batch_size=32, device=None, dim=256,
     ``clouds`` may live on the host (pinned memory recommended: the copies are issued non-blocking, ``super_chunk``
     batches at a time) or on the device.
     """
+    return extract_descriptor_sets(extract_fn, [clouds], batch_size, device, dim, group, out_device, super_chunk)[0]
+
+
+def extract_descriptor_sets(extract_fn, cloud_sets, batch_size=32, device=None, dim=256, group=None, out_device=None,
+                            super_chunk=64):
+    """``extract_descriptors`` for several cloud sets at once (database and queries of an evaluation): every set is sharded over
+    the ranks by contiguous index range, this rank's shards of ALL sets run through ONE pipelined batch sequence (the
+    pipeline fills and drains once, not once per set), then each set gets its own all_gather.  Returns a list of (M_i, dim)."""
     rank, world = _dist_info(group)
-    M = clouds.shape[0]
-    lo, hi = shard_range(M, rank, world)
-    device = device if device is not None else (clouds.device if clouds.is_cuda else torch.device("cpu"))
-    local = torch.empty(hi - lo, dim, dtype=torch.float32, device=device)
+    first = cloud_sets[0]
+    device = device if device is not None else (first.device if first.is_cuda else torch.device("cpu"))
+    shards = [shard_range(c.shape[0], rank, world) for c in cloud_sets]
+    locals_ = [torch.empty(hi - lo, dim, dtype=torch.float32, device=device) for lo, hi in shards]
     engine = None
     if hasattr(extract_fn, "engine") and hasattr(extract_fn, "fusable") and torch.device(device).type == "cuda" \
             and not extract_fn.training and extract_fn.fusable():
         engine = extract_fn.engine()
     if engine is not None:
-        step = batch_size * super_chunk
-        host_side = not clouds.is_cuda
+        # jobs: (set, start, end) batches of this rank; full batches of every set form one pipelined sequence, ragged tails follow
+        full_jobs, tail_jobs = [], []
+        for si, (lo, hi) in enumerate(shards):
+            for s0 in range(lo, hi, batch_size):
+                e0 = min(hi, s0 + batch_size)
+                (full_jobs if e0 - s0 == batch_size else tail_jobs).append((si, s0, e0))
+        host_side = not first.is_cuda
         copy_stream = _copy_stream(device) if host_side else None
-        for s in range(lo, hi, step):
-            e = min(hi, s + step)
-            full = (e - s) // batch_size * batch_size
-            if host_side:
-                # one upload per batch on a copy stream, each followed by an event: batch i's kernels wait for ITS upload only,
-                # so the copies of later batches run under the compute of earlier ones (the make_descs loop of the reference
-                # uploads and computes strictly in turn, scene_dataset.py:672-686)
-                batches, events = [], []
-                copy_stream.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(copy_stream):
-                    for i in range(s, e, batch_size):
-                        batches.append(clouds[i:min(e, i + batch_size)].to(device, non_blocking=True))
-                        ev = torch.cuda.Event()
-                        ev.record(copy_stream)
-                        events.append(ev)
-                for b in batches:
-                    b.record_stream(torch.cuda.current_stream())
-            else:
-                dev_chunk = clouds[s:e]
-                batches = [dev_chunk[i:min(e - s, i + batch_size)] for i in range(0, e - s, batch_size)]
-                events = None
-            n_full = full // batch_size
-            if n_full:
-                engine.forward_stream(batches[:n_full], out=local[s - lo:s - lo + full],
-                                      ready_events=events[:n_full] if events is not None else None)
-            if full < e - s:                                   # ragged tail batch
+
+        def stage(jobs):
+            """device batches of `jobs` (+ per-batch upload events when the clouds live on the host)"""
+            if not host_side:
+                return [cloud_sets[si][s0:e0] for si, s0, e0 in jobs], None
+            # one upload per batch on a copy stream, each followed by an event: batch i's kernels wait for ITS upload only,
+            # so the copies of later batches run under the compute of earlier ones (the make_descs loop of the reference
+            # uploads and computes strictly in turn, scene_dataset.py:672-686)
+            batches, events = [], []
+            copy_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(copy_stream):
+                for si, s0, e0 in jobs:
+                    batches.append(cloud_sets[si][s0:e0].to(device, non_blocking=True))
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                    events.append(ev)
+            for bt in batches:
+                bt.record_stream(torch.cuda.current_stream())
+            return batches, events
+
+        for c0 in range(0, len(full_jobs), super_chunk):
+            jobs = full_jobs[c0:c0 + super_chunk]
+            batches, events = stage(jobs)
+            out = engine.forward_stream(batches, ready_events=events)
+            for j, (si, s0, e0) in enumerate(jobs):
+                locals_[si][s0 - shards[si][0]:e0 - shards[si][0]] = out[j * batch_size:(j + 1) * batch_size]
+        if tail_jobs:
+            batches, events = stage(tail_jobs)
+            for j, (si, s0, e0) in enumerate(tail_jobs):
                 if events is not None:
-                    torch.cuda.current_stream().wait_event(events[-1])
-                local[s - lo + full:e - lo] = engine(batches[-1], return_feat=False, clone=False)
+                    torch.cuda.current_stream().wait_event(events[j])
+                locals_[si][s0 - shards[si][0]:e0 - shards[si][0]] = engine(batches[j], return_feat=False, clone=False)
     else:
-        for s in range(lo, hi, batch_size):
-            e = min(hi, s + batch_size)
-            x = clouds[s:e].to(device, non_blocking=True).unsqueeze(1)
-            out = extract_fn(x)
-            local[s - lo:e - lo] = out[0] if isinstance(out, (tuple, list)) else out
-    if world == 1:
-        return local if out_device is None else local.to(out_device)
-    # equal-size shards are required by all_gather_into_tensor: pad to the largest shard, trim after
-    per = (M + world - 1) // world
-    send = torch.zeros(per, dim, dtype=torch.float32, device=device)
-    send[: hi - lo] = local
-    recv = torch.empty(world * per, dim, dtype=torch.float32, device=device)
-    dist.all_gather_into_tensor(recv, send, group=group)
-    parts = []
-    for r in range(world):
-        rlo, rhi = shard_range(M, r, world)
-        parts.append(recv[r * per: r * per + (rhi - rlo)])
-    full = torch.cat(parts, 0)
-    return full if out_device is None else full.to(out_device)
+        for si, (lo, hi) in enumerate(shards):
+            for s0 in range(lo, hi, batch_size):
+                e0 = min(hi, s0 + batch_size)
+                x = cloud_sets[si][s0:e0].to(device, non_blocking=True).unsqueeze(1)
+                out = extract_fn(x)
+                locals_[si][s0 - lo:e0 - lo] = out[0] if isinstance(out, (tuple, list)) else out
+    results = []
+    for si, (lo, hi) in enumerate(shards):
+        local, M = locals_[si], cloud_sets[si].shape[0]
+        if world == 1:
+            results.append(local if out_device is None else local.to(out_device))
+            continue
+        # equal-size shards are required by all_gather_into_tensor: pad to the largest shard, trim after
+        per = (M + world - 1) // world
+        send = torch.zeros(per, dim, dtype=torch.float32, device=device)
+        send[: hi - lo] = local
+        recv = torch.empty(world * per, dim, dtype=torch.float32, device=device)
+        dist.all_gather_into_tensor(recv, send, group=group)
+        parts = []
+        for r in range(world):
+            rlo, rhi = shard_range(M, r, world)
+            parts.append(recv[r * per: r * per + (rhi - rlo)])
+        full = torch.cat(parts, 0)
+        results.append(full if out_device is None else full.to(out_device))
+    return results
 
 
 def retrieval_topk(db, queries, k):

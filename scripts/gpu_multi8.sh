@@ -1,6 +1,10 @@
 mkdir -p gpurun_out
-N=${1:-8}
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-timeout 600 $TR --master-port 29501 bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_${N}gpu.log 2>&1
-timeout 900 $TR --master-port 29502 scripts/retrieval_eval.py --db 10000 --queries 2000 > gpurun_out/retrieval_${N}gpu.log 2>&1
-for f in bench_${N}gpu retrieval_${N}gpu; do echo "== $f"; grep "^{" gpurun_out/$f.log | tail -1 | cut -c1-900; done
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29555 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/bench_8gpu.log 2>&1
+echo "exit $?"
+python - <<'PY'
+import json
+for line in open("gpurun_out/bench_8gpu.log"):
+    if line.startswith("{"):
+        d = json.loads(line); print("value", d["value"], "e2e", d["e2e"]["value"], "n", d["n_gpus"], "ms/step", d["ms_per_step"]); print(json.dumps(d["configs"], indent=1)[:3800])
+PY
+grep -v "^{" gpurun_out/bench_8gpu.log | tail -5 | cut -c1-300

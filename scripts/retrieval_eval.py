@@ -82,8 +82,8 @@ def main():
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     e0.record()
     with torch.no_grad():
-        db = retrieval.extract_descriptors(net, db_clouds, batch_size=args.batch, device=dev)       # shard + all-gather
-        qd = retrieval.extract_descriptors(net, q_clouds, batch_size=args.batch, device=dev)
+        # shard + one pipelined sequence per rank + one all-gather per set
+        db, qd = retrieval.extract_descriptor_sets(net, [db_clouds, q_clouds], batch_size=args.batch, device=dev)
     e1.record()
     positives = [{i} for i in range(args.queries)]
     res = retrieval.evaluate_recall(db, qd, positives, top_k=args.top_k)

@@ -175,6 +175,11 @@ def test_pipelined_forward_stream_matches_per_batch_forward(net):
         d = retrieval.extract_descriptors(net, host, batch_size=4, device=torch.device(DEV))
         torch.cuda.synchronize()
     assert torch.equal(d, want[:18])
+    # database and query sets through ONE pipelined sequence (retrieval.extract_descriptor_sets): same descriptors, set by set
+    with torch.no_grad():
+        a, b = retrieval.extract_descriptor_sets(net, [host[:13], host[5:18]], batch_size=4, device=torch.device(DEV))
+        torch.cuda.synchronize()
+    assert torch.equal(a, want[:13]) and torch.equal(b, want[5:18])
 
 
 @pytest.mark.parametrize("agg_type,gating", [(0, False), (1, False), (3, False), (4, False), (5, False), (2, True), (0, True)])
