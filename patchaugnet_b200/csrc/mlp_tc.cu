@@ -54,6 +54,8 @@ struct alignas(64) TcArgs {
     int n_layers, n_stages, mode;
     int stage_bytes;                           // bytes of one weight stage: 16 KB (one plane of a <=128-channel block) or, with `pair`,
     int pair;                                  // 32 KB: hi AND lo plane of a wide block behind ONE barrier round trip
+    int nbuf;                                  // layer-0 operand buffers in shared memory: 2 = the loaders stage tile i+1 while the layer-0
+                                               // MMAs of tile i still read theirs (narrow modules, where the region is small)
     int planes;                                // 2: bf16 hi/lo split, 3 MMAs per product (fp32 contract); 1: plain bf16 operands, 1 MMA
     int csize, iters;                          // CTAs per cluster sharing the weight stream (1 or 2); tile-loop trips (equal for all CTAs)
     int dynamic;                               // 1: CTAs draw tiles from *counter (atomic) instead of the static blockIdx + i*grid sequence
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *a1 = smem;                                            // layer-0 operand, hi plane
     uint8_t *a2 = a.planes == 2 ? a1 + (size_t)(a.a_region >> 1) : nullptr;   //            lo plane (bf16 hi/lo mode only)
-    uint8_t *stages = a1 + (size_t)a.a_region;
+    uint8_t *stages = a1 + (size_t)a.a_region * a.nbuf;
     uint8_t *stg = stages + (size_t)a.n_stages * a.stage_bytes;
     uint8_t *misc = stg + (a.mode == TC_SA ? STG_BYTES : STG_BYTES_FP);
     uint64_t *full = reinterpret_cast<uint64_t *>(misc);
@@ -136,6 +138,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     uint64_t *d_ready1 = reinterpret_cast<uint64_t *>(misc + 272);  // n-block 1
     uint64_t *t_ready1 = d_ready1 + 1;                             // D columns [128,256) / plane columns [64,128) (+ next tile's extras)
     uint64_t *p_free = d_ready1 + 2;
+    constexpr int ABUF_STEP = 21;                                  // the second operand buffer's a_full / a_empty sit 168 bytes further
+                                                                   // (misc + 296 / + 304): plain pointer arithmetic, no local arrays
     float *ctab = reinterpret_cast<float *>(misc + 384);           // [shift of every layer | pre layer]
 
     const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
@@ -147,8 +151,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
 
     if (tid == 0) {
         for (int s = 0; s < a.n_stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, a.csize); }
-        mbar_init(a_full, a.mode == TC_FP ? NLOAD : NLOAD_SA);
-        mbar_init(a_empty, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(a_full + i * ABUF_STEP, a.mode == TC_FP ? NLOAD : NLOAD_SA); mbar_init(a_empty + i * ABUF_STEP, 1); }
         mbar_init(d_ready, 1);
         mbar_init(t_ready, NEPI);
         mbar_init(d_ready1, 1);
@@ -254,7 +257,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                 const uint32_t idesc = umma_idesc(nbr);
                 const int gc = l == 0 ? a.gchunks : nkc, ngroups = l == 0 ? (nkc_main + gc - 1) / gc : 1;
                 for (int g = 0; g < ngroups; ++g) {
-                if (l == 0) mbar_wait(a_full, gcount & 1);       // this group of layer-0 operand chunks is staged
+                const uint32_t abuf = a.nbuf == 2 ? (gcount & 1u) : 0u, ause = a.nbuf == 2 ? (gcount >> 1) : gcount;
+                const uint32_t aoff = abuf * ((uint32_t)a.a_region >> 4);   // descriptor offset of this tile's operand buffer
+                if (l == 0) mbar_wait(a_full + abuf * ABUF_STEP, ause & 1);   // this group of layer-0 operand chunks is staged
                 const int kc_lo = g * gc, kc_hi = g == ngroups - 1 ? nkc : (g + 1) * gc;
                 const bool last_g = g == ngroups - 1;
                 for (int nb = 0; nb < nnb; ++nb) {
@@ -291,8 +296,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                         for (int ks = 0; ks < 4; ++ks) {
                             if (ks < kn) {
                                 if (from_smem) {
-                                    umma_f16_if(leader, d, a1_lo + ka + 2 * ks, UMMA_DESC_HI, sb + 2 * ks, UMMA_DESC_HI, idesc, (kc | ks) != 0);
-                                    if (two) umma_f16_if(leader, d, a2_lo + ka + 2 * ks, UMMA_DESC_HI, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
+                                    umma_f16_if(leader, d, a1_lo + aoff + ka + 2 * ks, UMMA_DESC_HI, sb + 2 * ks, UMMA_DESC_HI, idesc, (kc | ks) != 0);
+                                    if (two) umma_f16_if(leader, d, a2_lo + aoff + ka + 2 * ks, UMMA_DESC_HI, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
                                 } else {
                                     umma_f16_ts_if(leader, d, tmem + AH_COL + ta + ks * 8, sb + 2 * ks, UMMA_DESC_HI, idesc, (kc | ks) != 0);
                                     if (two) umma_f16_ts_if(leader, d, tmem + AL_COL + ta + ks * 8, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
@@ -313,7 +318,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
                             if (ks < kn) {
-                                if (from_smem) umma_f16_if(leader, d, a1_lo + ka + 2 * ks, UMMA_DESC_HI, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
+                                if (from_smem) umma_f16_if(leader, d, a1_lo + aoff + ka + 2 * ks, UMMA_DESC_HI, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
                                 else umma_f16_ts_if(leader, d, tmem + AH_COL + ta + ks * 8, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
                             }
                         }
@@ -346,7 +351,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                         }
                     }
                 }
-                if (l == 0) { umma_commit_if(leader, a_empty); ++gcount; }   // operand group consumed: loaders may stage the next one
+                if (l == 0) { umma_commit_if(leader, a_empty + abuf * ABUF_STEP); ++gcount; }   // operand group consumed: loaders may stage the next one
                 }
             }
         }
@@ -548,6 +553,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         const int gunits = a.gchunks * 8;                    // units per operand group (one group = the whole row unless K is wide)
         const int ngroups = (units0 + gunits - 1) / gunits;
         uint32_t gcount = 0;                                 // operand groups staged so far (a_full / a_empty completions)
+        // operand buffer of group gcount (two buffers: alternate; the wait is for the MMAs that read THIS buffer two groups ago)
+        auto a_wait_free = [&]() {
+            const uint32_t buf = a.nbuf == 2 ? (gcount & 1u) : 0u, use = a.nbuf == 2 ? (gcount >> 1) : gcount;
+            if (use > 0) mbar_wait(a_empty + buf * ABUF_STEP, (use - 1) & 1);
+        };
+        auto a_buf1 = [&]() { return a1 + (size_t)(a.nbuf == 2 ? (gcount & 1u) : 0u) * a.a_region; };
+        auto a_publish = [&]() {
+            mbar_arrive(a_full + (a.nbuf == 2 ? (gcount & 1u) : 0u) * ABUF_STEP);
+            ++gcount;
+        };
         // pre-layer mode (one thread per row): pipelined lookups, see the branch below
         float pre_in[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         long pre_pc = 0, pre_pn = 0;
@@ -627,7 +642,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                     const int t2 = tile_at((uint32_t)it + 2);
                     if (t2 >= 0) pre_hop1(t2, pre_pc, pre_pn, pre_valid2);
                 }
-                if (gcount > 0) mbar_wait(a_empty, (gcount - 1) & 1);
+                a_wait_free();
+                uint8_t *a1 = a_buf1(), *a2 = a.planes == 2 ? a1 + (size_t)(a.a_region >> 1) : nullptr;     // this group's buffer
                 const float *pw = ctab + a.pre_off, *ps = pw + a.pre_cin * a.pre_cout;
                 for (int u = 0; u < a.pre_cout / 8; ++u) {
                     float v[8];
@@ -662,7 +678,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                 }
                 for (int g = 0; g < ngroups; ++g) {
                 const int j_lo = g * gunits, j_hi = min(units0, j_lo + gunits);
-                if (gcount > 0) mbar_wait(a_empty, (gcount - 1) & 1);
+                a_wait_free();
+                uint8_t *a1 = a_buf1(), *a2 = a.planes == 2 ? a1 + (size_t)(a.a_region >> 1) : nullptr;     // this group's buffer
                 for (int rr = 0; rr < 32; rr += 4) {
                     long pc[4], pn[4];
 #pragma unroll
@@ -691,8 +708,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                 }
                 if (g + 1 < ngroups) {                        // more groups of this tile follow
                     fence_proxy_async();
-                    mbar_arrive(a_full);
-                    ++gcount;
+                    a_publish();
                 }
                 }
             } else {
@@ -721,7 +737,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                 }
                 for (int g = 0; g < ngroups; ++g) {
                 const int j_lo = g * gunits, j_hi = min(units0, j_lo + gunits);
-                if (gcount > 0) mbar_wait(a_empty, (gcount - 1) & 1);
+                a_wait_free();
+                uint8_t *a1 = a_buf1(), *a2 = a.planes == 2 ? a1 + (size_t)(a.a_region >> 1) : nullptr;     // this group's buffer
                 for (int bi = 0; lwarp + LW * bi < TM / RB; ++bi) {           // batch = lwarp + LW * bi, rows RB * batch ..
                     const int rr = RB * bi, row0 = RB * (lwarp + LW * bi);       // source lane of the batch's first row, its tile row
                     const float *f0[RB], *f1[RB], *f2[RB];
@@ -787,15 +804,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                 }
                 if (g + 1 < ngroups) {                        // more groups of this tile follow
                     fence_proxy_async();
-                    mbar_arrive(a_full);
-                    ++gcount;
+                    a_publish();
                 }
                 }
             }
             fence_proxy_async();
             if (lwarp == 0) TC_TRACE(it, 0, 5);
-            mbar_arrive(a_full);
-            ++gcount;
+            a_publish();
         }
     }
     tc_fence_before();
@@ -854,7 +869,9 @@ int g_tc_cluster = 0;      // weight multicast across CTA pairs (pab_tune_tensor
 
 // Shared-memory plan of one launch: layer-0 operand region, staging, weight stages, constant table.
 // `layers` are the TENSOR-CORE layers only (the optional pre-layer is passed separately).
-struct TcPlan { int a_region, gchunks, n_stages, stage_bytes, pair, coff[MAX_LAYERS], pre_off; size_t misc, smem; };
+struct TcPlan { int a_region, nbuf, gchunks, n_stages, stage_bytes, pair, coff[MAX_LAYERS], pre_off; size_t misc, smem; };
+
+int g_tc_nbuf = 2;         // two layer-0 operand buffers where they fit (pab_tune_tensor_core bit 5 = 32 forces one)
 
 int g_tc_pair = 1;         // wide weight blocks: hi + lo plane in one 32-KB stage (pab_tune_tensor_core bit 4 = 16 clears it)
 
@@ -876,15 +893,19 @@ bool tc_plan(const pab_layer_t *layers, int n_layers, const pab_layer_t *pre, in
         p->gchunks = 4;
     }
     p->a_region = planes * p->gchunks * A_CHUNK;
+    // a second operand buffer when the whole input is one group and two regions leave room for >= 4 weight stages
+    const bool one_group = layers[0].tc_k / KCH <= 5;
+    p->nbuf = (g_tc_nbuf == 2 && one_group && 2L * p->a_region + stg_bytes + 4 * (NBLK_MAX * 128) + 1024 + ctab * 4 <= 227L * 1024 &&
+               p->a_region <= 64 * 1024) ? 2 : 1;
     p->misc = 384 + (size_t)ctab * 4 + 64;
-    const long budget = 227L * 1024 - p->a_region - stg_bytes - (long)p->misc;
+    const long budget = 227L * 1024 - (long)p->a_region * p->nbuf - stg_bytes - (long)p->misc;
     bool wide = false;
     for (int l = 0; l < n_layers; ++l) wide = wide || layers[l].c_out > 64;
     p->pair = (g_tc_pair && wide && planes == 2 && budget / (2 * NBLK_MAX * 128) >= 2) ? 1 : 0;
     p->stage_bytes = p->pair ? 2 * NBLK_MAX * 128 : NBLK_MAX * 128;
     p->n_stages = (int)(budget / p->stage_bytes);
     if (p->n_stages > MAX_STAGES) p->n_stages = MAX_STAGES;
-    p->smem = (size_t)p->a_region + (size_t)p->n_stages * p->stage_bytes + stg_bytes + p->misc;
+    p->smem = (size_t)p->a_region * p->nbuf + (size_t)p->n_stages * p->stage_bytes + stg_bytes + p->misc;
     return p->n_stages >= 2;
 }
 
@@ -929,7 +950,7 @@ int pab_tc_launch(int mode, long rows, int k_group, const pab_layer_t *all_layer
     const int n_layers = kind == 2 ? n_all - 1 : n_all;
     TcPlan p;
     if (!tc_plan(layers, n_layers, pre, mode, &p)) return PAB_EINVAL;
-    a.a_region = p.a_region; a.gchunks = p.gchunks; a.n_stages = p.n_stages; a.stage_bytes = p.stage_bytes; a.pair = p.pair;
+    a.nbuf = p.nbuf; a.a_region = p.a_region; a.gchunks = p.gchunks; a.n_stages = p.n_stages; a.stage_bytes = p.stage_bytes; a.pair = p.pair;
     const long per_tile = mode == TC_SA ? (TM / k_group) : TM;
     if (rows >= (1L << 31)) return PAB_EINVAL;
     a.ntiles = (int)((rows + per_tile - 1) / per_tile);
@@ -1005,6 +1026,7 @@ PAB_API void pab_tune_tensor_core(int enable) {
     g_tc_cluster = (enable & 4) != 0;
     g_tc_dynamic = (enable & 8) != 0;
     g_tc_pair = (enable & 16) == 0;
+    g_tc_nbuf = (enable & 32) ? 1 : 2;
 }
 
 int pab_tc_sa(int kind, int b, int n, int m, int k, int nbr_stride, int c, const float *xyz, const float *feat, const int *center_idx,

@@ -223,3 +223,45 @@ def test_ball_query_grouper_through_the_fused_engine():
     assert (d_fused - d_knn).abs().max().item() > 1e-3          # the grouper really changed
     for a, b in zip(f_fused, f_ops):
         assert (a - b).abs().max().item() < 5e-4 * max(1.0, b.abs().max().item())
+
+
+def test_single_neighbour_groups_take_the_op_path_and_match_the_oracle_rule():
+    """QueryAndGroup_Edge skips the centre-feature subtraction when nsample == 1 (pointops.py:562-563); the fused
+    loaders always subtract, so such a configuration must not be fused."""
+    cfg = dict(util.PATCHAUGNET_CFG, SAMPLING=[256, 64, 16], MAX_SAMPLES=[64, 256, 1024], KNN=[1, 20, 20], KNN_DILATION=1)
+    small = util.build_network(DEV, cfg=cfg)
+    assert not small.fusable()
+    x = util.synthetic_batch(2, 1024, start=320).to(DEV)
+    before = L.lib().pab_num_launches()
+    with torch.no_grad():
+        d, f, c = small(x)
+    assert L.lib().pab_num_launches() > before and torch.isfinite(d).all() and d.shape == (2, 256)
+
+
+def test_engine_refolds_after_in_place_weight_updates_in_eval_mode(net):
+    """optimizer.step() / in-place edits / a child's load_state_dict while the model stays in eval() must not leave
+    a stale folded copy behind."""
+    other = util.build_network(DEV, seed=777)
+    x = util.synthetic_batch(1, 4096, 9).to(DEV)
+    with torch.no_grad():
+        a, _, _ = other(x)
+        other.aggregation.afa.fc.weight.mul_(0.5)                       # in place, eval mode
+        b, _, _ = other(x)
+        other.backbone.load_state_dict(net.backbone.state_dict())       # a CHILD's load_state_dict
+        other.aggregation.load_state_dict(net.aggregation.state_dict())
+        other.decoder.load_state_dict(net.decoder.state_dict())
+        c, _, _ = other(x)
+        want, _, _ = net(x)
+    assert not torch.equal(a, b) and torch.equal(c, want)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_data_parallel_eval_forward_matches_single_gpu(net):
+    """the reference wraps the model in nn.DataParallel when several GPUs are visible
+    (train_place_recognition.py:546-548); replicas have no parameters() and must not touch the master's fused engine."""
+    x = util.synthetic_batch(4, 4096, start=330).to(DEV)
+    dp = torch.nn.DataParallel(net, device_ids=[0, 1])
+    with torch.no_grad():
+        want, _, cw = net(x)
+        got, _, cg = dp(x)
+    assert (got - want).abs().max().item() < TOL and torch.equal(cg[0].cpu(), cw[0].cpu())
