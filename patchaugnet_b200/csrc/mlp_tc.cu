@@ -871,7 +871,7 @@ int g_tc_cluster = 0;      // weight multicast across CTA pairs (pab_tune_tensor
 // `layers` are the TENSOR-CORE layers only (the optional pre-layer is passed separately).
 struct TcPlan { int a_region, nbuf, gchunks, n_stages, stage_bytes, pair, coff[MAX_LAYERS], pre_off; size_t misc, smem; };
 
-int g_tc_nbuf = 2;         // two layer-0 operand buffers where they fit (pab_tune_tensor_core bit 5 = 32 forces one)
+int g_tc_nbuf = 1;         // layer-0 operand buffers; 2 = double-buffered where the region is small (measured: no gain, sa0 0.132 ms either way — the loaders are not what the narrow modules wait for); pab_tune_tensor_core bit 5 = 32 selects two
 
 int g_tc_pair = 1;         // wide weight blocks: hi + lo plane in one 32-KB stage (pab_tune_tensor_core bit 4 = 16 clears it)
 
@@ -1026,7 +1026,7 @@ PAB_API void pab_tune_tensor_core(int enable) {
     g_tc_cluster = (enable & 4) != 0;
     g_tc_dynamic = (enable & 8) != 0;
     g_tc_pair = (enable & 16) == 0;
-    g_tc_nbuf = (enable & 32) ? 1 : 2;
+    g_tc_nbuf = (enable & 32) ? 2 : 1;
 }
 
 int pab_tc_sa(int kind, int b, int n, int m, int k, int nbr_stride, int c, const float *xyz, const float *feat, const int *center_idx,
