@@ -225,6 +225,9 @@ int pab_sa_layer_forward(int b, int n, int c, const float *x, const pab_layer_t 
  * uses) = tcgen05 tensor cores on bf16 hi/lo operand planes, three MMAs per product — the fp32 contract; 1 = tensor cores on
  * plain bf16 operands (BASELINE.json configs[2]); 0 = the fp32 SIMT kernels.  Shapes the tensor-core kernel does not take
  * (c not in {64, 128}, n < 64) run on the SIMT kernels whatever the precision. */
+/* Tuning hook: 1 (default) = levels with n <= 64 points run the whole layer (projections, attention, trans_conv, residual) as ONE
+ * kernel, one CTA per cloud, everything in shared memory; 0 = the five-launch path for every size. */
+void pab_tune_attention_small(int on);
 int pab_sa_layer_forward_p(int b, int n, int c, const float *x, const pab_layer_t *q_layer, const pab_layer_t *v_layer,
                            const pab_layer_t *trans_layer, float *out, void *workspace, int precision, pab_stream_t s);
 

@@ -162,9 +162,152 @@ attn_apply_kernel(int n, int C, const float *__restrict__ q, const float *__rest
     }
 }
 
+
+// ---- whole SA_Layer of a SMALL level in one kernel ------------------------------------------------------------------------
+// The deep PPT-Net levels have few points and many channels (64 x 256, 16 x 512): five launches of latency-bound kernels
+// (two projections, statistics, apply, trans_conv) cost 0.29 / 0.54 ms for 64 clouds.  Here one CTA owns one cloud and keeps
+// x, Q, V (N x C each) and the N x N energies in shared memory: Q = x Wq, V = x Wv + bv (thread = output channel, all N rows in
+// registers, weight rows streamed coalesced from L2), E = Q Q^T, row softmax, column renormalisation, U = P^T-weighted V,
+// out = x + relu((x - U / (1e-9 + colsum)) Wt + bt).  fp32 SIMT throughout.
+constexpr int AS_T = 256;
+constexpr int AS_MAXN = 64;
+
+template <int NR>   // rows held per thread in the projections (N <= NR)
+__device__ __forceinline__ void as_project(int n, int C, int ld, const float *__restrict__ xs, const float *__restrict__ wt,
+                                           const float *__restrict__ shift, float *__restrict__ dst, bool relu_residual,
+                                           const float *__restrict__ res) {
+    // dst[r][co] = sum_ci xs[r][ci] * wt[ci][co] + shift[co]   (optionally res + relu(.))
+    for (int co = threadIdx.x; co < C; co += AS_T) {
+        float acc[NR];
+        const float sh = shift ? __ldg(shift + co) : 0.f;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) acc[r] = sh;
+        for (int ci0 = 0; ci0 < C; ci0 += 8) {
+            float w[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) w[u] = __ldg(wt + (size_t)(ci0 + u) * C + co);      // eight weight rows in flight
+            // branch-free over all NR rows (rows >= n are zero and never stored): the NR accumulator chains are independent, so the
+            // compiler interleaves them; two broadcast 16-byte loads feed eight FMAs
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                const float4 a0 = *reinterpret_cast<const float4 *>(xs + r * ld + ci0);
+                const float4 a1 = *reinterpret_cast<const float4 *>(xs + r * ld + ci0 + 4);
+                float a = acc[r];
+                a = fmaf(a0.x, w[0], a); a = fmaf(a0.y, w[1], a); a = fmaf(a0.z, w[2], a); a = fmaf(a0.w, w[3], a);
+                a = fmaf(a1.x, w[4], a); a = fmaf(a1.y, w[5], a); a = fmaf(a1.z, w[6], a); a = fmaf(a1.w, w[7], a);
+                acc[r] = a;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < NR; ++r)
+            if (r < n) dst[r * ld + co] = relu_residual ? res[r * ld + co] + fmaxf(acc[r], 0.f) : acc[r];
+    }
+}
+
+template <int NR>
+__global__ void __launch_bounds__(AS_T, 1)
+attn_small_kernel(int n, int C, const float *__restrict__ x, const float *__restrict__ wq, const float *__restrict__ wv,
+                  const float *__restrict__ bv, const float *__restrict__ wtr, const float *__restrict__ btr, float *__restrict__ out) {
+    extern __shared__ __align__(16) float sm[];
+    const int ld = C + 4;                                   // row stride: rows land in different banks
+    float *xs = sm, *qs = xs + NR * ld, *vs = qs + NR * ld, *es = vs + NR * ld;      // es: [NR][NR + 4] energies / probabilities
+    float *csum = es + NR * (NR + 4);                       // [NR] column sums
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5, cloud = blockIdx.x;
+    x += (size_t)cloud * n * C; out += (size_t)cloud * n * C;
+    for (int e = t; e < 3 * NR * ld; e += AS_T) xs[e] = 0.f;              // x, Q, V: rows >= n stay zero
+    for (int e = t; e < NR * (NR + 4); e += AS_T) es[e] = 0.f;            // padding columns / rows read as zeros
+    __syncthreads();
+    for (int e = t; e < n * C; e += AS_T) xs[(e / C) * ld + (e % C)] = __ldg(x + e);
+    __syncthreads();
+    as_project<NR>(n, C, ld, xs, wq, nullptr, qs, false, nullptr);
+    as_project<NR>(n, C, ld, xs, wv, bv, vs, false, nullptr);
+    __syncthreads();
+    // energies E[i][j] = Q_i . Q_j
+    for (int e = t; e < n * n; e += AS_T) {
+        const int i = e / n, j = e - i * n;
+        const float4 *qi = reinterpret_cast<const float4 *>(qs + i * ld), *qj = reinterpret_cast<const float4 *>(qs + j * ld);
+        float a = 0.f;
+        for (int c4 = 0; c4 < C / 4; ++c4) {
+            const float4 u = qi[c4], w = qj[c4];
+            a = fmaf(u.x, w.x, a); a = fmaf(u.y, w.y, a); a = fmaf(u.z, w.z, a); a = fmaf(u.w, w.w, a);
+        }
+        es[i * (NR + 4) + j] = a;
+    }
+    __syncthreads();
+    // row softmax (a warp per row), then column sums
+    for (int i = warp; i < n; i += AS_T / 32) {
+        float m = -INFINITY;
+        for (int j = lane; j < n; j += 32) m = fmaxf(m, es[i * (NR + 4) + j]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float s = 0.f;
+        for (int j = lane; j < n; j += 32) { const float p = expf(es[i * (NR + 4) + j] - m); es[i * (NR + 4) + j] = p; s += p; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float inv = 1.f / s;
+        for (int j = lane; j < n; j += 32) es[i * (NR + 4) + j] *= inv;
+    }
+    __syncthreads();
+    for (int j = t; j < n; j += AS_T) {
+        float s = 0.f;
+        for (int i = 0; i < n; ++i) s += es[i * (NR + 4) + j];
+        csum[j] = 1.f / (1e-9f + s);
+    }
+    __syncthreads();
+    // d[j][c] = x[j][c] - (sum_i V[i][c] P[i][j]) / (1e-9 + colsum_j), written over Q (no longer needed)
+    for (int c = t; c < C; c += AS_T) {
+        float acc[NR];
+#pragma unroll
+        for (int j = 0; j < NR; ++j) acc[j] = 0.f;
+        for (int i = 0; i < n; ++i) {
+            const float v = vs[i * ld + c];
+            const float4 *pr = reinterpret_cast<const float4 *>(es + i * (NR + 4));     // columns >= n hold zeros
+#pragma unroll
+            for (int j4 = 0; j4 < NR / 4; ++j4) {
+                const float4 pp = pr[j4];
+                acc[4 * j4] = fmaf(v, pp.x, acc[4 * j4]); acc[4 * j4 + 1] = fmaf(v, pp.y, acc[4 * j4 + 1]);
+                acc[4 * j4 + 2] = fmaf(v, pp.z, acc[4 * j4 + 2]); acc[4 * j4 + 3] = fmaf(v, pp.w, acc[4 * j4 + 3]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NR; ++j)
+            if (j < n) qs[j * ld + c] = xs[j * ld + c] - acc[j] * csum[j];
+    }
+    __syncthreads();
+    // out = x + relu(d Wt + bt), staged in V's buffer, then stored coalesced
+    as_project<NR>(n, C, ld, qs, wtr, btr, vs, true, xs);
+    __syncthreads();
+    for (int e = t; e < n * C; e += AS_T) out[e] = vs[(e / C) * ld + (e % C)];
+}
+
+size_t as_smem(int nr, int C) { return sizeof(float) * ((size_t)3 * nr * (C + 4) + (size_t)nr * (nr + 4) + nr); }
+
+// returns 0 when the layer was handled, PAB_EINVAL when the shape is not eligible
+int launch_attn_small(int b, int n, int c, const float *x, const pab_layer_t *q, const pab_layer_t *v, const pab_layer_t *tr, float *out,
+                      cudaStream_t st) {
+    if (n > AS_MAXN || c % 8 || b > 65535) return PAB_EINVAL;
+    const int nr = n <= 16 ? 16 : (n <= 32 ? 32 : 64);
+    const size_t smem = as_smem(nr, c);
+    if (smem > 220 * 1024) return PAB_EINVAL;
+    // the point-wise layers carry (c_in_pad, c_out) fp32 weights with c_in_pad == c (c % 4 == 0)
+    if (q->c_in_pad != c || v->c_in_pad != c || tr->c_in_pad != c) return PAB_EINVAL;
+#define AS_LAUNCH(NR)                                                                                                        \
+    do {                                                                                                                     \
+        PAB_CUDA(cudaFuncSetAttribute(attn_small_kernel<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+        attn_small_kernel<NR><<<b, AS_T, smem, st>>>(n, c, x, q->wt, v->wt, v->shift, tr->wt, tr->shift, out);               \
+    } while (0)
+    if (nr == 16) AS_LAUNCH(16); else if (nr == 32) AS_LAUNCH(32); else AS_LAUNCH(64);
+#undef AS_LAUNCH
+    PAB_LAUNCH_CHECK();
+    return 0;
+}
+
 inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace
+
+int g_attn_small = 1;
+PAB_API void pab_tune_attention_small(int on) { g_attn_small = on; }
 
 PAB_API size_t pab_sa_layer_workspace_bytes(int b, int n, int c) {
     return al(sizeof(float) * (size_t)b * n * 2 * c) + al(sizeof(float) * (size_t)b * n * c) + 2 * al(sizeof(float) * (size_t)b * n);
@@ -182,6 +325,7 @@ PAB_API int pab_sa_layer_forward_p(int b, int n, int c, const float *x, const pa
         trans_layer->c_out != c) return PAB_EINVAL;
     if (b == 0) return 0;
     cudaStream_t st = (cudaStream_t)s;
+    if (g_attn_small && launch_attn_small(b, n, c, x, q_layer, v_layer, trans_layer, out, st) == 0) return 0;   // small deep levels
     char *w = (char *)workspace;
     float *qv = (float *)w; w += al(sizeof(float) * (size_t)b * n * 2 * c);
     float *d = (float *)w; w += al(sizeof(float) * (size_t)b * n * c);
