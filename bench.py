@@ -261,6 +261,67 @@ def pointnetvlad_cpu():
         return {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
 
 
+def stock_pptnet(dev, ppt, x):
+    """configs[2] denominator: the reference's pptnet.Network (unchanged Python) over the reference's kernels + cuDNN, same batch."""
+    try:
+        from oracle import refgpu, refpy
+        if not (refpy.available() and refgpu.available()):
+            return {"unavailable": "oracle/_ref not built"}
+        ref_net = refpy.reference_pptnet(ppt.state_dict(), dev, "stock")
+        saved = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        with torch.no_grad():
+            for _ in range(2):
+                ref_net(x)
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                ref_net(x)
+                torch.cuda.synchronize()
+                ts.append(time.perf_counter() - t0)
+        torch.backends.cudnn.allow_tf32 = saved
+        med = sorted(ts)[1]
+        del ref_net
+        torch.cuda.empty_cache()
+        return dict(ms_per_batch=med * 1e3, submaps_per_s=x.shape[0] / med, what="reference pptnet.Network + pointops.py over the reference's "
+                    "kernels built for sm_100 + cuDNN, fp32, batch %d" % x.shape[0])
+    except Exception as ex:
+        return {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
+
+
+def stock_train_step(dev, net, feed, anchors):
+    """configs[4] denominator: the same training step with the reference's own Network / pointops.py over the reference's kernels
+    (fp32 atomics backward, cuDNN BatchNorm); the loss assembly is this repo's restatement of run_model (the reference's is broken
+    as shipped) with this repo's chamfer kernels, so only the model forward/backward differs."""
+    try:
+        from oracle import refgpu, refpy
+        from patchaugnet_b200 import training
+        if not (refpy.available() and refgpu.available()):
+            return {"unavailable": "oracle/_ref not built"}
+        ref = refpy.use_backend("stock")
+        ref_net = ref.patch_aug_net.Network(param=ref.cfg_patchaugnet, use_a2a_recon=True, use_l2_norm=True)
+        ref_net.load_state_dict(net.state_dict())
+        ref_net = ref_net.to(dev).train()
+        step = training.TrainStep(ref_net, torch.optim.Adam(ref_net.parameters(), lr=5e-4), n_anchors=anchors)
+        for _ in range(3):
+            step(feed)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            step(feed)
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        med = sorted(ts)[1]
+        del ref_net, step
+        torch.cuda.empty_cache()
+        return dict(ms_per_step=med * 1e3, clouds_per_s=feed.shape[0] / med,
+                    what="reference patch_aug_net.Network (train mode) + pointops.py over the reference's kernels + cuDNN, same tuples")
+    except Exception as ex:
+        return {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
+
+
 def other_configs(dev, world, rank):
     """Sub-records for the BASELINE.json configurations that are not the bench line."""
     import torch.distributed as dist
@@ -292,6 +353,8 @@ def other_configs(dev, world, rank):
             ms, ms_stream = e0.elapsed_time(e1) / 5, e1.elapsed_time(e2) / len(seq)
             rec[mode] = dict(ms_per_batch=ms, submaps_per_s_per_gpu=64 / (ms * 1e-3), ms_per_batch_stream=ms_stream,
                              submaps_per_s_per_gpu_stream=64 / (ms_stream * 1e-3))
+        if rank == 0:
+            rec["stock_gpu"] = stock_pptnet(dev, ppt, xs[0])
         rec["what"] = ("PPT-Net eval, batch 64 x 4096, fused engine, one GPU; f32 = the reference's fp32 contract (bf16 hi/lo tensor-core "
                        "operands), bf16 = plain bf16 operands for FP modules / NetVLAD / attention (SA modules keep hi/lo); stream = "
                        "geometry of batch i+1 under the dense kernels of batch i")
@@ -379,6 +442,27 @@ def other_configs(dev, world, rank):
             torch.cuda.synchronize()
             rec["allreduce_alone_ms"] = a0.elapsed_time(a1) / 5
             rec["allreduce_share_of_step"] = rec["allreduce_alone_ms"] / ms
+        if world == 1:      # the same step replayed as one CUDA graph (single process): GPU-bound whatever the host does
+            try:
+                net_g = util.build_network(dev).train()
+                gstep = training.GraphedTrainStep(net_g, torch.optim.Adam(net_g.parameters(), lr=5e-4, capturable=True), n_anchors=anchors)
+                gstep(feed)
+                gstep(feed)
+                torch.cuda.synchronize()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                for _ in range(5):
+                    gloss, _t = gstep(feed)
+                g1.record()
+                torch.cuda.synchronize()
+                rec["cuda_graph"] = dict(ms_per_step=g0.elapsed_time(g1) / 5, clouds_per_s=anchors * training.CLOUDS_PER_ANCHOR / (g0.elapsed_time(g1) / 5 * 1e-3),
+                                         loss=float(gloss), what="training.GraphedTrainStep: forward + losses + backward + Adam captured once, replayed")
+                del net_g, gstep
+                torch.cuda.empty_cache()
+            except Exception as ex:
+                rec["cuda_graph"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
+        if rank == 0 and world == 1:
+            rec["stock_gpu"] = stock_train_step(dev, net, feed, anchors)
         out["cfg5_train_step"] = rec
         del net, model, opt, step, feed
         torch.cuda.empty_cache()

@@ -110,14 +110,22 @@ class Network(nn.Module):
             related = list(related)
             centers, origin_out, feats, recon_out = [], [], [], []
             origin_patches = pointops.grouping(xyz.transpose(1, 2).contiguous(), sample_idx[0])   # B x 3 x M x K
-            for ci in related:
-                # the reference builds a one-element index tensor on the host and copies it to the device for every related
-                # cloud (patch_aug_net.py:84): slicing selects the same rows without the per-cloud host-to-device copy
-                f = fp_features[1][ci:ci + 1].squeeze().transpose(1, 0)                              # M x 256
+            # The reference selects every related cloud with its own one-element index tensor (host -> device copy, index_select,
+            # and in backward a zero-filled full-batch gradient per cloud: patch_aug_net.py:83-98).  One index_select of all
+            # related clouds + unbind gives the same per-cloud tensors with one gather forward and one stack backward.
+            key = (tuple(related), out.device)
+            if getattr(self, "_rel_key", None) != key:                          # cached: no host-to-device copy per step
+                self._rel_key, self._rel_idx = key, torch.as_tensor(related, dtype=torch.long, device=out.device)
+            rel = self._rel_idx
+            f_all = torch.index_select(fp_features[1], 0, rel)                  # R x 256 x M x 1
+            p_all = torch.index_select(origin_patches, 0, rel)                  # R x 3 x M x K
+            c_all = torch.index_select(center_idx[0], 0, rel)                   # R x M
+            for f_r, p_r, c_r in zip(f_all.unbind(0), p_all.unbind(0), c_all.unbind(0)):
+                f = f_r.squeeze().transpose(1, 0)                               # M x 256
                 if self.use_l2_norm:
                     f = F.normalize(f)
-                patches = origin_patches[ci:ci + 1].squeeze().transpose(2, 0).transpose(1, 0)
-                centers.append(center_idx[0][ci:ci + 1])
+                patches = p_r.transpose(2, 0).transpose(1, 0)                   # M x K x 3
+                centers.append(c_r.unsqueeze(0))
                 origin_out.append(patches)
                 feats.append(f)
                 if self.use_a2a_recon:

@@ -412,8 +412,17 @@ class QueryAndGroup_Edge(nn.Module):
         if self.knn_dilation > 1:
             # the first nsample of a sorted (dilation*nsample)-NN list are the sorted nsample-NN
             nearest = knnquery(self.nsample, xyz, new_xyz)
+            if torch.cuda.is_current_stream_capturing():
+                # CUDA-graph capture (training.GraphedTrainStep): a host-to-device copy of a fresh permutation cannot be
+                # captured, so the neighbour ORDER is the one drawn at the last eager call and stays frozen in the graph —
+                # everything downstream (max over K, chamfer) is order-invariant
+                perm_dev = getattr(self, "_perm_dev", None)
+                if perm_dev is None or perm_dev.device != nearest.device:
+                    raise RuntimeError("QueryAndGroup_Edge: run one eager forward on this device before capturing a CUDA graph")
+                return nearest[:, :, perm_dev].contiguous()
             perm = torch.randperm(self.nsample)
-            return nearest[:, :, perm.to(nearest.device)].contiguous()
+            self._perm_dev = perm.to(nearest.device)
+            return nearest[:, :, self._perm_dev].contiguous()
         return knnquery(self.nsample, xyz, new_xyz)
 
     def forward(self, xyz, new_xyz=None, features=None, center_features=None, idx=None):

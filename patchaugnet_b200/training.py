@@ -75,6 +75,51 @@ class TrainStep:
         return loss.detach(), {k: v.detach() for k, v in terms.items()}
 
 
+class GraphedTrainStep(TrainStep):
+    """``TrainStep`` captured ONCE into a CUDA graph (forward, losses, backward, optimiser step) and replayed: the ~1500 kernel
+    launches and the Python of a step cost the host ~55 ms on an idle box and several times that on a contended one, a graph
+    launch costs microseconds, so the step becomes GPU-bound whatever the host does.  Single process (no DDP).  The optimiser
+    must be created with ``capturable=True``.  Frozen in the graph: the tuple layout (``nn_dict``), the neighbour ORDER drawn by
+    the groupers' ``torch.randperm`` at the last eager step (order-invariant downstream), the learning rate."""
+
+    def __init__(self, model, optimizer, n_anchors, use_patch_recon=True, warmup=3):
+        super().__init__(model, optimizer, n_anchors, use_patch_recon)
+        if not all(g.get("capturable", False) for g in optimizer.param_groups):
+            raise ValueError("GraphedTrainStep needs an optimizer created with capturable=True")
+        self._graph, self._feed, self._out, self._warmup = None, None, None, warmup
+
+    def _body(self):
+        x = self._feed.detach().requires_grad_(True)
+        out = self.model(x, self.nn_dict, return_feat=False)
+        desc, recon = out if isinstance(out, tuple) else (out, None)
+        loss, terms = assemble_loss(desc, recon, self.n_anchors)
+        loss.backward()
+        self.optimizer.step()
+        return loss.detach(), {k: v.detach() for k, v in terms.items()}
+
+    def __call__(self, feed):
+        if self._graph is None:
+            self._feed = feed.detach().clone()
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream(device=feed.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):                       # eager warm-up on a side stream (allocator, cuDNN plans, Adam state)
+                for _ in range(self._warmup):
+                    self.optimizer.zero_grad(set_to_none=True)
+                    self._body()
+            cur.wait_stream(side)
+            torch.cuda.synchronize(feed.device)
+            self._graph = torch.cuda.CUDAGraph()
+            self.optimizer.zero_grad(set_to_none=True)
+            with torch.cuda.graph(self._graph):
+                self._out = self._body()
+            self._graph.replay()                                # capture records, it does not execute: this call's own step
+        else:
+            self._feed.copy_(feed)
+            self._graph.replay()
+        return self._out
+
+
 def build_ddp(model, device):
     """Wrap ``model`` for data-parallel training when a process group is initialised (one process per GPU)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
