@@ -544,6 +544,8 @@ def main():
             torch.cuda.synchronize()
 
     # ---- warm-up + per-stage profile (eager, events around every stage) -----------------------------------------
+    if os.environ.get("PAB_SN"):                       # experiment hook: "enable,ctas_per_sm" of pab_tune_sa_narrow
+        lib.pab_tune_sa_narrow(*[int(v) for v in os.environ["PAB_SN"].split(",")])
     eng.enable_stage_timing()
     with torch.no_grad():
         for i in range(W):
@@ -551,7 +553,7 @@ def main():
     torch.cuda.synchronize()
     st = eng.stage_times_ms()
     eng.disable_stage_timing()
-    stage_ms = {k: float(np.mean(v[1:] if len(v) > 1 else v)) for k, v in st.items()}
+    stage_ms = {k: float(np.median(v[1:] if len(v) > 1 else v)) for k, v in st.items()}   # median: one slow launch must not pick the dominant kernel
     work = eng.stage_work(B, NPTS)
 
     def occupancy(stage):

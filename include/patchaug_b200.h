@@ -228,6 +228,14 @@ int pab_sa_layer_forward(int b, int n, int c, const float *x, const pab_layer_t 
 /* Tuning hook: 1 (default) = levels with n <= 64 points run the whole layer (projections, attention, trans_conv, residual) as ONE
  * kernel, one CTA per cloud, everything in shared memory; 0 = the five-launch path for every size. */
 void pab_tune_attention_small(int on);
+/* Tuning hook: enable = 1 (default): a set-abstraction module with a tiny input (<= 8 channels) and layers <= 64 wide (SA0 of
+ * both networks) runs on sa_narrow_tc.cu — 128-thread CTAs, ctas_per_sm resident per SM (1..3; 0 = default: 3, or 2 while pab_tune_tc_max_ctas reserves SMs for another stream), weights resident in
+ * shared memory; 0: the warp-specialised one-CTA-per-SM kernel of mlp_tc.cu takes it.  Results are bit-identical. */
+void pab_tune_sa_narrow(int enable, int ctas_per_sm);
+/* Debugging aid: device buffer of 16 x 8 int64 receiving clock64 stamps of CTA 0's first 16 steps (NULL: off). */
+void pab_tune_sa_narrow_trace(void *device_buffer);
+/* Debugging aid (results become wrong): 1 = no gathers, 2 = pre-layer without its multiply-adds. */
+void pab_tune_sa_narrow_dbg(int flags);
 int pab_sa_layer_forward_p(int b, int n, int c, const float *x, const pab_layer_t *q_layer, const pab_layer_t *v_layer,
                            const pab_layer_t *trans_layer, float *out, void *workspace, int precision, pab_stream_t s);
 

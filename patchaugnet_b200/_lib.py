@@ -38,6 +38,9 @@ SIGNATURES = {
     "pab_tune_fps_clouds_per_cta": (None, [_I]),
     "pab_tune_fps_pruned": (None, [_I]),
     "pab_tune_attention_small": (None, [_I]),
+    "pab_tune_sa_narrow": (None, [_I, _I]),
+    "pab_tune_sa_narrow_trace": (None, [_P]),
+    "pab_tune_sa_narrow_dbg": (None, [_I]),
     "pab_tune_fps_exclusive": (None, [_I]),
     "pab_bn_train_workspace_bytes": (C.c_size_t, [_I]),
     "pab_bn_relu_train_forward": (_I, [_I, _I, C.c_long, _P, _P, _P, C.c_float, C.c_float, _P, _P, _P, _P, _P, _P, _P]),

@@ -12,6 +12,9 @@
 
 // tensor-core path (mlp_tc.cu)
 int pab_tc_eligible(const pab_layer_t *layers, int n_layers, int k_group, int allow_pre);
+int pab_sa_narrow_eligible(const pab_layer_t *layers, int n_layers, int k);
+int pab_sa_narrow_launch(int b, int n, int m, int k, int nbr_stride, int c, const float *xyz, const float *feat, const int *center_idx,
+                         const int *nbr_idx, const pab_layer_t *layers, int n_layers, float *out, cudaStream_t st);
 int pab_tc_sa(int kind, int b, int n, int m, int k, int nbr_stride, int c, const float *xyz, const float *feat, const int *center_idx,
               const int *nbr_idx, const pab_layer_t *layers, int n_layers, float *out, cudaStream_t st);
 int pab_tc_fp(int b, int n, int m, int c_known, int c_skip, const float *known_feat, const float *skip_feat, const int *idx,
@@ -228,6 +231,8 @@ PAB_API int pab_sa_module_forward(int b, int n, int m, int k, int nbr_stride, in
     if (layers[0].c_in != c + 3) return PAB_EINVAL;
     if (!new_xyz) {
         const int kind = pab_tc_eligible(layers, n_layers, k, c <= 5);
+        if (kind == 2 && pab_sa_narrow_eligible(layers, n_layers, k))       // tiny input, layers <= 64 wide: four small CTAs per SM
+            return pab_sa_narrow_launch(b, n, m, k, nbr_stride, c, xyz, feat, center_idx, nbr_idx, layers, n_layers, out, (cudaStream_t)s);
         if ((kind == 1 && c % 8 == 0 && layers[0].tc_k == c && layers[0].tc_k0 == 3) || kind == 2)
             return pab_tc_sa(kind, b, n, m, k, nbr_stride, c, xyz, feat, center_idx, nbr_idx, layers, n_layers, out, (cudaStream_t)s);
     }

@@ -165,3 +165,37 @@ def test_netvlad_tensor_core_matches_simt_and_fp64(n, K):
     assert (out_s.double() - ref).abs().max().item() < 2e-5
     assert torch.isfinite(out_t).all()
     assert (out_t.double() - ref).abs().max().item() < 5e-5
+
+
+@pytest.mark.parametrize("spec,c,k,n,m,B", [([6, 32, 32, 64], 3, 20, 4096, 1024, 32), ([6, 32, 64], 3, 9, 500, 77, 4),
+                                             ([6, 64, 32, 64], 3, 32, 700, 129, 3), ([3, 32, 32], 0, 128, 256, 5, 2),
+                                             ([8, 32, 64, 64, 32], 5, 1, 300, 300, 2), ([6, 32, 32, 64], 3, 20, 64, 1, 1)])
+def test_sa_narrow_kernel_bit_identical_to_warp_specialised_kernel(spec, c, k, n, m, B):
+    """sa_narrow_tc.cu (three 128-thread CTAs per SM, weights resident, running max in registers, items from a self-resetting counter) against mlp_tc.cu's
+    pre-layer mode: same arithmetic, so the outputs must be bit-identical — for every residency setting and on repeated launches
+    (the counter has to come back to zero)."""
+    g = torch.Generator(device="cpu").manual_seed(n * 7 + k)
+    mlp = _mlp(spec, n + 3)
+    layers = _Layers(mlp, DEV, extra_first=3)
+    assert layers.tensor_core
+    xyz = (torch.rand(B, n, 3, generator=g) * 2 - 1).to(DEV)
+    feat = torch.randn(B, n, max(c, 1), generator=g).to(DEV)
+    cidx = torch.stack([torch.randperm(n, generator=g)[:m] for _ in range(B)]).int().to(DEV)
+    nbr = torch.randint(0, n, (B, m, k), generator=g).int().to(DEV)
+
+    def run(enable, per_sm):
+        out = torch.full((B, m, layers.c_out), float("nan"), device=DEV)
+        L.lib().pab_tune_sa_narrow(enable, per_sm)
+        try:
+            L.check(L.lib().pab_sa_module_forward(B, n, m, k, k, c, L.ptr(xyz), L.ptr(feat), L.ptr(cidx), L.ptr(nbr), layers.arr,
+                                                  layers.n, L.ptr(out), L.ptr(None), L.stream_ptr()), "sa")
+            torch.cuda.synchronize()
+        finally:
+            L.lib().pab_tune_sa_narrow(1, 0)
+        return out
+
+    want = run(0, 3)
+    assert torch.isfinite(want).all()
+    for per_sm in (3, 3, 1, 2, 3):
+        got = run(1, per_sm)
+        assert torch.equal(got, want), (per_sm, (got - want).abs().max().item())
