@@ -490,6 +490,7 @@ def main():
     ap.add_argument("--fp-order", type=int, default=1, help="FP modules walk their points in Morton order (0 = index order)")
     ap.add_argument("--fps-threads", type=int, default=0, help="force the FPS CTA size (0 = automatic)")
     ap.add_argument("--fps-cpc", type=int, default=1, help="clouds per FPS CTA in stream mode (1..3)")
+    ap.add_argument("--fps-stream", type=int, default=1, help="stream mode: first-level FPS on a stream of its own (three-stage pipeline)")
     ap.add_argument("--fps-pruned", type=int, default=0, help="1 = pruned FPS sampler (exact, but slower at these sizes)")
     ap.add_argument("--prio", default="0,0", help="CUDA stream priorities geometry,dense (lower = higher priority)")
     ap.add_argument("--graph", type=int, default=None, help="deprecated alias: 1 -> --mode graph, 0 -> --mode eager")
@@ -525,6 +526,7 @@ def main():
     L.lib().pab_tune_fps_pruned(args.fps_pruned)
     eng.dense_streams = max(1, min(3, args.dense_streams))
     eng.stream_graphs = bool(args.stream_graphs)
+    eng.fps_stream = bool(args.fps_stream)
     eng.fp_row_order = bool(args.fp_order)
     eng.stream_priorities = tuple(int(v) for v in args.prio.split(","))
     lib = L.lib()

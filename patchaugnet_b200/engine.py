@@ -121,6 +121,7 @@ class FusedPatchAugNet:
         self.fp_row_order = True        # FP modules walk their points in the Morton order of the level's spatial index
         self.dense_streams = 2          # dense kernels of consecutive batches alternate between two streams
         self.stream_priorities = (0, 0)
+        self.fps_stream = True          # forward_stream: the first level's FPS on a stream of its own (three-stage pipeline, three slots)
         self.stream_graphs = True       # forward_stream: geometry / dense launch sequences replayed as CUDA graphs (2 launches per batch)
         self._sgraphs = {}
         self.reserve_fps_sms = True     # forward_stream: persistent tensor-core kernels leave the FPS CTAs' SMs alone
@@ -225,19 +226,24 @@ class FusedPatchAugNet:
                 L.check(rc_fn(), stage)
         return run
 
-    def _launch_geo(self, xyz0, ws, first_knn_event=None):
+    def _launch_geo(self, xyz0, ws, first_knn_event=None, part=None):
         """Geometry of every level — FPS, centre gather, kNN, 3-NN weights.  Depends on xyz only, never on features,
-        so it can run ahead of (and concurrently with) the dense part on another stream."""
+        so it can run ahead of (and concurrently with) the dense part on another stream.
+        part: None = everything; "fps0" = only the first level's sampler (one SM per cloud for 0.4 ms: forward_stream gives it
+        a stream of its own); "rest" = everything after it."""
         lib, st, p, run = L.lib(), L.stream_ptr(), L.ptr, self._runner()
         B = xyz0.shape[0]
         xyz = xyz0
         for i, (sa, lv) in enumerate(zip(self.sa, ws["levels"])):
             n, m, k = lv["n"], lv["m"], sa["k"]
-            temp = None                      # register-resident FPS initialises its own 1e10 distances
-            if n > 8192:                     # large-cloud fallback keeps them in global memory like the reference
-                temp = lv["temp"]
-                temp.fill_(1e10)
-            run(f"fps{i}", lambda: lib.pab_furthestsampling(B, n, m, p(xyz), p(temp), p(lv["cidx"]), st))
+            if not (part == "rest" and i == 0):
+                temp = None                      # register-resident FPS initialises its own 1e10 distances
+                if n > 8192:                     # large-cloud fallback keeps them in global memory like the reference
+                    temp = lv["temp"]
+                    temp.fill_(1e10)
+                run(f"fps{i}", lambda: lib.pab_furthestsampling(B, n, m, p(xyz), p(temp), p(lv["cidx"]), st))
+            if part == "fps0":
+                return
             run(f"gather{i}", lambda: lib.pab_gather_rows(B, n, m, 3, p(xyz), p(lv["cidx"]), p(lv["new_xyz"]), st))
             if lv["index"] is not None:
                 run(f"index{i}", lambda: lib.pab_knn_build_index(B, n, p(xyz), p(lv["index"]), st))
@@ -351,10 +357,20 @@ class FusedPatchAugNet:
             self._streams = (torch.cuda.Stream(device=self.device, priority=pg),) + tuple(
                 torch.cuda.Stream(device=self.device, priority=pd) for _ in range(3))
         s_geo, dense_streams = self._streams[0], self._streams[1:1 + self.dense_streams]
+        # Three-stage pipeline: the first level's FPS (a serial 1023-step chain on B SMs, 0.41 of the 0.76 ms geometry chain of a
+        # batch) runs on its own stream, so FPS of batch i+2, the remaining geometry of batch i+1 and the dense kernels of batch i
+        # overlap; with the whole geometry on one stream its chain was the period of the pipeline.
+        s_fps = None
+        if self.fps_stream:
+            if getattr(self, "_fps_cuda_stream", None) is None:
+                self._fps_cuda_stream = torch.cuda.Stream(device=self.device, priority=self.stream_priorities[0])
+            s_fps = self._fps_cuda_stream
+            s_fps.wait_stream(cur)
+        n_slots = 3 if s_fps is not None else 2
         s_geo.wait_stream(cur)
         for sd in dense_streams:
             sd.wait_stream(cur)
-        slots = [self._workspace(B, N, slot) for slot in (0, 1)]
+        slots = [self._workspace(B, N, slot) for slot in range(n_slots)]
         # FPS holds one SM per cloud for a third of the step.  A persistent tensor-core kernel launched with one CTA per SM
         # would leave B of its CTAs waiting for those SMs and then run their static share of the tiles alone at the end
         # (measured: 28.3 k -> 31.2 k submaps/s at B = 32 with the cap; 120 instead of 116 CTAs is already slower than no cap).
@@ -363,14 +379,15 @@ class FusedPatchAugNet:
             L.lib().pab_tune_fps_clouds_per_cta(self.fps_clouds_per_cta)
             cpc = max(1, L.lib().pab_fps_clouds_per_sm(N))          # what the sampler will really pack for this cloud size
             L.lib().pab_tune_tc_max_ctas(n_sm - (B + cpc - 1) // cpc if 0 < B <= n_sm // 2 else 0)
-        geo_done = [None, None]
-        dense_done = [None, None]
-        # The 30 launches of a batch are replayed as TWO CUDA graphs (geometry, dense) per workspace slot: the host then issues
-        # a copy + two graph launches + a few event operations per batch instead of ~30 ctypes calls, so the pipeline stays
+        fps_done = [None] * n_slots
+        geo_done = [None] * n_slots
+        dense_done = [None] * n_slots
+        # The 30 launches of a batch are replayed as CUDA graphs (FPS, geometry, dense) per workspace slot: the host then issues
+        # a copy + the graph launches + a few event operations per batch instead of ~30 ctypes calls, so the pipeline stays
         # GPU-bound when the host cores are contended (8 ranks on one box) — measured host time per batch 0.57 ms -> 0.1 ms.
         graphs = None
         if self.stream_graphs and self.fused_tail and self._events is None and len(batches) >= 4:
-            graphs = self._capture_stream_graphs(B, N, slots)
+            graphs = self._capture_stream_graphs(B, N, slots, s_fps is not None)
         self.last_stream_used_graphs = graphs is not None
         for i, x in enumerate(batches):
             L.require_cuda(x)
@@ -378,18 +395,30 @@ class FusedPatchAugNet:
             for sa in self.sa:                # keep the CPU RNG in lock-step with the reference (see forward)
                 if sa["dilation"] > 1:
                     torch.randperm(sa["k"])
-            slot = i & 1
+            slot = i % n_slots
             ws = slots[slot]
-            with torch.cuda.stream(s_geo):
+            with torch.cuda.stream(s_fps if s_fps is not None else s_geo):
+                first = torch.cuda.current_stream()
                 if ready_events is not None and ready_events[i] is not None:
-                    s_geo.wait_event(ready_events[i])
+                    first.wait_event(ready_events[i])
                 if dense_done[slot] is not None:
-                    s_geo.wait_event(dense_done[slot])          # workspace (and the slot's static input) free again
+                    first.wait_event(dense_done[slot])          # workspace (and the slot's static input) free again
                 if graphs is not None:
                     graphs[slot]["x"].copy_(xyz0, non_blocking=True)
+                if s_fps is not None:
+                    if graphs is not None:
+                        graphs[slot]["fps"].replay()
+                    else:
+                        self._launch_geo(xyz0, ws, part="fps0")
+                    fps_done[slot] = torch.cuda.Event()
+                    fps_done[slot].record()
+            with torch.cuda.stream(s_geo):
+                if s_fps is not None:
+                    s_geo.wait_event(fps_done[slot])
+                if graphs is not None:
                     graphs[slot]["geo"].replay()
                 else:
-                    self._launch_geo(xyz0, ws)
+                    self._launch_geo(xyz0, ws, part="rest" if s_fps is not None else None)
                 geo_done[slot] = torch.cuda.Event()
                 geo_done[slot].record()
             s_dense = dense_streams[i % len(dense_streams)]   # alternate: the tail of one batch's kernels overlaps the next's
@@ -404,6 +433,10 @@ class FusedPatchAugNet:
                 dense_done[slot].record()
             xyz0.record_stream(s_geo)
             xyz0.record_stream(s_dense)
+            if s_fps is not None:
+                xyz0.record_stream(s_fps)
+        if s_fps is not None:
+            cur.wait_stream(s_fps)
         for sd in dense_streams:
             cur.wait_stream(sd)
         cur.wait_stream(s_geo)
@@ -412,11 +445,11 @@ class FusedPatchAugNet:
             L.lib().pab_tune_fps_clouds_per_cta(1)
         return out
 
-    def _capture_stream_graphs(self, B, N, slots):
-        """Geometry and dense launch sequences of both workspace slots as CUDA graphs over a static per-slot input buffer.
-        Captured with the current tuning state (CTA cap of the persistent kernels, FPS packing): the key holds it."""
+    def _capture_stream_graphs(self, B, N, slots, split_fps=False):
+        """FPS (optional) / geometry / dense launch sequences of every workspace slot as CUDA graphs over a static per-slot input
+        buffer.  Captured with the current tuning state (CTA cap of the persistent kernels, FPS packing): the key holds it."""
         key = (B, N, L.lib().pab_fps_clouds_per_sm(N), self.reserve_fps_sms, self.fp_row_order, self.vlad_tensor_core,
-               torch.cuda.get_device_properties(self.device).multi_processor_count)
+               torch.cuda.get_device_properties(self.device).multi_processor_count, len(slots), split_fps)
         got = self._sgraphs.get(key)
         if got is not None:
             return got
@@ -431,12 +464,16 @@ class FusedPatchAugNet:
                 self._launch_dense(x, ws)
             cur.wait_stream(side)
             torch.cuda.synchronize(self.device)
-            g_geo, g_dense = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            g_fps, g_geo, g_dense = None, torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            if split_fps:
+                g_fps = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_fps):
+                    self._launch_geo(x, ws, part="fps0")
             with torch.cuda.graph(g_geo):
-                self._launch_geo(x, ws)
+                self._launch_geo(x, ws, part="rest" if split_fps else None)
             with torch.cuda.graph(g_dense):
                 self._launch_dense(x, ws)
-            got.append(dict(x=x, geo=g_geo, dense=g_dense))
+            got.append(dict(x=x, fps=g_fps, geo=g_geo, dense=g_dense))
         self._sgraphs[key] = got
         return got
 
