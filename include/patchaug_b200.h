@@ -259,6 +259,19 @@ int pab_netvlad_forward_tc(int b, int n, int c, int K, const float *x, const voi
 size_t pab_afa_workspace_bytes(int b, int c, int K, int c_out);
 int pab_afa_forward(int b, int c, int K, int c_out, const float *v, const float *w_att_t, const float *fc_wt,
                     const float *fc_scale, const float *fc_shift, int l2_norm, float *desc, void *workspace, pab_stream_t s);
+/* The same head with its two products (attention logits, fc) on the tcgen05 tensor cores: bf16 hi/lo operand planes, three MMAs
+ * per product, fp32 accumulation — the fp32 contract of the other tensor-core kernels.  watt_hi / watt_lo: the attention conv
+ * weight (c_out' = c rows, c inputs contiguous) split as W = hi + lo in bf16; wfc_hi / wfc_lo: the fc weight (c_out rows, c*K
+ * inputs contiguous, f = channel * K + cluster) split the same way.  pab_afa_tc_supported: 1 for the shapes the kernels take
+ * (c in {64,128,192,256}, c*K % 64 == 0, c_out % 32 == 0, c_out <= 256) — otherwise use pab_afa_forward.
+ * workspace >= pab_afa_tc_workspace_bytes. */
+int pab_afa_tc_supported(int c, int K, int c_out);
+size_t pab_afa_tc_workspace_bytes(int b, int c, int K, int c_out);
+int pab_afa_forward_tc(int b, int c, int K, int c_out, const float *v, const void *watt_hi, const void *watt_lo,
+                       const void *wfc_hi, const void *wfc_lo, const float *fc_scale, const float *fc_shift, int l2_norm,
+                       float *desc, void *workspace, pab_stream_t s);
+/* Tuning hook: 0 makes pab_afa_tc_supported return 0 (the engine then calls pab_afa_forward). */
+void pab_tune_afa_tc(int on);
 
 /* Dense head of the PPT-Net / PointNetVLAD style (pptnet_origin/models/loupe.py:99-136): desc = [normalize]( x * sigmoid(
  * (x G) * gate_scale + gate_shift) ),  x = (fc_wt^T v) * fc_scale + fc_shift.  v (b, f) row-major (the flattened VLAD);

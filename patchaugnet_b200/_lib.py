@@ -98,6 +98,10 @@ SIGNATURES = {
     "pab_prepare_clouds": (_I, [_I, _I, _P, _I, C.POINTER(C.c_double), _I, _I, _P, _P, _P]),
     "pab_patch_triplets": (_I, [_I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, C.c_ulonglong, _I, _P, _P, _P, _P, _P]),
     "pab_afa_forward": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P]),
+    "pab_afa_tc_supported": (_I, [_I, _I, _I]),
+    "pab_afa_tc_workspace_bytes": (C.c_size_t, [_I, _I, _I, _I]),
+    "pab_afa_forward_tc": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P]),
+    "pab_tune_afa_tc": (None, [_I]),
 }
 
 

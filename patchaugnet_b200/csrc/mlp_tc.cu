@@ -58,6 +58,7 @@ struct alignas(64) TcArgs {
                                                // MMAs of tile i still read theirs (narrow modules, where the region is small)
     int planes;                                // 2: bf16 hi/lo split, 3 MMAs per product (fp32 contract); 1: plain bf16 operands, 1 MMA
     int csize, iters;                          // CTAs per cluster sharing the weight stream (1 or 2); tile-loop trips (equal for all CTAs)
+    int serial_epi;                            // experiment: the epilogue of a split pass waits for BOTH n-blocks (no MMA / epilogue overlap)
     int dynamic;                               // 1: CTAs draw tiles from *counter (atomic) instead of the static blockIdx + i*grid sequence
     unsigned int *counter;                     // zeroed by the host before the launch
     int coff[MAX_LAYERS];                      // offset of each layer's shift vector in the smem constant table
@@ -115,6 +116,40 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
         ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
           "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
+// The MMAs of one 64-channel chunk against one weight plane, as straight-line code: operand source (shared memory / tensor
+// memory), one or two operand planes and "all four k-steps" are compile-time, so nothing but the tcgen05.mma and an address
+// add is left per MMA.  With those three decided by run-time branches inside the k-step loop every MMA sat behind uniform
+// branches and a reconvergence pair, and the issuing thread — not the tensor pipe — set the pace of the 128-column MMAs.
+// Order per chunk as before: [hi(A) hi(W), lo(A) hi(W)] per k-step.
+template <bool FROM_SMEM, bool TWO, bool FULL>
+__device__ __forceinline__ void issue_hi_plane(uint32_t leader, uint32_t d, uint32_t ah, uint32_t al, uint32_t sb, uint32_t idesc,
+                                               uint32_t acc0, int kn) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        if (FULL || ks < kn) {
+            const uint32_t acc = ks == 0 ? acc0 : 1u;
+            if (FROM_SMEM) {
+                umma_f16_if(leader, d, ah + 2 * ks, UMMA_DESC_HI, sb + 2 * ks, UMMA_DESC_HI, idesc, acc);
+                if (TWO) umma_f16_if(leader, d, al + 2 * ks, UMMA_DESC_HI, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
+            } else {
+                umma_f16_ts_if(leader, d, ah + 8 * ks, sb + 2 * ks, UMMA_DESC_HI, idesc, acc);
+                if (TWO) umma_f16_ts_if(leader, d, al + 8 * ks, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
+            }
+        }
+    }
+}
+// hi(A) lo(W) over the chunk's k-steps
+template <bool FROM_SMEM, bool FULL>
+__device__ __forceinline__ void issue_lo_plane(uint32_t leader, uint32_t d, uint32_t ah, uint32_t sb, uint32_t idesc, int kn) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        if (FULL || ks < kn) {
+            if (FROM_SMEM) umma_f16_if(leader, d, ah + 2 * ks, UMMA_DESC_HI, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
+            else umma_f16_ts_if(leader, d, ah + 8 * ks, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_constant__ TcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *a1 = smem;                                            // layer-0 operand, hi plane
@@ -292,17 +327,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                         // hi weight plane: hi(A) * hi(W) + lo(A) * hi(W)
                         mbar_wait(full + s, ph);
                         uint32_t sb = st_lo + s * st_step;
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            if (ks < kn) {
-                                if (from_smem) {
-                                    umma_f16_if(leader, d, a1_lo + aoff + ka + 2 * ks, UMMA_DESC_HI, sb + 2 * ks, UMMA_DESC_HI, idesc, (kc | ks) != 0);
-                                    if (two) umma_f16_if(leader, d, a2_lo + aoff + ka + 2 * ks, UMMA_DESC_HI, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
-                                } else {
-                                    umma_f16_ts_if(leader, d, tmem + AH_COL + ta + ks * 8, sb + 2 * ks, UMMA_DESC_HI, idesc, (kc | ks) != 0);
-                                    if (two) umma_f16_ts_if(leader, d, tmem + AL_COL + ta + ks * 8, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
-                                }
-                            }
+                        const uint32_t ah = from_smem ? a1_lo + aoff + ka : tmem + AH_COL + ta;
+                        const uint32_t al = from_smem ? a2_lo + aoff + ka : tmem + AL_COL + ta;
+                        const uint32_t acc0 = kc != 0;
+                        if (kn == 4) {
+                            if (from_smem) { if (two) issue_hi_plane<true, true, true>(leader, d, ah, al, sb, idesc, acc0, 4);
+                                             else issue_hi_plane<true, false, true>(leader, d, ah, al, sb, idesc, acc0, 4); }
+                            else           { if (two) issue_hi_plane<false, true, true>(leader, d, ah, al, sb, idesc, acc0, 4);
+                                             else issue_hi_plane<false, false, true>(leader, d, ah, al, sb, idesc, acc0, 4); }
+                        } else {
+                            if (from_smem) { if (two) issue_hi_plane<true, true, false>(leader, d, ah, al, sb, idesc, acc0, kn);
+                                             else issue_hi_plane<true, false, false>(leader, d, ah, al, sb, idesc, acc0, kn); }
+                            else           { if (two) issue_hi_plane<false, true, false>(leader, d, ah, al, sb, idesc, acc0, kn);
+                                             else issue_hi_plane<false, false, false>(leader, d, ah, al, sb, idesc, acc0, kn); }
                         }
                         if (two) {
                         if (nbr > 64 && !a.pair) {               // wide block, separate stages: the lo plane sits in the next slot
@@ -315,12 +352,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                             sb += (uint32_t)nbr * 8;
                         }
                         // lo weight plane: hi(A) * lo(W)
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            if (ks < kn) {
-                                if (from_smem) umma_f16_if(leader, d, a1_lo + aoff + ka + 2 * ks, UMMA_DESC_HI, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
-                                else umma_f16_ts_if(leader, d, tmem + AH_COL + ta + ks * 8, sb + 2 * ks, UMMA_DESC_HI, idesc, 1);
-                            }
+                        if (kn == 4) {
+                            if (from_smem) issue_lo_plane<true, true>(leader, d, ah, sb, idesc, 4);
+                            else issue_lo_plane<false, true>(leader, d, ah, sb, idesc, 4);
+                        } else {
+                            if (from_smem) issue_lo_plane<true, false>(leader, d, ah, sb, idesc, kn);
+                            else issue_lo_plane<false, false>(leader, d, ah, sb, idesc, kn);
                         }
                         }
                         if (a.csize == 1) umma_commit_if(leader, empty + s);
@@ -440,7 +477,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                     for (int seg = 0; seg < nseg; ++seg) {
                     const int segbase = split ? seg * NBLK_MAX : 0;
                     mbar_wait(seg == 0 ? d_ready : d_ready1, pcount & 1);
-                    if (!split) mbar_wait(d_ready1, pcount & 1);
+                    if (!split || a.serial_epi) mbar_wait(d_ready1, pcount & 1);
                     tc_fence_after();
                     if (ewarp == 0) TC_TRACE(it, l, (split && seg == 0) ? 7 : 2);
                     for (int cb = 0; cb < per; cb += 32) {
@@ -873,6 +910,7 @@ struct TcPlan { int a_region, nbuf, gchunks, n_stages, stage_bytes, pair, coff[M
 
 int g_tc_nbuf = 1;         // layer-0 operand buffers; 2 = double-buffered where the region is small (measured: no gain, sa0 0.132 ms either way — the loaders are not what the narrow modules wait for); pab_tune_tensor_core bit 5 = 32 selects two
 
+int g_tc_serial_epi = 0;   // experiment (pab_tune_tensor_core bit 6 = 64)
 int g_tc_pair = 1;         // wide weight blocks: hi + lo plane in one 32-KB stage (pab_tune_tensor_core bit 4 = 16 clears it)
 
 bool tc_plan(const pab_layer_t *layers, int n_layers, const pab_layer_t *pre, int mode, TcPlan *p) {
@@ -950,6 +988,7 @@ int pab_tc_launch(int mode, long rows, int k_group, const pab_layer_t *all_layer
     const int n_layers = kind == 2 ? n_all - 1 : n_all;
     TcPlan p;
     if (!tc_plan(layers, n_layers, pre, mode, &p)) return PAB_EINVAL;
+    a.serial_epi = g_tc_serial_epi;
     a.nbuf = p.nbuf; a.a_region = p.a_region; a.gchunks = p.gchunks; a.n_stages = p.n_stages; a.stage_bytes = p.stage_bytes; a.pair = p.pair;
     const long per_tile = mode == TC_SA ? (TM / k_group) : TM;
     if (rows >= (1L << 31)) return PAB_EINVAL;
@@ -1027,6 +1066,7 @@ PAB_API void pab_tune_tensor_core(int enable) {
     g_tc_dynamic = (enable & 8) != 0;
     g_tc_pair = (enable & 16) == 0;
     g_tc_nbuf = (enable & 32) ? 2 : 1;
+    g_tc_serial_epi = (enable & 64) != 0;
 }
 
 int pab_tc_sa(int kind, int b, int n, int m, int k, int nbr_stride, int c, const float *xyz, const float *feat, const int *center_idx,

@@ -216,14 +216,14 @@ constexpr int FCH = 64;    // reduction slice per CTA in the fc kernel
 constexpr int FB = 32;     // clouds per register pass
 
 // wsm[b][k] = softmax_k(mx[b][:])      (MLPAttentionLayer softmax over the K clusters, loupe.py:31)
-__global__ void __launch_bounds__(128) afa_softmax_kernel(int b, int K, float *__restrict__ mx, float *__restrict__ wsm) {
+__global__ void __launch_bounds__(128) afa_softmax_kernel(int b, int K, int nsplit, float *__restrict__ mx, float *__restrict__ wsm) {
     __shared__ float red[4];
     const int t = threadIdx.x, cloud = blockIdx.x, lane = t & 31, warp = t >> 5;
     float *m = mx + (size_t)cloud * K;
     float mm = -INFINITY;
     for (int k = t; k < K; k += 128) {                       // combine the attention kernel's channel parts (in place, part 0)
         float a = m[k];
-        for (int z = 1; z < ATT_SPLIT; ++z) a = fmaxf(a, mx[((size_t)z * b + cloud) * K + k]);
+        for (int z = 1; z < nsplit; ++z) a = fmaxf(a, mx[((size_t)z * b + cloud) * K + k]);
         m[k] = a;
         mm = fmaxf(mm, a);
     }
@@ -436,10 +436,52 @@ PAB_API int pab_afa_forward(int b, int c, int K, int c_out, const float *v, cons
     if (smem > 48 * 1024) PAB_CUDA(cudaFuncSetAttribute(afa_att_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     afa_att_kernel<<<dim3(pab_divup(K, AKC), b, ATT_SPLIT), 128, smem, st>>>(b, c, K, v, w_att_t, mx);
     PAB_LAUNCH_CHECK();
-    afa_softmax_kernel<<<b, 128, 0, st>>>(b, K, mx, wsm);
+    afa_softmax_kernel<<<b, 128, 0, st>>>(b, K, ATT_SPLIT, mx, wsm);
     PAB_LAUNCH_CHECK();
     afa_fc_kernel<<<nslice, 256, 0, st>>>(b, c, K, c_out, v, wsm, fc_wt, part);
     PAB_LAUNCH_CHECK();
+    afa_finalize_kernel<<<b, 1024, 0, st>>>(b, c_out, nslice, part, fc_scale, fc_shift, l2_norm, desc);
+    PAB_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- the same head with the two products on the tensor cores (afa_tc.cu) ------------------------------------------------
+int pab_afa_tc_eligible(int c, int K, int c_out);
+int pab_afa_tc_att_parts(int c);
+int pab_afa_tc_fc_slices(int c, int K);
+int pab_afa_tc_att(int b, int c, int K, const float *v, const void *w_hi, const void *w_lo, float *mx, cudaStream_t st);
+int pab_afa_tc_fused_softmax(int b, int K);
+int pab_afa_tc_fc(int b, int c, int K, int c_out, const float *v, const float *wsm, const float *mx, int nparts, const void *w_hi,
+                  const void *w_lo, float *part, cudaStream_t st);
+
+PAB_API int pab_afa_tc_supported(int c, int K, int c_out) { return pab_afa_tc_eligible(c, K, c_out); }
+
+PAB_API size_t pab_afa_tc_workspace_bytes(int b, int c, int K, int c_out) {
+    if (!pab_afa_tc_eligible(c, K, c_out)) return 0;
+    return (1 + (size_t)pab_afa_tc_att_parts(c)) * align256(sizeof(float) * (size_t)b * K) +
+           align256(sizeof(float) * (size_t)pab_afa_tc_fc_slices(c, K) * b * c_out);
+}
+
+PAB_API int pab_afa_forward_tc(int b, int c, int K, int c_out, const float *v, const void *watt_hi, const void *watt_lo,
+                               const void *wfc_hi, const void *wfc_lo, const float *fc_scale, const float *fc_shift, int l2_norm,
+                               float *desc, void *workspace, pab_stream_t s) {
+    if (b < 0 || c <= 0 || K <= 0 || c_out <= 0 || !workspace || !watt_hi || !watt_lo || !wfc_hi || !wfc_lo) return PAB_EINVAL;
+    if (!pab_afa_tc_eligible(c, K, c_out)) return PAB_EINVAL;
+    if (b == 0) return 0;
+    cudaStream_t st = (cudaStream_t)s;
+    const int nparts = pab_afa_tc_att_parts(c), nslice = pab_afa_tc_fc_slices(c, K);
+    float *wsm = (float *)workspace;
+    float *mx = (float *)((char *)workspace + align256(sizeof(float) * (size_t)b * K));
+    float *part = (float *)((char *)workspace + (1 + (size_t)nparts) * align256(sizeof(float) * (size_t)b * K));
+    int rc = pab_afa_tc_att(b, c, K, v, watt_hi, watt_lo, mx, st);
+    if (rc) return rc;
+    const bool fused = pab_afa_tc_fused_softmax(b, K) != 0;                 // softmax inside the fc kernel: three launches
+    if (!fused) {
+        afa_softmax_kernel<<<b, 128, 0, st>>>(b, K, nparts, mx, wsm);
+        PAB_LAUNCH_CHECK();
+    }
+    rc = pab_afa_tc_fc(b, c, K, c_out, v, wsm, fused ? mx : nullptr, nparts, wfc_hi, wfc_lo, part, st);
+    if (rc) return rc;
     afa_finalize_kernel<<<b, 1024, 0, st>>>(b, c_out, nslice, part, fc_scale, fc_shift, l2_norm, desc);
     PAB_LAUNCH_CHECK();
     return 0;

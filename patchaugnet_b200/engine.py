@@ -168,6 +168,9 @@ class FusedPatchAugNet:
         afa = agg.afa
         self.w_att_t = afa.mlpa.mlps[0].weight.detach().float()[:, :, 0].t().contiguous().to(dev)   # (c_in, c_out)
         self.fc_wt = afa.fc.weight.detach().float().t().contiguous().to(dev)                        # (C*K, c_out)
+        # tensor-core head (afa_tc.cu): both weights row-major over their inputs, split into bf16 hi/lo planes
+        self.watt_planes = _split_bf16(afa.mlpa.mlps[0].weight.detach().float()[:, :, 0].contiguous().to(dev))   # (c_out', c_in)
+        self.wfc_planes = _split_bf16(afa.fc.weight.detach().float().contiguous().to(dev))                       # (c_out, C*K)
         scale, shift = _fold_bn(afa.bn)
         self.fc_scale = scale.contiguous().to(dev)
         self.fc_shift = (afa.fc.bias.detach().float() * scale + shift).contiguous().to(dev)
@@ -204,7 +207,8 @@ class FusedPatchAugNet:
         nbytes = max(lib.pab_netvlad_workspace_bytes(B, n_l, v["C"], v["K"])
                      for n_l, v in zip([ns[2], ns[1], ns[0]], self.vlad))
         if self.fused_tail:
-            nbytes = max(nbytes, lib.pab_afa_workspace_bytes(B, self.vlad[0]["C"], self.sumK, self.c_out))
+            nbytes = max(nbytes, lib.pab_afa_workspace_bytes(B, self.vlad[0]["C"], self.sumK, self.c_out),
+                         lib.pab_afa_tc_workspace_bytes(B, self.vlad[0]["C"], self.sumK, self.c_out))
         ws["scratch"] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         ws["desc"] = torch.empty(B, self.c_out, **f32)
         self._ws[key] = ws
@@ -323,8 +327,13 @@ class FusedPatchAugNet:
             self._tail_shape = tuple(out.shape[1:])               # (c_out,) — or (c_out, 1): type 5 keeps AFA's last dim
             ws["desc"].copy_(out.reshape(B, -1))
             return fp_out
-        run("afa", lambda: lib.pab_afa_forward(B, self.vlad[0]["C"], self.sumK, self.c_out, p(v), p(self.w_att_t), p(self.fc_wt),
-                                               p(self.fc_scale), p(self.fc_shift), self.l2_norm, p(ws["desc"]), p(ws["scratch"]), st))
+        if lib.pab_afa_tc_supported(self.vlad[0]["C"], self.sumK, self.c_out):
+            run("afa", lambda: lib.pab_afa_forward_tc(B, self.vlad[0]["C"], self.sumK, self.c_out, p(v), p(self.watt_planes[0]),
+                                                      p(self.watt_planes[1]), p(self.wfc_planes[0]), p(self.wfc_planes[1]),
+                                                      p(self.fc_scale), p(self.fc_shift), self.l2_norm, p(ws["desc"]), p(ws["scratch"]), st))
+        else:
+            run("afa", lambda: lib.pab_afa_forward(B, self.vlad[0]["C"], self.sumK, self.c_out, p(v), p(self.w_att_t), p(self.fc_wt),
+                                                   p(self.fc_scale), p(self.fc_shift), self.l2_norm, p(ws["desc"]), p(ws["scratch"]), st))
         return fp_out
 
     def _launch(self, xyz0, ws):
@@ -581,4 +590,9 @@ class FusedPatchAugNet:
     def launches_per_forward(self):
         """Kernels this library launches per forward (for bench.py's gpu_launches)."""
         n_index = max((sum(1 for lv in ws["levels"] if lv["index"] is not None) for ws in self._ws.values()), default=0)
-        return 4 * len(self.sa) + n_index + 2 * len(self.fp) + 2 * len(self.vlad) + (4 if self.fused_tail else 0)
+        tail = 0
+        if self.fused_tail:           # AFA head: attention logits, softmax, fc, finalize — the tensor-core fc kernel absorbs the softmax
+            B = max((k[0] for k in self._ws), default=1)
+            tc = L.lib().pab_afa_tc_supported(self.vlad[0]["C"], self.sumK, self.c_out)
+            tail = 3 if (tc and min(B, 128) * self.sumK * 4 <= 32 * 1024) else 4
+        return 4 * len(self.sa) + n_index + 2 * len(self.fp) + 2 * len(self.vlad) + tail

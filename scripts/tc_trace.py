@@ -18,6 +18,8 @@ torch.cuda.synchronize()
 buf = torch.zeros(8 * 4 * 8 + 256 + 2 * 148, dtype=torch.int64, device=dev)
 # run the forward with tracing on: every TC launch overwrites the buffer, so snapshot right after the wanted stage
 lib = L.lib()
+if os.environ.get("PAB_TC_TUNE"):
+    lib.pab_tune_tensor_core(int(os.environ["PAB_TC_TUNE"]))
 orig_run = eng._runner
 snap = {}
 def runner():

@@ -199,3 +199,48 @@ def test_sa_narrow_kernel_bit_identical_to_warp_specialised_kernel(spec, c, k, n
     for per_sm in (3, 3, 1, 2, 3):
         got = run(1, per_sm)
         assert torch.equal(got, want), (per_sm, (got - want).abs().max().item())
+
+
+@pytest.mark.parametrize("b,c,K,c_out", [(32, 256, 84, 256), (5, 256, 84, 256), (3, 64, 8, 32), (130, 128, 20, 128), (1, 192, 3, 64)])
+def test_afa_head_tensor_core_matches_simt_and_fp64(b, c, K, c_out):
+    """afa_tc.cu (attention logits and fc as bf16 hi/lo tcgen05 GEMMs) against the fp32 SIMT kernels of vlad.cu and a float64
+    evaluation of AdaptiveFeatureAggregator.forward (loupe.py:23-60, eval): conv1d -> max over channels -> softmax over clusters
+    -> x + x * w -> ReLU -> fc -> BatchNorm (folded) -> L2 norm."""
+    g = torch.Generator(device="cpu").manual_seed(b * 1000 + K)
+    v = torch.randn(b, c, K, generator=g).to(DEV)
+    watt = (torch.randn(c, c, generator=g) / c ** 0.5).to(DEV)                 # (c_out', c_in)
+    wfc = (torch.randn(c_out, c * K, generator=g) / (c * K) ** 0.5).to(DEV)    # (c_out, C*K)
+    scale = (torch.rand(c_out, generator=g) + 0.5).to(DEV)
+    shift = torch.randn(c_out, generator=g).to(DEV)
+    lib = L.lib()
+    assert lib.pab_afa_tc_supported(c, K, c_out)
+
+    def split(w):
+        hi = w.to(torch.bfloat16)
+        return hi.contiguous(), (w - hi.float()).to(torch.bfloat16).contiguous()
+
+    outs = []
+    for tc in (False, True):
+        desc = torch.full((b, c_out), float("nan"), device=DEV)
+        if tc:
+            ws = torch.empty(lib.pab_afa_tc_workspace_bytes(b, c, K, c_out), dtype=torch.uint8, device=DEV)
+            (ah, al), (fh, fl) = split(watt), split(wfc)
+            L.check(lib.pab_afa_forward_tc(b, c, K, c_out, L.ptr(v), L.ptr(ah), L.ptr(al), L.ptr(fh), L.ptr(fl), L.ptr(scale), L.ptr(shift),
+                                           1, L.ptr(desc), L.ptr(ws), L.stream_ptr()), "afa_tc")
+        else:
+            ws = torch.empty(lib.pab_afa_workspace_bytes(b, c, K, c_out), dtype=torch.uint8, device=DEV)
+            watt_t, wfc_t = watt.t().contiguous(), wfc.t().contiguous()          # (c_in, c_out') / (C*K, c_out): keep them alive
+            L.check(lib.pab_afa_forward(b, c, K, c_out, L.ptr(v), L.ptr(watt_t), L.ptr(wfc_t), L.ptr(scale),
+                                        L.ptr(shift), 1, L.ptr(desc), L.ptr(ws), L.stream_ptr()), "afa")
+        torch.cuda.synchronize()
+        outs.append(desc)
+    simt, tcore = outs
+    vd = v.double()
+    att = torch.einsum("oc,bck->bok", watt.double(), vd).max(dim=1)[0]          # (b, K)
+    w = torch.softmax(att, dim=1)[:, None, :]
+    y = torch.relu(vd + vd * w).reshape(b, c * K)
+    want = y @ wfc.double().t() * scale.double() + shift.double()
+    want = want / want.norm(dim=1, keepdim=True).clamp_min(1e-12)
+    assert torch.isfinite(tcore).all()
+    e_simt, e_tc = (simt.double() - want).abs().max().item(), (tcore.double() - want).abs().max().item()
+    assert e_simt < 2e-6 and e_tc < 5e-6, (e_simt, e_tc)
