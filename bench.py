@@ -490,6 +490,8 @@ def main():
     ap.add_argument("--fp-order", type=int, default=1, help="FP modules walk their points in Morton order (0 = index order)")
     ap.add_argument("--fps-threads", type=int, default=0, help="force the FPS CTA size (0 = automatic)")
     ap.add_argument("--fps-cpc", type=int, default=1, help="clouds per FPS CTA in stream mode (1..3)")
+    ap.add_argument("--reserve-fps-sms", type=int, default=0, help="stream mode: cap the persistent tensor-core kernels at (SMs - FPS CTAs)")
+    ap.add_argument("--dynamic-tiles", type=int, default=1, help="stream mode: tensor-core CTAs draw tiles from a counter")
     ap.add_argument("--fps-stream", type=int, default=1, help="stream mode: first-level FPS on a stream of its own (three-stage pipeline)")
     ap.add_argument("--fps-pruned", type=int, default=0, help="1 = pruned FPS sampler (exact, but slower at these sizes)")
     ap.add_argument("--prio", default="0,0", help="CUDA stream priorities geometry,dense (lower = higher priority)")
@@ -522,11 +524,14 @@ def main():
         L.lib().pab_tune_tc_max_ctas(args.tc_ctas)
     eng.fps_clouds_per_cta = args.fps_cpc
     L.lib().pab_tune_tensor_core(args.tc_tune)
+    eng.tc_tune = args.tc_tune
     L.lib().pab_tune_fps_threads(args.fps_threads)
     L.lib().pab_tune_fps_pruned(args.fps_pruned)
     eng.dense_streams = max(1, min(3, args.dense_streams))
     eng.stream_graphs = bool(args.stream_graphs)
     eng.fps_stream = bool(args.fps_stream)
+    eng.reserve_fps_sms = bool(args.reserve_fps_sms)
+    eng.stream_dynamic_tiles = bool(args.dynamic_tiles)
     eng.fp_row_order = bool(args.fp_order)
     eng.stream_priorities = tuple(int(v) for v in args.prio.split(","))
     lib = L.lib()

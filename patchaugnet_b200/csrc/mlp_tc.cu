@@ -60,7 +60,7 @@ struct alignas(64) TcArgs {
     int csize, iters;                          // CTAs per cluster sharing the weight stream (1 or 2); tile-loop trips (equal for all CTAs)
     int serial_epi;                            // experiment: the epilogue of a split pass waits for BOTH n-blocks (no MMA / epilogue overlap)
     int dynamic;                               // 1: CTAs draw tiles from *counter (atomic) instead of the static blockIdx + i*grid sequence
-    unsigned int *counter;                     // zeroed by the host before the launch
+    unsigned int *counter;                     // [0] next tile, [1] CTAs finished: the last CTA to leave zeroes both for the next launch
     int coff[MAX_LAYERS];                      // offset of each layer's shift vector in the smem constant table
     int a_region;                              // bytes of the layer-0 operand region (hi plane, then lo plane)
     int gchunks;                               // 64-channel chunks of the layer-0 operand staged at a time: a wide input (FP2's
@@ -862,6 +862,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
     }
+    if (a.dynamic && tid == 0) {                                   // every CTA has drawn its last tile before it gets here
+        __threadfence();
+        if (atomicAdd(a.counter + 1, 1u) == gridDim.x - 1) {
+            a.counter[0] = 0;
+            a.counter[1] = 0;
+            __threadfence();
+        }
+    }
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
@@ -1032,14 +1040,16 @@ int pab_tc_launch(int mode, long rows, int k_group, const pab_layer_t *all_layer
         const int extra_row0 = layers[0].tc_k0 == 0 ? layers[0].tc_k : 0;
         a.w_extra = layers[0].wt + (size_t)extra_row0 * layers[0].c_out;
     }
-    // dynamic tile scheduling (not with CTA pairs: they run in lock-step): one zeroed counter per launch out of a small pool
+    // dynamic tile scheduling (not with CTA pairs: they run in lock-step): one counter pair per launch out of a small pool
     a.dynamic = 0; a.counter = nullptr;
     if (g_tc_dynamic && a.csize == 1 && a.ntiles > grid) {
         static unsigned int *pool = nullptr;
         static unsigned int seq = 0;
-        if (!pool) PAB_CUDA(cudaMalloc(&pool, 256 * sizeof(unsigned int)));
-        a.counter = pool + (seq++ & 255u);
-        PAB_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), st));
+        if (!pool) {                                               // self-resetting (tile, finished) pairs, one per launch in flight
+            PAB_CUDA(cudaMalloc(&pool, 2 * 256 * sizeof(unsigned int)));
+            PAB_CUDA(cudaMemset(pool, 0, 2 * 256 * sizeof(unsigned int)));
+        }
+        a.counter = pool + 2 * (seq++ & 255u);
         a.dynamic = 1;
     }
     PAB_CUDA(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));

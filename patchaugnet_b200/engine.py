@@ -124,7 +124,10 @@ class FusedPatchAugNet:
         self.fps_stream = True          # forward_stream: the first level's FPS on a stream of its own (three-stage pipeline, three slots)
         self.stream_graphs = True       # forward_stream: geometry / dense launch sequences replayed as CUDA graphs (2 launches per batch)
         self._sgraphs = {}
-        self.reserve_fps_sms = True     # forward_stream: persistent tensor-core kernels leave the FPS CTAs' SMs alone
+        self.reserve_fps_sms = False    # forward_stream: persistent tensor-core kernels capped so that they leave the FPS CTAs' SMs alone
+        self.stream_dynamic_tiles = True   # forward_stream: tensor-core CTAs draw their tiles from a counter (no cap needed: a CTA
+                                           # whose SM is held by an FPS CTA starts late and takes fewer) — 40.6 k -> 42.3 k submaps/s
+        self.tc_tune = 1                # pab_tune_tensor_core bits outside forward_stream
         self.fps_clouds_per_cta = 1     # forward_stream: clouds sharing one FPS CTA (2 = half the SMs held by the sampler)
         self.refold()
 
@@ -388,6 +391,10 @@ class FusedPatchAugNet:
             L.lib().pab_tune_fps_clouds_per_cta(self.fps_clouds_per_cta)
             cpc = max(1, L.lib().pab_fps_clouds_per_sm(N))          # what the sampler will really pack for this cloud size
             L.lib().pab_tune_tc_max_ctas(n_sm - (B + cpc - 1) // cpc if 0 < B <= n_sm // 2 else 0)
+        else:
+            L.lib().pab_tune_tc_max_ctas(n_sm)                      # no cap; tells the small-CTA kernels that the SMs are shared
+        if self.stream_dynamic_tiles:
+            L.lib().pab_tune_tensor_core(self.tc_tune | 8)
         fps_done = [None] * n_slots
         geo_done = [None] * n_slots
         dense_done = [None] * n_slots
@@ -449,16 +456,19 @@ class FusedPatchAugNet:
         for sd in dense_streams:
             cur.wait_stream(sd)
         cur.wait_stream(s_geo)
+        L.lib().pab_tune_tc_max_ctas(0)
         if self.reserve_fps_sms:
-            L.lib().pab_tune_tc_max_ctas(0)
             L.lib().pab_tune_fps_clouds_per_cta(1)
+        if self.stream_dynamic_tiles:
+            L.lib().pab_tune_tensor_core(self.tc_tune)
         return out
 
     def _capture_stream_graphs(self, B, N, slots, split_fps=False):
         """FPS (optional) / geometry / dense launch sequences of every workspace slot as CUDA graphs over a static per-slot input
         buffer.  Captured with the current tuning state (CTA cap of the persistent kernels, FPS packing): the key holds it."""
         key = (B, N, L.lib().pab_fps_clouds_per_sm(N), self.reserve_fps_sms, self.fp_row_order, self.vlad_tensor_core,
-               torch.cuda.get_device_properties(self.device).multi_processor_count, len(slots), split_fps)
+               torch.cuda.get_device_properties(self.device).multi_processor_count, len(slots), split_fps,
+               self.stream_dynamic_tiles, self.tc_tune)
         got = self._sgraphs.get(key)
         if got is not None:
             return got
