@@ -283,6 +283,12 @@ size_t pab_gated_fc_workspace_bytes(int b, int f, int c_out);
 int pab_gated_fc_forward(int b, int f, int c_out, const float *v, const float *fc_wt, const float *fc_scale, const float *fc_shift,
                          const float *gate_wt, const float *gate_scale, const float *gate_shift, int l2_norm, float *desc,
                          void *workspace, pab_stream_t s);
+/* The same head with the fc product on the tcgen05 tensor cores (bf16 hi/lo planes of the fc weight, (c_out, f) with the inputs
+ * contiguous).  pab_gated_fc_tc_supported: f % 64 == 0, c_out % 32 == 0, c_out <= 256.  Same workspace as pab_gated_fc_forward. */
+int pab_gated_fc_tc_supported(int f, int c_out);
+int pab_gated_fc_forward_tc(int b, int f, int c_out, const float *v, const void *wfc_hi, const void *wfc_lo, const float *fc_scale,
+                            const float *fc_shift, const float *gate_wt, const float *gate_scale, const float *gate_shift,
+                            int l2_norm, float *desc, void *workspace, pab_stream_t s);
 
 /* Device side of the input pipeline (SceneDataSet.get_pc + normalize_point_cloud, datasets/scene_dataset.py:713-740,
  * utils/loading_pointclouds.py:51-63): raw (b,n,3) clouds as stored in the .bin files (float64 when raw_is_f64, else float32;

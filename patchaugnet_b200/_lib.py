@@ -102,6 +102,8 @@ SIGNATURES = {
     "pab_afa_tc_workspace_bytes": (C.c_size_t, [_I, _I, _I, _I]),
     "pab_afa_forward_tc": (_I, [_I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P]),
     "pab_tune_afa_tc": (None, [_I]),
+    "pab_gated_fc_tc_supported": (_I, [_I, _I]),
+    "pab_gated_fc_forward_tc": (_I, [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P]),
 }
 
 

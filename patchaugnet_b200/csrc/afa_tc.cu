@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) afa_fc_tc_kernel(int b, int c, 
     };
     // A: y = relu(v + v * wsm[cloud][f % K]) for the chunk's 64 features of every cloud of the tile; (cloud, unit) pairs over the
     // threads, the loads of a pair issued together, the stores after the caller's wait
+    const bool plain = !wsm && !mx;                                            // y = x: a plain fc over the flattened vector (PPT-Net head)
     constexpr int AR = (TM * 8 + AT_THREADS - 1) / AT_THREADS;                 // pairs per thread (2)
     float ax[AR][8], aw[AR][8];
     auto load_a = [&](int ch) {
@@ -205,11 +206,13 @@ __global__ void __launch_bounds__(AT_THREADS, 1) afa_fc_tc_kernel(int b, int c, 
                 const float4 x0 = __ldg(p), x1 = __ldg(p + 1);
                 ax[rr][0] = x0.x; ax[rr][1] = x0.y; ax[rr][2] = x0.z; ax[rr][3] = x0.w;
                 ax[rr][4] = x1.x; ax[rr][5] = x1.y; ax[rr][6] = x1.z; ax[rr][7] = x1.w;
-                int k = (int)(f0 % K);
+                if (!plain) {
+                    int k = (int)(f0 % K);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    aw[rr][i] = mx ? wsm_s[row * K + k] : __ldg(wsm + (long)(cloud0 + row) * K + k);
-                    if (++k == K) k = 0;
+                    for (int i = 0; i < 8; ++i) {
+                        aw[rr][i] = mx ? wsm_s[row * K + k] : __ldg(wsm + (long)(cloud0 + row) * K + k);
+                        if (++k == K) k = 0;
+                    }
                 }
             }
         }
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) afa_fc_tc_kernel(int b, int c, 
             if (row < nb) {
                 float y[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) y[i] = fmaxf(ax[rr][i] + ax[rr][i] * aw[rr][i], 0.f);
+                for (int i = 0; i < 8; ++i) y[i] = plain ? ax[rr][i] : fmaxf(ax[rr][i] + ax[rr][i] * aw[rr][i], 0.f);
                 store_units(a1, a2, row, j, y);
             }
         }

@@ -717,14 +717,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                 const int j_lo = g * gunits, j_hi = min(units0, j_lo + gunits);
                 a_wait_free();
                 uint8_t *a1 = a_buf1(), *a2 = a.planes == 2 ? a1 + (size_t)(a.a_region >> 1) : nullptr;     // this group's buffer
-                for (int rr = 0; rr < 32; rr += 4) {
+                // lanes -> (row of the pass, 16-byte unit): a narrow input (64 channels = 8 units per row) puts four rows on the
+                // 32 lanes of one pass instead of leaving 24 lanes without loads; four passes' worth of rows are in flight together
+                const int ug = j_hi - j_lo;
+                const int lpr = ug >= 32 ? 32 : (ug >= 16 ? 16 : 8), rpp = 32 / lpr;     // lanes per row, rows per pass
+                const int sub = lane / lpr, jl = lane - sub * lpr;
+                for (int rr = 0; rr < 32; rr += 4 * rpp) {
                     long pc[4], pn[4];
 #pragma unroll
                     for (int t4 = 0; t4 < 4; ++t4) {
-                        pc[t4] = __shfl_sync(0xffffffffu, my_pc, rr + t4);
-                        pn[t4] = __shfl_sync(0xffffffffu, my_pn, rr + t4);
+                        pc[t4] = __shfl_sync(0xffffffffu, my_pc, rr + t4 * rpp + sub);
+                        pn[t4] = __shfl_sync(0xffffffffu, my_pn, rr + t4 * rpp + sub);
                     }
-                    for (int j = j_lo + lane; j < j_hi; j += 32) {
+                    for (int j = j_lo + jl; j < j_hi; j += lpr) {
                         float4 n0[4], n1[4], c0[4], c1[4];
 #pragma unroll
                         for (int t4 = 0; t4 < 4; ++t4) {
@@ -739,7 +744,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                         for (int t4 = 0; t4 < 4; ++t4) {
                             const float v[8] = {n0[t4].x - c0[t4].x, n0[t4].y - c0[t4].y, n0[t4].z - c0[t4].z, n0[t4].w - c0[t4].w,
                                                 n1[t4].x - c1[t4].x, n1[t4].y - c1[t4].y, n1[t4].z - c1[t4].z, n1[t4].w - c1[t4].w};
-                            store_units(a1, a2, lwarp * 32 + rr + t4, j - j_lo, v);
+                            store_units(a1, a2, lwarp * 32 + rr + t4 * rpp + sub, j - j_lo, v);
                         }
                     }
                 }

@@ -487,6 +487,25 @@ PAB_API int pab_afa_forward_tc(int b, int c, int K, int c_out, const float *v, c
     return 0;
 }
 
+// gated fc head (PPT-Net / PointNetVLAD) with the fc product on the tensor cores: the fc kernel of afa_tc.cu in plain mode
+PAB_API int pab_gated_fc_tc_supported(int f, int c_out) { return f > 0 && f % 64 == 0 && pab_afa_tc_eligible(64, f / 64, c_out); }
+
+PAB_API int pab_gated_fc_forward_tc(int b, int f, int c_out, const float *v, const void *wfc_hi, const void *wfc_lo, const float *fc_scale,
+                                    const float *fc_shift, const float *gate_wt, const float *gate_scale, const float *gate_shift,
+                                    int l2_norm, float *desc, void *workspace, pab_stream_t s) {
+    if (b < 0 || f <= 0 || c_out <= 0 || !workspace || !v || !wfc_hi || !wfc_lo || !pab_gated_fc_tc_supported(f, c_out)) return PAB_EINVAL;
+    if (gate_wt && (!gate_scale || !gate_shift)) return PAB_EINVAL;
+    if (b == 0) return 0;
+    cudaStream_t st = (cudaStream_t)s;
+    float *part = (float *)workspace;                       // pab_gated_fc_workspace_bytes: f / 64 slices >= the kernel's CTAs
+    const int nslice = pab_afa_tc_fc_slices(f, 1);
+    int rc = pab_afa_tc_fc(b, f, 1, c_out, v, nullptr, nullptr, 0, wfc_hi, wfc_lo, part, st);
+    if (rc) return rc;
+    gated_finalize_kernel<<<b, 256, 0, st>>>(b, c_out, nslice, part, fc_scale, fc_shift, gate_wt, gate_scale, gate_shift, l2_norm, desc);
+    PAB_LAUNCH_CHECK();
+    return 0;
+}
+
 PAB_API size_t pab_gated_fc_workspace_bytes(int b, int f, int c_out) {
     const size_t nslice = ((size_t)f + FCH - 1) / FCH;
     return align256(sizeof(float) * nslice * b * c_out);

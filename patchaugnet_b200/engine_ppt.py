@@ -81,6 +81,7 @@ class FusedPPTNet:
         # head: hidden_weights -> bn2 -> context gating (bn1 or biases folded) -> L2, one split-K fc + one finalize kernel
         self.fc_wt = agg.hidden_weights.detach().float().contiguous().to(dev)                  # (flat, c_out)
         self.c_out = self.fc_wt.shape[1]
+        self.fc_planes = _split_bf16(self.fc_wt.t().contiguous())                              # (c_out, flat) hi / lo for the tensor-core head
         sc, sh = _fold_bn(agg.bn2)
         self.fc_scale, self.fc_shift = sc.contiguous().to(dev), sh.contiguous().to(dev)
         self.gate = None
@@ -210,8 +211,13 @@ class FusedPPTNet:
                 flat[:, off:off + Cf * K] = pad[:, :, :K].reshape(B, Cf * K)
             off += Cf * K
         gw, gs, gb = self.gate if self.gate is not None else (None, None, None)
-        chk(lib.pab_gated_fc_forward(B, self.flat, self.c_out, p(flat), p(self.fc_wt), p(self.fc_scale), p(self.fc_shift), p(gw), p(gs),
-                                     p(gb), 1 if net.use_normalize else 0, p(ws["desc"]), p(ws["scratch"]), st), "head")
+        if lib.pab_gated_fc_tc_supported(self.flat, self.c_out):
+            chk(lib.pab_gated_fc_forward_tc(B, self.flat, self.c_out, p(flat), p(self.fc_planes[0]), p(self.fc_planes[1]), p(self.fc_scale),
+                                            p(self.fc_shift), p(gw), p(gs), p(gb), 1 if net.use_normalize else 0, p(ws["desc"]),
+                                            p(ws["scratch"]), st), "head")
+        else:
+            chk(lib.pab_gated_fc_forward(B, self.flat, self.c_out, p(flat), p(self.fc_wt), p(self.fc_scale), p(self.fc_shift), p(gw), p(gs),
+                                         p(gb), 1 if net.use_normalize else 0, p(ws["desc"]), p(ws["scratch"]), st), "head")
         return fp_out
 
     # ---- forward -------------------------------------------------------------------------------------------------
