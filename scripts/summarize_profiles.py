@@ -16,8 +16,8 @@ COLS = ["gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak
 ORDER = {"fps_kernel": ["fps0", "fps1", "fps2"], "gather_rows_kernel": ["gather0", "gather1", "gather2"],
          "knn_index_kernel": ["index0", "index1"], "knn_pruned32_kernel": ["knn0", "knn1"], "knn_kernel": ["knn2"],
          "three_nn_kernel": ["three_nn2", "three_nn1"], "three_nn_pruned_kernel": ["three_nn0"],
-         "mlp_tc_kernel": ["sa0", "sa1", "sa2", "fp2", "fp1", "fp0"], "vlad_tc_kernel": ["vlad0", "vlad1", "vlad2"],
-         "vlad_finalize_kernel": ["vlad0_fin", "vlad1_fin", "vlad2_fin"], "afa_att_kernel": ["afa_att"],
+         "sa_narrow_tc_kernel": ["sa0"], "mlp_tc_kernel": ["sa1", "sa2", "fp2", "fp1", "fp0"], "vlad_tc_kernel": ["vlad0", "vlad1", "vlad2"],
+         "vlad_finalize_kernel": ["vlad0_fin", "vlad1_fin", "vlad2_fin"], "afa_att_kernel": ["afa_att"], "afa_att_tc_kernel": ["afa_att"], "afa_fc_tc_kernel": ["afa_fc"],
          "afa_softmax_kernel": ["afa_softmax"], "afa_fc_kernel": ["afa_fc"], "afa_finalize_kernel": ["afa_finalize"]}
 UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "us": 1, "ms": 1e3, "ns": 1e-3, "s": 1e6}
 
@@ -64,7 +64,7 @@ def main():
     total = sum(r["gpu__time_duration.sum"] for r in step)
     traffic = {}
     lines = ["# One eager forward (batch 32 x 4096) under ncu: share of the step per kernel, tensor-pipe activity, DRAM and L2 traffic", "",
-             "`ncu --metrics ... --clock-control none -k regex:<all hand-written kernels> -s 60 -c 30 python bench.py --mode eager` "
+             "`ncu --metrics ... --clock-control none -k regex:<all hand-written kernels> -s 58 -c 29 python bench.py --mode eager` "
              "(scripts/gpu_profile.sh).  Times under ncu are serialised and cold-cache: the SHARE column is what compares with the "
              "live per-stage events of bench.py (`stage_ms`).", "",
              "| stage | kernel | grid | us | share | tensor pipe active % | issue active % | DRAM MB | L2 MB | regs |", "|---|---|---|---|---|---|---|---|---|---|"]
@@ -81,7 +81,7 @@ def main():
     lines.append("Sum of kernel times under ncu: %.1f us." % total)
     open(os.path.join(PROF, "r02_share_of_step.md"), "w").write("\n".join(lines) + "\n")
     json.dump({"source": "profiles/r02_top_kernels.csv (ncu metric capture of one eager forward, --clock-control none, batch 32 x 4096): "
-                         "dram__bytes_read.sum + dram__bytes_write.sum per launch (afa = its four launches)",
+                         "dram__bytes_read.sum + dram__bytes_write.sum per launch (afa = its three launches)",
                "dram_bytes_per_launch": traffic}, open(os.path.join(PROF, "r02_traffic.json"), "w"), indent=1)
     extra = os.path.join(OUT, "r02_extra_metrics.csv")
     if os.path.exists(extra):
