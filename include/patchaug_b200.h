@@ -228,6 +228,10 @@ int pab_sa_layer_forward(int b, int n, int c, const float *x, const pab_layer_t 
 /* Tuning hook: 1 (default) = levels with n <= 64 points run the whole layer (projections, attention, trans_conv, residual) as ONE
  * kernel, one CTA per cloud, everything in shared memory; 0 = the five-launch path for every size. */
 void pab_tune_attention_small(int on);
+/* Tuning hook: 1 (default) = single point-wise layers whose pab_layer_t carries bf16 hi/lo planes (c_in % 64 == 0, c_out % 32 == 0) run
+ * on the tcgen05 kernel of pw_tc.cu; 0 = always the fp32 tile kernel.  pab_tune_attention_small(2) forces the single-kernel
+ * SA_Layer for small levels even when its projections could use the tensor cores. */
+void pab_tune_pointwise_tc(int on);
 /* Tuning hook: enable = 1 (default): a set-abstraction module with a tiny input (<= 8 channels) and layers <= 64 wide (SA0 of
  * both networks) runs on sa_narrow_tc.cu — 128-thread CTAs, ctas_per_sm resident per SM (1..3; 0 = default: 3, or 2 while pab_tune_tc_max_ctas reserves SMs for another stream), weights resident in
  * shared memory; 0: the warp-specialised one-CTA-per-SM kernel of mlp_tc.cu takes it.  Results are bit-identical. */

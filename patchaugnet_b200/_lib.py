@@ -38,6 +38,7 @@ SIGNATURES = {
     "pab_tune_fps_clouds_per_cta": (None, [_I]),
     "pab_tune_fps_pruned": (None, [_I]),
     "pab_tune_attention_small": (None, [_I]),
+    "pab_tune_pointwise_tc": (None, [_I]),
     "pab_tune_sa_narrow": (None, [_I, _I]),
     "pab_tune_sa_narrow_trace": (None, [_P]),
     "pab_tune_sa_narrow_dbg": (None, [_I]),

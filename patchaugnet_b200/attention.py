@@ -28,11 +28,21 @@ def _fold(layer, device):
     tr_wt = (wt * scale[:, None]).t().contiguous().to(device)                           # (C, C)
     tr_shift = (scale * (layer.trans_conv.bias.detach().float() - bn.running_mean.detach().float())
                 + bn.bias.detach().float()).contiguous().to(device)
+    # the same three weights as (c_out, c_in) bf16 hi/lo planes: the projections then run on the tensor cores (csrc/pw_tc.cu)
+    def planes(w_out_in):
+        w = w_out_in.contiguous().to(device)
+        hi = w.to(torch.bfloat16)
+        return hi.contiguous(), (w - hi.float()).to(torch.bfloat16).contiguous()
+    # q and v as the two halves of ONE (2C, C) weight with one (2C) shift: the C side then runs both projections as a single product
+    qvh, qvl = planes(torch.cat([wq_dense.to(wv.device), wv], 0))
+    qv_shift = torch.cat([q_shift, v_shift]).contiguous()
+    q_shift, v_shift = qv_shift[:C], qv_shift[C:]
+    th, tl = planes(wt * scale[:, None])
     arr = (L.PabLayer * 3)()
-    arr[0] = L.PabLayer(q_wt.data_ptr(), q_shift.data_ptr(), C, C, C, 0, 0, 0, 0, 0)
-    arr[1] = L.PabLayer(v_wt.data_ptr(), v_shift.data_ptr(), C, C, C, 0, 0, 0, 0, 0)
-    arr[2] = L.PabLayer(tr_wt.data_ptr(), tr_shift.data_ptr(), C, C, C, 1, 0, 0, 0, 0)
-    return dict(arr=arr, keep=(q_wt, q_shift, v_wt, v_shift, tr_wt, tr_shift), C=C)
+    arr[0] = L.PabLayer(q_wt.data_ptr(), q_shift.data_ptr(), C, C, C, 0, qvh[:C].data_ptr(), qvl[:C].data_ptr(), 0, C)
+    arr[1] = L.PabLayer(v_wt.data_ptr(), v_shift.data_ptr(), C, C, C, 0, qvh[C:].data_ptr(), qvl[C:].data_ptr(), 0, C)
+    arr[2] = L.PabLayer(tr_wt.data_ptr(), tr_shift.data_ptr(), C, C, C, 1, th.data_ptr(), tl.data_ptr(), 0, C)
+    return dict(arr=arr, keep=(q_wt, qv_shift, v_wt, tr_wt, tr_shift, qvh, qvl, th, tl), C=C)
 
 
 def _versions(layer):

@@ -17,6 +17,8 @@
 #include <math.h>
 #include "tile_gemm.cuh"
 
+int pab_pw_tc_eligible(const pab_layer_t *L, long out_ld);
+int pab_pw_tc_launch(long rows, const float *x, const pab_layer_t *L, const float *residual, float *out, long out_ld, cudaStream_t st);
 int pab_pointwise_mlp_residual(int rows, const float *x, const pab_layer_t *layers, int n_layers, const float *residual,
                                float *out, long out_ld, cudaStream_t st);   // mlp.cu
 
@@ -207,7 +209,10 @@ __device__ __forceinline__ void as_project(int n, int C, int ld, const float *__
 template <int NR>
 __global__ void __launch_bounds__(AS_T, 1)
 attn_small_kernel(int n, int C, const float *__restrict__ x, const float *__restrict__ wq, const float *__restrict__ wv,
-                  const float *__restrict__ bv, const float *__restrict__ wtr, const float *__restrict__ btr, float *__restrict__ out) {
+                  const float *__restrict__ bv, const float *__restrict__ wtr, const float *__restrict__ btr, float *__restrict__ out,
+                  const float *__restrict__ qv) {
+    // qv != NULL ("core" mode): the projections ran on the tensor cores (pw_tc.cu): Q and V are read from the interleaved
+    // (rows, 2C) buffer, and the kernel stops after d = x - x_r (written to out); trans_conv follows as another pw_tc launch
     extern __shared__ __align__(16) float sm[];
     const int ld = C + 4;                                   // row stride: rows land in different banks
     float *xs = sm, *qs = xs + NR * ld, *vs = qs + NR * ld, *es = vs + NR * ld;      // es: [NR][NR + 4] energies / probabilities
@@ -219,8 +224,16 @@ attn_small_kernel(int n, int C, const float *__restrict__ x, const float *__rest
     __syncthreads();
     for (int e = t; e < n * C; e += AS_T) xs[(e / C) * ld + (e % C)] = __ldg(x + e);
     __syncthreads();
-    as_project<NR>(n, C, ld, xs, wq, nullptr, qs, false, nullptr);
-    as_project<NR>(n, C, ld, xs, wv, bv, vs, false, nullptr);
+    if (qv) {
+        qv += (size_t)cloud * n * 2 * C;
+        for (int e = t; e < n * 2 * C; e += AS_T) {
+            const int r = e / (2 * C), cc = e - r * 2 * C;
+            (cc < C ? qs + r * ld + cc : vs + r * ld + cc - C)[0] = __ldg(qv + e);
+        }
+    } else {
+        as_project<NR>(n, C, ld, xs, wq, nullptr, qs, false, nullptr);
+        as_project<NR>(n, C, ld, xs, wv, bv, vs, false, nullptr);
+    }
     __syncthreads();
     // energies E[i][j] = Q_i . Q_j
     for (int e = t; e < n * n; e += AS_T) {
@@ -274,6 +287,10 @@ attn_small_kernel(int n, int C, const float *__restrict__ x, const float *__rest
             if (j < n) qs[j * ld + c] = xs[j * ld + c] - acc[j] * csum[j];
     }
     __syncthreads();
+    if (qv) {
+        for (int e = t; e < n * C; e += AS_T) out[e] = qs[(e / C) * ld + (e % C)];
+        return;
+    }
     // out = x + relu(d Wt + bt), staged in V's buffer, then stored coalesced
     as_project<NR>(n, C, ld, qs, wtr, btr, vs, true, xs);
     __syncthreads();
@@ -284,7 +301,7 @@ size_t as_smem(int nr, int C) { return sizeof(float) * ((size_t)3 * nr * (C + 4)
 
 // returns 0 when the layer was handled, PAB_EINVAL when the shape is not eligible
 int launch_attn_small(int b, int n, int c, const float *x, const pab_layer_t *q, const pab_layer_t *v, const pab_layer_t *tr, float *out,
-                      cudaStream_t st) {
+                      cudaStream_t st, const float *qv = nullptr) {
     if (n > AS_MAXN || c % 8 || b > 65535) return PAB_EINVAL;
     const int nr = n <= 16 ? 16 : (n <= 32 ? 32 : 64);
     const size_t smem = as_smem(nr, c);
@@ -294,7 +311,7 @@ int launch_attn_small(int b, int n, int c, const float *x, const pab_layer_t *q,
 #define AS_LAUNCH(NR)                                                                                                        \
     do {                                                                                                                     \
         PAB_CUDA(cudaFuncSetAttribute(attn_small_kernel<NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
-        attn_small_kernel<NR><<<b, AS_T, smem, st>>>(n, c, x, q->wt, v->wt, v->shift, tr->wt, tr->shift, out);               \
+        attn_small_kernel<NR><<<b, AS_T, smem, st>>>(n, c, x, q->wt, v->wt, v->shift, tr->wt, tr->shift, out, qv);           \
     } while (0)
     if (nr == 16) AS_LAUNCH(16); else if (nr == 32) AS_LAUNCH(32); else AS_LAUNCH(64);
 #undef AS_LAUNCH
@@ -325,17 +342,35 @@ PAB_API int pab_sa_layer_forward_p(int b, int n, int c, const float *x, const pa
         trans_layer->c_out != c) return PAB_EINVAL;
     if (b == 0) return 0;
     cudaStream_t st = (cudaStream_t)s;
-    if (g_attn_small && launch_attn_small(b, n, c, x, q_layer, v_layer, trans_layer, out, st) == 0) return 0;   // small deep levels
+    // small deep levels: the whole layer as one kernel — unless the projections can run on the tensor cores (pw_tc.cu), which
+    // beats it (g_attn_small = 2 forces the single kernel)
+    const bool tc_proj = pab_pw_tc_eligible(q_layer, 2L * c) && pab_pw_tc_eligible(v_layer, 2L * c) && pab_pw_tc_eligible(trans_layer, 0);
+    if (g_attn_small && (g_attn_small == 2 || !tc_proj) && launch_attn_small(b, n, c, x, q_layer, v_layer, trans_layer, out, st) == 0) return 0;
     char *w = (char *)workspace;
     float *qv = (float *)w; w += al(sizeof(float) * (size_t)b * n * 2 * c);
     float *d = (float *)w; w += al(sizeof(float) * (size_t)b * n * c);
     float *rmax = (float *)w; w += al(sizeof(float) * (size_t)b * n);
     float *rsum = (float *)w;
     const long ld = 2L * c;                                   // [Q | V] interleaved per point
-    int rc = pab_pointwise_mlp_residual(b * n, x, q_layer, 1, nullptr, qv, ld, st);
-    if (rc) return rc;
-    rc = pab_pointwise_mlp_residual(b * n, x, v_layer, 1, nullptr, qv + c, ld, st);
-    if (rc) return rc;
+    int rc;
+    // the host may hand q and v as the two halves of ONE (2c, c) weight (planes and shifts contiguous): a single N = 2c product
+    const bool merged = tc_proj && (const char *)v_layer->w_hi == (const char *)q_layer->w_hi + (size_t)c * q_layer->tc_k * 2 &&
+                        (const char *)v_layer->w_lo == (const char *)q_layer->w_lo + (size_t)c * q_layer->tc_k * 2 &&
+                        v_layer->shift == q_layer->shift + c && v_layer->tc_k == q_layer->tc_k && !q_layer->relu && !v_layer->relu;
+    if (merged) {
+        pab_layer_t qvl = *q_layer;
+        qvl.c_out = 2 * c;
+        rc = pab_pw_tc_launch((long)b * n, x, &qvl, nullptr, qv, ld, st);
+        if (rc) return rc;
+    } else {
+        rc = pab_pointwise_mlp_residual(b * n, x, q_layer, 1, nullptr, qv, ld, st);
+        if (rc) return rc;
+        rc = pab_pointwise_mlp_residual(b * n, x, v_layer, 1, nullptr, qv + c, ld, st);
+        if (rc) return rc;
+    }
+    // small levels with tensor-core projections: the attention core of the single-kernel path between them
+    if (tc_proj && g_attn_small && launch_attn_small(b, n, c, x, q_layer, v_layer, trans_layer, d, st, qv) == 0)
+        return pab_pointwise_mlp_residual(b * n, d, trans_layer, 1, x, out, 0, st);
     if (precision > 0 && pab_attention_tc(b, n, c, qv, qv + c, ld, x, rmax, rsum, d, precision, st) == 0)
         return pab_pointwise_mlp_residual(b * n, d, trans_layer, 1, x, out, 0, st);
     const dim3 grid(pab_divup(n, AT_R), b);

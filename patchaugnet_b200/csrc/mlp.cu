@@ -265,9 +265,14 @@ PAB_API int pab_fp_module_forward(int b, int n, int m, int c_known, int c_skip, 
     return pab_fp_module_forward_ordered(b, n, m, c_known, c_skip, known_feat, skip_feat, idx, weight, nullptr, 0, layers, n_layers, out, s);
 }
 
+int pab_pw_tc_eligible(const pab_layer_t *L, long out_ld);
+int pab_pw_tc_launch(long rows, const float *x, const pab_layer_t *L, const float *residual, float *out, long out_ld, cudaStream_t st);
+
 int pab_pointwise_mlp_residual(int rows, const float *x, const pab_layer_t *layers, int n_layers, const float *residual,
                                float *out, long out_ld, cudaStream_t st) {
     if (rows < 0 || !layers) return PAB_EINVAL;
+    if (n_layers == 1 && pab_pw_tc_eligible(&layers[0], out_ld))       // one wide layer with bf16 hi/lo planes: tensor cores (pw_tc.cu)
+        return pab_pw_tc_launch(rows, x, &layers[0], residual, out, out_ld, st);
     MlpArgs a{};
     a.mode = MODE_PLAIN; a.rows = rows; a.x = x; a.residual = residual; a.out = out; a.out_ld = out_ld;
     return run(a, layers, n_layers, 0, st);

@@ -244,3 +244,33 @@ def test_afa_head_tensor_core_matches_simt_and_fp64(b, c, K, c_out):
     assert torch.isfinite(tcore).all()
     e_simt, e_tc = (simt.double() - want).abs().max().item(), (tcore.double() - want).abs().max().item()
     assert e_simt < 2e-6 and e_tc < 5e-6, (e_simt, e_tc)
+
+
+@pytest.mark.parametrize("K,N,rows", [(64, 64, 65536), (128, 128, 1000), (256, 256, 4096), (512, 512, 1024), (64, 32, 77), (192, 64, 130)])
+def test_pointwise_layer_tensor_core_matches_simt_and_fp64(K, N, rows):
+    """pw_tc.cu (one point-wise layer as a K-chunked bf16 hi/lo tcgen05 GEMM) against the fp32 tile kernel of mlp.cu and float64,
+    through pab_pointwise_mlp_forward."""
+    g = torch.Generator(device="cpu").manual_seed(K + N)
+    mlp = _mlp([K, N], K + 1)
+    layers = _Layers(mlp, DEV)
+    assert layers.tensor_core
+    x = torch.randn(rows, K, generator=g).to(DEV)
+    outs = []
+    for tc in (0, 1):
+        out = torch.full((rows, N), float("nan"), device=DEV)
+        L.lib().pab_tune_pointwise_tc(tc)
+        try:
+            L.check(L.lib().pab_pointwise_mlp_forward(rows, L.ptr(x), layers.arr, layers.n, L.ptr(out), L.stream_ptr()), "pw")
+            torch.cuda.synchronize()
+        finally:
+            L.lib().pab_tune_pointwise_tc(1)
+        outs.append(out)
+    simt, tcore = outs
+    with torch.no_grad():
+        want = mlp.double()(x.double().t()[None, :, :, None])[0, :, :, 0].t()
+    mlp.float()
+    scale = want.abs().max().item()
+    assert torch.isfinite(tcore).all()
+    assert (simt.double() - want).abs().max().item() < 2e-5 * scale
+    assert (tcore.double() - want).abs().max().item() < 5e-5 * scale
+    assert not torch.equal(simt, tcore) or K == 0            # the two paths really are different kernels
