@@ -260,6 +260,13 @@ class FusedPPTNet:
         s_dense.wait_stream(cur)
         slots = [self._workspace(B, N, slot) for slot in (0, 1)]
         geo_done, dense_done = [None, None], [None, None]
+        # as engine.FusedPatchAugNet.forward_stream: the persistent tensor-core kernels draw their tiles from a counter (a CTA whose
+        # SM is held by an FPS CTA of the other stream starts late and takes fewer), the small-CTA SA0 kernel leaves registers free
+        dyn = getattr(self, "stream_dynamic_tiles", True)
+        if dyn:
+            n_sm = torch.cuda.get_device_properties(self.device).multi_processor_count
+            L.lib().pab_tune_tc_max_ctas(n_sm)
+            L.lib().pab_tune_tensor_core(1 | 8)
         for i, x in enumerate(batches):
             L.require_cuda(x)
             xyz0 = (x.squeeze(1) if x.dim() == 4 else x).contiguous().float()
@@ -281,6 +288,9 @@ class FusedPPTNet:
             xyz0.record_stream(s_dense)
         cur.wait_stream(s_dense)
         cur.wait_stream(s_geo)
+        if dyn:
+            L.lib().pab_tune_tc_max_ctas(0)
+            L.lib().pab_tune_tensor_core(1)
         return out
 
     __call__ = forward
