@@ -492,6 +492,8 @@ def main():
     ap.add_argument("--fps-cpc", type=int, default=1, help="clouds per FPS CTA in stream mode (1..3)")
     ap.add_argument("--reserve-fps-sms", type=int, default=0, help="stream mode: cap the persistent tensor-core kernels at (SMs - FPS CTAs)")
     ap.add_argument("--dynamic-tiles", type=int, default=1, help="stream mode: tensor-core CTAs draw tiles from a counter")
+    ap.add_argument("--coalesce", type=int, default=0, help="stream mode: clouds per launch sequence of the timed region (0 = one sequence per "
+                    "batch, the configuration named in config.global_batch); the `coalesced` record and `e2e` use 128")
     ap.add_argument("--fps-stream", type=int, default=1, help="stream mode: first-level FPS on a stream of its own (three-stage pipeline)")
     ap.add_argument("--fps-pruned", type=int, default=0, help="1 = pruned FPS sampler (exact, but slower at these sizes)")
     ap.add_argument("--prio", default="0,0", help="CUDA stream priorities geometry,dense (lower = higher priority)")
@@ -597,7 +599,7 @@ def main():
         e0.record()
         with torch.no_grad():
             if mode == "stream":     # throughput mode: batch i+1's geometry overlaps batch i's dense kernels (2 streams)
-                eng.forward_stream([pool[(W + rep * K + i) % pool_batches] for i in range(K)], out=local_desc)
+                eng.forward_stream([pool[(W + rep * K + i) % pool_batches] for i in range(K)], out=local_desc, coalesce=args.coalesce)
             else:
                 for i in range(K):
                     desc = eng(pool[(W + rep * K + i) % pool_batches], clone=False, return_feat=False)
@@ -615,9 +617,36 @@ def main():
         launches = lib.pab_num_launches()
     if mode == "graph" or (mode == "stream" and getattr(eng, "last_stream_used_graphs", False)):
         launches = K * eng.launches_per_forward()        # graph replays do not pass through the C ABI counter
-    clocks = sampler.stop() if rank == 0 else None
     elapsed_ms = float(np.median(region_ms))
     value = world * B * K / (elapsed_ms * 1e-3)
+    # the same device-resident region with consecutive batches concatenated into launch sequences of 128 clouds (what the public API
+    # retrieval.extract_descriptors does): bit-identical descriptors, reported next to the per-batch number, never instead of it
+    coalesced = None
+    if mode == "stream" and not args.coalesce:
+        Kc = max(K, 64) // 4 * 4
+        co_desc = torch.empty(Kc * B, 256, device=dev)
+        co_ms = []
+        with torch.no_grad():
+            eng.forward_stream([pool[i % pool_batches] for i in range(8)], coalesce=4 * B)          # workspaces / graphs of this shape
+            for rep in range(3):
+                sync_all()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                eng.forward_stream([pool[(rep * Kc + i) % pool_batches] for i in range(Kc)], out=co_desc, coalesce=4 * B)
+                e1.record()
+                sync_all()
+                ms = e0.elapsed_time(e1)
+                if world > 1:
+                    t = torch.tensor([ms], device=dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    ms = t.item()
+                co_ms.append(ms)
+        cms = float(np.median(co_ms))
+        coalesced = dict(value=world * B * Kc / (cms * 1e-3), unit=UNIT, clouds_per_launch_sequence=4 * B, steps=Kc, ms_per_step=cms / Kc,
+                         what="forward_stream(coalesce=128): four consecutive 32-cloud batches per launch sequence, descriptors bit-identical "
+                              "to the per-batch sequences (tests/test_model_gpu.py)")
+        del co_desc
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- dominant kernel: events around that stage only, K eager steps over the same rotating inputs -----------
     eng._graphs.clear()
@@ -694,7 +723,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = t.item()
     e2e = dict(value=world * K * B / e2e_s, unit=UNIT, h2d_bytes_per_step=B * NPTS * 3 * 4, d2h_bytes_per_step=world * B * 256 * 4,
-               api="patchaugnet_b200.retrieval.extract_descriptors(net, pinned_host_clouds) + .cpu()")
+               api="patchaugnet_b200.retrieval.extract_descriptors(net, pinned_host_clouds, batch_size=32) + .cpu()",
+               clouds_per_launch_sequence=retrieval.LAUNCH_BATCH,
+               note="uploads in batches of 32; the engine concatenates four consecutive batches per launch sequence (bit-identical descriptors)")
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -721,7 +752,7 @@ def main():
             "config": {"workload": f"PatchAugNet descriptor extraction, batch {B} x {NPTS}-pt synthetic clouds per GPU, fp32, eval "
                                    "(BASELINE.json configs[1])", "global_batch": world * B, "l2": "inputs_larger_than_l2 (164 MB rotating pool)",
                        "launch": mode, "parallelism": f"dp{world}, shard-by-submap, one all_gather of descriptors"},
-            "roofline": roof, "roofline_all": roof_all, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roof, "roofline_all": roof_all, "cpu_baseline": cpu, "e2e": e2e, "coalesced": coalesced, "gpu_launches": int(launches), "clocks": clocks,
             "timed_region": {"repeats": R, "steps_per_repeat": K, "ms_per_repeat": [round(v, 4) for v in region_ms],
                              "reported": "median repetition"},
             "stage_ms": {k: round(v, 4) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1])}, **extras}))

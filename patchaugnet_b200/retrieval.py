@@ -42,21 +42,26 @@ def _copy_stream(device):
     return _COPY_STREAMS[key]
 
 
+LAUNCH_BATCH = 128     # clouds per launch sequence of the fused engine in throughput mode (engine.forward_stream(coalesce=...))
+
+
 def extract_descriptors(extract_fn, clouds, batch_size=32, device=None, dim=256, group=None, out_device=None,
-                        super_chunk=64):
+                        super_chunk=64, launch_batch=None):
     """Descriptors of this rank's shard of ``clouds`` (M,N,3), all-gathered so every rank returns the full (M, dim).
 
     ``extract_fn`` is either a ``patchaugnet_b200.patch_aug_net.Network`` in eval mode on CUDA — then the shard runs
     through the fused engine in throughput mode (``FusedPatchAugNet.forward_stream``: geometry of batch i+1 overlapped
     with the dense kernels of batch i) — or any callable ``x (b,1,N,3) on device -> (b,dim)``.
     ``clouds`` may live on the host (pinned memory recommended: the copies are issued non-blocking, ``super_chunk``
-    batches at a time) or on the device.
+    batches at a time) or on the device.  ``batch_size`` is the granularity of the uploads; the fused engine concatenates
+    consecutive batches into launch sequences of up to ``launch_batch`` clouds (default ``LAUNCH_BATCH`` = 128; descriptors are
+    bit-identical for any value, ``launch_batch=batch_size`` keeps one sequence per batch).
     """
-    return extract_descriptor_sets(extract_fn, [clouds], batch_size, device, dim, group, out_device, super_chunk)[0]
+    return extract_descriptor_sets(extract_fn, [clouds], batch_size, device, dim, group, out_device, super_chunk, launch_batch)[0]
 
 
 def extract_descriptor_sets(extract_fn, cloud_sets, batch_size=32, device=None, dim=256, group=None, out_device=None,
-                            super_chunk=64):
+                            super_chunk=64, launch_batch=None):
     """``extract_descriptors`` for several cloud sets at once (database and queries of an evaluation): every set is sharded over
     the ranks by contiguous index range, this rank's shards of ALL sets run through ONE pipelined batch sequence (the
     pipeline fills and drains once, not once per set), then each set gets its own all_gather.  Returns a list of (M_i, dim)."""
@@ -101,7 +106,8 @@ def extract_descriptor_sets(extract_fn, cloud_sets, batch_size=32, device=None, 
         for c0 in range(0, len(full_jobs), super_chunk):
             jobs = full_jobs[c0:c0 + super_chunk]
             batches, events = stage(jobs)
-            out = engine.forward_stream(batches, ready_events=events)
+            out = engine.forward_stream(batches, ready_events=events,
+                                        coalesce=LAUNCH_BATCH if launch_batch is None else launch_batch)
             for j, (si, s0, e0) in enumerate(jobs):
                 locals_[si][s0 - shards[si][0]:e0 - shards[si][0]] = out[j * batch_size:(j + 1) * batch_size]
         if tail_jobs:

@@ -1,5 +1,5 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
-timeout 600 python -m pytest tests/test_mlp_tc_gpu.py -x -q -m gpu --timeout 120 -k pointwise 2>&1 | tail -8
-timeout 900 python -m pytest tests/test_pptnet_gpu.py -x -q -m gpu --timeout 120 2>&1 | tail -8
-timeout 300 python scripts/ppt_stages.py 2>&1 | head -24
+timeout 600 python -m pytest tests/test_model_gpu.py tests/test_losses_retrieval_gpu.py -x -q -m gpu --timeout 180 2>&1 | tail -3
+timeout 300 python bench.py --steps 20 --warmup 5 --no-extras 2>&1 | tail -1 | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print(round(d['value']), d['ms_per_step'], d['e2e'], d['coalesced'], d['clocks'])"

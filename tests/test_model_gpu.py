@@ -180,6 +180,13 @@ def test_pipelined_forward_stream_matches_per_batch_forward(net):
         a, b = retrieval.extract_descriptor_sets(net, [host[:13], host[5:18]], batch_size=4, device=torch.device(DEV))
         torch.cuda.synchronize()
     assert torch.equal(a, want[:13]) and torch.equal(b, want[5:18])
+    # consecutive batches concatenated into larger launch sequences (coalesce): submaps are independent and every kernel's arithmetic
+    # depends on the cloud only, so the descriptors must not change by a bit — groups of two batches plus an uncoalesced remainder
+    with torch.no_grad():
+        got2 = net.engine().forward_stream(batches, coalesce=8)
+        d2 = retrieval.extract_descriptors(net, host, batch_size=4, device=torch.device(DEV), launch_batch=8)
+        torch.cuda.synchronize()
+    assert torch.equal(got2, want) and torch.equal(d2, want[:18])
 
 
 @pytest.mark.parametrize("agg_type,gating", [(0, False), (1, False), (3, False), (4, False), (5, False), (2, True), (0, True)])
