@@ -369,7 +369,7 @@ def other_configs(dev, world, rank):
         g = torch.Generator(device=dev).manual_seed(4321)         # same clouds on every rank; each rank reads its shard only
         clouds = (torch.rand(n_db + n_q, NPTS, 3, generator=g, device=dev) * 2 - 1) * 0.57
         with torch.no_grad():                                        # warm-up: kernels / lazily loaded modules of the retrieval ops
-            wd = retrieval.extract_descriptors(net, clouds[:64 * world], batch_size=32, device=dev)
+            wd = retrieval.extract_descriptors(net, clouds[:512 * world], batch_size=32, device=dev)   # incl. the CUDA graphs of the coalesced launch shape (captured from 4 groups on, ~1 s)
         retrieval.evaluate_recall(wd, wd[: 8 * world], [{i} for i in range(8 * world)], top_k=25)
         if world > 1:
             dist.barrier()
@@ -707,7 +707,7 @@ def main():
     host_clouds = (torch.rand(world * K * B, NPTS, 3, generator=g2) * 2 - 1).mul_(0.57).contiguous().pin_memory()
     out_host = torch.empty(world * K * B, 256).pin_memory()
     with torch.no_grad():
-        retrieval.extract_descriptors(net, host_clouds[: world * 4 * B], batch_size=B, device=dev)     # warm-up
+        retrieval.extract_descriptors(net, host_clouds[: world * 16 * B], batch_size=B, device=dev)    # warm-up (incl. the graphs of the coalesced shape)
     e2e_runs = []
     for _ in range(3):                                      # median of 3 repetitions of the K-step region
         sync_all()

@@ -368,7 +368,7 @@ class FusedPatchAugNet:
             out = torch.empty(len(batches) * B, self.c_out, dtype=torch.float32, device=self.device)
         cur = torch.cuda.current_stream()
         g = int(coalesce) // B if coalesce else 0
-        if g >= 2 and len(batches) >= 2 * g:
+        if g >= 2 and len(batches) >= g:
             # whole groups of g batches go through the pipeline as one batch each; a ragged remainder follows uncoalesced
             n_groups = len(batches) // g
             merged, events = [], []
