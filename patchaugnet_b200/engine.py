@@ -417,6 +417,7 @@ class FusedPatchAugNet:
             cpc = max(1, L.lib().pab_fps_clouds_per_sm(N))          # what the sampler will really pack for this cloud size
             L.lib().pab_tune_tc_max_ctas(n_sm - (B + cpc - 1) // cpc if 0 < B <= n_sm // 2 else 0)
         else:
+            L.lib().pab_tune_fps_clouds_per_cta(self.fps_clouds_per_cta)
             L.lib().pab_tune_tc_max_ctas(n_sm)                      # no cap; tells the small-CTA kernels that the SMs are shared
         if self.stream_dynamic_tiles:
             L.lib().pab_tune_tensor_core(self.tc_tune | 8)
@@ -482,8 +483,7 @@ class FusedPatchAugNet:
             cur.wait_stream(sd)
         cur.wait_stream(s_geo)
         L.lib().pab_tune_tc_max_ctas(0)
-        if self.reserve_fps_sms:
-            L.lib().pab_tune_fps_clouds_per_cta(1)
+        L.lib().pab_tune_fps_clouds_per_cta(1)
         if self.stream_dynamic_tiles:
             L.lib().pab_tune_tensor_core(self.tc_tune)
         return out
