@@ -502,12 +502,13 @@ PAB_API int pab_furthestsampling(int b, int n, int m, const float *xyz, float *t
     while (threads < 512 && threads * 2 < n) threads <<= 1;
     if (n > 4096) threads = 1024;
     if (g_fps_threads_override >= 32 && g_fps_threads_override <= 1024 &&
-        (g_fps_threads_override & (g_fps_threads_override - 1)) == 0 && g_fps_threads_override * 16 >= n)
+        (g_fps_threads_override & (g_fps_threads_override - 1)) == 0 && g_fps_threads_override * 32 >= n)
         threads = g_fps_threads_override;
     const int ppt = (n + threads - 1) / threads;
     if (ppt <= 1) return launch_fps<1, 1024>(b, n, m, threads, log2bs, xyz, temp, idx, st);
     if (ppt <= 2) return launch_fps<2, 1024>(b, n, m, threads, log2bs, xyz, temp, idx, st);
     if (ppt <= 4) return launch_fps<4, 1024>(b, n, m, threads, log2bs, xyz, temp, idx, st);
     if (ppt <= 8) return launch_fps<8, 1024>(b, n, m, threads, log2bs, xyz, temp, idx, st);
-    return launch_fps<16, 512>(b, n, m, threads, log2bs, xyz, temp, idx, st);     // 16 points per thread: <= 512 threads (registers)
+    if (ppt <= 16) return launch_fps<16, 512>(b, n, m, threads, log2bs, xyz, temp, idx, st);     // 16 points per thread: <= 512 threads (registers)
+    return launch_fps<32, 256>(b, n, m, threads, log2bs, xyz, temp, idx, st);                    // 32 points per thread: <= 256 threads
 }

@@ -128,6 +128,7 @@ class FusedPatchAugNet:
         self.stream_dynamic_tiles = True   # forward_stream: tensor-core CTAs draw their tiles from a counter (no cap needed: a CTA
                                            # whose SM is held by an FPS CTA starts late and takes fewer) — 40.6 k -> 42.3 k submaps/s
         self.tc_tune = 1                # pab_tune_tensor_core bits outside forward_stream
+        self.fps_pack_from = 64         # forward_stream: launch sequences of at least this many clouds pack two clouds per FPS CTA
         self.fps_clouds_per_cta = 1     # forward_stream: clouds sharing one FPS CTA (2 = half the SMs held by the sampler)
         self.refold()
 
@@ -417,7 +418,12 @@ class FusedPatchAugNet:
             cpc = max(1, L.lib().pab_fps_clouds_per_sm(N))          # what the sampler will really pack for this cloud size
             L.lib().pab_tune_tc_max_ctas(n_sm - (B + cpc - 1) // cpc if 0 < B <= n_sm // 2 else 0)
         else:
-            L.lib().pab_tune_fps_clouds_per_cta(self.fps_clouds_per_cta)
+            # large launch sequences: two clouds per FPS CTA at 256 threads each (0.53 ms for the pair instead of 0.40 ms per
+            # cloud: a third less SM-time for the sampler, its longer latency is hidden by the pipeline) — +3 % at 128 clouds
+            # per sequence, -1 % at 32, hence the threshold
+            pack = B >= self.fps_pack_from and self.fps_clouds_per_cta == 1
+            L.lib().pab_tune_fps_threads(256 if pack else 0)
+            L.lib().pab_tune_fps_clouds_per_cta(2 if pack else self.fps_clouds_per_cta)
             L.lib().pab_tune_tc_max_ctas(n_sm)                      # no cap; tells the small-CTA kernels that the SMs are shared
         if self.stream_dynamic_tiles:
             L.lib().pab_tune_tensor_core(self.tc_tune | 8)
@@ -484,6 +490,8 @@ class FusedPatchAugNet:
         cur.wait_stream(s_geo)
         L.lib().pab_tune_tc_max_ctas(0)
         L.lib().pab_tune_fps_clouds_per_cta(1)
+        if not self.reserve_fps_sms:
+            L.lib().pab_tune_fps_threads(0)
         if self.stream_dynamic_tiles:
             L.lib().pab_tune_tensor_core(self.tc_tune)
         return out
