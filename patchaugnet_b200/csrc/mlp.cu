@@ -231,8 +231,10 @@ PAB_API int pab_sa_module_forward(int b, int n, int m, int k, int nbr_stride, in
     if (layers[0].c_in != c + 3) return PAB_EINVAL;
     if (!new_xyz) {
         const int kind = pab_tc_eligible(layers, n_layers, k, c <= 5);
-        if (kind == 2 && pab_sa_narrow_eligible(layers, n_layers, k))       // tiny input, layers <= 64 wide: four small CTAs per SM
-            return pab_sa_narrow_launch(b, n, m, k, nbr_stride, c, xyz, feat, center_idx, nbr_idx, layers, n_layers, out, (cudaStream_t)s);
+        if (kind == 2 && pab_sa_narrow_eligible(layers, n_layers, k)) {     // tiny input, layers <= 64 wide: small CTAs, several per SM
+            const int rc = pab_sa_narrow_launch(b, n, m, k, nbr_stride, c, xyz, feat, center_idx, nbr_idx, layers, n_layers, out, (cudaStream_t)s);
+            if (rc != PAB_EINVAL) return rc;                                // EINVAL: no tile counter left for a graph capture
+        }
         if ((kind == 1 && c % 8 == 0 && layers[0].tc_k == c && layers[0].tc_k0 == 3) || kind == 2)
             return pab_tc_sa(kind, b, n, m, k, nbr_stride, c, xyz, feat, center_idx, nbr_idx, layers, n_layers, out, (cudaStream_t)s);
     }

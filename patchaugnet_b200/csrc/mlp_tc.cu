@@ -22,6 +22,8 @@
 //     either max-pooled over the K neighbours (SA) or stored as coalesced rows (FP).
 #include "tc_common.cuh"
 
+unsigned int *pab_tile_counter_pair(cudaStream_t st);   // api.cu
+
 int g_tc_max_ctas = 0;      // 0 = one persistent CTA per SM; otherwise a cap (leaves SMs to kernels of other streams); shared with vlad_tc.cu
 
 namespace {
@@ -1048,14 +1050,8 @@ int pab_tc_launch(int mode, long rows, int k_group, const pab_layer_t *all_layer
     // dynamic tile scheduling (not with CTA pairs: they run in lock-step): one counter pair per launch out of a small pool
     a.dynamic = 0; a.counter = nullptr;
     if (g_tc_dynamic && a.csize == 1 && a.ntiles > grid) {
-        static unsigned int *pool = nullptr;
-        static unsigned int seq = 0;
-        if (!pool) {                                               // self-resetting (tile, finished) pairs, one per launch in flight
-            PAB_CUDA(cudaMalloc(&pool, 2 * 256 * sizeof(unsigned int)));
-            PAB_CUDA(cudaMemset(pool, 0, 2 * 256 * sizeof(unsigned int)));
-        }
-        a.counter = pool + 2 * (seq++ & 255u);
-        a.dynamic = 1;
+        a.counter = pab_tile_counter_pair(st);                     // self-resetting (tile, finished) pair (api.cu); none left: static tiles
+        a.dynamic = a.counter ? 1 : 0;
     }
     PAB_CUDA(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     cudaLaunchConfig_t cfg = {};

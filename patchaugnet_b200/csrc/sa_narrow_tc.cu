@@ -375,6 +375,7 @@ int g_sn_dbg = 0;
 }  // namespace
 
 extern int g_tc_max_ctas;
+unsigned int *pab_tile_counter_pair(cudaStream_t st);
 
 PAB_API void pab_tune_sa_narrow_trace(void *device_buffer) { g_sn_trace = (long long *)device_buffer; }
 PAB_API void pab_tune_sa_narrow_dbg(int flags) { g_sn_dbg = flags; }
@@ -433,13 +434,8 @@ int pab_sa_narrow_launch(int b, int n, int m, int k, int nbr_stride, int c, cons
         PAB_CUDA(cudaGetDevice(&dev));
         PAB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     }
-    static unsigned int *pool = nullptr;                           // self-resetting (tile, finished) counter pairs, one per launch in flight
-    static unsigned int seq = 0;
-    if (!pool) {
-        PAB_CUDA(cudaMalloc(&pool, 2 * 256 * sizeof(unsigned int)));
-        PAB_CUDA(cudaMemset(pool, 0, 2 * 256 * sizeof(unsigned int)));
-    }
-    a.counter = pool + 2 * (seq++ & 255u);
+    a.counter = pab_tile_counter_pair(st);                         // self-resetting (item, finished) pair (api.cu)
+    if (!a.counter) return PAB_EINVAL;                             // caller falls back to the warp-specialised kernel
     const size_t smem = (size_t)a.wbytes + SN_STG_BYTES + SN_CTAB_BYTES + 64;
     int sms = n_sm;
     if (g_tc_max_ctas > 0 && sms > g_tc_max_ctas) sms = g_tc_max_ctas;
