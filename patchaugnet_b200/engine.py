@@ -427,73 +427,75 @@ class FusedPatchAugNet:
             L.lib().pab_tune_tc_max_ctas(n_sm)                      # no cap; tells the small-CTA kernels that the SMs are shared
         if self.stream_dynamic_tiles:
             L.lib().pab_tune_tensor_core(self.tc_tune | 8)
-        fps_done = [None] * n_slots
-        geo_done = [None] * n_slots
-        dense_done = [None] * n_slots
-        # The 30 launches of a batch are replayed as CUDA graphs (FPS, geometry, dense) per workspace slot: the host then issues
-        # a copy + the graph launches + a few event operations per batch instead of ~30 ctypes calls, so the pipeline stays
-        # GPU-bound when the host cores are contended (8 ranks on one box) — measured host time per batch 0.57 ms -> 0.1 ms.
-        graphs = None
-        if self.stream_graphs and self.fused_tail and self._events is None and len(batches) >= 4:
-            graphs = self._capture_stream_graphs(B, N, slots, s_fps is not None)
-        self.last_stream_used_graphs = graphs is not None
-        for i, x in enumerate(batches):
-            L.require_cuda(x)
-            xyz0 = (x.squeeze(1) if x.dim() == 4 else x).contiguous().float()
-            for sa in self.sa:                # keep the CPU RNG in lock-step with the reference (see forward)
-                if sa["dilation"] > 1:
-                    torch.randperm(sa["k"])
-            slot = i % n_slots
-            ws = slots[slot]
-            with torch.cuda.stream(s_fps if s_fps is not None else s_geo):
-                first = torch.cuda.current_stream()
-                if ready_events is not None and ready_events[i] is not None:
-                    first.wait_event(ready_events[i])
-                if dense_done[slot] is not None:
-                    first.wait_event(dense_done[slot])          # workspace (and the slot's static input) free again
-                if graphs is not None:
-                    graphs[slot]["x"].copy_(xyz0, non_blocking=True)
-                if s_fps is not None:
+        try:                                  # the tuning state above is process-global: restore it whatever happens
+            fps_done = [None] * n_slots
+            geo_done = [None] * n_slots
+            dense_done = [None] * n_slots
+            # The 30 launches of a batch are replayed as CUDA graphs (FPS, geometry, dense) per workspace slot: the host then issues
+            # a copy + the graph launches + a few event operations per batch instead of ~30 ctypes calls, so the pipeline stays
+            # GPU-bound when the host cores are contended (8 ranks on one box) — measured host time per batch 0.57 ms -> 0.1 ms.
+            graphs = None
+            if self.stream_graphs and self.fused_tail and self._events is None and len(batches) >= 4:
+                graphs = self._capture_stream_graphs(B, N, slots, s_fps is not None)
+            self.last_stream_used_graphs = graphs is not None
+            for i, x in enumerate(batches):
+                L.require_cuda(x)
+                xyz0 = (x.squeeze(1) if x.dim() == 4 else x).contiguous().float()
+                for sa in self.sa:                # keep the CPU RNG in lock-step with the reference (see forward)
+                    if sa["dilation"] > 1:
+                        torch.randperm(sa["k"])
+                slot = i % n_slots
+                ws = slots[slot]
+                with torch.cuda.stream(s_fps if s_fps is not None else s_geo):
+                    first = torch.cuda.current_stream()
+                    if ready_events is not None and ready_events[i] is not None:
+                        first.wait_event(ready_events[i])
+                    if dense_done[slot] is not None:
+                        first.wait_event(dense_done[slot])          # workspace (and the slot's static input) free again
                     if graphs is not None:
-                        graphs[slot]["fps"].replay()
+                        graphs[slot]["x"].copy_(xyz0, non_blocking=True)
+                    if s_fps is not None:
+                        if graphs is not None:
+                            graphs[slot]["fps"].replay()
+                        else:
+                            self._launch_geo(xyz0, ws, part="fps0")
+                        fps_done[slot] = torch.cuda.Event()
+                        fps_done[slot].record()
+                with torch.cuda.stream(s_geo):
+                    if s_fps is not None:
+                        s_geo.wait_event(fps_done[slot])
+                    if graphs is not None:
+                        graphs[slot]["geo"].replay()
                     else:
-                        self._launch_geo(xyz0, ws, part="fps0")
-                    fps_done[slot] = torch.cuda.Event()
-                    fps_done[slot].record()
-            with torch.cuda.stream(s_geo):
+                        self._launch_geo(xyz0, ws, part="rest" if s_fps is not None else None)
+                    geo_done[slot] = torch.cuda.Event()
+                    geo_done[slot].record()
+                s_dense = dense_streams[i % len(dense_streams)]   # alternate: the tail of one batch's kernels overlaps the next's
+                with torch.cuda.stream(s_dense):
+                    s_dense.wait_event(geo_done[slot])
+                    if graphs is not None:
+                        graphs[slot]["dense"].replay()
+                    else:
+                        self._launch_dense(xyz0, ws)
+                    out[i * B:(i + 1) * B].copy_(ws["desc"], non_blocking=True)
+                    dense_done[slot] = torch.cuda.Event()
+                    dense_done[slot].record()
+                xyz0.record_stream(s_geo)
+                xyz0.record_stream(s_dense)
                 if s_fps is not None:
-                    s_geo.wait_event(fps_done[slot])
-                if graphs is not None:
-                    graphs[slot]["geo"].replay()
-                else:
-                    self._launch_geo(xyz0, ws, part="rest" if s_fps is not None else None)
-                geo_done[slot] = torch.cuda.Event()
-                geo_done[slot].record()
-            s_dense = dense_streams[i % len(dense_streams)]   # alternate: the tail of one batch's kernels overlaps the next's
-            with torch.cuda.stream(s_dense):
-                s_dense.wait_event(geo_done[slot])
-                if graphs is not None:
-                    graphs[slot]["dense"].replay()
-                else:
-                    self._launch_dense(xyz0, ws)
-                out[i * B:(i + 1) * B].copy_(ws["desc"], non_blocking=True)
-                dense_done[slot] = torch.cuda.Event()
-                dense_done[slot].record()
-            xyz0.record_stream(s_geo)
-            xyz0.record_stream(s_dense)
+                    xyz0.record_stream(s_fps)
             if s_fps is not None:
-                xyz0.record_stream(s_fps)
-        if s_fps is not None:
-            cur.wait_stream(s_fps)
-        for sd in dense_streams:
-            cur.wait_stream(sd)
-        cur.wait_stream(s_geo)
-        L.lib().pab_tune_tc_max_ctas(0)
-        L.lib().pab_tune_fps_clouds_per_cta(1)
-        if not self.reserve_fps_sms:
-            L.lib().pab_tune_fps_threads(0)
-        if self.stream_dynamic_tiles:
-            L.lib().pab_tune_tensor_core(self.tc_tune)
+                cur.wait_stream(s_fps)
+            for sd in dense_streams:
+                cur.wait_stream(sd)
+            cur.wait_stream(s_geo)
+        finally:
+            L.lib().pab_tune_tc_max_ctas(0)
+            L.lib().pab_tune_fps_clouds_per_cta(1)
+            if not self.reserve_fps_sms:
+                L.lib().pab_tune_fps_threads(0)
+            if self.stream_dynamic_tiles:
+                L.lib().pab_tune_tensor_core(self.tc_tune)
         return out
 
     def _capture_stream_graphs(self, B, N, slots, split_fps=False):

@@ -279,30 +279,32 @@ class FusedPPTNet:
             n_sm = torch.cuda.get_device_properties(self.device).multi_processor_count
             L.lib().pab_tune_tc_max_ctas(n_sm)
             L.lib().pab_tune_tensor_core(1 | 8)
-        for i, x in enumerate(batches):
-            L.require_cuda(x)
-            xyz0 = (x.squeeze(1) if x.dim() == 4 else x).contiguous().float()
-            slot = i & 1
-            ws = slots[slot]
-            with torch.cuda.stream(s_geo):
-                if dense_done[slot] is not None:
-                    s_geo.wait_event(dense_done[slot])             # workspace free again
-                self._launch_geo(xyz0, ws)
-                geo_done[slot] = torch.cuda.Event()
-                geo_done[slot].record()
-            with torch.cuda.stream(s_dense):
-                s_dense.wait_event(geo_done[slot])
-                self._launch_dense(xyz0, ws)
-                out[i * B:(i + 1) * B].copy_(ws["desc"], non_blocking=True)
-                dense_done[slot] = torch.cuda.Event()
-                dense_done[slot].record()
-            xyz0.record_stream(s_geo)
-            xyz0.record_stream(s_dense)
-        cur.wait_stream(s_dense)
-        cur.wait_stream(s_geo)
-        if dyn:
-            L.lib().pab_tune_tc_max_ctas(0)
-            L.lib().pab_tune_tensor_core(1)
+        try:                                  # the tuning state is process-global: restore it whatever happens
+            for i, x in enumerate(batches):
+                L.require_cuda(x)
+                xyz0 = (x.squeeze(1) if x.dim() == 4 else x).contiguous().float()
+                slot = i & 1
+                ws = slots[slot]
+                with torch.cuda.stream(s_geo):
+                    if dense_done[slot] is not None:
+                        s_geo.wait_event(dense_done[slot])             # workspace free again
+                    self._launch_geo(xyz0, ws)
+                    geo_done[slot] = torch.cuda.Event()
+                    geo_done[slot].record()
+                with torch.cuda.stream(s_dense):
+                    s_dense.wait_event(geo_done[slot])
+                    self._launch_dense(xyz0, ws)
+                    out[i * B:(i + 1) * B].copy_(ws["desc"], non_blocking=True)
+                    dense_done[slot] = torch.cuda.Event()
+                    dense_done[slot].record()
+                xyz0.record_stream(s_geo)
+                xyz0.record_stream(s_dense)
+            cur.wait_stream(s_dense)
+            cur.wait_stream(s_geo)
+        finally:
+            if dyn:
+                L.lib().pab_tune_tc_max_ctas(0)
+                L.lib().pab_tune_tensor_core(1)
         return out
 
     __call__ = forward
