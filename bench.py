@@ -385,6 +385,11 @@ def other_configs(dev, world, rank):
             dist.barrier()
         torch.cuda.synchronize()
         e0, em, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+        with torch.no_grad():      # untimed first pass: workspaces of the ragged tail shapes, allocator growth
+            retrieval.extract_descriptor_sets(net, [clouds[:n_db], clouds[n_db:]], batch_size=32, device=dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
         e0.record()
         with torch.no_grad():      # database and queries as ONE pipelined sequence per rank, one all_gather per set
             db, qd = retrieval.extract_descriptor_sets(net, [clouds[:n_db], clouds[n_db:]], batch_size=32, device=dev)
