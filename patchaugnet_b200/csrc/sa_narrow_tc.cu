@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(SN_THREADS, 3) sa_narrow_tc_kernel(const __gri
         o.valid = item >= 0 && ci < a.rows && !(a.dbg & 1);
         o.base = 0; o.c = 0; o.n = 0;
         if (o.valid) {
-            o.base = (ci / a.m) * a.n;
+            o.base = (long)((unsigned)ci / (unsigned)a.m) * a.n;   // rows < 2^31 (checked by the launcher): 32-bit division
             o.c = __ldg(a.center_idx + ci);
             o.n = __ldg(a.nbr_idx + ci * a.nbr_stride + min(step * S + slot, a.k - 1));   // surplus slots repeat the last neighbour
         }
@@ -249,12 +249,21 @@ __global__ void __launch_bounds__(SN_THREADS, 3) sa_narrow_tc_kernel(const __gri
                 const uint32_t idesc = umma_idesc(N);
                 const uint32_t bh = w_lo32 + ((uint32_t)a.woff[l] >> 4), bl = bh + (uint32_t)N * 8;
                 const int kn = a.K[l] >> 4;
-                for (int ks = 0; ks < kn; ++ks) {
-                    sn_umma_ts(leader, tmem + SN_D, tmem + SN_AH + ks * 8, bh + 2 * ks, idesc, ks != 0);
-                    if (a.planes == 2) sn_umma_ts(leader, tmem + SN_D, tmem + SN_AL + ks * 8, bh + 2 * ks, idesc, 1);
+                if (a.planes == 2 && kn == 2) {                    // the common case (32 input channels, hi/lo) as straight-line code
+                    sn_umma_ts(leader, tmem + SN_D, tmem + SN_AH, bh, idesc, 0);
+                    sn_umma_ts(leader, tmem + SN_D, tmem + SN_AL, bh, idesc, 1);
+                    sn_umma_ts(leader, tmem + SN_D, tmem + SN_AH + 8, bh + 2, idesc, 1);
+                    sn_umma_ts(leader, tmem + SN_D, tmem + SN_AL + 8, bh + 2, idesc, 1);
+                    sn_umma_ts(leader, tmem + SN_D, tmem + SN_AH, bl, idesc, 1);
+                    sn_umma_ts(leader, tmem + SN_D, tmem + SN_AH + 8, bl + 2, idesc, 1);
+                } else {
+                    for (int ks = 0; ks < kn; ++ks) {
+                        sn_umma_ts(leader, tmem + SN_D, tmem + SN_AH + ks * 8, bh + 2 * ks, idesc, ks != 0);
+                        if (a.planes == 2) sn_umma_ts(leader, tmem + SN_D, tmem + SN_AL + ks * 8, bh + 2 * ks, idesc, 1);
+                    }
+                    if (a.planes == 2)
+                        for (int ks = 0; ks < kn; ++ks) sn_umma_ts(leader, tmem + SN_D, tmem + SN_AH + ks * 8, bl + 2 * ks, idesc, 1);
                 }
-                if (a.planes == 2)
-                    for (int ks = 0; ks < kn; ++ks) sn_umma_ts(leader, tmem + SN_D, tmem + SN_AH + ks * 8, bl + 2 * ks, idesc, 1);
                 umma_commit_if(leader, bar);
                 __syncwarp();
                 SN_TRACE(3 + 2 * (l != 0));
