@@ -241,13 +241,14 @@ class FusedPPTNet:
         return out, fp_features, origin
 
     @torch.no_grad()
-    def forward_stream(self, batches, out=None, coalesce=0):
+    def forward_stream(self, batches, out=None, ready_events=None, coalesce=0):
         """Throughput mode (as engine.FusedPatchAugNet.forward_stream): descriptors of a sequence of equally shaped batches, the
         geometry of batch i+1 (FPS is a serial chain on B of the 148 SMs) on a second stream under the dense kernels of batch i;
         two workspaces ping-pong, events order their reuse.  ``coalesce`` (clouds, 0 = off): consecutive batches are concatenated
         into launch sequences of up to that many clouds — bit-identical descriptors (every kernel's arithmetic depends on the cloud
         only), 28.8 k -> 32.7 k submaps/s (fp32 contract) and 31.2 k -> 35.4 k (bf16 mode) with 128 instead of 64 clouds per
-        sequence.  Returns (len(batches)*B, c_out) on the device."""
+        sequence.  ``ready_events[i]`` (optional): a CUDA event batch i's geometry waits for (its upload on a copy stream).
+        Returns (len(batches)*B, c_out) on the device."""
         batches = list(batches)
         if not batches:
             return torch.empty(0, self.c_out, device=self.device)
@@ -256,15 +257,24 @@ class FusedPPTNet:
         if out is None:
             out = torch.empty(len(batches) * B, self.c_out, dtype=torch.float32, device=self.device)
         g = int(coalesce) // B if coalesce else 0
+        cur = torch.cuda.current_stream()
         if g >= 2 and len(batches) >= g:
             n_groups = len(batches) // g
-            merged = [torch.cat([(x.squeeze(1) if x.dim() == 4 else x).float() for x in batches[gi * g:(gi + 1) * g]])
-                      for gi in range(n_groups)]
-            self.forward_stream(merged, out=out[:n_groups * g * B])
+            merged, events = [], []
+            for gi in range(n_groups):
+                if ready_events is not None:
+                    for ev in ready_events[gi * g:(gi + 1) * g]:
+                        if ev is not None:
+                            cur.wait_event(ev)
+                merged.append(torch.cat([(x.squeeze(1) if x.dim() == 4 else x).float() for x in batches[gi * g:(gi + 1) * g]]))
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                events.append(ev)
+            self.forward_stream(merged, out=out[:n_groups * g * B], ready_events=events)
             if len(batches) > n_groups * g:
-                self.forward_stream(batches[n_groups * g:], out=out[n_groups * g * B:])
+                self.forward_stream(batches[n_groups * g:], out=out[n_groups * g * B:],
+                                    ready_events=None if ready_events is None else ready_events[n_groups * g:])
             return out
-        cur = torch.cuda.current_stream()
         if getattr(self, "_streams", None) is None:
             self._streams = (torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device))
         s_geo, s_dense = self._streams
@@ -286,6 +296,8 @@ class FusedPPTNet:
                 slot = i & 1
                 ws = slots[slot]
                 with torch.cuda.stream(s_geo):
+                    if ready_events is not None and ready_events[i] is not None:
+                        s_geo.wait_event(ready_events[i])
                     if dense_done[slot] is not None:
                         s_geo.wait_event(dense_done[slot])             # workspace free again
                     self._launch_geo(xyz0, ws)

@@ -52,6 +52,11 @@ class Network(nn.Module):
         self._engine = None
         return super().train(mode)
 
+    def fusable(self):
+        """True when the eval forward runs on the fused engine (what retrieval.extract_descriptors checks before it uses the
+        engine's throughput mode)."""
+        return bool(self.use_fused) and isinstance(self.aggregation, lp.SpatialPyramidNetVLAD)
+
     def forward(self, x, return_feat=True):
         """x: B x 1 x N x 3"""
         if (self.use_fused and not self.training and x.is_cuda and not torch.is_grad_enabled()

@@ -49,7 +49,7 @@ def extract_descriptors(extract_fn, clouds, batch_size=32, device=None, dim=256,
                         super_chunk=64, launch_batch=None):
     """Descriptors of this rank's shard of ``clouds`` (M,N,3), all-gathered so every rank returns the full (M, dim).
 
-    ``extract_fn`` is either a ``patchaugnet_b200.patch_aug_net.Network`` in eval mode on CUDA — then the shard runs
+    ``extract_fn`` is either a ``patchaugnet_b200.patch_aug_net.Network`` / ``pptnet.Network`` in eval mode on CUDA — then the shard runs
     through the fused engine in throughput mode (``FusedPatchAugNet.forward_stream``: geometry of batch i+1 overlapped
     with the dense kernels of batch i) — or any callable ``x (b,1,N,3) on device -> (b,dim)``.
     ``clouds`` may live on the host (pinned memory recommended: the copies are issued non-blocking, ``super_chunk``
@@ -115,7 +115,9 @@ def extract_descriptor_sets(extract_fn, cloud_sets, batch_size=32, device=None, 
             for j, (si, s0, e0) in enumerate(tail_jobs):
                 if events is not None:
                     torch.cuda.current_stream().wait_event(events[j])
-                locals_[si][s0 - shards[si][0]:e0 - shards[si][0]] = engine(batches[j], return_feat=False, clone=False)
+                takes_clone = "clone" in engine.forward.__code__.co_varnames        # FusedPatchAugNet: return the workspace view
+                locals_[si][s0 - shards[si][0]:e0 - shards[si][0]] = (
+                    engine(batches[j], return_feat=False, clone=False) if takes_clone else engine(batches[j], return_feat=False))
     else:
         for si, (lo, hi) in enumerate(shards):
             for s0 in range(lo, hi, batch_size):

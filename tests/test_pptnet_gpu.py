@@ -124,3 +124,10 @@ def test_pptnet_pipelined_forward_stream_matches_per_batch_forward():
         torch.cuda.synchronize()
     assert torch.equal(got, want)
     assert torch.equal(got2, want[:9])                                   # coalescing must not change a bit
+    # through the retrieval API: pinned host clouds, uploads overlapped with the compute, a ragged tail batch
+    from patchaugnet_b200 import retrieval
+    host = torch.cat([b.squeeze(1) for b in batches]).cpu()[:11].pin_memory()
+    with torch.no_grad():
+        d = retrieval.extract_descriptors(net, host, batch_size=3, device=torch.device(DEV), launch_batch=6)
+        torch.cuda.synchronize()
+    assert torch.equal(d, want[:11])
