@@ -509,6 +509,7 @@ def main():
     ap.add_argument("--dynamic-tiles", type=int, default=1, help="stream mode: tensor-core CTAs draw tiles from a counter")
     ap.add_argument("--coalesce", type=int, default=0, help="stream mode: clouds per launch sequence of the timed region (0 = one sequence per "
                     "batch, the configuration named in config.global_batch); the `coalesced` record and `e2e` use 128")
+    ap.add_argument("--slots", type=int, default=4, help="stream mode: workspace slots of the three-stage pipeline")
     ap.add_argument("--fps-stream", type=int, default=1, help="stream mode: first-level FPS on a stream of its own (three-stage pipeline)")
     ap.add_argument("--fps-pruned", type=int, default=0, help="1 = pruned FPS sampler (exact, but slower at these sizes)")
     ap.add_argument("--prio", default="0,0", help="CUDA stream priorities geometry,dense (lower = higher priority)")
@@ -547,6 +548,7 @@ def main():
     eng.dense_streams = max(1, min(3, args.dense_streams))
     eng.stream_graphs = bool(args.stream_graphs)
     eng.fps_stream = bool(args.fps_stream)
+    eng.stream_slots = args.slots
     eng.reserve_fps_sms = bool(args.reserve_fps_sms)
     eng.stream_dynamic_tiles = bool(args.dynamic_tiles)
     eng.fp_row_order = bool(args.fp_order)
